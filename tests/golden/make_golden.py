@@ -1,0 +1,78 @@
+"""Generates tests/golden/*.npz by IMPORTING the reference's own Python (run in the
+build container only; /root/reference does not exist on the GPU box).
+
+Pins the parts of the oracle that the reference's present files define:
+  sh_deg{0..3}.npz : utils/sh_utils.py:57-112 eval_sh + the +0.5/clamp of
+                     gaussian_renderer/__init__.py:85-89
+  cov3d.npz        : utils/general_utils.py:68-114 build_scaling_rotation/strip_symmetric,
+                     composed as scene/gaussian_model.py:30-34
+  camera.npz       : utils/graphics_utils.py:38-77, composed as scene/cameras.py:95-98
+The hierarchy-rasterizer / gaussian-hierarchy kernels themselves are absent from
+/root/reference (empty submodules) -- no golden vectors can be produced for them.
+"""
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+sys.path.insert(0, REF)
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# the reference helpers allocate with device="cuda"; run them on CPU unchanged otherwise
+_zeros = torch.zeros
+def _cpu_zeros(*a, **k):
+    k.pop("device", None)
+    return _zeros(*a, **k)
+torch.zeros = _cpu_zeros
+
+from utils.sh_utils import eval_sh                      # noqa: E402
+from utils.general_utils import build_scaling_rotation, strip_symmetric   # noqa: E402
+from utils.graphics_utils import getWorld2View2, getProjectionMatrix      # noqa: E402
+
+g = torch.Generator().manual_seed(1234)
+N = 257
+
+# ---- SH colour (features [N,16,3] as scene/gaussian_model.py:121-124) ----
+feats = torch.randn(N, 16, 3, generator=g) * 0.4
+xyz = torch.randn(N, 3, generator=g) * 3
+campos = torch.tensor([0.3, -0.2, 0.1])
+for deg in range(4):
+    shs_view = feats.transpose(1, 2).view(-1, 3, 16)
+    dir_pp = xyz - campos.repeat(N, 1)
+    dirn = dir_pp / dir_pp.norm(dim=1, keepdim=True)
+    sh2rgb = eval_sh(deg, shs_view, dirn)
+    col = torch.clamp_min(sh2rgb + 0.5, 0.0)
+    np.savez(os.path.join(HERE, f"sh_deg{deg}.npz"), feats=feats.numpy(), xyz=xyz.numpy(), campos=campos.numpy(),
+             colors=col.numpy(), clamped=(sh2rgb + 0.5 < 0).numpy())
+
+# ---- cov3D ----
+s = torch.exp(torch.randn(N, 3, generator=g))
+q = torch.randn(N, 4, generator=g)
+qn = torch.nn.functional.normalize(q)
+for mod in (1.0,):
+    L = build_scaling_rotation(mod * s, qn)
+    cov = strip_symmetric(L @ L.transpose(1, 2))
+np.savez(os.path.join(HERE, "cov3d.npz"), scales=s.numpy(), rotations=qn.numpy(), cov6=cov.numpy())
+
+# ---- camera matrices ----
+cams = []
+rs = np.random.RandomState(7)
+for i in range(6):
+    a, b = rs.uniform(-0.5, 0.5, 2)
+    Ry = np.array([[math.cos(a), 0, math.sin(a)], [0, 1, 0], [-math.sin(a), 0, math.cos(a)]])
+    Rx = np.array([[1, 0, 0], [0, math.cos(b), -math.sin(b)], [0, math.sin(b), math.cos(b)]])
+    R = Ry @ Rx
+    T = rs.uniform(-1, 1, 3)
+    fovx = rs.uniform(0.6, 1.4); fovy = rs.uniform(0.5, 1.2)
+    primx, primy = (0.5, 0.5) if i < 3 else tuple(rs.uniform(0.4, 0.6, 2))
+    wv = torch.tensor(getWorld2View2(R, T, np.array([0.0, 0.0, 0.0]), 1.0)).transpose(0, 1)
+    pr = getProjectionMatrix(znear=0.01, zfar=100.0, fovX=fovx, fovY=fovy, primx=primx, primy=primy).transpose(0, 1)
+    full = (wv.unsqueeze(0).bmm(pr.unsqueeze(0))).squeeze(0)
+    center = wv.inverse()[3, :3]
+    cams.append(dict(R=R, T=T, fovx=fovx, fovy=fovy, primx=primx, primy=primy, wv=wv.numpy(), pr=pr.numpy(),
+                     full=full.numpy(), center=center.numpy()))
+np.savez(os.path.join(HERE, "camera.npz"), **{f"{k}_{i}": np.asarray(c[k]) for i, c in enumerate(cams) for k in c})
+print("golden written")
