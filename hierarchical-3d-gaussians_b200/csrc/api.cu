@@ -1,0 +1,164 @@
+// api.cu -- the extern "C" entry points declared in include/h3dgs.h: argument checks
+// (same exclusivity rules the reference's Python shim enforces), state-buffer
+// carving, and the stage sequence.  No torch types; device pointers only.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace h3dgs {
+
+static thread_local char g_err[1024] = "";
+int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static int check_args(const h3dgs_raster_args* a) {
+    if (!a) { set_error("args is NULL"); return H3DGS_EINVAL; }
+    if (a->P < 0 || a->image_width <= 0 || a->image_height <= 0) { set_error("bad sizes P=%d W=%d H=%d", a->P, a->image_width, a->image_height); return H3DGS_EINVAL; }
+    if ((a->shs == nullptr) == (a->colors_precomp == nullptr) && a->P > 0) {
+        set_error("Please provide excatly one of either SHs or precomputed colors!"); return H3DGS_EINVAL;
+    }
+    const bool have_sr = a->scales != nullptr && a->rotations != nullptr;
+    const bool any_sr = a->scales != nullptr || a->rotations != nullptr;
+    if (a->P > 0 && ((have_sr && a->cov3D_precomp) || (!any_sr && !a->cov3D_precomp) || (any_sr && !have_sr))) {
+        set_error("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!"); return H3DGS_EINVAL;
+    }
+    if (a->shs && (a->sh_degree < 0 || a->sh_degree > 3 || (a->sh_degree + 1) * (a->sh_degree + 1) > a->sh_coeffs || a->sh_coeffs > 16)) {
+        set_error("sh_degree %d does not fit %d SH coefficients", a->sh_degree, a->sh_coeffs); return H3DGS_EINVAL;
+    }
+    if ((a->interpolation_weights == nullptr) != (a->num_node_kids == nullptr)) {
+        set_error("interpolation_weights and num_node_kids must be given together"); return H3DGS_EINVAL;
+    }
+    if (a->shard_count > 1 && (a->shard_index < 0 || a->shard_index >= a->shard_count)) {
+        set_error("bad tile shard %d/%d", a->shard_index, a->shard_count); return H3DGS_EINVAL;
+    }
+    if (!a->means3D && a->P > 0) { set_error("means3D is NULL"); return H3DGS_EINVAL; }
+    if (!a->bg || !a->viewmatrix || !a->projmatrix || !a->campos) { set_error("bg/viewmatrix/projmatrix/campos must be device pointers"); return H3DGS_EINVAL; }
+    return H3DGS_OK;
+}
+
+}  // namespace h3dgs
+
+using namespace h3dgs;
+
+extern "C" const char* h3dgs_last_error(void) { return g_err; }
+extern "C" int h3dgs_version(void) { return H3DGS_VERSION; }
+extern "C" int64_t h3dgs_launch_count(void) { return g_launches; }
+extern "C" size_t h3dgs_backward_scratch_bytes(int32_t P) { return align_up((size_t)(P > 0 ? P : 1) * kAccum * sizeof(float)); }
+
+extern "C" int h3dgs_rasterize_forward(const h3dgs_raster_args* a, h3dgs_alloc_fn alloc, void* user,
+                                       float* out_color, int32_t* out_radii, float* out_invdepth,
+                                       int64_t* num_rendered, void* stream)
+{
+    int rc = check_args(a);
+    if (rc) return rc;
+    if (!alloc || !out_color || (!out_radii && a->P > 0) || (a->do_depth && !out_invdepth)) {
+        set_error("missing output buffer or alloc callback"); return H3DGS_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int P = a->P;
+    const GeomLayout gl = geom_layout(P);
+    uint8_t* geom = (uint8_t*)alloc(user, 0, gl.total);
+    const ImgLayout il = img_layout(a->image_width, a->image_height);
+    uint8_t* img = (uint8_t*)alloc(user, 2, il.total);
+    if (!geom || !img) { set_error("alloc callback returned NULL"); return H3DGS_ENOMEM; }
+    float* depths = (float*)(geom + gl.depths);
+    uint32_t* tiles = (uint32_t*)(geom + gl.tiles_touched);
+    uint32_t* offsets = (uint32_t*)(geom + gl.offsets);
+    Record* records = (Record*)(geom + gl.records);
+
+    rc = launch_preprocess(*a, out_radii, depths, tiles, records, s);
+    if (rc) return rc;
+    rc = launch_scan(tiles, offsets, P, geom + gl.scan_temp, gl.scan_temp_bytes, s, a->debug);
+    if (rc) return rc;
+    // The reference API sizes the binning buffer from num_rendered: one D2H + sync.
+    uint32_t D32 = 0;
+    if (P > 0) {
+        H3_CUDA(cudaMemcpyAsync(&D32, offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        H3_CUDA(cudaStreamSynchronize(s));
+    }
+    const int64_t D = (int64_t)D32;
+    if (num_rendered) *num_rendered = D;
+    const BinLayout bl = bin_layout(D);
+    uint8_t* bin = (uint8_t*)alloc(user, 1, bl.total);
+    if (!bin) { set_error("alloc callback returned NULL"); return H3DGS_ENOMEM; }
+    uint32_t* ranges = (uint32_t*)(img + il.ranges);
+    rc = launch_binning(*a, out_radii, depths, offsets, records, D, bin, bl, ranges, s);
+    if (rc) return rc;
+    rc = launch_render_forward(*a, ranges, (const Record*)(bin + bl.sorted_records), out_color, out_invdepth,
+                               (float*)(img + il.final_T), (uint32_t*)(img + il.n_contrib),
+                               (uint32_t*)(img + il.tile_max_contrib), s);
+    return rc;
+}
+
+extern "C" int h3dgs_rasterize_backward(const h3dgs_raster_args* a, const int32_t* radii, const void* geom_state,
+                                        const void* binning_state, const void* image_state, int64_t D,
+                                        const float* dL_dcolor, const float* dL_dinvdepth, float* dL_dmeans3D,
+                                        float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors_precomp,
+                                        float* dL_dopacities, float* dL_dscales, float* dL_drotations,
+                                        float* dL_dcov3D, void* scratch, void* stream)
+{
+    int rc = check_args(a);
+    if (rc) return rc;
+    if (a->P == 0) return H3DGS_OK;
+    if (!geom_state || !binning_state || !image_state || !dL_dcolor || !scratch || !radii) {
+        set_error("backward: missing saved state / scratch"); return H3DGS_EINVAL;
+    }
+    if (!dL_dmeans3D || !dL_dmeans2D || !dL_dopacities || (a->shs && !dL_dsh) ||
+        (a->scales && (!dL_dscales || !dL_drotations)) || (a->cov3D_precomp && !dL_dcov3D)) {
+        set_error("backward: missing gradient output"); return H3DGS_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const GeomLayout gl = geom_layout(a->P);
+    const BinLayout bl = bin_layout(D);
+    const ImgLayout il = img_layout(a->image_width, a->image_height);
+    const uint8_t* geom = (const uint8_t*)geom_state;
+    const uint8_t* bin = (const uint8_t*)binning_state;
+    const uint8_t* img = (const uint8_t*)image_state;
+    float* accum = (float*)scratch;
+    H3_CUDA(cudaMemsetAsync(accum, 0, (size_t)a->P * kAccum * sizeof(float), s));
+    h3dgs_raster_args b = *a;
+    if (!dL_dinvdepth) b.do_depth = 0;
+    if (D > 0) {
+        rc = launch_render_backward(b, (const uint32_t*)(img + il.ranges), (const Record*)(bin + bl.sorted_records),
+                                    (const uint32_t*)(bin + bl.vals_sorted), (const float*)(img + il.final_T),
+                                    (const uint32_t*)(img + il.n_contrib), (const uint32_t*)(img + il.tile_max_contrib),
+                                    dL_dcolor, dL_dinvdepth, accum, s);
+        if (rc) return rc;
+    }
+    return launch_preprocess_backward(b, radii, (const Record*)(geom + gl.records), accum, dL_dmeans3D, dL_dmeans2D,
+                                      dL_dsh, dL_dcolors_precomp, dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D, s);
+}
+
+extern "C" int h3dgs_state_layout(int32_t P, int32_t W, int32_t H, int64_t D, const void* geom_state,
+                                  const void* binning_state, const void* image_state, h3dgs_state_view* out)
+{
+    if (!out) { set_error("out is NULL"); return H3DGS_EINVAL; }
+    const GeomLayout gl = geom_layout(P);
+    const BinLayout bl = bin_layout(D);
+    const ImgLayout il = img_layout(W, H);
+    const uint8_t* geom = (const uint8_t*)geom_state;
+    const uint8_t* bin = (const uint8_t*)binning_state;
+    const uint8_t* img = (const uint8_t*)image_state;
+    memset(out, 0, sizeof(*out));
+    if (geom) {
+        out->depths = (const float*)(geom + gl.depths);
+        out->tiles_touched = (const uint32_t*)(geom + gl.tiles_touched);
+        out->point_offsets = (const uint32_t*)(geom + gl.offsets);
+        out->records = (const float*)(geom + gl.records);
+    }
+    if (bin) {
+        out->keys_sorted = (const uint64_t*)(bin + bl.keys_sorted);
+        out->point_list = (const uint32_t*)(bin + bl.vals_sorted);
+    }
+    if (img) {
+        out->ranges = (const uint32_t*)(img + il.ranges);
+        out->final_T = (const float*)(img + il.final_T);
+        out->n_contrib = (const uint32_t*)(img + il.n_contrib);
+    }
+    return H3DGS_OK;
+}

@@ -1,0 +1,158 @@
+// binning.cu -- K2..K5 of the path: inclusive scan of tiles_touched, duplicateWithKeys,
+// (tile | depth) radix sort, identifyTileRanges, plus the B200-specific step that
+// MATERIALISES the depth-sorted per-tile record lists contiguously so that the
+// blend kernels stream them with cp.async.bulk (TMA) instead of gathering.
+// Semantics per oracle/oracle.c::oracle_bin.  Compiled with -fmad=false like
+// preprocess.cu (the rect is re-derived from the stored pixel centre and radius).
+#include <cub/cub.cuh>
+#include "common.cuh"
+
+namespace h3dgs {
+
+size_t scan_temp_bytes(int n) {
+    size_t bytes = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, n > 0 ? n : 1);
+    return bytes;
+}
+size_t sort_temp_bytes(int64_t n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
+                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, n > 0 ? n : 1);
+    return bytes;
+}
+
+int launch_scan(const uint32_t* in, uint32_t* out, int n, void* temp, size_t temp_bytes, cudaStream_t s, bool debug) {
+    if (n == 0) return H3DGS_OK;
+    H3_CUDA(cub::DeviceScan::InclusiveSum(temp, temp_bytes, in, out, n, s));
+    H3_LAUNCHED("scan", debug, s);
+    return H3DGS_OK;
+}
+
+// One thread per Gaussian; emission order inside a Gaussian is y-outer, x-inner, and
+// across Gaussians it is index order (offsets from the scan) -- with the stable sort
+// this fixes the order of equal-depth entries exactly as the oracle's.
+__global__ void __launch_bounds__(256)
+duplicate_with_keys_kernel(int P, int W, int H, int shard_count, int shard_index, const int* __restrict__ radii,
+                           const float* __restrict__ depths, const uint32_t* __restrict__ offsets,
+                           const Record* __restrict__ records, uint64_t* __restrict__ keys,
+                           uint32_t* __restrict__ vals)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const int rad = radii[i];
+    if (rad <= 0) return;
+    const float4 a = records[i].a;
+    const float ix = a.x, iy = a.y;
+    const int gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
+    const int rminx = min(gx, max(0, (int)((ix - rad) / kTile)));
+    const int rminy = min(gy, max(0, (int)((iy - rad) / kTile)));
+    const int rmaxx = min(gx, max(0, (int)((ix + rad + kTile - 1) / kTile)));
+    const int rmaxy = min(gy, max(0, (int)((iy + rad + kTile - 1) / kTile)));
+    uint32_t off = (i == 0) ? 0u : offsets[i - 1];
+    const uint32_t dbits = __float_as_uint(depths[i]);
+    for (int y = rminy; y < rmaxy; y++) {
+        if (shard_count > 1 && (y % shard_count) != shard_index) continue;
+        for (int x = rminx; x < rmaxx; x++) {
+            uint64_t key = (uint64_t)(y * gx + x);
+            key = (key << 32) | dbits;
+            keys[off] = key;
+            vals[off] = (uint32_t)i;
+            off++;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+identify_tile_ranges_kernel(int64_t D, const uint64_t* __restrict__ keys, uint32_t* __restrict__ ranges)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D) return;
+    const uint32_t tile = (uint32_t)(keys[i] >> 32);
+    if (i == 0) ranges[2 * tile] = 0;
+    else {
+        const uint32_t prev = (uint32_t)(keys[i - 1] >> 32);
+        if (prev != tile) { ranges[2 * prev + 1] = (uint32_t)i; ranges[2 * tile] = (uint32_t)i; }
+    }
+    if (i == D - 1) ranges[2 * tile + 1] = (uint32_t)D;
+}
+
+// sorted_records[j] = records[point_list[j]] : 48-B gathers out of an L2-resident
+// array, fully coalesced 48-B writes.  3 lanes per entry (one float4 each).
+__global__ void __launch_bounds__(256)
+gather_records_kernel(int64_t D, const uint32_t* __restrict__ point_list, const float4* __restrict__ records,
+                      float4* __restrict__ sorted)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * D) return;
+    const int64_t j = t / 3; const int part = (int)(t - 3 * j);
+    const uint32_t g = point_list[j];
+    sorted[t] = __ldg(records + 3 * (size_t)g + part);
+}
+
+int launch_binning(const h3dgs_raster_args& a, const int32_t* radii, const float* depths, const uint32_t* offsets,
+                   const Record* records, int64_t D, uint8_t* bin, const BinLayout& bl, uint32_t* ranges,
+                   cudaStream_t s)
+{
+    const int W = a.image_width, H = a.image_height;
+    const int gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
+    H3_CUDA(cudaMemsetAsync(ranges, 0, (size_t)gx * gy * 2 * sizeof(uint32_t), s));
+    if (D == 0 || a.P == 0) return H3DGS_OK;
+    uint64_t* keys_u = (uint64_t*)(bin + bl.keys_unsorted);
+    uint64_t* keys_s = (uint64_t*)(bin + bl.keys_sorted);
+    uint32_t* vals_u = (uint32_t*)(bin + bl.vals_unsorted);
+    uint32_t* vals_s = (uint32_t*)(bin + bl.vals_sorted);
+    duplicate_with_keys_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a.P, W, H, a.shard_count > 0 ? a.shard_count : 1,
+                                                                 a.shard_count > 0 ? a.shard_index : 0, radii, depths,
+                                                                 offsets, records, keys_u, vals_u);
+    H3_LAUNCHED("duplicate_with_keys", a.debug, s);
+    int tile_bits = 0;
+    while ((1 << tile_bits) < gx * gy) tile_bits++;
+    size_t temp = bl.sort_temp_bytes;
+    H3_CUDA(cub::DeviceRadixSort::SortPairs(bin + bl.sort_temp, temp, keys_u, keys_s, vals_u, vals_s, D, 0,
+                                            32 + tile_bits, s));
+    H3_LAUNCHED("radix_sort", a.debug, s);
+    identify_tile_ranges_kernel<<<(unsigned)((D + 255) / 256), 256, 0, s>>>(D, keys_s, ranges);
+    H3_LAUNCHED("identify_tile_ranges", a.debug, s);
+    gather_records_kernel<<<(unsigned)((3 * D + 255) / 256), 256, 0, s>>>(D, vals_s, (const float4*)records,
+                                                                           (float4*)(bin + bl.sorted_records));
+    H3_LAUNCHED("gather_records", a.debug, s);
+    return H3DGS_OK;
+}
+
+GeomLayout geom_layout(int P) {
+    GeomLayout l; size_t o = 0; const size_t n = (size_t)(P > 0 ? P : 1);
+    l.depths = o; o = align_up(o + n * 4);
+    l.tiles_touched = o; o = align_up(o + n * 4);
+    l.offsets = o; o = align_up(o + n * 4);
+    l.records = o; o = align_up(o + n * sizeof(Record));
+    l.scan_temp_bytes = scan_temp_bytes(P);
+    l.scan_temp = o; o = align_up(o + l.scan_temp_bytes);
+    l.total = o;
+    return l;
+}
+BinLayout bin_layout(int64_t D) {
+    BinLayout l; size_t o = 0; const size_t n = (size_t)(D > 0 ? D : 1);
+    l.keys_unsorted = o; o = align_up(o + n * 8);
+    l.keys_sorted = o; o = align_up(o + n * 8);
+    l.vals_unsorted = o; o = align_up(o + n * 4);
+    l.vals_sorted = o; o = align_up(o + n * 4);
+    l.sort_temp_bytes = sort_temp_bytes(D);
+    l.sort_temp = o; o = align_up(o + l.sort_temp_bytes);
+    l.sorted_records = o; o = align_up(o + (n + 1) * sizeof(Record));
+    l.total = o;
+    return l;
+}
+ImgLayout img_layout(int W, int H) {
+    ImgLayout l; size_t o = 0;
+    const size_t px = (size_t)W * H;
+    const size_t tiles = (size_t)((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile);
+    l.final_T = o; o = align_up(o + px * 4);
+    l.n_contrib = o; o = align_up(o + px * 4);
+    l.ranges = o; o = align_up(o + tiles * 8);
+    l.tile_max_contrib = o; o = align_up(o + tiles * 4);
+    l.bucket_offsets = o; o = align_up(o + (tiles + 1) * 4);
+    l.total = o;
+    return l;
+}
+
+}  // namespace h3dgs

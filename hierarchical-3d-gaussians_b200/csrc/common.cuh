@@ -1,0 +1,125 @@
+// common.cuh -- shared definitions for the sm_100a kernels of libh3dgs.so.
+// Constants are the published algorithm's (see oracle/oracle.c and DESIGN.md
+// "recalled constants"; the hierarchy-rasterizer source is absent from /root/reference).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/h3dgs.h"
+
+namespace h3dgs {
+
+constexpr float kNearPlane = 0.2f;
+constexpr float kFovClamp = 1.3f;
+constexpr float kDilation = 0.3f;
+constexpr float kLambdaFloor = 0.1f;
+constexpr int kTile = H3DGS_TILE;
+constexpr int kTilePixels = kTile * kTile;
+constexpr float kAlphaCap = 0.99f;
+constexpr float kAlphaSkip = 1.0f / 255.0f;
+constexpr float kTStop = 0.0001f;
+constexpr float kWEps = 0.0000001f;
+constexpr int kBucket = H3DGS_BUCKET;
+
+// Per-Gaussian projected record: 3 x float4 = 48 B, 16-B aligned, so a batch of
+// records is one contiguous cp.async.bulk (TMA) transfer.
+//   a = {x, y, conic.x, conic.y}
+//   b = {conic.z, opacity, t, kbits}     kbits: low 24 bits = num_node_kids, bits 24..26 = SH clamp flags
+//   c = {r, g, b, invdepth}
+struct __align__(16) Record { float4 a, b, c; };
+static_assert(sizeof(Record) == 48, "record must be 48 bytes");
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// ---- state buffer layouts (byte offsets inside the three alloc'd buffers) ----
+struct GeomLayout {
+    size_t depths, tiles_touched, offsets, records, scan_temp, total;
+    size_t scan_temp_bytes;
+};
+struct BinLayout {
+    size_t keys_unsorted, keys_sorted, vals_unsorted, vals_sorted, sort_temp, sorted_records, total;
+    size_t sort_temp_bytes;
+};
+struct ImgLayout {
+    size_t final_T, n_contrib, ranges, tile_max_contrib, bucket_offsets, total;
+};
+
+GeomLayout geom_layout(int P);
+BinLayout bin_layout(int64_t D);
+ImgLayout img_layout(int W, int H);
+
+// error plumbing (api.cu)
+void set_error(const char* fmt, ...);
+extern int64_t g_launches;
+
+#define H3_CUDA(call)                                                                      \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            h3dgs::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,          \
+                             cudaGetErrorString(e__));                                     \
+            return H3DGS_ECUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+
+// after a kernel launch: count it, catch launch errors; in debug mode also sync
+#define H3_LAUNCHED(name, debug, stream)                                                   \
+    do {                                                                                   \
+        h3dgs::g_launches++;                                                               \
+        cudaError_t e__ = cudaGetLastError();                                              \
+        if (e__ == cudaSuccess && (debug)) e__ = cudaStreamSynchronize(stream);            \
+        if (e__ != cudaSuccess) {                                                          \
+            h3dgs::set_error("kernel %s failed: %s", name, cudaGetErrorString(e__));       \
+            return H3DGS_ECUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+
+// ---- stage entry points (one per .cu file) ----
+int launch_preprocess(const h3dgs_raster_args& a, int32_t* radii, float* depths, uint32_t* tiles_touched,
+                      Record* records, cudaStream_t s);
+int launch_scan(const uint32_t* in, uint32_t* out, int n, void* temp, size_t temp_bytes, cudaStream_t s, bool debug);
+size_t scan_temp_bytes(int n);
+size_t sort_temp_bytes(int64_t n);
+int launch_binning(const h3dgs_raster_args& a, const int32_t* radii, const float* depths, const uint32_t* offsets,
+                   const Record* records, int64_t D, uint8_t* bin, const BinLayout& bl, uint32_t* ranges,
+                   cudaStream_t s);
+int launch_render_forward(const h3dgs_raster_args& a, const uint32_t* ranges, const Record* sorted_records,
+                          float* out_color, float* out_invdepth, float* final_T, uint32_t* n_contrib,
+                          uint32_t* tile_max_contrib, cudaStream_t s);
+int launch_render_backward(const h3dgs_raster_args& a, const uint32_t* ranges, const Record* sorted_records,
+                           const uint32_t* point_list, const float* final_T, const uint32_t* n_contrib,
+                           const uint32_t* tile_max_contrib, const float* dL_dcolor, const float* dL_dinvdepth,
+                           float* accum /*[P][10] zeroed*/, cudaStream_t s);
+int launch_preprocess_backward(const h3dgs_raster_args& a, const int32_t* radii, const Record* records,
+                               const float* accum, float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh,
+                               float* dL_dcolors, float* dL_dopacities, float* dL_dscales, float* dL_drots,
+                               float* dL_dcov3D, cudaStream_t s);
+
+// Hierarchy transition weight on the per-pixel blending weight (UNPINNED semantics,
+// DESIGN.md "hierarchy alpha"): a' = t a + (1-t)(1 - (1-a)^(1/k)); identity for k<=1 or t>=1.
+// One definition for forward and backward so both take identical skip decisions.
+#ifdef __CUDACC__
+template <bool HIER>
+__device__ __forceinline__ void hier_alpha_grad(float a, float t, uint32_t kbits, float& alpha, float& dadb) {
+    alpha = a; dadb = 1.0f;
+    if (!HIER) return;
+    const uint32_t k = kbits & 0xFFFFFFu;
+    if (k <= 1u || t >= 1.0f) return;
+    const float ik = 1.0f / (float)k;
+    const float l2 = log2f(1.0f - a);
+    const float root = exp2f(l2 * ik);
+    alpha = t * a + (1.0f - t) * (1.0f - root);
+    dadb = t + (1.0f - t) * ik * exp2f(l2 * (ik - 1.0f));
+}
+template <bool HIER>
+__device__ __forceinline__ float hier_alpha(float a, float t, uint32_t kbits) {
+    float alpha, dadb;
+    hier_alpha_grad<HIER>(a, t, kbits, alpha, dadb);
+    return alpha;
+}
+#endif
+
+// accum row layout (floats): 0,1 dmean2D.xy | 2,3,4 dconic | 5 dopacity | 6,7,8 dcolor | 9 dinvdepth
+constexpr int kAccum = 10;
+
+}  // namespace h3dgs

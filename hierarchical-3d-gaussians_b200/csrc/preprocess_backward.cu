@@ -1,0 +1,306 @@
+// preprocess_backward.cu -- K8 + K9 fused: per-Gaussian chain rule from the 2D-space
+// accumulators (dmean2D, dconic, dopacity, dcolor, dinvdepth) back to the inputs
+// (replaces BACKWARD::computeCov2DCUDA + BACKWARD::preprocessCUDA).  Semantics per
+// oracle/oracle.c::oracle_preprocess_backward.  One thread per Gaussian; a pure HBM
+// stream: reads 40 B accum + 44 B params + 192 B SH, writes 248 B of gradients.
+// Every output row is written (zeros for culled Gaussians) so the caller never
+// pays a separate memset pass over the gradient tensors.
+#include "common.cuh"
+
+namespace h3dgs {
+
+__device__ __constant__ float bSH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                           -1.0925484305920792f, 0.5462742152960396f};
+__device__ __constant__ float bSH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                           0.3731763325901154f, -0.4570457994644658f, 1.445305721320277f,
+                                           -0.5900435899266435f};
+constexpr float bSH_C0 = 0.28209479177387814f;
+constexpr float bSH_C1 = 0.4886025119029199f;
+
+__device__ __forceinline__ void store_zero(float* p, int n) {
+    for (int k = 0; k < n; k++) p[k] = 0.f;
+}
+
+__global__ void __launch_bounds__(256)
+preprocess_backward_kernel(int P, int deg, int M, const float* __restrict__ means3D, const float* __restrict__ scales,
+                           float scale_mod, const float* __restrict__ rots, const float* __restrict__ shs,
+                           const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp,
+                           const float* __restrict__ view, const float* __restrict__ proj,
+                           const float* __restrict__ campos, int W, int H, float tanx, float tany, float fx, float fy,
+                           int use_depth, const int* __restrict__ radii, const Record* __restrict__ records,
+                           const float* __restrict__ accum, float* __restrict__ dL_dmeans3D,
+                           float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dsh, float* __restrict__ dL_dcolors,
+                           float* __restrict__ dL_dopacities, float* __restrict__ dL_dscales,
+                           float* __restrict__ dL_drots, float* __restrict__ dL_dcov3D)
+{
+    __shared__ float s_view[16], s_proj[16], s_cam[3];
+    if (threadIdx.x < 16) { s_view[threadIdx.x] = view[threadIdx.x]; s_proj[threadIdx.x] = proj[threadIdx.x]; }
+    if (threadIdx.x < 3) s_cam[threadIdx.x] = campos[threadIdx.x];
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const int SH3 = M * 3;
+
+    if (radii[i] <= 0) {
+        store_zero(dL_dmeans3D + 3 * i, 3);
+        store_zero(dL_dmeans2D + 3 * i, 3);
+        dL_dopacities[i] = 0.f;
+        if (dL_dsh) {
+            float* o = dL_dsh + (size_t)i * SH3;
+            if ((SH3 & 3) == 0) { for (int k = 0; k < SH3 / 4; k++) reinterpret_cast<float4*>(o)[k] = make_float4(0, 0, 0, 0); }
+            else store_zero(o, SH3);
+        }
+        if (dL_dcolors) store_zero(dL_dcolors + 3 * i, 3);
+        if (dL_dscales) store_zero(dL_dscales + 3 * i, 3);
+        if (dL_drots) store_zero(dL_drots + 4 * i, 4);
+        if (dL_dcov3D) store_zero(dL_dcov3D + 6 * i, 6);
+        return;
+    }
+
+    const float* v = s_view;
+    const float* ac = accum + (size_t)i * kAccum;
+    const float g_mx = ac[0], g_my = ac[1], dcx = ac[2], dcy = ac[3], dcz = ac[4], g_op = ac[5];
+    const float g_r = ac[6], g_g = ac[7], g_b = ac[8], g_iv = ac[9];
+    const float mx = means3D[3 * i], my = means3D[3 * i + 1], mz = means3D[3 * i + 2];
+
+    // cov3D (recomputed: cheaper than a 24-B round trip through HBM)
+    float cov6[6];
+    float R[3][3], Mm[3][3], sc[3];
+    float qr = 1.f, qx = 0.f, qy = 0.f, qz = 0.f;
+    if (cov3D_precomp) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) cov6[k] = cov3D_precomp[6 * i + k];
+    } else {
+        const float4 qq = *reinterpret_cast<const float4*>(rots + 4 * i);
+        qr = qq.x; qx = qq.y; qy = qq.z; qz = qq.w;
+        R[0][0] = 1.f - 2.f * (qy * qy + qz * qz); R[0][1] = 2.f * (qx * qy - qr * qz); R[0][2] = 2.f * (qx * qz + qr * qy);
+        R[1][0] = 2.f * (qx * qy + qr * qz); R[1][1] = 1.f - 2.f * (qx * qx + qz * qz); R[1][2] = 2.f * (qy * qz - qr * qx);
+        R[2][0] = 2.f * (qx * qz - qr * qy); R[2][1] = 2.f * (qy * qz + qr * qx); R[2][2] = 1.f - 2.f * (qx * qx + qy * qy);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            sc[k] = scale_mod * scales[3 * i + k];
+#pragma unroll
+            for (int j = 0; j < 3; j++) Mm[k][j] = sc[k] * R[j][k];
+        }
+        int o = 0;
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = a; b < 3; b++) cov6[o++] = Mm[0][a] * Mm[0][b] + Mm[1][a] * Mm[1][b] + Mm[2][a] * Mm[2][b];
+    }
+
+    float dmean[3] = {0.f, 0.f, 0.f};
+    float g6[6];
+    // ---- K8: conic -> cov2D -> cov3D, and mean through the Jacobian ----
+    {
+        float tx = v[0] * mx + v[4] * my + v[8] * mz + v[12];
+        float ty = v[1] * mx + v[5] * my + v[9] * mz + v[13];
+        const float tz = v[2] * mx + v[6] * my + v[10] * mz + v[14];
+        const float limx = kFovClamp * tanx, limy = kFovClamp * tany;
+        const float txtz = tx / tz, tytz = ty / tz;
+        tx = fminf(limx, fmaxf(-limx, txtz)) * tz;
+        ty = fminf(limy, fmaxf(-limy, tytz)) * tz;
+        const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
+        const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
+        const float J00 = fx / tz, J02 = -(fx * tx) / (tz * tz);
+        const float J11 = fy / tz, J12 = -(fy * ty) / (tz * tz);
+        float A[2][3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            A[0][c] = J00 * v[4 * c + 0] + J02 * v[4 * c + 2];
+            A[1][c] = J11 * v[4 * c + 1] + J12 * v[4 * c + 2];
+        }
+        const float V[3][3] = {{cov6[0], cov6[1], cov6[2]}, {cov6[1], cov6[3], cov6[4]}, {cov6[2], cov6[4], cov6[5]}};
+        float AV[2][3];
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) AV[r][c] = A[r][0] * V[0][c] + A[r][1] * V[1][c] + A[r][2] * V[2][c];
+        const float a = (AV[0][0] * A[0][0] + AV[0][1] * A[0][1] + AV[0][2] * A[0][2]) + kDilation;
+        const float b = AV[0][0] * A[1][0] + AV[0][1] * A[1][1] + AV[0][2] * A[1][2];
+        const float c_ = (AV[1][0] * A[1][0] + AV[1][1] * A[1][1] + AV[1][2] * A[1][2]) + kDilation;
+        const float denom = a * c_ - b * b;
+        float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
+        const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+#pragma unroll
+        for (int k = 0; k < 6; k++) g6[k] = 0.f;
+        if (denom2inv != 0.f) {
+            dL_da = denom2inv * (-c_ * c_ * dcx + 2 * b * c_ * dcy + (denom - a * c_) * dcz);
+            dL_dc = denom2inv * (-a * a * dcz + 2 * a * b * dcy + (denom - a * c_) * dcx);
+            dL_db = denom2inv * 2 * (b * c_ * dcx - (denom + 2 * b * b) * dcy + a * b * dcz);
+            g6[0] = A[0][0] * A[0][0] * dL_da + A[0][0] * A[1][0] * dL_db + A[1][0] * A[1][0] * dL_dc;
+            g6[3] = A[0][1] * A[0][1] * dL_da + A[0][1] * A[1][1] * dL_db + A[1][1] * A[1][1] * dL_dc;
+            g6[5] = A[0][2] * A[0][2] * dL_da + A[0][2] * A[1][2] * dL_db + A[1][2] * A[1][2] * dL_dc;
+            g6[1] = 2 * A[0][0] * A[0][1] * dL_da + (A[0][0] * A[1][1] + A[0][1] * A[1][0]) * dL_db + 2 * A[1][0] * A[1][1] * dL_dc;
+            g6[2] = 2 * A[0][0] * A[0][2] * dL_da + (A[0][0] * A[1][2] + A[0][2] * A[1][0]) * dL_db + 2 * A[1][0] * A[1][2] * dL_dc;
+            g6[4] = 2 * A[0][2] * A[0][1] * dL_da + (A[0][1] * A[1][2] + A[0][2] * A[1][1]) * dL_db + 2 * A[1][1] * A[1][2] * dL_dc;
+        }
+        float dA[2][3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            dA[0][c] = 2 * AV[0][c] * dL_da + AV[1][c] * dL_db;
+            dA[1][c] = 2 * AV[1][c] * dL_dc + AV[0][c] * dL_db;
+        }
+        const float dJ00 = dA[0][0] * v[0] + dA[0][1] * v[4] + dA[0][2] * v[8];
+        const float dJ02 = dA[0][0] * v[2] + dA[0][1] * v[6] + dA[0][2] * v[10];
+        const float dJ11 = dA[1][0] * v[1] + dA[1][1] * v[5] + dA[1][2] * v[9];
+        const float dJ12 = dA[1][0] * v[2] + dA[1][1] * v[6] + dA[1][2] * v[10];
+        const float itz = 1.f / tz, tz2 = itz * itz, tz3 = tz2 * itz;
+        const float dL_dtx = x_grad_mul * -fx * tz2 * dJ02;
+        const float dL_dty = y_grad_mul * -fy * tz2 * dJ12;
+        float dL_dtz = -fx * tz2 * dJ00 - fy * tz2 * dJ11 + (2 * fx * tx) * tz3 * dJ02 + (2 * fy * ty) * tz3 * dJ12;
+        if (use_depth) dL_dtz -= g_iv / (tz * tz);
+        dmean[0] += v[0] * dL_dtx + v[1] * dL_dty + v[2] * dL_dtz;
+        dmean[1] += v[4] * dL_dtx + v[5] * dL_dty + v[6] * dL_dtz;
+        dmean[2] += v[8] * dL_dtx + v[9] * dL_dty + v[10] * dL_dtz;
+    }
+    // ---- K9a: screen-space mean -> 3D mean ----
+    {
+        const float* q = s_proj;
+        const float hw = q[3] * mx + q[7] * my + q[11] * mz + q[15];
+        const float m_w = 1.0f / (hw + kWEps);
+        const float mul1 = (q[0] * mx + q[4] * my + q[8] * mz + q[12]) * m_w * m_w;
+        const float mul2 = (q[1] * mx + q[5] * my + q[9] * mz + q[13]) * m_w * m_w;
+        dmean[0] += (q[0] * m_w - q[3] * mul1) * g_mx + (q[1] * m_w - q[3] * mul2) * g_my;
+        dmean[1] += (q[4] * m_w - q[7] * mul1) * g_mx + (q[5] * m_w - q[7] * mul2) * g_my;
+        dmean[2] += (q[8] * m_w - q[11] * mul1) * g_mx + (q[9] * m_w - q[11] * mul2) * g_my;
+    }
+    dL_dmeans2D[3 * i] = g_mx; dL_dmeans2D[3 * i + 1] = g_my; dL_dmeans2D[3 * i + 2] = 0.f;
+    dL_dopacities[i] = g_op;
+
+    // ---- K9b: colour -> SH and view direction ----
+    if (colors_precomp) {
+        if (dL_dcolors) { dL_dcolors[3 * i] = g_r; dL_dcolors[3 * i + 1] = g_g; dL_dcolors[3 * i + 2] = g_b; }
+    } else {
+        const uint32_t kb = __float_as_uint(records[i].b.w);
+        const float dRGB[3] = {(kb >> 24) & 1u ? 0.f : g_r, (kb >> 25) & 1u ? 0.f : g_g, (kb >> 26) & 1u ? 0.f : g_b};
+        const float d0x = mx - s_cam[0], d0y = my - s_cam[1], d0z = mz - s_cam[2];
+        const float len = sqrtf(d0x * d0x + d0y * d0y + d0z * d0z);
+        const float x = d0x / len, y = d0y / len, z = d0z / len;
+        const float* sh = shs + (size_t)i * SH3;
+        float* dsh = dL_dsh + (size_t)i * SH3;
+        float out[48];
+        float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+        const int ncoef = (deg + 1) * (deg + 1);
+        float c[48];
+        if ((SH3 & 3) == 0) {
+#pragma unroll
+            for (int k = 0; k < 12; k++)
+                if (4 * k < 3 * ncoef) {
+                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(sh) + k);
+                    c[4 * k] = t4.x; c[4 * k + 1] = t4.y; c[4 * k + 2] = t4.z; c[4 * k + 3] = t4.w;
+                }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 48; k++) if (k < 3 * ncoef) c[k] = __ldg(sh + k);
+        }
+#pragma unroll
+        for (int k = 0; k < 48; k++) out[k] = 0.f;
+#define S(k, ch) c[(k) * 3 + (ch)]
+#define DS(k, ch) out[(k) * 3 + (ch)]
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+            const float g = dRGB[ch];
+            float dx_ = 0.f, dy_ = 0.f, dz_ = 0.f;
+            DS(0, ch) = bSH_C0 * g;
+            if (deg > 0) {
+                DS(1, ch) = -bSH_C1 * y * g; DS(2, ch) = bSH_C1 * z * g; DS(3, ch) = -bSH_C1 * x * g;
+                dx_ = -bSH_C1 * S(3, ch); dy_ = -bSH_C1 * S(1, ch); dz_ = bSH_C1 * S(2, ch);
+                if (deg > 1) {
+                    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                    DS(4, ch) = bSH_C2[0] * xy * g; DS(5, ch) = bSH_C2[1] * yz * g;
+                    DS(6, ch) = bSH_C2[2] * (2.f * zz - xx - yy) * g;
+                    DS(7, ch) = bSH_C2[3] * xz * g; DS(8, ch) = bSH_C2[4] * (xx - yy) * g;
+                    dx_ += bSH_C2[0] * y * S(4, ch) + bSH_C2[2] * 2.f * -x * S(6, ch) + bSH_C2[3] * z * S(7, ch) + bSH_C2[4] * 2.f * x * S(8, ch);
+                    dy_ += bSH_C2[0] * x * S(4, ch) + bSH_C2[1] * z * S(5, ch) + bSH_C2[2] * 2.f * -y * S(6, ch) + bSH_C2[4] * 2.f * -y * S(8, ch);
+                    dz_ += bSH_C2[1] * y * S(5, ch) + bSH_C2[2] * 2.f * 2.f * z * S(6, ch) + bSH_C2[3] * x * S(7, ch);
+                    if (deg > 2) {
+                        DS(9, ch) = bSH_C3[0] * y * (3.f * xx - yy) * g;
+                        DS(10, ch) = bSH_C3[1] * xy * z * g;
+                        DS(11, ch) = bSH_C3[2] * y * (4.f * zz - xx - yy) * g;
+                        DS(12, ch) = bSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy) * g;
+                        DS(13, ch) = bSH_C3[4] * x * (4.f * zz - xx - yy) * g;
+                        DS(14, ch) = bSH_C3[5] * z * (xx - yy) * g;
+                        DS(15, ch) = bSH_C3[6] * x * (xx - 3.f * yy) * g;
+                        dx_ += bSH_C3[0] * S(9, ch) * 3.f * 2.f * xy + bSH_C3[1] * S(10, ch) * yz + bSH_C3[2] * S(11, ch) * -2.f * xy
+                             + bSH_C3[3] * S(12, ch) * -3.f * 2.f * xz + bSH_C3[4] * S(13, ch) * (-3.f * xx + 4.f * zz - yy)
+                             + bSH_C3[5] * S(14, ch) * 2.f * xz + bSH_C3[6] * S(15, ch) * 3.f * (xx - yy);
+                        dy_ += bSH_C3[0] * S(9, ch) * 3.f * (xx - yy) + bSH_C3[1] * S(10, ch) * xz + bSH_C3[2] * S(11, ch) * (-3.f * yy + 4.f * zz - xx)
+                             + bSH_C3[3] * S(12, ch) * -3.f * 2.f * yz + bSH_C3[4] * S(13, ch) * -2.f * xy
+                             + bSH_C3[5] * S(14, ch) * -2.f * yz + bSH_C3[6] * S(15, ch) * -3.f * 2.f * xy;
+                        dz_ += bSH_C3[1] * S(10, ch) * xy + bSH_C3[2] * S(11, ch) * 4.f * 2.f * yz + bSH_C3[3] * S(12, ch) * 3.f * (2.f * zz - xx - yy)
+                             + bSH_C3[4] * S(13, ch) * 4.f * 2.f * xz + bSH_C3[5] * S(14, ch) * (xx - yy);
+                    }
+                }
+            }
+            ddx += dx_ * g; ddy += dy_ * g; ddz += dz_ * g;
+        }
+#undef S
+#undef DS
+        if ((SH3 & 3) == 0) {
+#pragma unroll
+            for (int k = 0; k < 12; k++)
+                if (4 * k < SH3) reinterpret_cast<float4*>(dsh)[k] = make_float4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 48; k++) if (k < SH3) dsh[k] = out[k];
+        }
+        const float sum2 = d0x * d0x + d0y * d0y + d0z * d0z;
+        const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+        dmean[0] += ((sum2 - d0x * d0x) * ddx - d0y * d0x * ddy - d0z * d0x * ddz) * invsum32;
+        dmean[1] += (-d0x * d0y * ddx + (sum2 - d0y * d0y) * ddy - d0z * d0y * ddz) * invsum32;
+        dmean[2] += (-d0x * d0z * ddx - d0y * d0z * ddy + (sum2 - d0z * d0z) * ddz) * invsum32;
+    }
+    dL_dmeans3D[3 * i] = dmean[0]; dL_dmeans3D[3 * i + 1] = dmean[1]; dL_dmeans3D[3 * i + 2] = dmean[2];
+
+    // ---- K9c: cov3D -> scale, rotation ----
+    if (cov3D_precomp) {
+        if (dL_dcov3D) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) dL_dcov3D[6 * i + k] = g6[k];
+        }
+    } else {
+        const float dS[3][3] = {{g6[0], 0.5f * g6[1], 0.5f * g6[2]}, {0.5f * g6[1], g6[3], 0.5f * g6[4]}, {0.5f * g6[2], 0.5f * g6[4], g6[5]}};
+        float dM[3][3];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) dM[k][j] = 2.0f * (Mm[k][0] * dS[0][j] + Mm[k][1] * dS[1][j] + Mm[k][2] * dS[2][j]);
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            dL_dscales[3 * i + k] = scale_mod * (R[0][k] * dM[k][0] + R[1][k] * dM[k][1] + R[2][k] * dM[k][2]);
+        float dR[3][3];
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) dR[j][k] = sc[k] * dM[k][j];
+        float4 dq;
+        dq.x = 2 * qz * (dR[1][0] - dR[0][1]) + 2 * qy * (dR[0][2] - dR[2][0]) + 2 * qx * (dR[2][1] - dR[1][2]);
+        dq.y = 2 * qy * (dR[0][1] + dR[1][0]) + 2 * qz * (dR[0][2] + dR[2][0]) + 2 * qr * (dR[2][1] - dR[1][2]) - 4 * qx * (dR[1][1] + dR[2][2]);
+        dq.z = 2 * qx * (dR[0][1] + dR[1][0]) + 2 * qr * (dR[0][2] - dR[2][0]) + 2 * qz * (dR[1][2] + dR[2][1]) - 4 * qy * (dR[0][0] + dR[2][2]);
+        dq.w = 2 * qr * (dR[1][0] - dR[0][1]) + 2 * qx * (dR[0][2] + dR[2][0]) + 2 * qy * (dR[1][2] + dR[2][1]) - 4 * qz * (dR[0][0] + dR[1][1]);
+        *reinterpret_cast<float4*>(dL_drots + 4 * i) = dq;
+        if (dL_dcov3D) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) dL_dcov3D[6 * i + k] = g6[k];
+        }
+    }
+}
+
+int launch_preprocess_backward(const h3dgs_raster_args& a, const int32_t* radii, const Record* records,
+                               const float* accum, float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh,
+                               float* dL_dcolors, float* dL_dopacities, float* dL_dscales, float* dL_drots,
+                               float* dL_dcov3D, cudaStream_t s)
+{
+    if (a.P == 0) return H3DGS_OK;
+    const float fx = a.image_width / (2.0f * a.tanfovx), fy = a.image_height / (2.0f * a.tanfovy);
+    preprocess_backward_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(
+        a.P, a.sh_degree, a.sh_coeffs, a.means3D, a.scales, a.scale_modifier, a.rotations, a.shs, a.cov3D_precomp,
+        a.colors_precomp, a.viewmatrix, a.projmatrix, a.campos, a.image_width, a.image_height, a.tanfovx, a.tanfovy,
+        fx, fy, a.do_depth, radii, records, accum, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacities,
+        dL_dscales, dL_drots, dL_dcov3D);
+    H3_LAUNCHED("preprocess_backward", a.debug, s);
+    return H3DGS_OK;
+}
+
+}  // namespace h3dgs

@@ -1,0 +1,88 @@
+"""ctypes binding of libh3dgs.so (include/h3dgs.h).
+
+There is NO CPU fallback: if the library is missing or a call fails this raises.
+The oracle under /oracle is never imported from here.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libh3dgs.so")
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int, C.c_size_t)
+
+EXPORTS = [
+    "h3dgs_rasterize_forward", "h3dgs_rasterize_backward", "h3dgs_backward_scratch_bytes", "h3dgs_mark_visible",
+    "h3dgs_state_layout", "h3dgs_expand_to_size", "h3dgs_expand_scratch_bytes", "h3dgs_get_interpolation_weights",
+    "h3dgs_last_error", "h3dgs_version", "h3dgs_launch_count",
+]
+
+
+class RasterArgs(C.Structure):
+    """struct h3dgs_raster_args"""
+    _fields_ = [
+        ("P", C.c_int32), ("sh_degree", C.c_int32), ("sh_coeffs", C.c_int32),
+        ("image_width", C.c_int32), ("image_height", C.c_int32),
+        ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
+        ("prefiltered", C.c_int32), ("debug", C.c_int32), ("do_depth", C.c_int32),
+        ("bg", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
+        ("means3D", C.c_void_p), ("shs", C.c_void_p), ("colors_precomp", C.c_void_p), ("opacities", C.c_void_p),
+        ("scales", C.c_void_p), ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p),
+        ("interpolation_weights", C.c_void_p), ("num_node_kids", C.c_void_p),
+        ("shard_count", C.c_int32), ("shard_index", C.c_int32),
+    ]
+
+
+class StateView(C.Structure):
+    """struct h3dgs_state_view"""
+    _fields_ = [(n, C.c_void_p) for n in ("depths", "tiles_touched", "point_offsets", "records", "keys_sorted",
+                                          "point_list", "ranges", "final_T", "n_contrib")]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python hierarchical-3d-gaussians_b200/build.py` "
+            "(nvcc, sm_100a). There is no CPU fallback for this path.")
+    l = C.CDLL(LIB_PATH)
+    l.h3dgs_last_error.restype = C.c_char_p
+    l.h3dgs_launch_count.restype = C.c_int64
+    l.h3dgs_backward_scratch_bytes.restype = C.c_size_t
+    l.h3dgs_backward_scratch_bytes.argtypes = [C.c_int32]
+    l.h3dgs_expand_scratch_bytes.restype = C.c_size_t
+    l.h3dgs_expand_scratch_bytes.argtypes = [C.c_int32]
+    l.h3dgs_rasterize_forward.restype = C.c_int
+    l.h3dgs_rasterize_forward.argtypes = [C.POINTER(RasterArgs), ALLOC_FN, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]
+    l.h3dgs_rasterize_backward.restype = C.c_int
+    l.h3dgs_rasterize_backward.argtypes = [C.POINTER(RasterArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_int64, C.c_void_p, C.c_void_p] + [C.c_void_p] * 8 + [C.c_void_p, C.c_void_p]
+    l.h3dgs_mark_visible.restype = C.c_int
+    l.h3dgs_mark_visible.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    l.h3dgs_state_layout.restype = C.c_int
+    l.h3dgs_state_layout.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.POINTER(StateView)]
+    l.h3dgs_expand_to_size.restype = C.c_int
+    l.h3dgs_expand_to_size.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_float,
+                                       C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    l.h3dgs_get_interpolation_weights.restype = C.c_int
+    l.h3dgs_get_interpolation_weights.argtypes = [C.c_int32, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p] + \
+        [C.c_float] * 6 + [C.c_void_p, C.c_void_p, C.c_void_p]
+    _lib = l
+    return l
+
+
+def check(rc):
+    if rc < 0:
+        raise RuntimeError(f"libh3dgs error {rc}: {lib().h3dgs_last_error().decode()}")
+    return rc
+
+
+def launch_count():
+    return int(lib().h3dgs_launch_count())

@@ -1,0 +1,153 @@
+/*
+ * h3dgs.h -- C-ABI of libh3dgs.so, the B200-native (sm_100a) replacement for the
+ * native ops below the reference's drop-in boundary:
+ *
+ *   diff_gaussian_rasterization._C.rasterize_gaussians          -> h3dgs_rasterize_forward
+ *   diff_gaussian_rasterization._C.rasterize_gaussians_backward -> h3dgs_rasterize_backward
+ *   diff_gaussian_rasterization._C.mark_visible                 -> h3dgs_mark_visible
+ *   gaussian_hierarchy._C.expand_to_size                        -> h3dgs_expand_to_size
+ *   gaussian_hierarchy._C.get_interpolation_weights             -> h3dgs_get_interpolation_weights
+ *
+ * The reference binds those through two pip packages whose source is absent from
+ * /root/reference (empty submodules, .gitmodules:5-13); the interface is pinned by
+ * the call sites:
+ *   GaussianRasterizationSettings(17 kwargs) gaussian_renderer/__init__.py:44-62, 247-265, 319-337
+ *   rasterizer(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp)
+ *                                            gaussian_renderer/__init__.py:105-113, 267-277, 381-389
+ *   expand_to_size(nodes, boxes, thr, viewpoint(cuda), viewdir(cpu), out x3) -> int   train_post.py:91-99
+ *   get_interpolation_weights(node_idx, thr, nodes, boxes, viewpoint(cpu), viewdir(cpu), out x2)
+ *                                            train_post.py:104-113
+ *
+ * Every pointer is a DEVICE pointer unless marked [host].  No torch types cross
+ * this boundary; the Python shim (hierarchical-3d-gaussians_b200/diff_gaussian_rasterization)
+ * passes tensor.data_ptr() values through ctypes.  All work is enqueued on `stream`;
+ * the only host synchronisations are the ones the reference API itself forces
+ * (num_rendered sizing of the binning buffer; the int returned by expand_to_size).
+ * Every entry point returns 0 on success, a negative H3DGS_E* code on error and
+ * leaves a message retrievable with h3dgs_last_error().
+ */
+#ifndef H3DGS_H
+#define H3DGS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define H3DGS_VERSION 1
+#define H3DGS_TILE 16            /* 16x16-pixel tiles                                         */
+#define H3DGS_BUCKET 32          /* entries per backward bucket (one warp lane per entry)     */
+
+#define H3DGS_OK 0
+#define H3DGS_EINVAL (-1)        /* bad argument combination (shs xor colors, scales xor cov) */
+#define H3DGS_ECUDA (-2)         /* a CUDA call or kernel failed (message has the detail)     */
+#define H3DGS_ENOMEM (-3)        /* the alloc callback returned NULL                          */
+
+/* Variable-size scratch is obtained through this callback (the reference's
+ * "resizeFunctional" pattern: three byte buffers kept alive by the autograd ctx
+ * until backward).  `which`: 0 = geometry state (size known from P), 1 = binning
+ * state (size known only after num_rendered), 2 = image state (from W,H).  Must
+ * return a device pointer aligned to 256 bytes, valid on `stream`. */
+typedef void* (*h3dgs_alloc_fn)(void* user, int which, size_t bytes);
+
+typedef struct h3dgs_raster_args {
+    /* sizes */
+    int32_t P;              /* Gaussians handed to the rasterizer                              */
+    int32_t sh_degree;      /* active degree 0..3                                              */
+    int32_t sh_coeffs;      /* K_max = shs.shape[1] (1,4,9,16); 0 when colors_precomp is used  */
+    int32_t image_width, image_height;
+    /* per-call constants (GaussianRasterizationSettings) */
+    float tanfovx, tanfovy, scale_modifier;
+    int32_t prefiltered, debug, do_depth;
+    const float* bg;            /* [3]                                                          */
+    const float* viewmatrix;    /* [16] world->view, transposed storage (scene/cameras.py:95)   */
+    const float* projmatrix;    /* [16] full projection, transposed storage (:97)               */
+    const float* campos;        /* [3]                                                          */
+    /* per-Gaussian inputs */
+    const float* means3D;       /* [P,3]                                                        */
+    const float* shs;           /* [P,K_max,3] or NULL                                          */
+    const float* colors_precomp;/* [P,3] or NULL                                                */
+    const float* opacities;     /* [P]                                                          */
+    const float* scales;        /* [P,3] or NULL                                                */
+    const float* rotations;     /* [P,4] wxyz, normalised, or NULL                              */
+    const float* cov3D_precomp; /* [P,6] xx,xy,xz,yy,yz,zz or NULL                              */
+    /* hierarchy extras (empty tensors at the flat call sites -> NULL) */
+    const float* interpolation_weights; /* t  [>=P] or NULL                                     */
+    const int32_t* num_node_kids;       /* k  [>=P] or NULL                                     */
+    /* screen-tile shard for the multi-GPU mode: this call bins and renders only
+     * tile rows y with (y % shard_count) == shard_index.  (1,0) = whole image. */
+    int32_t shard_count, shard_index;
+} h3dgs_raster_args;
+
+/* Forward: K1 preprocess -> scan -> duplicateWithKeys -> radix sort -> tile ranges
+ * -> record gather -> per-tile blend.  Outputs: out_color [3,H,W], out_radii [P]
+ * (int32), out_invdepth [1,H,W] (written only when do_depth).  The three state
+ * buffers obtained from `alloc` must be kept alive and passed to backward.
+ * num_rendered [host] receives D = sum of tiles touched. */
+int h3dgs_rasterize_forward(const h3dgs_raster_args* args, h3dgs_alloc_fn alloc, void* alloc_user,
+                            float* out_color, int32_t* out_radii, float* out_invdepth,
+                            int64_t* num_rendered, void* stream);
+
+/* Backward: per-tile gradient replay -> per-Gaussian chain rule.  All dL_d*
+ * outputs are fully written (zeros for culled Gaussians); NULL skips an output
+ * that does not apply (dL_dsh when colors_precomp, dL_dscales/rots when cov3D_precomp...).
+ * dL_dmeans2D is [P,3] with .z = 0 (consumers read [:, :2], scene/gaussian_model.py:688). */
+int h3dgs_rasterize_backward(const h3dgs_raster_args* args, const int32_t* radii,
+                             const void* geom_state, const void* binning_state, const void* image_state,
+                             int64_t num_rendered,
+                             const float* dL_dcolor /*[3,H,W]*/, const float* dL_dinvdepth /*[1,H,W] or NULL*/,
+                             float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors_precomp,
+                             float* dL_dopacities, float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
+                             void* scratch /* >= h3dgs_backward_scratch_bytes(P) device bytes */,
+                             void* stream);
+size_t h3dgs_backward_scratch_bytes(int32_t P);
+
+/* Frustum visibility (near plane), one byte per Gaussian (bool tensor). */
+int h3dgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                       uint8_t* present, void* stream);
+
+/* Layout introspection for tests (integer artefacts must be bit-exact vs the oracle). */
+typedef struct h3dgs_state_view {
+    const float* depths;              /* [P] view-space z (key low 32 bits)                    */
+    const uint32_t* tiles_touched;    /* [P]                                                    */
+    const uint32_t* point_offsets;    /* [P] inclusive scan                                     */
+    const float* records;             /* [P][12] x,y,conic.xyz,opacity | t,k-bits,r,g | b,invdepth,pad,pad */
+    const uint64_t* keys_sorted;      /* [D] (tile << 32) | depth bits                          */
+    const uint32_t* point_list;       /* [D] Gaussian index, sorted                             */
+    const uint32_t* ranges;           /* [tiles][2]                                             */
+    const float* final_T;             /* [H*W]                                                  */
+    const uint32_t* n_contrib;        /* [H*W]                                                  */
+} h3dgs_state_view;
+int h3dgs_state_layout(int32_t P, int32_t W, int32_t H, int64_t num_rendered,
+                       const void* geom_state, const void* binning_state, const void* image_state,
+                       h3dgs_state_view* out);
+
+/* ---- hierarchy LOD cut ---- */
+/* nodes: [N,7] int32 {depth,parent,start,count_leafs,count_merged,start_children,count_children};
+ * boxes: [N,2,4] float {min.xyz,size ; max.xyz,_}.  viewpoint is a DEVICE pointer here
+ * (train_post.py:95 passes the cuda camera_center).  Returns the number of rendered
+ * Gaussians (>= 0) or a negative error code; synchronises `stream` (the reference API returns a Python int). */
+int h3dgs_expand_to_size(int32_t N, const int32_t* nodes, const float* boxes, float target_size,
+                         const float* viewpoint, float viewdir_x, float viewdir_y, float viewdir_z,
+                         int32_t* render_indices, int32_t* parent_indices, int32_t* nodes_for_render_indices,
+                         void* scratch /* >= h3dgs_expand_scratch_bytes(N) */, void* stream);
+size_t h3dgs_expand_scratch_bytes(int32_t N);
+
+/* viewpoint passed BY VALUE (train_post.py:109 passes camera_center.cpu()). */
+int h3dgs_get_interpolation_weights(int32_t n, const int32_t* node_indices, float target_size,
+                                    const int32_t* nodes, const float* boxes,
+                                    float viewpoint_x, float viewpoint_y, float viewpoint_z,
+                                    float viewdir_x, float viewdir_y, float viewdir_z,
+                                    float* ts, int32_t* num_kids, void* stream);
+
+const char* h3dgs_last_error(void);
+int h3dgs_version(void);
+/* number of kernel launches issued by this library since load (bench.py "gpu_launches") */
+int64_t h3dgs_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* H3DGS_H */

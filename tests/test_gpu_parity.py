@@ -1,0 +1,152 @@
+"""GPU: CUDA path (public Python API -> C-ABI -> sm_100a kernels) vs the CPU oracle on
+identical seeded inputs.  Bar (BASELINE.json north_star): integer artefacts bit-exact
+(radii, tiles touched, depth-key bits, sort order, tile ranges); RGB and every returned
+gradient within 1e-5 relative fp32 (norm-wise: max|a-b| <= 1e-5 * max|b| per tensor).
+PARITY UNPINNED vs the real hierarchy-rasterizer (source absent) -- the oracle restates
+the published algorithm (oracle/oracle.c)."""
+import numpy as np
+import pytest
+
+from util import make_scene, oracle_run, cuda_run, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def check_integer_artefacts(f, out, st):
+    vis = f["radii"] > 0
+    assert np.array_equal(out["radii"], f["radii"])
+    assert np.array_equal(st["tiles_touched"].astype(np.uint32), f["tiles_touched"])
+    assert np.array_equal(st["depths"][vis].view(np.uint32), f["depths"][vis].view(np.uint32))
+    assert st["num_rendered"] == f["num_rendered"]
+    if f["num_rendered"]:
+        assert np.array_equal(st["keys_sorted"].view(np.uint64), f["keys"])
+        assert np.array_equal(st["point_list"].astype(np.uint32), f["point_list"])
+    assert np.array_equal(st["ranges"].astype(np.uint32), f["ranges"])
+    # xy and conic feed the blend: bitwise equal as well (same fp32 op order, no FMA contraction)
+    rec = st["records"]
+    assert np.array_equal(rec[vis, 0:2], f["xy"][vis])
+    assert np.array_equal(rec[vis][:, [2, 3, 4]], f["conic_opacity"][vis][:, :3])
+
+
+def check_image(f, out, st, do_depth=False):
+    assert rel_err(out["color"], f["color"]) < TOL
+    assert np.abs(st["final_T"] - f["final_T"]).max() < 1e-5
+    # n_contrib depends on exp(): allow a vanishing fraction of threshold flips
+    assert (st["n_contrib"].astype(np.uint32) != f["n_contrib"]).mean() < 2e-3
+    if do_depth:
+        assert rel_err(out["invdepth"], f["invdepth"]) < TOL
+
+
+def check_grads(b, g, names):
+    for n in names:
+        assert g[n] is not None, n
+        e = rel_err(g[n], b[n])
+        assert e < TOL, f"{n}: rel err {e:.3e}"
+
+
+@pytest.mark.parametrize("mode,do_depth", [("flat", False), ("flat", True), ("hier", False)])
+def test_forward_backward_parity(mode, do_depth):
+    cam, sc, ts, kids, bg = make_scene(4000, 336, 250, mode=mode, seed=1)      # W,H not multiples of 16
+    f, b, gcol, gdep = oracle_run(cam, sc, bg, ts, kids, do_depth)
+    assert f["num_rendered"] > 10000 and (f["radii"] > 0).sum() > 2000
+    out, g, st = cuda_run(cam, sc, bg, gcol, gdep, ts, kids, do_depth)
+    check_integer_artefacts(f, out, st)
+    check_image(f, out, st, do_depth)
+    check_grads(b, g, ["means3D", "means2D", "sh", "opacities", "scales", "rotations"])
+
+
+@pytest.mark.parametrize("deg,K", [(0, 1), (1, 4), (2, 9), (1, 16), (0, 16)])
+def test_sh_degrees_and_layouts(deg, K):
+    cam, sc, ts, kids, bg = make_scene(1500, 160, 128, sh_degree=3, seed=2)
+    sc["shs"] = np.ascontiguousarray(sc["shs"][:, :K])
+    f, b, gcol, gdep = oracle_run(cam, sc, bg, sh_degree=deg)
+    out, g, st = cuda_run(cam, sc, bg, gcol, gdep, sh_degree=deg)
+    check_integer_artefacts(f, out, st)
+    check_image(f, out, st)
+    check_grads(b, g, ["means3D", "sh", "opacities", "scales", "rotations"])
+    assert np.all(g["sh"][:, (deg + 1) ** 2:] == 0)
+
+
+def test_precomputed_colour_and_covariance():
+    cam, sc, ts, kids, bg = make_scene(1500, 160, 128, seed=3)
+    rng = np.random.default_rng(0)
+    colors = rng.uniform(0, 1, (1500, 3)).astype(np.float32)
+    f0, *_ = oracle_run(cam, sc, bg, backward=False)
+    cov = f0["cov3Ds"].copy()
+    f, b, gcol, gdep = oracle_run(cam, sc, bg, colors=colors, cov=cov)
+    out, g, st = cuda_run(cam, sc, bg, gcol, gdep, colors=colors, cov=cov)
+    check_integer_artefacts(f, out, st)
+    check_image(f, out, st)
+    check_grads(b, g, ["means3D", "colors_precomp", "opacities", "cov3Ds_precomp"])
+
+
+def test_deep_tiles_early_termination_and_big_splats():
+    """Many opaque, large Gaussians: tiles hold >> 256 entries (several TMA batches), pixels
+    terminate early, and some splats cover the whole screen."""
+    cam, sc, ts, kids, bg = make_scene(6000, 128, 96, seed=4, zmin=1.0, zmax=4.0, scale_k=8e-2)
+    sc["opacities"][:] = np.clip(sc["opacities"] * 3, 0, 0.999)
+    sc["scales"][:20] *= 30
+    f, b, gcol, gdep = oracle_run(cam, sc, bg)
+    assert (f["ranges"][:, 1] - f["ranges"][:, 0]).max() > 600
+    assert (f["final_T"] < 1e-3).mean() > 0.2
+    out, g, st = cuda_run(cam, sc, bg, gcol, gdep)
+    check_integer_artefacts(f, out, st)
+    check_image(f, out, st)
+    check_grads(b, g, ["means3D", "means2D", "sh", "opacities", "scales", "rotations"])
+
+
+def test_scale_modifier_and_offcentre_principal_point():
+    cam, sc, ts, kids, bg = make_scene(2000, 200, 120, seed=5, primx=0.45, primy=0.57)
+    f, b, gcol, gdep = oracle_run(cam, sc, bg, scale_modifier=1.7)
+    out, g, st = cuda_run(cam, sc, bg, gcol, gdep, scale_modifier=1.7)
+    check_integer_artefacts(f, out, st)
+    check_image(f, out, st)
+    check_grads(b, g, ["means3D", "sh", "opacities", "scales", "rotations"])
+
+
+def test_empty_and_fully_culled_inputs():
+    import torch
+    from diff_gaussian_rasterization import GaussianRasterizer
+    from util import cuda_settings
+    cam, sc, ts, kids, bg = make_scene(64, 64, 48, seed=6)
+    # everything behind the camera
+    sc["means3D"][:, 2] = -np.abs(sc["means3D"][:, 2])
+    f, b, gcol, gdep = oracle_run(cam, sc, bg)
+    out, g, st = cuda_run(cam, sc, bg, gcol, gdep)
+    assert st["num_rendered"] == 0 and (out["radii"] == 0).all()
+    assert np.allclose(out["color"], bg[:, None, None])
+    for n in ["means3D", "sh", "opacities", "scales", "rotations"]:
+        assert np.all(g[n] == 0)
+    # P == 0
+    rs = cuda_settings(cam, bg)
+    z = lambda *s: torch.zeros(*s, device="cuda")
+    color, radii, _ = GaussianRasterizer(rs)(means3D=z(0, 3), means2D=z(0, 3), shs=z(0, 16, 3), colors_precomp=None,
+                                            opacities=z(0, 1), scales=z(0, 3), rotations=z(0, 4), cov3D_precomp=None)
+    assert radii.numel() == 0 and np.allclose(color.cpu().numpy(), bg[:, None, None])
+
+
+def test_argument_validation_matches_reference_shim():
+    import torch
+    from diff_gaussian_rasterization import GaussianRasterizer
+    from util import cuda_settings
+    cam, sc, ts, kids, bg = make_scene(16, 64, 48, seed=7)
+    rs = cuda_settings(cam, bg)
+    t = lambda a: torch.tensor(a, device="cuda")
+    r = GaussianRasterizer(rs)
+    with pytest.raises(Exception, match="SHs or precomputed colors"):
+        r(means3D=t(sc["means3D"]), means2D=t(sc["means3D"]), shs=None, colors_precomp=None, opacities=t(sc["opacities"]),
+          scales=t(sc["scales"]), rotations=t(sc["rotations"]))
+    with pytest.raises(Exception, match="scale/rotation pair or precomputed 3D covariance"):
+        r(means3D=t(sc["means3D"]), means2D=t(sc["means3D"]), shs=t(sc["shs"]), opacities=t(sc["opacities"]),
+          scales=t(sc["scales"]), rotations=t(sc["rotations"]), cov3D_precomp=torch.zeros(16, 6, device="cuda"))
+
+
+def test_mark_visible():
+    import torch
+    from diff_gaussian_rasterization import GaussianRasterizer
+    from util import cuda_settings
+    cam, sc, ts, kids, bg = make_scene(500, 64, 48, seed=8, zmin=-3, zmax=3)
+    rs = cuda_settings(cam, bg)
+    vis = GaussianRasterizer(rs).markVisible(torch.tensor(sc["means3D"], device="cuda")).cpu().numpy()
+    assert np.array_equal(vis, sc["means3D"][:, 2] > 0.2)      # identity view matrix

@@ -1,0 +1,100 @@
+"""Shared helpers for the GPU parity tests: run the same seeded scene through the
+CUDA path (via the reference-facing Python API -> C-ABI) and through the oracle."""
+import numpy as np
+
+from h3dgs import synth
+
+
+def make_scene(P, W, H, sh_degree=3, seed=0, zmin=2.0, zmax=12.0, scale_k=6e-3, mode="flat", **cam_kw):
+    cam = synth.make_camera(W, H, **cam_kw)
+    sc = synth.cloud_v1(P, cam, sh_degree=sh_degree, zmin=zmin, zmax=zmax, scale_k=scale_k, seed=seed)
+    ts = kids = None
+    if mode == "hier":
+        g = np.random.default_rng(seed + 5)
+        ts = g.uniform(0, 1, P).astype(np.float32)
+        ts[g.uniform(size=P) < 0.3] = 1.0
+        kids = g.integers(1, 5, P).astype(np.int32)
+        sc["opacities"] = (sc["opacities"] * 1.4).astype(np.float32)
+    bg = np.array([0.1, 0.4, 0.9], np.float32)
+    return cam, sc, ts, kids, bg
+
+
+def oracle_run(cam, sc, bg, ts=None, kids=None, do_depth=False, sh_degree=3, colors=None, cov=None, scale_modifier=1.0,
+               grad_seed=3, backward=True):
+    from oracle import oracle
+    f = oracle.rasterize_forward(sc["means3D"], None if colors is not None else sc["shs"], colors, sc["opacities"],
+                                 None if cov is not None else sc["scales"], None if cov is not None else sc["rotations"],
+                                 cov, cam.world_view_transform, cam.full_proj_transform, cam.camera_center, bg,
+                                 cam.W, cam.H, cam.tanfovx, cam.tanfovy, sh_degree=sh_degree,
+                                 scale_modifier=scale_modifier, ts=ts, kids=kids, do_depth=do_depth)
+    gcol = synth.l1_grad(f["color"], seed=grad_seed)
+    gdep = (np.random.default_rng(grad_seed + 1).standard_normal((1, cam.H, cam.W)) / (cam.H * cam.W)).astype(np.float32)
+    b = oracle.rasterize_backward(f, gcol, gdep) if backward else None
+    return f, b, gcol, gdep
+
+
+def cuda_settings(cam, bg, sh_degree=3, ts=None, kids=None, do_depth=False, scale_modifier=1.0, debug=False):
+    import torch
+    from diff_gaussian_rasterization import GaussianRasterizationSettings
+    dev = "cuda"
+    e_i = torch.empty(0, dtype=torch.int32, device=dev)
+    return GaussianRasterizationSettings(
+        image_height=cam.H, image_width=cam.W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+        bg=torch.tensor(bg, device=dev), scale_modifier=scale_modifier,
+        viewmatrix=torch.tensor(cam.world_view_transform, device=dev),
+        projmatrix=torch.tensor(cam.full_proj_transform, device=dev), sh_degree=sh_degree,
+        campos=torch.tensor(cam.camera_center, device=dev), prefiltered=False, debug=debug,
+        render_indices=e_i, parent_indices=e_i,
+        interpolation_weights=torch.tensor(ts, device=dev) if ts is not None else torch.empty(0, device=dev),
+        num_node_kids=torch.tensor(kids, device=dev) if kids is not None else e_i, do_depth=do_depth)
+
+
+def cuda_run(cam, sc, bg, gcol, gdep, ts=None, kids=None, do_depth=False, sh_degree=3, colors=None, cov=None,
+             scale_modifier=1.0, backward=True):
+    """Through the public API (GaussianRasterizer autograd module).  Returns (outputs dict, grads dict, state)."""
+    import torch
+    from diff_gaussian_rasterization import GaussianRasterizer, _C
+    dev = "cuda"
+    rs = cuda_settings(cam, bg, sh_degree, ts, kids, do_depth, scale_modifier)
+    t = lambda a: torch.tensor(a, device=dev, requires_grad=backward)
+    means3D = t(sc["means3D"]); opac = t(sc["opacities"])
+    means2D = torch.zeros_like(means3D, requires_grad=backward)
+    shs = t(sc["shs"]) if colors is None else None
+    colors_t = t(colors) if colors is not None else None
+    scales = t(sc["scales"]) if cov is None else None
+    rots = t(sc["rotations"]) if cov is None else None
+    cov_t = t(cov) if cov is not None else None
+    rast = GaussianRasterizer(raster_settings=rs)
+    color, radii, depth = rast(means3D=means3D, means2D=means2D, shs=shs, colors_precomp=colors_t, opacities=opac,
+                               scales=scales, rotations=rots, cov3D_precomp=cov_t)
+    out = dict(color=color.detach().cpu().numpy(), radii=radii.cpu().numpy(),
+               invdepth=depth.detach().cpu().numpy() if do_depth else None)
+    grads = None
+    if backward:
+        loss = (color * torch.tensor(gcol, device=dev)).sum()
+        if do_depth:
+            loss = loss + (depth * torch.tensor(gdep, device=dev)).sum()
+        loss.backward()
+        g = lambda x: None if x is None else x.grad.detach().cpu().numpy()
+        grads = dict(means3D=g(means3D), means2D=g(means2D), sh=g(shs), colors_precomp=g(colors_t), opacities=g(opac),
+                     scales=g(scales), rotations=g(rots), cov3Ds_precomp=g(cov_t))
+    # integer artefacts straight from the op-level API
+    P = sc["means3D"].shape[0]
+    e = torch.empty(0, device=dev)
+    n, color2, radii2, gb, bb, ib, _ = _C.rasterize_gaussians(
+        rs.bg, means3D.detach(), colors_t.detach() if colors_t is not None else e, opac.detach(),
+        scales.detach() if scales is not None else e, rots.detach() if rots is not None else e, scale_modifier,
+        cov_t.detach() if cov_t is not None else e, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, cam.H, cam.W,
+        shs.detach() if shs is not None else e, sh_degree, rs.campos, False, False, rs.render_indices,
+        rs.parent_indices, rs.interpolation_weights, rs.num_node_kids, do_depth)
+    sv = _C.state_view(P, cam.W, cam.H, n, gb, bb, ib)
+    state = {k: v.cpu().numpy() for k, v in sv.items()}
+    state["num_rendered"] = n
+    assert torch.equal(color2, color.detach())       # deterministic forward
+    return out, grads, state
+
+
+def rel_err(a, b):
+    """norm-wise relative error max|a-b| / max|b|"""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
