@@ -99,6 +99,14 @@ int launch_preprocess_backward(const h3dgs_raster_args& a, const int32_t* radii,
 // DESIGN.md "hierarchy alpha"): a' = t a + (1-t)(1 - (1-a)^(1/k)); identity for k<=1 or t>=1.
 // One definition for forward and backward so both take identical skip decisions.
 #ifdef __CUDACC__
+// exp(x) for x <= 0 as one FMUL + MUFU.EX2 (ftz: results below 2^-126 flush to 0, far
+// below the 1/255 alpha cut).  Shared by forward and backward so both see the same alpha.
+__device__ __forceinline__ float fast_exp(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
+
 template <bool HIER>
 __device__ __forceinline__ void hier_alpha_grad(float a, float t, uint32_t kbits, float& alpha, float& dadb) {
     alpha = a; dadb = 1.0f;

@@ -1,7 +1,10 @@
 // preprocess_backward.cu -- K8 + K9 fused: per-Gaussian chain rule from the 2D-space
 // accumulators (dmean2D, dconic, dopacity, dcolor, dinvdepth) back to the inputs
 // (replaces BACKWARD::computeCov2DCUDA + BACKWARD::preprocessCUDA).  Semantics per
-// oracle/oracle.c::oracle_preprocess_backward.  One thread per Gaussian; a pure HBM
+// oracle/oracle.c::oracle_preprocess_backward.  The covariance chain (K8, K9c) is evaluated in
+// fp64: the published formulas contain cancellations (denom - a*c = -b^2; the rotation
+// gradient of a near-isotropic Gaussian) that cost fp32 one to two digits, and a few hundred
+// DFMA per Gaussian are free in an HBM-bound stream.  One thread per Gaussian; a pure HBM
 // stream: reads 40 B accum + 44 B params + 192 B SH, writes 248 B of gradients.
 // Every output row is written (zeros for culled Gaussians) so the caller never
 // pays a separate memset pass over the gradient tensors.
@@ -64,21 +67,21 @@ preprocess_backward_kernel(int P, int deg, int M, const float* __restrict__ mean
     const float mx = means3D[3 * i], my = means3D[3 * i + 1], mz = means3D[3 * i + 2];
 
     // cov3D (recomputed: cheaper than a 24-B round trip through HBM)
-    float cov6[6];
-    float R[3][3], Mm[3][3], sc[3];
-    float qr = 1.f, qx = 0.f, qy = 0.f, qz = 0.f;
+    double cov6[6];
+    double R[3][3], Mm[3][3], sc[3];
+    double qr = 1., qx = 0., qy = 0., qz = 0.;
     if (cov3D_precomp) {
 #pragma unroll
         for (int k = 0; k < 6; k++) cov6[k] = cov3D_precomp[6 * i + k];
     } else {
         const float4 qq = *reinterpret_cast<const float4*>(rots + 4 * i);
         qr = qq.x; qx = qq.y; qy = qq.z; qz = qq.w;
-        R[0][0] = 1.f - 2.f * (qy * qy + qz * qz); R[0][1] = 2.f * (qx * qy - qr * qz); R[0][2] = 2.f * (qx * qz + qr * qy);
-        R[1][0] = 2.f * (qx * qy + qr * qz); R[1][1] = 1.f - 2.f * (qx * qx + qz * qz); R[1][2] = 2.f * (qy * qz - qr * qx);
-        R[2][0] = 2.f * (qx * qz - qr * qy); R[2][1] = 2.f * (qy * qz + qr * qx); R[2][2] = 1.f - 2.f * (qx * qx + qy * qy);
+        R[0][0] = 1. - 2. * (qy * qy + qz * qz); R[0][1] = 2. * (qx * qy - qr * qz); R[0][2] = 2. * (qx * qz + qr * qy);
+        R[1][0] = 2. * (qx * qy + qr * qz); R[1][1] = 1. - 2. * (qx * qx + qz * qz); R[1][2] = 2. * (qy * qz - qr * qx);
+        R[2][0] = 2. * (qx * qz - qr * qy); R[2][1] = 2. * (qy * qz + qr * qx); R[2][2] = 1. - 2. * (qx * qx + qy * qy);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            sc[k] = scale_mod * scales[3 * i + k];
+            sc[k] = (double)scale_mod * (double)scales[3 * i + k];
 #pragma unroll
             for (int j = 0; j < 3; j++) Mm[k][j] = sc[k] * R[j][k];
         }
@@ -89,42 +92,42 @@ preprocess_backward_kernel(int P, int deg, int M, const float* __restrict__ mean
             for (int b = a; b < 3; b++) cov6[o++] = Mm[0][a] * Mm[0][b] + Mm[1][a] * Mm[1][b] + Mm[2][a] * Mm[2][b];
     }
 
-    float dmean[3] = {0.f, 0.f, 0.f};
-    float g6[6];
+    double dmean[3] = {0., 0., 0.};
+    double g6[6];
     // ---- K8: conic -> cov2D -> cov3D, and mean through the Jacobian ----
     {
-        float tx = v[0] * mx + v[4] * my + v[8] * mz + v[12];
-        float ty = v[1] * mx + v[5] * my + v[9] * mz + v[13];
-        const float tz = v[2] * mx + v[6] * my + v[10] * mz + v[14];
-        const float limx = kFovClamp * tanx, limy = kFovClamp * tany;
-        const float txtz = tx / tz, tytz = ty / tz;
-        tx = fminf(limx, fmaxf(-limx, txtz)) * tz;
-        ty = fminf(limy, fmaxf(-limy, tytz)) * tz;
-        const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
-        const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
-        const float J00 = fx / tz, J02 = -(fx * tx) / (tz * tz);
-        const float J11 = fy / tz, J12 = -(fy * ty) / (tz * tz);
-        float A[2][3];
+        double tx = (double)v[0] * mx + (double)v[4] * my + (double)v[8] * mz + (double)v[12];
+        double ty = (double)v[1] * mx + (double)v[5] * my + (double)v[9] * mz + (double)v[13];
+        const double tz = (double)v[2] * mx + (double)v[6] * my + (double)v[10] * mz + (double)v[14];
+        const double limx = kFovClamp * tanx, limy = kFovClamp * tany;
+        const double txtz = tx / tz, tytz = ty / tz;
+        tx = fmin(limx, fmax(-limx, txtz)) * tz;
+        ty = fmin(limy, fmax(-limy, tytz)) * tz;
+        const double x_grad_mul = (txtz < -limx || txtz > limx) ? 0. : 1.;
+        const double y_grad_mul = (tytz < -limy || tytz > limy) ? 0. : 1.;
+        const double J00 = fx / tz, J02 = -(fx * tx) / (tz * tz);
+        const double J11 = fy / tz, J12 = -(fy * ty) / (tz * tz);
+        double A[2][3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            A[0][c] = J00 * v[4 * c + 0] + J02 * v[4 * c + 2];
-            A[1][c] = J11 * v[4 * c + 1] + J12 * v[4 * c + 2];
+            A[0][c] = J00 * (double)v[4 * c + 0] + J02 * (double)v[4 * c + 2];
+            A[1][c] = J11 * (double)v[4 * c + 1] + J12 * (double)v[4 * c + 2];
         }
-        const float V[3][3] = {{cov6[0], cov6[1], cov6[2]}, {cov6[1], cov6[3], cov6[4]}, {cov6[2], cov6[4], cov6[5]}};
-        float AV[2][3];
+        const double V[3][3] = {{cov6[0], cov6[1], cov6[2]}, {cov6[1], cov6[3], cov6[4]}, {cov6[2], cov6[4], cov6[5]}};
+        double AV[2][3];
 #pragma unroll
         for (int r = 0; r < 2; r++)
 #pragma unroll
             for (int c = 0; c < 3; c++) AV[r][c] = A[r][0] * V[0][c] + A[r][1] * V[1][c] + A[r][2] * V[2][c];
-        const float a = (AV[0][0] * A[0][0] + AV[0][1] * A[0][1] + AV[0][2] * A[0][2]) + kDilation;
-        const float b = AV[0][0] * A[1][0] + AV[0][1] * A[1][1] + AV[0][2] * A[1][2];
-        const float c_ = (AV[1][0] * A[1][0] + AV[1][1] * A[1][1] + AV[1][2] * A[1][2]) + kDilation;
-        const float denom = a * c_ - b * b;
-        float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
-        const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+        const double a = (AV[0][0] * A[0][0] + AV[0][1] * A[0][1] + AV[0][2] * A[0][2]) + kDilation;
+        const double b = AV[0][0] * A[1][0] + AV[0][1] * A[1][1] + AV[0][2] * A[1][2];
+        const double c_ = (AV[1][0] * A[1][0] + AV[1][1] * A[1][1] + AV[1][2] * A[1][2]) + kDilation;
+        const double denom = a * c_ - b * b;
+        double dL_da = 0., dL_db = 0., dL_dc = 0.;
+        const double denom2inv = 1.0 / ((denom * denom) + 0.0000001);
 #pragma unroll
-        for (int k = 0; k < 6; k++) g6[k] = 0.f;
-        if (denom2inv != 0.f) {
+        for (int k = 0; k < 6; k++) g6[k] = 0.;
+        if (denom2inv != 0.) {
             dL_da = denom2inv * (-c_ * c_ * dcx + 2 * b * c_ * dcy + (denom - a * c_) * dcz);
             dL_dc = denom2inv * (-a * a * dcz + 2 * a * b * dcy + (denom - a * c_) * dcx);
             dL_db = denom2inv * 2 * (b * c_ * dcx - (denom + 2 * b * b) * dcy + a * b * dcz);
@@ -135,24 +138,24 @@ preprocess_backward_kernel(int P, int deg, int M, const float* __restrict__ mean
             g6[2] = 2 * A[0][0] * A[0][2] * dL_da + (A[0][0] * A[1][2] + A[0][2] * A[1][0]) * dL_db + 2 * A[1][0] * A[1][2] * dL_dc;
             g6[4] = 2 * A[0][2] * A[0][1] * dL_da + (A[0][1] * A[1][2] + A[0][2] * A[1][1]) * dL_db + 2 * A[1][1] * A[1][2] * dL_dc;
         }
-        float dA[2][3];
+        double dA[2][3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             dA[0][c] = 2 * AV[0][c] * dL_da + AV[1][c] * dL_db;
             dA[1][c] = 2 * AV[1][c] * dL_dc + AV[0][c] * dL_db;
         }
-        const float dJ00 = dA[0][0] * v[0] + dA[0][1] * v[4] + dA[0][2] * v[8];
-        const float dJ02 = dA[0][0] * v[2] + dA[0][1] * v[6] + dA[0][2] * v[10];
-        const float dJ11 = dA[1][0] * v[1] + dA[1][1] * v[5] + dA[1][2] * v[9];
-        const float dJ12 = dA[1][0] * v[2] + dA[1][1] * v[6] + dA[1][2] * v[10];
-        const float itz = 1.f / tz, tz2 = itz * itz, tz3 = tz2 * itz;
-        const float dL_dtx = x_grad_mul * -fx * tz2 * dJ02;
-        const float dL_dty = y_grad_mul * -fy * tz2 * dJ12;
-        float dL_dtz = -fx * tz2 * dJ00 - fy * tz2 * dJ11 + (2 * fx * tx) * tz3 * dJ02 + (2 * fy * ty) * tz3 * dJ12;
+        const double dJ00 = dA[0][0] * (double)v[0] + dA[0][1] * (double)v[4] + dA[0][2] * (double)v[8];
+        const double dJ02 = dA[0][0] * (double)v[2] + dA[0][1] * (double)v[6] + dA[0][2] * (double)v[10];
+        const double dJ11 = dA[1][0] * (double)v[1] + dA[1][1] * (double)v[5] + dA[1][2] * (double)v[9];
+        const double dJ12 = dA[1][0] * (double)v[2] + dA[1][1] * (double)v[6] + dA[1][2] * (double)v[10];
+        const double itz = 1. / tz, tz2 = itz * itz, tz3 = tz2 * itz;
+        const double dL_dtx = x_grad_mul * -fx * tz2 * dJ02;
+        const double dL_dty = y_grad_mul * -fy * tz2 * dJ12;
+        double dL_dtz = -fx * tz2 * dJ00 - fy * tz2 * dJ11 + (2 * fx * tx) * tz3 * dJ02 + (2 * fy * ty) * tz3 * dJ12;
         if (use_depth) dL_dtz -= g_iv / (tz * tz);
-        dmean[0] += v[0] * dL_dtx + v[1] * dL_dty + v[2] * dL_dtz;
-        dmean[1] += v[4] * dL_dtx + v[5] * dL_dty + v[6] * dL_dtz;
-        dmean[2] += v[8] * dL_dtx + v[9] * dL_dty + v[10] * dL_dtz;
+        dmean[0] += (double)v[0] * dL_dtx + (double)v[1] * dL_dty + (double)v[2] * dL_dtz;
+        dmean[1] += (double)v[4] * dL_dtx + (double)v[5] * dL_dty + (double)v[6] * dL_dtz;
+        dmean[2] += (double)v[8] * dL_dtx + (double)v[9] * dL_dty + (double)v[10] * dL_dtz;
     }
     // ---- K9a: screen-space mean -> 3D mean ----
     {
@@ -251,38 +254,38 @@ preprocess_backward_kernel(int P, int deg, int M, const float* __restrict__ mean
         dmean[1] += (-d0x * d0y * ddx + (sum2 - d0y * d0y) * ddy - d0z * d0y * ddz) * invsum32;
         dmean[2] += (-d0x * d0z * ddx - d0y * d0z * ddy + (sum2 - d0z * d0z) * ddz) * invsum32;
     }
-    dL_dmeans3D[3 * i] = dmean[0]; dL_dmeans3D[3 * i + 1] = dmean[1]; dL_dmeans3D[3 * i + 2] = dmean[2];
+    dL_dmeans3D[3 * i] = (float)dmean[0]; dL_dmeans3D[3 * i + 1] = (float)dmean[1]; dL_dmeans3D[3 * i + 2] = (float)dmean[2];
 
     // ---- K9c: cov3D -> scale, rotation ----
     if (cov3D_precomp) {
         if (dL_dcov3D) {
 #pragma unroll
-            for (int k = 0; k < 6; k++) dL_dcov3D[6 * i + k] = g6[k];
+            for (int k = 0; k < 6; k++) dL_dcov3D[6 * i + k] = (float)g6[k];
         }
     } else {
-        const float dS[3][3] = {{g6[0], 0.5f * g6[1], 0.5f * g6[2]}, {0.5f * g6[1], g6[3], 0.5f * g6[4]}, {0.5f * g6[2], 0.5f * g6[4], g6[5]}};
-        float dM[3][3];
+        const double dS[3][3] = {{g6[0], 0.5 * g6[1], 0.5 * g6[2]}, {0.5 * g6[1], g6[3], 0.5 * g6[4]}, {0.5 * g6[2], 0.5 * g6[4], g6[5]}};
+        double dM[3][3];
 #pragma unroll
         for (int k = 0; k < 3; k++)
 #pragma unroll
-            for (int j = 0; j < 3; j++) dM[k][j] = 2.0f * (Mm[k][0] * dS[0][j] + Mm[k][1] * dS[1][j] + Mm[k][2] * dS[2][j]);
+            for (int j = 0; j < 3; j++) dM[k][j] = 2.0 * (Mm[k][0] * dS[0][j] + Mm[k][1] * dS[1][j] + Mm[k][2] * dS[2][j]);
 #pragma unroll
         for (int k = 0; k < 3; k++)
-            dL_dscales[3 * i + k] = scale_mod * (R[0][k] * dM[k][0] + R[1][k] * dM[k][1] + R[2][k] * dM[k][2]);
-        float dR[3][3];
+            dL_dscales[3 * i + k] = (float)((double)scale_mod * (R[0][k] * dM[k][0] + R[1][k] * dM[k][1] + R[2][k] * dM[k][2]));
+        double dR[3][3];
 #pragma unroll
         for (int j = 0; j < 3; j++)
 #pragma unroll
             for (int k = 0; k < 3; k++) dR[j][k] = sc[k] * dM[k][j];
         float4 dq;
-        dq.x = 2 * qz * (dR[1][0] - dR[0][1]) + 2 * qy * (dR[0][2] - dR[2][0]) + 2 * qx * (dR[2][1] - dR[1][2]);
-        dq.y = 2 * qy * (dR[0][1] + dR[1][0]) + 2 * qz * (dR[0][2] + dR[2][0]) + 2 * qr * (dR[2][1] - dR[1][2]) - 4 * qx * (dR[1][1] + dR[2][2]);
-        dq.z = 2 * qx * (dR[0][1] + dR[1][0]) + 2 * qr * (dR[0][2] - dR[2][0]) + 2 * qz * (dR[1][2] + dR[2][1]) - 4 * qy * (dR[0][0] + dR[2][2]);
-        dq.w = 2 * qr * (dR[1][0] - dR[0][1]) + 2 * qx * (dR[0][2] + dR[2][0]) + 2 * qy * (dR[1][2] + dR[2][1]) - 4 * qz * (dR[0][0] + dR[1][1]);
+        dq.x = (float)(2 * qz * (dR[1][0] - dR[0][1]) + 2 * qy * (dR[0][2] - dR[2][0]) + 2 * qx * (dR[2][1] - dR[1][2]));
+        dq.y = (float)(2 * qy * (dR[0][1] + dR[1][0]) + 2 * qz * (dR[0][2] + dR[2][0]) + 2 * qr * (dR[2][1] - dR[1][2]) - 4 * qx * (dR[1][1] + dR[2][2]));
+        dq.z = (float)(2 * qx * (dR[0][1] + dR[1][0]) + 2 * qr * (dR[0][2] - dR[2][0]) + 2 * qz * (dR[1][2] + dR[2][1]) - 4 * qy * (dR[0][0] + dR[2][2]));
+        dq.w = (float)(2 * qr * (dR[1][0] - dR[0][1]) + 2 * qx * (dR[0][2] + dR[2][0]) + 2 * qy * (dR[1][2] + dR[2][1]) - 4 * qz * (dR[0][0] + dR[1][1]));
         *reinterpret_cast<float4*>(dL_drots + 4 * i) = dq;
         if (dL_dcov3D) {
 #pragma unroll
-            for (int k = 0; k < 6; k++) dL_dcov3D[6 * i + k] = g6[k];
+            for (int k = 0; k < 6; k++) dL_dcov3D[6 * i + k] = (float)g6[k];
         }
     }
 }

@@ -102,7 +102,7 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
                 const float dx = a.x - fpx, dy = a.y - fpy;
                 const float power = -0.5f * (a.z * dx * dx + bb.x * dy * dy) - a.w * dx * dy;
                 if (power <= 0.0f) {
-                    const float G = __expf(power);
+                    const float G = fast_exp(power);
                     const float abase = fminf(kAlphaCap, bb.y * G);
                     float alpha, dadb;
                     hier_alpha_grad<HIER>(abase, bb.z, __float_as_uint(bb.w), alpha, dadb);

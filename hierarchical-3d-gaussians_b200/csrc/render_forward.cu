@@ -57,7 +57,7 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
     const float fpx = (float)px, fpy = (float)py;
     bool done = !inside;
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, invd = 0.f;
-    uint32_t contributor = 0, last = 0;
+    uint32_t last = 0;
 
     int waited = 0;
     for (int b = 0; b < nb; b++) {
@@ -65,26 +65,32 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
         mbar_wait(&s_full[st], (uint32_t)((b / kFwdStages) & 1));
         waited = b + 1;
         const int cnt = min(kFwdBatch, n - b * kFwdBatch);
-        if (!done) {
+        // The body is straight-line + one short reconvergent `if`: a per-thread
+        // `continue`/`break` here leaves the warp split into fragments that each re-walk
+        // the list (measured: 18x the instructions).  A warp leaves the batch only when
+        // all of its 32 pixels are done (warp-uniform branch).
+        if (!__all_sync(0xffffffffu, done)) {
             const Record* rec = &s_rec[st][0];
+            const uint32_t base = (uint32_t)(b * kFwdBatch);
             for (int j = 0; j < cnt; j++) {
-                contributor++;
                 const float4 a = rec[j].a;
                 const float4 bb = rec[j].b;
                 const float dx = a.x - fpx, dy = a.y - fpy;
                 const float power = -0.5f * (a.z * dx * dx + bb.x * dy * dy) - a.w * dx * dy;
-                if (power > 0.0f) continue;
-                float alpha = fminf(kAlphaCap, bb.y * __expf(power));
+                float alpha = fminf(kAlphaCap, bb.y * fast_exp(power));
                 alpha = hier_alpha<HIER>(alpha, bb.z, __float_as_uint(bb.w));
-                if (alpha < kAlphaSkip) continue;
                 const float test_T = T * (1.0f - alpha);
-                if (test_T < kTStop) { done = true; break; }
-                const float4 c = rec[j].c;
-                const float w = alpha * T;
-                C0 += c.x * w; C1 += c.y * w; C2 += c.z * w;
-                if (DEPTH) invd += c.w * w;
-                T = test_T;
-                last = contributor;
+                bool valid = !done && power <= 0.0f && alpha >= kAlphaSkip;
+                if (valid && test_T < kTStop) { done = true; valid = false; }
+                if (valid) {
+                    const float4 c = rec[j].c;
+                    const float w = alpha * T;
+                    C0 += c.x * w; C1 += c.y * w; C2 += c.z * w;
+                    if (DEPTH) invd += c.w * w;
+                    T = test_T;
+                    last = base + (uint32_t)j + 1u;
+                }
+                if ((j & 31) == 31 && __all_sync(0xffffffffu, done)) break;
             }
         }
         const int ndone = __syncthreads_count(done);

@@ -24,12 +24,13 @@
  * The constants below that are NOT derivable from present files are listed in
  * DESIGN.md ("recalled constants") and each is a named #define here.
  *
- * All arithmetic is fp32 with contraction disabled (-ffp-contract=off) so that the
+ * Forward arithmetic is fp32 with contraction disabled (-ffp-contract=off) so that the
  * integer artefacts (radii, tile rects, depth-key bits, sort order, tile ranges)
  * are reproducible bit-for-bit by the CUDA path, which evaluates the same
- * expressions with explicit round-to-nearest mul/add.  Per-Gaussian gradient sums
- * are accumulated in double (the reference uses fp32 atomics in arbitrary order;
- * a double sum is the order-free value every fp32 order approximates).
+ * expressions without FMA contraction.  The BACKWARD evaluates the published formulas in
+ * double on the fp32 inputs (decisions such as the alpha skip stay fp32): the reference uses
+ * fp32 atomics in arbitrary order, so its own result is only defined up to fp32 rounding;
+ * the exact-arithmetic value is the order-free target every fp32 implementation approximates.
  */
 #include <math.h>
 #include <stdint.h>
@@ -345,8 +346,13 @@ void oracle_render_backward(int W, int H, const uint32_t* ranges, const uint32_t
                             double* dL_dmean2D /*[P][2]*/, double* dL_dconic /*[P][3]*/, double* dL_dopacity /*[P]*/,
                             double* dL_dcolor /*[P][3]*/, double* dL_dinvdepth /*[P]*/)
 {
+    /* DECISIONS (power > 0, alpha < 1/255, which entries contributed) are taken in fp32
+     * exactly as the forward took them; VALUES are then evaluated in double, so the result
+     * is the exact-arithmetic value of the published backward formulas for the fp32 inputs.
+     * Any fp32 implementation (the reference's atomics in arbitrary order included) can
+     * only differ from it by its own rounding. */
     const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
-    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+    const double ddelx_dx = 0.5 * W, ddely_dy = 0.5 * H;
 #pragma omp parallel for schedule(dynamic, 4)
     for (int tile = 0; tile < gx * gy; tile++) {
         int tx = tile % gx, ty = tile / gx;
@@ -354,68 +360,78 @@ void oracle_render_backward(int W, int H, const uint32_t* ranges, const uint32_t
         for (int py = ty * TILE; py < (ty + 1) * TILE && py < H; py++)
             for (int px = tx * TILE; px < (tx + 1) * TILE && px < W; px++) {
                 size_t pix = (size_t)py * W + px;
-                const float T_final = final_T[pix];
-                float T = T_final;
+                const double T_final = final_T[pix];
+                double T = T_final;
                 uint32_t last = n_contrib[pix];
-                float accum_rec[3] = { 0, 0, 0 }, last_color[3] = { 0, 0, 0 }, last_alpha = 0.f;
-                float accum_invd = 0.f, last_invd = 0.f;
-                float dpix[3];
+                double accum_rec[3] = { 0, 0, 0 }, last_color[3] = { 0, 0, 0 }, last_alpha = 0.;
+                double accum_invd = 0., last_invd = 0.;
+                double dpix[3];
                 for (int c = 0; c < 3; c++) dpix[c] = dL_dpix[(size_t)c * H * W + pix];
-                float dinv = dL_dinvdepth_pix ? dL_dinvdepth_pix[pix] : 0.f;
+                double dinv = dL_dinvdepth_pix ? dL_dinvdepth_pix[pix] : 0.;
+                double bg_dot = 0.;
+                for (int c = 0; c < 3; c++) bg_dot += (double)bg[c] * dpix[c];
                 for (uint32_t jj = last; jj-- > 0;) {
                     uint32_t g = point_list[s + jj];
-                    float dx = xy[2 * g] - (float)px, dy = xy[2 * g + 1] - (float)py;
                     const float* co = conic_opacity + 4 * g;
-                    float power = -0.5f * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
-                    if (power > 0.0f) continue;
-                    float G = expf(power);
-                    float abase = fminf(ALPHA_CAP, co[3] * G);
-                    float alpha = abase, dadb = 1.0f;
-                    if (ts) { alpha = hier_alpha(abase, ts[g], kids[g]); dadb = hier_dalpha(abase, ts[g], kids[g]); }
-                    if (alpha < ALPHA_SKIP) continue;
-                    T = T / (1.f - alpha);
-                    const float dchannel_dcolor = alpha * T;
-                    float dL_dalpha = 0.f;
+                    /* fp32 decision path (identical to oracle_render_forward) */
+                    float dxf = xy[2 * g] - (float)px, dyf = xy[2 * g + 1] - (float)py;
+                    float powerf = -0.5f * (co[0] * dxf * dxf + co[2] * dyf * dyf) - co[1] * dxf * dyf;
+                    if (powerf > 0.0f) continue;
+                    float alphaf = fminf(ALPHA_CAP, co[3] * expf(powerf));
+                    if (ts) alphaf = hier_alpha(alphaf, ts[g], kids[g]);
+                    if (alphaf < ALPHA_SKIP) continue;
+                    /* double value path */
+                    double dx = (double)xy[2 * g] - px, dy = (double)xy[2 * g + 1] - py;
+                    double power = -0.5 * ((double)co[0] * dx * dx + (double)co[2] * dy * dy) - (double)co[1] * dx * dy;
+                    double G = exp(power);
+                    double abase = fmin((double)ALPHA_CAP, (double)co[3] * G);
+                    double alpha = abase, dadb = 1.0;
+                    if (ts && kids[g] > 1 && ts[g] < 1.0f) {
+                        double t = ts[g], ik = 1.0 / kids[g];
+                        alpha = t * abase + (1.0 - t) * (1.0 - pow(1.0 - abase, ik));
+                        dadb = t + (1.0 - t) * ik * pow(1.0 - abase, ik - 1.0);
+                    }
+                    T = T / (1. - alpha);
+                    const double dchannel_dcolor = alpha * T;
+                    double dL_dalpha = 0.;
                     for (int c = 0; c < 3; c++) {
-                        float col = rgb[3 * g + c];
-                        accum_rec[c] = last_alpha * last_color[c] + (1.f - last_alpha) * accum_rec[c];
+                        double col = rgb[3 * g + c];
+                        accum_rec[c] = last_alpha * last_color[c] + (1. - last_alpha) * accum_rec[c];
                         last_color[c] = col;
                         dL_dalpha += (col - accum_rec[c]) * dpix[c];
 #pragma omp atomic
-                        dL_dcolor[3 * (size_t)g + c] += (double)(dchannel_dcolor * dpix[c]);
+                        dL_dcolor[3 * (size_t)g + c] += dchannel_dcolor * dpix[c];
                     }
                     if (dL_dinvdepth_pix) {
-                        float invd = 1.f / depths[g];
-                        accum_invd = last_alpha * last_invd + (1.f - last_alpha) * accum_invd;
+                        double invd = 1. / (double)depths[g];
+                        accum_invd = last_alpha * last_invd + (1. - last_alpha) * accum_invd;
                         last_invd = invd;
                         dL_dalpha += (invd - accum_invd) * dinv;
 #pragma omp atomic
-                        dL_dinvdepth[g] += (double)(dchannel_dcolor * dinv);
+                        dL_dinvdepth[g] += dchannel_dcolor * dinv;
                     }
                     dL_dalpha *= T;
                     last_alpha = alpha;
-                    float bg_dot = 0.f;
-                    for (int c = 0; c < 3; c++) bg_dot += bg[c] * dpix[c];
-                    dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+                    dL_dalpha += (-T_final / (1. - alpha)) * bg_dot;
                     /* chain through the hierarchy weight; the 0.99 cap is NOT differentiated
                      * (published backward treats alpha = o*G). */
-                    const float dL_dab = dL_dalpha * dadb;
-                    const float dL_dG = co[3] * dL_dab;
-                    const float gdx = G * dx, gdy = G * dy;
-                    const float dG_ddelx = -gdx * co[0] - gdy * co[1];
-                    const float dG_ddely = -gdy * co[2] - gdx * co[1];
+                    const double dL_dab = dL_dalpha * dadb;
+                    const double dL_dG = (double)co[3] * dL_dab;
+                    const double gdx = G * dx, gdy = G * dy;
+                    const double dG_ddelx = -gdx * co[0] - gdy * co[1];
+                    const double dG_ddely = -gdy * co[2] - gdx * co[1];
 #pragma omp atomic
-                    dL_dmean2D[2 * (size_t)g] += (double)(dL_dG * dG_ddelx * ddelx_dx);
+                    dL_dmean2D[2 * (size_t)g] += dL_dG * dG_ddelx * ddelx_dx;
 #pragma omp atomic
-                    dL_dmean2D[2 * (size_t)g + 1] += (double)(dL_dG * dG_ddely * ddely_dy);
+                    dL_dmean2D[2 * (size_t)g + 1] += dL_dG * dG_ddely * ddely_dy;
 #pragma omp atomic
-                    dL_dconic[3 * (size_t)g] += (double)(-0.5f * gdx * dx * dL_dG);
+                    dL_dconic[3 * (size_t)g] += -0.5 * gdx * dx * dL_dG;
 #pragma omp atomic
-                    dL_dconic[3 * (size_t)g + 1] += (double)(-0.5f * gdx * dy * dL_dG);
+                    dL_dconic[3 * (size_t)g + 1] += -0.5 * gdx * dy * dL_dG;
 #pragma omp atomic
-                    dL_dconic[3 * (size_t)g + 2] += (double)(-0.5f * gdy * dy * dL_dG);
+                    dL_dconic[3 * (size_t)g + 2] += -0.5 * gdy * dy * dL_dG;
 #pragma omp atomic
-                    dL_dopacity[g] += (double)(G * dL_dab);
+                    dL_dopacity[g] += G * dL_dab;
                 }
             }
     }
@@ -424,53 +440,73 @@ void oracle_render_backward(int W, int H, const uint32_t* ranges, const uint32_t
 /* ------------------------------------------------------------------ */
 /* K8 + K9: per-Gaussian chain rule back to the inputs                 */
 /* ------------------------------------------------------------------ */
+typedef struct { double x, y, z; } d3;
+static inline d3 xform4x3d(const float* m, d3 p) {
+    d3 r;
+    r.x = (double)m[0] * p.x + (double)m[4] * p.y + (double)m[8] * p.z + m[12];
+    r.y = (double)m[1] * p.x + (double)m[5] * p.y + (double)m[9] * p.z + m[13];
+    r.z = (double)m[2] * p.x + (double)m[6] * p.y + (double)m[10] * p.z + m[14];
+    return r;
+}
+static inline void xform4x4d(const float* m, d3 p, double out[4]) {
+    for (int j = 0; j < 4; j++) out[j] = (double)m[j] * p.x + (double)m[4 + j] * p.y + (double)m[8 + j] * p.z + m[12 + j];
+}
+static inline void quat_to_Rd(const float* q, double R[3][3]) {
+    double r = q[0], x = q[1], y = q[2], z = q[3];
+    R[0][0] = 1. - 2. * (y * y + z * z); R[0][1] = 2. * (x * y - r * z); R[0][2] = 2. * (x * z + r * y);
+    R[1][0] = 2. * (x * y + r * z); R[1][1] = 1. - 2. * (x * x + z * z); R[1][2] = 2. * (y * z - r * x);
+    R[2][0] = 2. * (x * z - r * y); R[2][1] = 2. * (y * z + r * x); R[2][2] = 1. - 2. * (x * x + y * y);
+}
+/* K8 + K9 evaluate the published chain-rule formulas in DOUBLE on the fp32 inputs
+ * (see the note in oracle_render_backward); outputs are rounded to fp32 once. */
 void oracle_preprocess_backward(int P, int deg, int M,
                                 const float* means3D, const float* scales, float scale_mod, const float* rots,
                                 const float* shs, const float* cov3D_precomp, const float* colors_precomp,
                                 const float* view, const float* proj, const float* campos,
                                 int W, int H, float tanx, float tany,
                                 const int* radii, const float* cov3Ds, const uint8_t* clamped,
-                                const float* dL_dmean2D /*[P][2]*/, const float* dL_dconic /*[P][3]*/,
-                                const float* dL_dcolor /*[P][3]*/, const float* dL_dinvdepth /*[P] or NULL*/,
+                                const double* dL_dmean2D /*[P][2]*/, const double* dL_dconic /*[P][3]*/,
+                                const double* dL_dcolor /*[P][3]*/, const double* dL_dinvdepth /*[P] or NULL*/,
                                 /* out, zero-initialised by caller */
                                 float* dL_dmeans3D, float* dL_dcov3D, float* dL_dsh, float* dL_dscale, float* dL_drot)
 {
-    const float fx = W / (2.0f * tanx), fy = H / (2.0f * tany);
+    const double fx = W / (2.0 * tanx), fy = H / (2.0 * tany);
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < P; i++) {
         if (radii[i] <= 0) continue;
-        f3 mean = { means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2] };
+        d3 mean = { means3D[3 * i], means3D[3 * i + 1], means3D[3 * i + 2] };
         const float* cov6 = cov3D_precomp ? cov3D_precomp + 6 * i : cov3Ds + 6 * i;
-        float dmean[3] = { 0, 0, 0 };
+        double dmean[3] = { 0, 0, 0 };
+        double g6d[6] = { 0, 0, 0, 0, 0, 0 };
 
         /* ---- K8: conic -> cov2D -> cov3D and mean (through J) ---- */
         {
-            f3 t = xform4x3(view, mean);
-            const float limx = FOV_CLAMP * tanx, limy = FOV_CLAMP * tany;
-            const float txtz = t.x / t.z, tytz = t.y / t.z;
-            t.x = fminf(limx, fmaxf(-limx, txtz)) * t.z;
-            t.y = fminf(limy, fmaxf(-limy, tytz)) * t.z;
-            const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
-            const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
-            float J00 = fx / t.z, J02 = -(fx * t.x) / (t.z * t.z);
-            float J11 = fy / t.z, J12 = -(fy * t.y) / (t.z * t.z);
-            float A[2][3];
+            d3 t = xform4x3d(view, mean);
+            const double limx = FOV_CLAMP * tanx, limy = FOV_CLAMP * tany;
+            const double txtz = t.x / t.z, tytz = t.y / t.z;
+            t.x = fmin(limx, fmax(-limx, txtz)) * t.z;
+            t.y = fmin(limy, fmax(-limy, tytz)) * t.z;
+            const double x_grad_mul = (txtz < -limx || txtz > limx) ? 0. : 1.;
+            const double y_grad_mul = (tytz < -limy || tytz > limy) ? 0. : 1.;
+            double J00 = fx / t.z, J02 = -(fx * t.x) / (t.z * t.z);
+            double J11 = fy / t.z, J12 = -(fy * t.y) / (t.z * t.z);
+            double A[2][3];
             for (int c = 0; c < 3; c++) {
                 A[0][c] = J00 * view[4 * c + 0] + J02 * view[4 * c + 2];
                 A[1][c] = J11 * view[4 * c + 1] + J12 * view[4 * c + 2];
             }
-            float V[3][3] = { { cov6[0], cov6[1], cov6[2] }, { cov6[1], cov6[3], cov6[4] }, { cov6[2], cov6[4], cov6[5] } };
-            float AV[2][3];
+            double V[3][3] = { { cov6[0], cov6[1], cov6[2] }, { cov6[1], cov6[3], cov6[4] }, { cov6[2], cov6[4], cov6[5] } };
+            double AV[2][3];
             for (int r = 0; r < 2; r++)
                 for (int c = 0; c < 3; c++)
                     AV[r][c] = A[r][0] * V[0][c] + A[r][1] * V[1][c] + A[r][2] * V[2][c];
-            float a = (AV[0][0] * A[0][0] + AV[0][1] * A[0][1] + AV[0][2] * A[0][2]) + DILATION;
-            float b = AV[0][0] * A[1][0] + AV[0][1] * A[1][1] + AV[0][2] * A[1][2];
-            float c_ = (AV[1][0] * A[1][0] + AV[1][1] * A[1][1] + AV[1][2] * A[1][2]) + DILATION;
-            float denom = a * c_ - b * b;
-            float dL_da = 0, dL_db = 0, dL_dc = 0;
-            float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
-            const float dcx = dL_dconic[3 * i], dcy = dL_dconic[3 * i + 1], dcz = dL_dconic[3 * i + 2];
+            double a = (AV[0][0] * A[0][0] + AV[0][1] * A[0][1] + AV[0][2] * A[0][2]) + DILATION;
+            double b = AV[0][0] * A[1][0] + AV[0][1] * A[1][1] + AV[0][2] * A[1][2];
+            double c_ = (AV[1][0] * A[1][0] + AV[1][1] * A[1][1] + AV[1][2] * A[1][2]) + DILATION;
+            double denom = a * c_ - b * b;
+            double dL_da = 0, dL_db = 0, dL_dc = 0;
+            double denom2inv = 1.0 / ((denom * denom) + 0.0000001);
+            const double dcx = dL_dconic[3 * i], dcy = dL_dconic[3 * i + 1], dcz = dL_dconic[3 * i + 2];
             if (denom2inv != 0) {
                 /* conic = (c, -b, a)/denom ; dL_dconic.y holds the gradient of the
                  * single stored off-diagonal (used twice in the quadratic form). */
@@ -478,7 +514,7 @@ void oracle_preprocess_backward(int P, int deg, int M,
                 dL_dc = denom2inv * (-a * a * dcz + 2 * a * b * dcy + (denom - a * c_) * dcx);
                 dL_db = denom2inv * 2 * (b * c_ * dcx - (denom + 2 * b * b) * dcy + a * b * dcz);
                 /* cov2D = A V A^T : d/dV */
-                float* o = dL_dcov3D + 6 * i;
+                double* o = g6d;
                 o[0] = A[0][0] * A[0][0] * dL_da + A[0][0] * A[1][0] * dL_db + A[1][0] * A[1][0] * dL_dc;
                 o[3] = A[0][1] * A[0][1] * dL_da + A[0][1] * A[1][1] * dL_db + A[1][1] * A[1][1] * dL_dc;
                 o[5] = A[0][2] * A[0][2] * dL_da + A[0][2] * A[1][2] * dL_db + A[1][2] * A[1][2] * dL_dc;
@@ -487,21 +523,22 @@ void oracle_preprocess_backward(int P, int deg, int M,
                 o[2] = 2 * A[0][0] * A[0][2] * dL_da + (A[0][0] * A[1][2] + A[0][2] * A[1][0]) * dL_db + 2 * A[1][0] * A[1][2] * dL_dc;
                 o[4] = 2 * A[0][2] * A[0][1] * dL_da + (A[0][1] * A[1][2] + A[0][2] * A[1][1]) * dL_db + 2 * A[1][1] * A[1][2] * dL_dc;
             }
+            for (int k6 = 0; k6 < 6; k6++) dL_dcov3D[6 * i + k6] = (float)g6d[k6];
             /* d/dA[r][c] = 2*(AV)[r][c]*dL_d{a,c} + (AV)[other][c]*dL_db */
-            float dA[2][3];
+            double dA[2][3];
             for (int c = 0; c < 3; c++) {
                 dA[0][c] = 2 * AV[0][c] * dL_da + AV[1][c] * dL_db;
                 dA[1][c] = 2 * AV[1][c] * dL_dc + AV[0][c] * dL_db;
             }
             /* A = J Rwv, Rwv[k][c] = view[4c+k] : dJ[r][k] = sum_c dA[r][c] Rwv[k][c] */
-            float dJ00 = dA[0][0] * view[0] + dA[0][1] * view[4] + dA[0][2] * view[8];
-            float dJ02 = dA[0][0] * view[2] + dA[0][1] * view[6] + dA[0][2] * view[10];
-            float dJ11 = dA[1][0] * view[1] + dA[1][1] * view[5] + dA[1][2] * view[9];
-            float dJ12 = dA[1][0] * view[2] + dA[1][1] * view[6] + dA[1][2] * view[10];
-            float tz = 1.f / t.z, tz2 = tz * tz, tz3 = tz2 * tz;
-            float dL_dtx = x_grad_mul * -fx * tz2 * dJ02;
-            float dL_dty = y_grad_mul * -fy * tz2 * dJ12;
-            float dL_dtz = -fx * tz2 * dJ00 - fy * tz2 * dJ11 + (2 * fx * t.x) * tz3 * dJ02 + (2 * fy * t.y) * tz3 * dJ12;
+            double dJ00 = dA[0][0] * view[0] + dA[0][1] * view[4] + dA[0][2] * view[8];
+            double dJ02 = dA[0][0] * view[2] + dA[0][1] * view[6] + dA[0][2] * view[10];
+            double dJ11 = dA[1][0] * view[1] + dA[1][1] * view[5] + dA[1][2] * view[9];
+            double dJ12 = dA[1][0] * view[2] + dA[1][1] * view[6] + dA[1][2] * view[10];
+            double tz = 1. / t.z, tz2 = tz * tz, tz3 = tz2 * tz;
+            double dL_dtx = x_grad_mul * -fx * tz2 * dJ02;
+            double dL_dty = y_grad_mul * -fy * tz2 * dJ12;
+            double dL_dtz = -fx * tz2 * dJ00 - fy * tz2 * dJ11 + (2 * fx * t.x) * tz3 * dJ02 + (2 * fy * t.y) * tz3 * dJ12;
             /* inverse-depth output: invdepth = 1/t.z */
             if (dL_dinvdepth) dL_dtz -= dL_dinvdepth[i] / (t.z * t.z);
             /* t = p . view(4x3): dmean_k = sum_j view[4k + j] dt_j */
@@ -512,11 +549,11 @@ void oracle_preprocess_backward(int P, int deg, int M,
 
         /* ---- K9a: screen-space mean -> 3D mean through the projection ---- */
         {
-            float mh[4]; xform4x4(proj, mean, mh);
-            float m_w = 1.0f / (mh[3] + W_EPS);
-            float mul1 = (proj[0] * mean.x + proj[4] * mean.y + proj[8] * mean.z + proj[12]) * m_w * m_w;
-            float mul2 = (proj[1] * mean.x + proj[5] * mean.y + proj[9] * mean.z + proj[13]) * m_w * m_w;
-            float gx_ = dL_dmean2D[2 * i], gy_ = dL_dmean2D[2 * i + 1];
+            double mh[4]; xform4x4d(proj, mean, mh);
+            double m_w = 1.0 / (mh[3] + W_EPS);
+            double mul1 = (proj[0] * mean.x + proj[4] * mean.y + proj[8] * mean.z + proj[12]) * m_w * m_w;
+            double mul2 = (proj[1] * mean.x + proj[5] * mean.y + proj[9] * mean.z + proj[13]) * m_w * m_w;
+            double gx_ = dL_dmean2D[2 * i], gy_ = dL_dmean2D[2 * i + 1];
             dmean[0] += (proj[0] * m_w - proj[3] * mul1) * gx_ + (proj[1] * m_w - proj[3] * mul2) * gy_;
             dmean[1] += (proj[4] * m_w - proj[7] * mul1) * gx_ + (proj[5] * m_w - proj[7] * mul2) * gy_;
             dmean[2] += (proj[8] * m_w - proj[11] * mul1) * gx_ + (proj[9] * m_w - proj[11] * mul2) * gy_;
@@ -526,45 +563,45 @@ void oracle_preprocess_backward(int P, int deg, int M,
         if (!colors_precomp) {
             const float* sh = shs + (size_t)i * M * 3;
             float* dsh = dL_dsh + (size_t)i * M * 3;
-            f3 d0 = { mean.x - campos[0], mean.y - campos[1], mean.z - campos[2] };
-            float len = sqrtf(d0.x * d0.x + d0.y * d0.y + d0.z * d0.z);
-            float x = d0.x / len, y = d0.y / len, z = d0.z / len;
-            float dRGB[3];
-            for (int c = 0; c < 3; c++) dRGB[c] = clamped[3 * i + c] ? 0.f : dL_dcolor[3 * i + c];
-            float ddx = 0, ddy = 0, ddz = 0; /* dL/d(dir) */
+            d3 d0 = { mean.x - campos[0], mean.y - campos[1], mean.z - campos[2] };
+            double len = sqrt(d0.x * d0.x + d0.y * d0.y + d0.z * d0.z);
+            double x = d0.x / len, y = d0.y / len, z = d0.z / len;
+            double dRGB[3];
+            for (int c = 0; c < 3; c++) dRGB[c] = clamped[3 * i + c] ? 0. : dL_dcolor[3 * i + c];
+            double ddx = 0, ddy = 0, ddz = 0; /* dL/d(dir) */
 #define S(k, c) sh[(k) * 3 + (c)]
 #define DS(k, c) dsh[(k) * 3 + (c)]
             for (int c = 0; c < 3; c++) {
-                float g = dRGB[c];
-                float dx_ = 0, dy_ = 0, dz_ = 0;
+                double g = dRGB[c];
+                double dx_ = 0, dy_ = 0, dz_ = 0;
                 DS(0, c) = SH_C0 * g;
                 if (deg > 0) {
                     DS(1, c) = -SH_C1 * y * g; DS(2, c) = SH_C1 * z * g; DS(3, c) = -SH_C1 * x * g;
                     dx_ = -SH_C1 * S(3, c); dy_ = -SH_C1 * S(1, c); dz_ = SH_C1 * S(2, c);
                     if (deg > 1) {
-                        float xx = x * x, yy = y * y, zz = z * z, xy_ = x * y, yz = y * z, xz = x * z;
+                        double xx = x * x, yy = y * y, zz = z * z, xy_ = x * y, yz = y * z, xz = x * z;
                         DS(4, c) = SH_C2[0] * xy_ * g; DS(5, c) = SH_C2[1] * yz * g;
-                        DS(6, c) = SH_C2[2] * (2.f * zz - xx - yy) * g;
+                        DS(6, c) = SH_C2[2] * (2. * zz - xx - yy) * g;
                         DS(7, c) = SH_C2[3] * xz * g; DS(8, c) = SH_C2[4] * (xx - yy) * g;
-                        dx_ += SH_C2[0] * y * S(4, c) + SH_C2[2] * 2.f * -x * S(6, c) + SH_C2[3] * z * S(7, c) + SH_C2[4] * 2.f * x * S(8, c);
-                        dy_ += SH_C2[0] * x * S(4, c) + SH_C2[1] * z * S(5, c) + SH_C2[2] * 2.f * -y * S(6, c) + SH_C2[4] * 2.f * -y * S(8, c);
-                        dz_ += SH_C2[1] * y * S(5, c) + SH_C2[2] * 2.f * 2.f * z * S(6, c) + SH_C2[3] * x * S(7, c);
+                        dx_ += SH_C2[0] * y * S(4, c) + SH_C2[2] * 2. * -x * S(6, c) + SH_C2[3] * z * S(7, c) + SH_C2[4] * 2. * x * S(8, c);
+                        dy_ += SH_C2[0] * x * S(4, c) + SH_C2[1] * z * S(5, c) + SH_C2[2] * 2. * -y * S(6, c) + SH_C2[4] * 2. * -y * S(8, c);
+                        dz_ += SH_C2[1] * y * S(5, c) + SH_C2[2] * 2. * 2. * z * S(6, c) + SH_C2[3] * x * S(7, c);
                         if (deg > 2) {
-                            DS(9, c) = SH_C3[0] * y * (3.f * xx - yy) * g;
+                            DS(9, c) = SH_C3[0] * y * (3. * xx - yy) * g;
                             DS(10, c) = SH_C3[1] * xy_ * z * g;
-                            DS(11, c) = SH_C3[2] * y * (4.f * zz - xx - yy) * g;
-                            DS(12, c) = SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy) * g;
-                            DS(13, c) = SH_C3[4] * x * (4.f * zz - xx - yy) * g;
+                            DS(11, c) = SH_C3[2] * y * (4. * zz - xx - yy) * g;
+                            DS(12, c) = SH_C3[3] * z * (2. * zz - 3. * xx - 3. * yy) * g;
+                            DS(13, c) = SH_C3[4] * x * (4. * zz - xx - yy) * g;
                             DS(14, c) = SH_C3[5] * z * (xx - yy) * g;
-                            DS(15, c) = SH_C3[6] * x * (xx - 3.f * yy) * g;
-                            dx_ += SH_C3[0] * S(9, c) * 3.f * 2.f * xy_ + SH_C3[1] * S(10, c) * yz + SH_C3[2] * S(11, c) * -2.f * xy_
-                                 + SH_C3[3] * S(12, c) * -3.f * 2.f * xz + SH_C3[4] * S(13, c) * (-3.f * xx + 4.f * zz - yy)
-                                 + SH_C3[5] * S(14, c) * 2.f * xz + SH_C3[6] * S(15, c) * 3.f * (xx - yy);
-                            dy_ += SH_C3[0] * S(9, c) * 3.f * (xx - yy) + SH_C3[1] * S(10, c) * xz + SH_C3[2] * S(11, c) * (-3.f * yy + 4.f * zz - xx)
-                                 + SH_C3[3] * S(12, c) * -3.f * 2.f * yz + SH_C3[4] * S(13, c) * -2.f * xy_
-                                 + SH_C3[5] * S(14, c) * -2.f * yz + SH_C3[6] * S(15, c) * -3.f * 2.f * xy_;
-                            dz_ += SH_C3[1] * S(10, c) * xy_ + SH_C3[2] * S(11, c) * 4.f * 2.f * yz + SH_C3[3] * S(12, c) * 3.f * (2.f * zz - xx - yy)
-                                 + SH_C3[4] * S(13, c) * 4.f * 2.f * xz + SH_C3[5] * S(14, c) * (xx - yy);
+                            DS(15, c) = SH_C3[6] * x * (xx - 3. * yy) * g;
+                            dx_ += SH_C3[0] * S(9, c) * 3. * 2. * xy_ + SH_C3[1] * S(10, c) * yz + SH_C3[2] * S(11, c) * -2. * xy_
+                                 + SH_C3[3] * S(12, c) * -3. * 2. * xz + SH_C3[4] * S(13, c) * (-3. * xx + 4. * zz - yy)
+                                 + SH_C3[5] * S(14, c) * 2. * xz + SH_C3[6] * S(15, c) * 3. * (xx - yy);
+                            dy_ += SH_C3[0] * S(9, c) * 3. * (xx - yy) + SH_C3[1] * S(10, c) * xz + SH_C3[2] * S(11, c) * (-3. * yy + 4. * zz - xx)
+                                 + SH_C3[3] * S(12, c) * -3. * 2. * yz + SH_C3[4] * S(13, c) * -2. * xy_
+                                 + SH_C3[5] * S(14, c) * -2. * yz + SH_C3[6] * S(15, c) * -3. * 2. * xy_;
+                            dz_ += SH_C3[1] * S(10, c) * xy_ + SH_C3[2] * S(11, c) * 4. * 2. * yz + SH_C3[3] * S(12, c) * 3. * (2. * zz - xx - yy)
+                                 + SH_C3[4] * S(13, c) * 4. * 2. * xz + SH_C3[5] * S(14, c) * (xx - yy);
                         }
                     }
                 }
@@ -573,8 +610,8 @@ void oracle_preprocess_backward(int P, int deg, int M,
 #undef S
 #undef DS
             /* through dir = d0/|d0| */
-            float sum2 = d0.x * d0.x + d0.y * d0.y + d0.z * d0.z;
-            float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+            double sum2 = d0.x * d0.x + d0.y * d0.y + d0.z * d0.z;
+            double invsum32 = 1.0 / sqrt(sum2 * sum2 * sum2);
             dmean[0] += ((+sum2 - d0.x * d0.x) * ddx - d0.y * d0.x * ddy - d0.z * d0.x * ddz) * invsum32;
             dmean[1] += (-d0.x * d0.y * ddx + (sum2 - d0.y * d0.y) * ddy - d0.z * d0.y * ddz) * invsum32;
             dmean[2] += (-d0.x * d0.z * ddx - d0.y * d0.z * ddy + (sum2 - d0.z * d0.z) * ddz) * invsum32;
@@ -584,30 +621,30 @@ void oracle_preprocess_backward(int P, int deg, int M,
         /* ---- K9c: cov3D -> scale, rotation ---- */
         if (!cov3D_precomp) {
             const float* q = rots + 4 * i;
-            float r = q[0], x = q[1], y = q[2], z = q[3];
-            float R[3][3]; quat_to_R(q, R);
-            float s[3] = { scale_mod * scales[3 * i], scale_mod * scales[3 * i + 1], scale_mod * scales[3 * i + 2] };
+            double r = q[0], x = q[1], y = q[2], z = q[3];
+            double R[3][3]; quat_to_Rd(q, R);
+            double s[3] = { scale_mod * scales[3 * i], scale_mod * scales[3 * i + 1], scale_mod * scales[3 * i + 2] };
             /* M[k][i] = s_k R[i][k] ; Sigma = M^T M */
-            float Mm[3][3];
+            double Mm[3][3];
             for (int k = 0; k < 3; k++) for (int j = 0; j < 3; j++) Mm[k][j] = s[k] * R[j][k];
-            const float* g6 = dL_dcov3D + 6 * i;
+            const double* g6 = g6d;
             /* symmetric dL/dSigma with off-diagonals halved (they were accumulated for both uses) */
-            float dS[3][3] = { { g6[0], 0.5f * g6[1], 0.5f * g6[2] }, { 0.5f * g6[1], g6[3], 0.5f * g6[4] }, { 0.5f * g6[2], 0.5f * g6[4], g6[5] } };
+            double dS[3][3] = { { g6[0], 0.5 * g6[1], 0.5 * g6[2] }, { 0.5 * g6[1], g6[3], 0.5 * g6[4] }, { 0.5 * g6[2], 0.5 * g6[4], g6[5] } };
             /* dL/dM = 2 M dSigma */
-            float dM[3][3];
+            double dM[3][3];
             for (int k = 0; k < 3; k++) for (int j = 0; j < 3; j++)
-                dM[k][j] = 2.0f * (Mm[k][0] * dS[0][j] + Mm[k][1] * dS[1][j] + Mm[k][2] * dS[2][j]);
+                dM[k][j] = 2.0 * (Mm[k][0] * dS[0][j] + Mm[k][1] * dS[1][j] + Mm[k][2] * dS[2][j]);
             /* M[k][j] = s_k R[j][k] : dscale_k = sum_j R[j][k] dM[k][j] (times scale_mod) */
             for (int k = 0; k < 3; k++)
                 dL_dscale[3 * i + k] = scale_mod * (R[0][k] * dM[k][0] + R[1][k] * dM[k][1] + R[2][k] * dM[k][2]);
             /* dR[j][k] = s_k dM[k][j] */
-            float dR[3][3];
+            double dR[3][3];
             for (int j = 0; j < 3; j++) for (int k = 0; k < 3; k++) dR[j][k] = s[k] * dM[k][j];
             /* R entries as functions of (r,x,y,z) */
-            float dq_r = 2 * z * (dR[1][0] - dR[0][1]) + 2 * y * (dR[0][2] - dR[2][0]) + 2 * x * (dR[2][1] - dR[1][2]);
-            float dq_x = 2 * y * (dR[0][1] + dR[1][0]) + 2 * z * (dR[0][2] + dR[2][0]) + 2 * r * (dR[2][1] - dR[1][2]) - 4 * x * (dR[1][1] + dR[2][2]);
-            float dq_y = 2 * x * (dR[0][1] + dR[1][0]) + 2 * r * (dR[0][2] - dR[2][0]) + 2 * z * (dR[1][2] + dR[2][1]) - 4 * y * (dR[0][0] + dR[2][2]);
-            float dq_z = 2 * r * (dR[1][0] - dR[0][1]) + 2 * x * (dR[0][2] + dR[2][0]) + 2 * y * (dR[1][2] + dR[2][1]) - 4 * z * (dR[0][0] + dR[1][1]);
+            double dq_r = 2 * z * (dR[1][0] - dR[0][1]) + 2 * y * (dR[0][2] - dR[2][0]) + 2 * x * (dR[2][1] - dR[1][2]);
+            double dq_x = 2 * y * (dR[0][1] + dR[1][0]) + 2 * z * (dR[0][2] + dR[2][0]) + 2 * r * (dR[2][1] - dR[1][2]) - 4 * x * (dR[1][1] + dR[2][2]);
+            double dq_y = 2 * x * (dR[0][1] + dR[1][0]) + 2 * r * (dR[0][2] - dR[2][0]) + 2 * z * (dR[1][2] + dR[2][1]) - 4 * y * (dR[0][0] + dR[2][2]);
+            double dq_z = 2 * r * (dR[1][0] - dR[0][1]) + 2 * x * (dR[0][2] + dR[2][0]) + 2 * y * (dR[1][2] + dR[2][1]) - 4 * z * (dR[0][0] + dR[1][1]);
             dL_drot[4 * i] = dq_r; dL_drot[4 * i + 1] = dq_x; dL_drot[4 * i + 2] = dq_y; dL_drot[4 * i + 3] = dq_z;
         }
     }

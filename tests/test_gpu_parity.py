@@ -39,10 +39,13 @@ def check_image(f, out, st, do_depth=False):
 
 
 def check_grads(b, g, names):
+    errs = {}
     for n in names:
         assert g[n] is not None, n
-        e = rel_err(g[n], b[n])
-        assert e < TOL, f"{n}: rel err {e:.3e}"
+        errs[n] = rel_err(g[n], b[n])
+    print("grad rel errs:", {k: f"{v:.2e}" for k, v in errs.items()})
+    bad = {k: v for k, v in errs.items() if not v < TOL}
+    assert not bad, f"rel err above {TOL}: {bad} (all: {errs})"
 
 
 @pytest.mark.parametrize("mode,do_depth", [("flat", False), ("flat", True), ("hier", False)])
