@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- train-step images/sec (fwd+bwd) @1080p, 3M Gaussians, SH-3 (BASELINE.json).
+
+  python bench.py --gpus N --steps K --warmup W            our sm_100a path
+  python bench.py --impl reference --gpus N ...            the CPU restatement of the same path
+                                                           (the reference's own source for it is absent)
+
+A "step"  = LOD cut (expand_to_size + get_interpolation_weights) -> cut gather/parent
+lerp -> rasterizer forward -> L1 loss gradient -> rasterizer backward -> gradient scatter to the full
+parameter arrays, all through the public drop-in API (gaussian_hierarchy._C / GaussianRasterizer).
+N > 1: one process per GPU, the frame is screen-tile-sharded (h3dgs.dist), strong scaling.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "hierarchical-3d-gaussians_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "train-step images/sec (fwd+bwd) @1080p, 3M Gaussians, SH-3"
+UNIT = "images/s"
+W, H = 1920, 1080
+TAU = 6.0
+N_VIEWS = 8
+
+
+# ----------------------------------------------------------------------------- workload
+def build_workload(name, cache_dir="/tmp/h3dgs_cache"):
+    """Synthetic scene + cameras (numpy).  hier3m: 1.5M leaves + 1,499,999 interior nodes (config #3);
+    flat1m: 1M flat Gaussians (config #2)."""
+    from h3dgs import synth
+    os.makedirs(cache_dir, exist_ok=True)
+    path = os.path.join(cache_dir, f"{name}_v3.npz")
+    cams = [synth.make_camera(W, H)]
+    rs = np.random.default_rng(2)
+    for i in range(1, N_VIEWS):
+        cams.append(synth.yaw_camera(W, H, float(rs.uniform(-15, 15)), rs.uniform(-0.5, 0.5, 3)))
+    if os.path.exists(path):
+        z = np.load(path)
+        return {k: z[k] for k in z.files}, cams
+    cam = cams[0]
+    if name == "hier3m":
+        # Cloud v2: like cloud v1 but world-space size grows as sqrt(z) (screen size shrinks with
+        # distance), so the tau=6px cut really merges far leaves; z ~ U[2,60]
+        leaves = synth.cloud_v1(1_500_000, cam, sh_degree=3, zmin=2.0, zmax=60.0, seed=0, scale_k=1.0)
+        z = leaves["means3D"][:, 2:3]
+        g = np.random.default_rng(7)
+        leaves["scales"] = (2.4e-3 * np.sqrt(2.0 * z) * np.exp(0.5 * g.standard_normal((z.shape[0], 3)))).astype(np.float32)
+        arrays = synth.build_hierarchy(leaves)
+    elif name == "flat1m":
+        arrays = synth.cloud_v1(1_000_000, cam, sh_degree=3, seed=0)
+    elif name == "tiny":
+        leaves = synth.cloud_v1(20_000, cam, sh_degree=3, zmin=2.0, zmax=60.0, seed=0, scale_k=8e-3)
+        arrays = synth.build_hierarchy(leaves)
+    else:
+        raise ValueError(name)
+    tmp = path + f".{os.getpid()}.tmp.npz"
+    np.savez(tmp, **arrays)
+    os.replace(tmp, path)
+    return arrays, cams
+
+
+def alg_bytes(P, V, D, hier):
+    """ALGORITHMIC bytes per image, per stage (SURVEY.md 8d derivation: every array once per stage
+    that must produce/consume it, fp32/i32, sort idealised as one read + one write)."""
+    Px, T = W * H, ((W + 15) // 16) * ((H + 15) // 16)
+    b = {
+        "preprocess": 44 * P + 8 * P + 192 * V + 40 * V + (8 * P if hier else 0),
+        "scan": 8 * P,
+        "duplicate_with_keys": 12 * D,
+        "radix_sort": 24 * D,
+        "identify_tile_ranges": 8 * D + 8 * T,
+        "gather_records": 0,                       # implementation choice (TMA staging), not algorithmic
+        "render_forward": 40 * D + 20 * Px,
+        "render_backward": 40 * D + 36 * D + 32 * Px,
+        "preprocess_backward": (36 + 44 + 192 + 40) * V + 248 * V,
+    }
+    b["total"] = sum(b.values())
+    return b
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_step_fn(arrays, cams, frac):
+    """Returns a callable running ONE step of the path on the host cores with the oracle
+    (kind "port"): LOD cut + weights + gather/lerp + forward + L1 grad + backward, on a
+    bounded sample: every `frac`-th Gaussian of the cut at full 1080p."""
+    from oracle import oracle
+    from h3dgs import synth
+    hier = "nodes" in arrays
+
+    def step(i):
+        cam = cams[i % len(cams)]
+        if hier:
+            thr = synth.tau_threshold(TAU, cam)
+            n, ri, pi, ni = oracle.expand_to_size(arrays["nodes"], arrays["boxes"], thr, cam.camera_center)
+            ts, kids = oracle.get_interpolation_weights(ni, thr, arrays["nodes"], arrays["boxes"], cam.camera_center)
+            sel = slice(0, n, frac)
+            ri, pi, ts, kids = ri[sel], np.where(pi[sel] < 0, ri[sel], pi[sel]), ts[sel], kids[sel]
+            t = ts[:, None]
+            lerp = lambda a: t.reshape((-1,) + (1,) * (a.ndim - 1)) * a[ri] + (1 - t).reshape((-1,) + (1,) * (a.ndim - 1)) * a[pi]
+            qc, qp = arrays["rotations"][ri], arrays["rotations"][pi]
+            sign = np.where((qc * qp).sum(1, keepdims=True) < 0, -1.0, 1.0).astype(np.float32)
+            means, scales, shs, opac = lerp(arrays["means3D"]), lerp(arrays["scales"]), lerp(arrays["shs"]), lerp(arrays["opacities"])
+            rots = t * qc + (1 - t) * qp * sign
+        else:
+            sel = slice(0, None, frac)
+            means, scales, shs, opac, rots = (arrays[k][sel] for k in ("means3D", "scales", "shs", "opacities", "rotations"))
+            ts = kids = None
+        f = oracle.rasterize_forward(means, shs, None, opac, scales, rots, None, cam.world_view_transform,
+                                     cam.full_proj_transform, cam.camera_center, np.zeros(3, np.float32), W, H,
+                                     cam.tanfovx, cam.tanfovy, ts=ts, kids=kids)
+        g = synth.l1_grad(f["color"], seed=3 + i)
+        oracle.rasterize_backward(f, g)
+        return f["num_rendered"]
+    return step
+
+
+def run_cpu_arm(arrays, cams, steps, warmup, frac, budget_s=25.0):
+    from oracle import oracle
+    step = cpu_step_fn(arrays, cams, frac)
+    for i in range(warmup):
+        step(i)
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(steps):
+        step(warmup + i)
+        done += 1
+        if time.perf_counter() - t0 > budget_s and done >= 1:
+            break
+    dt = (time.perf_counter() - t0) / done
+    # the sample holds 1/frac of the cut's Gaussians at full resolution: linear extrapolation in D
+    return dict(ms_per_sample_step=dt * 1e3, value=1.0 / (dt * frac), steps_run=done, cores=oracle.num_threads())
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="hier3m", choices=["hier3m", "flat1m", "tiny"])
+    ap.add_argument("--cpu-frac", type=int, default=16, help="CPU arm renders every k-th cut Gaussian")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    hier = args.workload != "flat1m"
+    config = {"workload": {"hier3m": "config #3: N_all=3M (1.5M leaves + 1,499,999 interior nodes), 1920x1080, SH-3, "
+                                     "LOD cut tau=6px, fwd+bwd, 8 synthetic views",
+                           "flat1m": "config #2: 1M flat Gaussians, 1920x1080, SH-3, fwd+bwd",
+                           "tiny": "smoke-size hierarchy"}[args.workload],
+              "l2": "inputs larger than L2 (parameter arrays 0.7 GB, per-step state > 1 GB); no explicit flush",
+              "parallelism": f"screen-tile-sharded x{world}" if world > 1 else "single GPU"}
+
+    # ---------------- reference arm: rank 0 alone, CPU restatement of the path ----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        arrays, cams = build_workload(args.workload)
+        r = run_cpu_arm(arrays, cams, args.steps, min(args.warmup, 1), args.cpu_frac, budget_s=150.0)
+        sample = (f"every {args.cpu_frac}th Gaussian of the cut at full 1080p, {r['steps_run']} step(s), "
+                  f"images/s extrapolated linearly (x1/{args.cpu_frac}); oracle/oracle.c with OpenMP")
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": r["steps_run"], "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_sample_step"] * args.cpu_frac,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config,
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the reference's own implementation of this path (hierarchy-rasterizer, gaussian-hierarchy) is "
+                    "absent from /root/reference and is CUDA-only; this arm times the CPU restatement (oracle port)"}))
+        return
+
+    # ---------------- our arm ----------------
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a CUDA device: there is no CPU fallback for this path")
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    if rank == 0:
+        arrays, cams = build_workload(args.workload)
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        arrays, cams = build_workload(args.workload)
+
+    from h3dgs import _lib, pipeline, synth
+    from h3dgs import dist as hdist
+    scene = pipeline.Scene(arrays, device=dev)
+    dcams = [pipeline.DeviceCamera(c, device=dev) for c in cams]
+    thr = [synth.tau_threshold(TAU, c) for c in cams]
+    bg = torch.zeros(3, device=dev)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    gts_host = [torch.rand((3, H, W), generator=g).pin_memory() for _ in range(N_VIEWS)]
+    gts_dev = [t.to(dev) for t in gts_host]
+    sharder = hdist.TileSharder(world, rank, dev) if world > 1 else None
+
+    def step(i, resident=True):
+        v = i % N_VIEWS
+        if resident:
+            cam, gt = dcams[v], gts_dev[v]
+        else:       # e2e: this step's camera and target come from pinned host memory
+            cam = pipeline.DeviceCamera.__new__(pipeline.DeviceCamera)
+            c = cams[v]
+            cam.W, cam.H, cam.tanfovx, cam.tanfovy = c.W, c.H, c.tanfovx, c.tanfovy
+            cam.viewmatrix = host_cams[v][0].to(dev, non_blocking=True)
+            cam.projmatrix = host_cams[v][1].to(dev, non_blocking=True)
+            cam.campos = host_cams[v][2].to(dev, non_blocking=True)
+            cam.campos_cpu = host_cams[v][2]
+            gt = gts_host[v].to(dev, non_blocking=True)
+        if sharder is None:
+            loss, radii, n = pipeline.l1_step(scene, cam, bg, gt, thr[v] if hier else None)
+        else:
+            loss, radii, n = sharder.l1_step(scene, cam, bg, gt, thr[v] if hier else None)
+        return loss, radii, n
+
+    host_cams = [(torch.tensor(c.world_view_transform).pin_memory(), torch.tensor(c.full_proj_transform).pin_memory(),
+                  torch.tensor(c.camera_center).pin_memory()) for c in cams]
+
+    def timed(nsteps, resident, collect=None):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(nsteps):
+            loss, radii, n = step(i, resident)
+            if not resident:
+                loss_host = loss.item()          # D2H read of the step's result
+            if collect is not None:
+                collect.append((n, radii))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.barrier()
+            ms = float(t.item())
+        return ms
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.profile_reset(); _lib.profile_enable(True)
+    l0 = _lib.launch_count()
+    stats = []
+    ms_total = timed(args.steps, True, stats)
+    launches = _lib.launch_count() - l0
+    prof = _lib.profile_read(); _lib.profile_enable(False)
+    ms_e2e = timed(args.steps, False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # bookkeeping for the roofline: P (cut), V, D averaged over the timed steps
+    Pm = float(np.mean([s[0] for s in stats]))
+    Vm = float(np.mean([int((s[1] > 0).sum().item()) for s in stats[:N_VIEWS]]))
+    stage_ms = {k: (v[0] / max(v[1], 1)) for k, v in prof.items() if v[1] > 0}
+    Dm = None
+    try:
+        from diff_gaussian_rasterization import _C as rc
+        Dm = float(rc.last_num_rendered())
+    except Exception:
+        pass
+
+    if rank == 0:
+        ms_step = ms_total / args.steps
+        value = 1000.0 / ms_step
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+               "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+               "clocks": clocks, "gpu_launches": int(launches),
+               "e2e": {"value": 1000.0 / (ms_e2e / args.steps), "unit": UNIT,
+                       "h2d_bytes_per_step": 3 * H * W * 4 + 16 * 4 * 2 + 3 * 4, "d2h_bytes_per_step": 4},
+               "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
+               "counts": {"P_cut": Pm, "V": Vm, "D": Dm, "N_all": int(scene.means3D.shape[0])}}
+        # roofline of the dominant kernel
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        if stage_ms and Dm:
+            dom = max((k for k in stage_ms if k not in ("lod_cut", "lod_weights")), key=lambda k: stage_ms[k])
+            ab = alg_bytes(Pm, Vm, Dm / max(world, 1) if dom.startswith("render") else Dm, hier)
+            achieved = ab[dom] / (stage_ms[dom] * 1e-3) / 1e9
+            out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                               "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                               "alg_bytes_per_launch": ab[dom], "kernel_ms": stage_ms[dom],
+                               "note": "the blend kernels are FP32-issue-bound, not HBM-bound (SURVEY.md 8d); "
+                                       "see profiles/ for the ncu pipe utilisation"}
+            out["step_roofline"] = {"alg_bytes_per_image": ab["total"], "achieved_gbs": ab["total"] / (ms_step * 1e-3) / 1e9,
+                                    "frac_of_hbm_peak": ab["total"] / (ms_step * 1e-3) / 1e9 / peak}
+        if world == 1 and not args.no_cpu_baseline:
+            r = run_cpu_arm(arrays, cams, 2, 0, args.cpu_frac, budget_s=25.0)
+            out["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                   "sample": f"every {args.cpu_frac}th Gaussian of the cut at full 1080p, "
+                                             f"{r['steps_run']} step(s), {r['ms_per_sample_step']:.0f} ms each, images/s "
+                                             f"extrapolated linearly (x1/{args.cpu_frac}); oracle/oracle.c, OpenMP"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -3,6 +3,8 @@
 // carving, and the stage sequence.  No torch types; device pointers only.
 #include <stdarg.h>
 #include <string.h>
+#include <mutex>
+#include <vector>
 #include "common.cuh"
 
 namespace h3dgs {
@@ -14,6 +16,44 @@ void set_error(const char* fmt, ...) {
     va_list ap; va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// ---- stage profiler ----
+struct ProfRec { int stage; cudaEvent_t e0, e1; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof_pending;
+static std::vector<cudaEvent_t> g_prof_pool;
+static double g_prof_ms[H3DGS_STAGE_COUNT];
+static int64_t g_prof_n[H3DGS_STAGE_COUNT];
+static cudaEvent_t g_prof_open[H3DGS_STAGE_COUNT];
+static std::mutex g_prof_mu;
+
+static cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void prof_begin(int stage, cudaStream_t s) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEvent_t e = prof_event();
+    cudaEventRecord(e, s);
+    g_prof_open[stage] = e;
+}
+void prof_end(int stage, cudaStream_t s) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEvent_t e = prof_event();
+    cudaEventRecord(e, s);
+    g_prof_pending.push_back({stage, g_prof_open[stage], e});
+}
+static void prof_drain() {
+    for (auto& r : g_prof_pending) {
+        float ms = 0.f;
+        cudaEventSynchronize(r.e1);
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { g_prof_ms[r.stage] += ms; g_prof_n[r.stage]++; }
+        g_prof_pool.push_back(r.e0); g_prof_pool.push_back(r.e1);
+    }
+    g_prof_pending.clear();
 }
 
 static int check_args(const h3dgs_raster_args* a) {
@@ -45,6 +85,26 @@ static int check_args(const h3dgs_raster_args* a) {
 
 using namespace h3dgs;
 
+extern "C" int h3dgs_profile_enable(int on) { std::lock_guard<std::mutex> lk(g_prof_mu); prof_drain(); g_prof_on = on != 0; return H3DGS_OK; }
+extern "C" int h3dgs_profile_reset(void) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    prof_drain();
+    for (int i = 0; i < H3DGS_STAGE_COUNT; i++) { g_prof_ms[i] = 0; g_prof_n[i] = 0; }
+    return H3DGS_OK;
+}
+extern "C" int h3dgs_profile_read(int stage, double* total_ms, int64_t* launches) {
+    if (stage < 0 || stage >= H3DGS_STAGE_COUNT) { set_error("bad stage %d", stage); return H3DGS_EINVAL; }
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    prof_drain();
+    if (total_ms) *total_ms = g_prof_ms[stage];
+    if (launches) *launches = g_prof_n[stage];
+    return H3DGS_OK;
+}
+extern "C" const char* h3dgs_stage_name(int stage) {
+    static const char* names[H3DGS_STAGE_COUNT] = {"preprocess", "scan", "duplicate_with_keys", "radix_sort", "identify_tile_ranges",
+        "gather_records", "render_forward", "render_backward", "preprocess_backward", "lod_cut", "lod_weights"};
+    return (stage >= 0 && stage < H3DGS_STAGE_COUNT) ? names[stage] : "?";
+}
 extern "C" const char* h3dgs_last_error(void) { return g_err; }
 extern "C" int h3dgs_version(void) { return H3DGS_VERSION; }
 extern "C" int64_t h3dgs_launch_count(void) { return g_launches; }
@@ -100,16 +160,16 @@ extern "C" int h3dgs_rasterize_backward(const h3dgs_raster_args* a, const int32_
                                         const float* dL_dcolor, const float* dL_dinvdepth, float* dL_dmeans3D,
                                         float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors_precomp,
                                         float* dL_dopacities, float* dL_dscales, float* dL_drotations,
-                                        float* dL_dcov3D, void* scratch, void* stream)
+                                        float* dL_dcov3D, void* scratch, int phases, void* stream)
 {
     int rc = check_args(a);
     if (rc) return rc;
     if (a->P == 0) return H3DGS_OK;
-    if (!geom_state || !binning_state || !image_state || !dL_dcolor || !scratch || !radii) {
+    if (!geom_state || !binning_state || !image_state || ((phases & 1) && !dL_dcolor) || !scratch || !radii) {
         set_error("backward: missing saved state / scratch"); return H3DGS_EINVAL;
     }
-    if (!dL_dmeans3D || !dL_dmeans2D || !dL_dopacities || (a->shs && !dL_dsh) ||
-        (a->scales && (!dL_dscales || !dL_drotations)) || (a->cov3D_precomp && !dL_dcov3D)) {
+    if ((phases & 2) && (!dL_dmeans3D || !dL_dmeans2D || !dL_dopacities || (a->shs && !dL_dsh) ||
+        (a->scales && (!dL_dscales || !dL_drotations)) || (a->cov3D_precomp && !dL_dcov3D))) {
         set_error("backward: missing gradient output"); return H3DGS_EINVAL;
     }
     cudaStream_t s = (cudaStream_t)stream;
@@ -120,16 +180,17 @@ extern "C" int h3dgs_rasterize_backward(const h3dgs_raster_args* a, const int32_
     const uint8_t* bin = (const uint8_t*)binning_state;
     const uint8_t* img = (const uint8_t*)image_state;
     float* accum = (float*)scratch;
-    H3_CUDA(cudaMemsetAsync(accum, 0, (size_t)a->P * kAccum * sizeof(float), s));
     h3dgs_raster_args b = *a;
-    if (!dL_dinvdepth) b.do_depth = 0;
-    if (D > 0) {
+    if (!dL_dinvdepth && (phases & 1)) b.do_depth = 0;
+    if (phases & 1) H3_CUDA(cudaMemsetAsync(accum, 0, (size_t)a->P * kAccum * sizeof(float), s));
+    if (D > 0 && (phases & 1)) {
         rc = launch_render_backward(b, (const uint32_t*)(img + il.ranges), (const Record*)(bin + bl.sorted_records),
                                     (const uint32_t*)(bin + bl.vals_sorted), (const float*)(img + il.final_T),
                                     (const uint32_t*)(img + il.n_contrib), (const uint32_t*)(img + il.tile_max_contrib),
                                     dL_dcolor, dL_dinvdepth, accum, s);
         if (rc) return rc;
     }
+    if (!(phases & 2)) return H3DGS_OK;
     return launch_preprocess_backward(b, radii, (const Record*)(geom + gl.records), accum, dL_dmeans3D, dL_dmeans2D,
                                       dL_dsh, dL_dcolors_precomp, dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D, s);
 }

@@ -23,6 +23,7 @@ size_t sort_temp_bytes(int64_t n) {
 
 int launch_scan(const uint32_t* in, uint32_t* out, int n, void* temp, size_t temp_bytes, cudaStream_t s, bool debug) {
     if (n == 0) return H3DGS_OK;
+    ProfScope prof(H3DGS_STAGE_SCAN, s);
     H3_CUDA(cub::DeviceScan::InclusiveSum(temp, temp_bytes, in, out, n, s));
     H3_LAUNCHED("scan", debug, s);
     return H3DGS_OK;
@@ -101,21 +102,25 @@ int launch_binning(const h3dgs_raster_args& a, const int32_t* radii, const float
     uint64_t* keys_s = (uint64_t*)(bin + bl.keys_sorted);
     uint32_t* vals_u = (uint32_t*)(bin + bl.vals_unsorted);
     uint32_t* vals_s = (uint32_t*)(bin + bl.vals_sorted);
+    { ProfScope prof(H3DGS_STAGE_DUPLICATE, s);
     duplicate_with_keys_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a.P, W, H, a.shard_count > 0 ? a.shard_count : 1,
                                                                  a.shard_count > 0 ? a.shard_index : 0, radii, depths,
                                                                  offsets, records, keys_u, vals_u);
-    H3_LAUNCHED("duplicate_with_keys", a.debug, s);
+    H3_LAUNCHED("duplicate_with_keys", a.debug, s); }
     int tile_bits = 0;
     while ((1 << tile_bits) < gx * gy) tile_bits++;
     size_t temp = bl.sort_temp_bytes;
+    { ProfScope prof(H3DGS_STAGE_SORT, s);
     H3_CUDA(cub::DeviceRadixSort::SortPairs(bin + bl.sort_temp, temp, keys_u, keys_s, vals_u, vals_s, D, 0,
                                             32 + tile_bits, s));
-    H3_LAUNCHED("radix_sort", a.debug, s);
+    H3_LAUNCHED("radix_sort", a.debug, s); }
+    { ProfScope prof(H3DGS_STAGE_RANGES, s);
     identify_tile_ranges_kernel<<<(unsigned)((D + 255) / 256), 256, 0, s>>>(D, keys_s, ranges);
-    H3_LAUNCHED("identify_tile_ranges", a.debug, s);
+    H3_LAUNCHED("identify_tile_ranges", a.debug, s); }
+    { ProfScope prof(H3DGS_STAGE_GATHER, s);
     gather_records_kernel<<<(unsigned)((3 * D + 255) / 256), 256, 0, s>>>(D, vals_s, (const float4*)records,
                                                                            (float4*)(bin + bl.sorted_records));
-    H3_LAUNCHED("gather_records", a.debug, s);
+    H3_LAUNCHED("gather_records", a.debug, s); }
     return H3DGS_OK;
 }
 

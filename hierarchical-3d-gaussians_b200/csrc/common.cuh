@@ -48,6 +48,15 @@ GeomLayout geom_layout(int P);
 BinLayout bin_layout(int64_t D);
 ImgLayout img_layout(int W, int H);
 
+// per-stage event timing (api.cu); no-ops unless h3dgs_profile_enable(1)
+void prof_begin(int stage, cudaStream_t s);
+void prof_end(int stage, cudaStream_t s);
+struct ProfScope {
+    int stage; cudaStream_t s;
+    ProfScope(int st, cudaStream_t ss) : stage(st), s(ss) { prof_begin(stage, s); }
+    ~ProfScope() { prof_end(stage, s); }
+};
+
 // error plumbing (api.cu)
 void set_error(const char* fmt, ...);
 extern int64_t g_launches;

@@ -119,13 +119,14 @@ extern "C" int h3dgs_expand_to_size(int32_t N, const int32_t* nodes, const float
     void* temp = base + 2 * align_up((size_t)N * 4);
     size_t temp_bytes = expand_scan_bytes(N);
     const int blocks = (N + 255) / 256;
+    { ProfScope prof(H3DGS_STAGE_LOD_CUT, s);
     mark_nodes_kernel<<<blocks, 256, 0, s>>>(N, nodes, (const float4*)boxes, target_size, viewpoint, counts);
     H3_LAUNCHED("mark_nodes", 0, s);
     H3_CUDA(cub::DeviceScan::InclusiveSum(temp, temp_bytes, counts, offsets, N, s));
     H3_LAUNCHED("expand_scan", 0, s);
     put_render_indices_kernel<<<blocks, 256, 0, s>>>(N, nodes, counts, offsets, render_indices, parent_indices,
                                                      nodes_for_render_indices);
-    H3_LAUNCHED("put_render_indices", 0, s);
+    H3_LAUNCHED("put_render_indices", 0, s); }
     int total = 0;
     H3_CUDA(cudaMemcpyAsync(&total, offsets + (N - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
     H3_CUDA(cudaStreamSynchronize(s));
@@ -138,6 +139,7 @@ extern "C" int h3dgs_get_interpolation_weights(int32_t n, const int32_t* node_in
 {
     if (n <= 0) return H3DGS_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    ProfScope prof(H3DGS_STAGE_LOD_WEIGHTS, s);
     interpolation_weights_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, node_indices, target_size, nodes,
                                                                  (const float4*)boxes, vx, vy, vz, ts, num_kids);
     H3_LAUNCHED("interpolation_weights", 0, s);

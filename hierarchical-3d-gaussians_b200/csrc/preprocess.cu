@@ -201,6 +201,7 @@ int launch_preprocess(const h3dgs_raster_args& a, int32_t* radii, float* depths,
     if (a.P == 0) return H3DGS_OK;
     const float fx = a.image_width / (2.0f * a.tanfovx), fy = a.image_height / (2.0f * a.tanfovy);
     const int threads = 256, blocks = (a.P + threads - 1) / threads;
+    ProfScope prof(H3DGS_STAGE_PREPROCESS, s);
     preprocess_kernel<<<blocks, threads, 0, s>>>(a.P, a.sh_degree, a.sh_coeffs, a.means3D, a.scales, a.scale_modifier,
                                                  a.rotations, a.opacities, a.shs, a.cov3D_precomp, a.colors_precomp,
                                                  a.interpolation_weights, a.num_node_kids, a.viewmatrix, a.projmatrix,

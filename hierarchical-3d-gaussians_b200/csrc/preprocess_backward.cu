@@ -297,6 +297,7 @@ int launch_preprocess_backward(const h3dgs_raster_args& a, const int32_t* radii,
 {
     if (a.P == 0) return H3DGS_OK;
     const float fx = a.image_width / (2.0f * a.tanfovx), fy = a.image_height / (2.0f * a.tanfovy);
+    ProfScope prof(H3DGS_STAGE_PREPROCESS_BWD, s);
     preprocess_backward_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(
         a.P, a.sh_degree, a.sh_coeffs, a.means3D, a.scales, a.scale_modifier, a.rotations, a.shs, a.cov3D_precomp,
         a.colors_precomp, a.viewmatrix, a.projmatrix, a.campos, a.image_width, a.image_height, a.tanfovx, a.tanfovy,

@@ -175,6 +175,7 @@ int launch_render_backward(const h3dgs_raster_args& a, const uint32_t* ranges, c
     const bool hier = a.interpolation_weights != nullptr;
     const bool depth = a.do_depth != 0 && dL_dinvdepth != nullptr;
     const dim3 grid(gx * rows), block(256);
+    ProfScope prof(H3DGS_STAGE_RENDER_BWD, s);
 #define LAUNCH(HI, DE)                                                                                          \
     render_backward_kernel<HI, DE><<<grid, block, 0, s>>>(W, H, gx, sc, si, (const uint2*)ranges, sorted_records, \
                                                           point_list, a.bg, final_T, n_contrib, tile_max_contrib, \

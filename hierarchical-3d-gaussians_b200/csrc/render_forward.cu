@@ -110,13 +110,26 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
         for (int b = waited; b < issued; b++) mbar_wait(&s_full[b % kFwdStages], (uint32_t)((b / kFwdStages) & 1));
 
     if (inside) {
-        const size_t pix = (size_t)py * W + px, plane = (size_t)H * W;
+        const size_t pix = (size_t)py * W + px;
         final_T[pix] = T;
         n_contrib[pix] = last;
-        out_color[pix] = C0 + T * bg[0];
-        out_color[plane + pix] = C1 + T * bg[1];
-        out_color[2 * plane + pix] = C2 + T * bg[2];
-        if (DEPTH) out_invdepth[pix] = invd;
+        if (shard_count > 1) {
+            // packed shard layout [local tile row][channel][16][W]: one contiguous slab per
+            // rank, so the image exchange is a single all-gather (h3dgs/dist.py)
+            const size_t local_row = blockIdx.x / gx;
+            const size_t o = ((local_row * 3) * kTile + (size_t)(py & (kTile - 1))) * W + px;
+            const size_t cs = (size_t)kTile * W;
+            out_color[o] = C0 + T * bg[0];
+            out_color[o + cs] = C1 + T * bg[1];
+            out_color[o + 2 * cs] = C2 + T * bg[2];
+            if (DEPTH) out_invdepth[(local_row * kTile + (size_t)(py & (kTile - 1))) * W + px] = invd;
+        } else {
+            const size_t plane = (size_t)H * W;
+            out_color[pix] = C0 + T * bg[0];
+            out_color[plane + pix] = C1 + T * bg[1];
+            out_color[2 * plane + pix] = C2 + T * bg[2];
+            if (DEPTH) out_invdepth[pix] = invd;
+        }
     }
     const uint32_t wmax = __reduce_max_sync(0xffffffffu, last);
     if ((tid & 31) == 0) atomicMax(&s_max, wmax);
@@ -136,6 +149,7 @@ int launch_render_forward(const h3dgs_raster_args& a, const uint32_t* ranges, co
     const bool hier = a.interpolation_weights != nullptr;
     const bool depth = a.do_depth != 0;
     const dim3 grid(gx * rows), block(256);
+    ProfScope prof(H3DGS_STAGE_RENDER_FWD, s);
 #define LAUNCH(HI, DE)                                                                                         \
     render_forward_kernel<HI, DE><<<grid, block, 0, s>>>(W, H, gx, sc, si, (const uint2*)ranges, sorted_records, \
                                                          a.bg, out_color, out_invdepth, final_T, n_contrib,      \

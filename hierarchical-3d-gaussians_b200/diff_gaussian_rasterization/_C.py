@@ -12,6 +12,14 @@ import torch
 from h3dgs import _lib
 
 
+_last_num_rendered = 0
+
+
+def last_num_rendered():
+    """D of the most recent forward on this process (bench bookkeeping)."""
+    return _last_num_rendered
+
+
 def _ptr(t):
     return None if (t is None or t.numel() == 0) else t.data_ptr()
 
@@ -95,9 +103,15 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     H, W = int(image_height), int(image_width)
     a = _make_args(P, means3D, sh, colors, opacity, scales, rotations, cov3D_precomp, background, viewmatrix, projmatrix,
                    campos, tan_fovx, tan_fovy, H, W, degree, scale_modifier, prefiltered, debug, ts, kids, do_depth, shard)
-    color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+    if shard[0] > 1:      # packed shard layout [owned tile rows][3][16][W]
+        gy = (H + 15) // 16
+        rows = (gy + shard[0] - 1 - shard[1]) // shard[0]
+        color = torch.zeros((max(rows, 1), 3, 16, W), dtype=torch.float32, device=dev)
+        invdepth = torch.zeros((max(rows, 1), 1, 16, W), dtype=torch.float32, device=dev) if do_depth else torch.empty((0,), dtype=torch.float32, device=dev)
+    else:
+        color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        invdepth = torch.empty((1, H, W), dtype=torch.float32, device=dev) if do_depth else torch.empty((0,), dtype=torch.float32, device=dev)
     radii = torch.empty((P,), dtype=torch.int32, device=dev)
-    invdepth = torch.empty((1, H, W), dtype=torch.float32, device=dev) if do_depth else torch.empty((0,), dtype=torch.float32, device=dev)
     bufs = [None, None, None]
 
     def _alloc(_user, which, nbytes):
@@ -110,6 +124,8 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     with torch.cuda.device(dev):
         _lib.check(L.h3dgs_rasterize_forward(C.byref(a), cb, None, color.data_ptr(), _ptr(radii),
                                              _ptr(invdepth), C.byref(n), _stream()))
+    global _last_num_rendered
+    _last_num_rendered = int(n.value)
     return int(n.value), color, radii, bufs[0], bufs[1], bufs[2], invdepth
 
 
@@ -118,7 +134,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, opacities, 
                                  dL_dout_invdepth, sh, degree, campos, geomBuffer, num_rendered, binningBuffer,
                                  imageBuffer, debug, render_indices=None, parent_indices=None,
                                  interpolation_weights=None, num_node_kids=None, do_depth=False, image_height=None,
-                                 image_width=None, shard=(1, 0)):
+                                 image_width=None, shard=(1, 0), phases=3, scratch=None, grads=None):
     """-> (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)"""
     L = _lib.lib()
     (P, means3D, sh, colors, opacities, scales, rotations, cov3D_precomp, background, viewmatrix, projmatrix, campos,
@@ -134,19 +150,25 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, opacities, 
     g_depth = _f32c(dL_dout_invdepth, "dL_dout_invdepth") if (do_depth and dL_dout_invdepth is not None) else None
     e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
     M = sh.shape[1] if sh is not None else 0
-    d_means3D, d_means2D, d_opac = e(P, 3), e(P, 3), e(P, 1)
-    d_sh = e(P, M, 3) if sh is not None else e(0)
-    d_colors = e(P, 3) if colors is not None else e(0)
-    d_scales = e(P, 3) if scales is not None else e(0)
-    d_rots = e(P, 4) if rotations is not None else e(0)
-    d_cov = e(P, 6) if cov3D_precomp is not None else e(0)
-    scratch = torch.empty((L.h3dgs_backward_scratch_bytes(P),), dtype=torch.uint8, device=dev)
+    if phases & 2:
+        d_means3D, d_means2D, d_opac = e(P, 3), e(P, 3), e(P, 1)
+        d_sh = e(P, M, 3) if sh is not None else e(0)
+        d_colors = e(P, 3) if colors is not None else e(0)
+        d_scales = e(P, 3) if scales is not None else e(0)
+        d_rots = e(P, 4) if rotations is not None else e(0)
+        d_cov = e(P, 6) if cov3D_precomp is not None else e(0)
+    else:
+        d_means3D = d_means2D = d_opac = d_sh = d_colors = d_scales = d_rots = d_cov = None
+    if scratch is None:
+        scratch = torch.empty((L.h3dgs_backward_scratch_bytes(P),), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         _lib.check(L.h3dgs_rasterize_backward(C.byref(a), _ptr(radii), _ptr(geomBuffer), _ptr(binningBuffer),
                                               _ptr(imageBuffer), int(num_rendered), _ptr(g_color), _ptr(g_depth),
                                               _ptr(d_means3D), _ptr(d_means2D), _ptr(d_sh), _ptr(d_colors),
                                               _ptr(d_opac), _ptr(d_scales), _ptr(d_rots), _ptr(d_cov),
-                                              scratch.data_ptr(), _stream()))
+                                              scratch.data_ptr(), int(phases), _stream()))
+    if phases == 1:
+        return scratch
     return d_means2D, d_colors, d_opac, d_means3D, d_cov, d_sh, d_scales, d_rots
 
 

@@ -15,6 +15,7 @@ EXPORTS = [
     "h3dgs_rasterize_forward", "h3dgs_rasterize_backward", "h3dgs_backward_scratch_bytes", "h3dgs_mark_visible",
     "h3dgs_state_layout", "h3dgs_expand_to_size", "h3dgs_expand_scratch_bytes", "h3dgs_get_interpolation_weights",
     "h3dgs_last_error", "h3dgs_version", "h3dgs_launch_count",
+    "h3dgs_profile_enable", "h3dgs_profile_reset", "h3dgs_profile_read", "h3dgs_stage_name",
 ]
 
 
@@ -62,7 +63,7 @@ def lib():
                                           C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]
     l.h3dgs_rasterize_backward.restype = C.c_int
     l.h3dgs_rasterize_backward.argtypes = [C.POINTER(RasterArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                           C.c_int64, C.c_void_p, C.c_void_p] + [C.c_void_p] * 8 + [C.c_void_p, C.c_void_p]
+                                           C.c_int64, C.c_void_p, C.c_void_p] + [C.c_void_p] * 8 + [C.c_void_p, C.c_int, C.c_void_p]
     l.h3dgs_mark_visible.restype = C.c_int
     l.h3dgs_mark_visible.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     l.h3dgs_state_layout.restype = C.c_int
@@ -74,6 +75,8 @@ def lib():
     l.h3dgs_get_interpolation_weights.restype = C.c_int
     l.h3dgs_get_interpolation_weights.argtypes = [C.c_int32, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p] + \
         [C.c_float] * 6 + [C.c_void_p, C.c_void_p, C.c_void_p]
+    l.h3dgs_profile_read.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    l.h3dgs_stage_name.restype = C.c_char_p
     _lib = l
     return l
 
@@ -86,3 +89,24 @@ def check(rc):
 
 def launch_count():
     return int(lib().h3dgs_launch_count())
+
+
+STAGES = 11
+
+
+def profile_enable(on=True):
+    check(lib().h3dgs_profile_enable(1 if on else 0))
+
+
+def profile_reset():
+    check(lib().h3dgs_profile_reset())
+
+
+def profile_read():
+    """-> {stage_name: (total_ms, launches)} since the last reset (synchronises the recorded events)."""
+    out = {}
+    for st in range(STAGES):
+        ms, n = C.c_double(0), C.c_int64(0)
+        check(lib().h3dgs_profile_read(st, C.byref(ms), C.byref(n)))
+        out[lib().h3dgs_stage_name(st).decode()] = (ms.value, n.value)
+    return out

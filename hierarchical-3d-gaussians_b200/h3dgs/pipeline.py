@@ -1,0 +1,136 @@
+"""One training-style step of the hot path on synthetic data, through the same public
+API the reference's scripts use:
+
+  expand_to_size -> get_interpolation_weights        (train_post.py:91-113)
+  gather cut rows + lerp with parents (PyTorch ops)  (gaussian_renderer/__init__.py:199-234)
+  GaussianRasterizer(settings)(...)                  (gaussian_renderer/__init__.py:247-277)
+  L1 loss -> backward                                (train_post.py:134-142, lambda_dssim term omitted:
+                                                      SSIM is outside the path)
+
+Used by bench.py and the GPU tests; nothing here touches oracle/.
+"""
+import math
+
+import torch
+
+from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+from gaussian_hierarchy._C import expand_to_size, get_interpolation_weights
+
+
+class Scene:
+    """Device-resident Gaussians (already-activated values are the leaves, i.e. what
+    GaussianModel.get_* would return) plus, for hierarchy scenes, nodes/boxes and the
+    caller-preallocated LOD scratch of train_post.py:59-63."""
+
+    def __init__(self, arrays, device="cuda", requires_grad=True):
+        t = lambda a: torch.tensor(a, device=device)
+        self.device = device
+        self.means3D = t(arrays["means3D"]).requires_grad_(requires_grad)
+        self.scales = t(arrays["scales"]).requires_grad_(requires_grad)
+        self.rotations = t(arrays["rotations"]).requires_grad_(requires_grad)
+        self.opacities = t(arrays["opacities"]).requires_grad_(requires_grad)
+        self.shs = t(arrays["shs"]).requires_grad_(requires_grad)
+        self.hier = "nodes" in arrays
+        N = self.means3D.shape[0]
+        if self.hier:
+            self.nodes = t(arrays["nodes"])
+            self.boxes = t(arrays["boxes"])
+            z = lambda dt: torch.zeros(N, dtype=dt, device=device)
+            self.render_indices, self.parent_indices, self.nodes_for_render = z(torch.int32), z(torch.int32), z(torch.int32)
+            self.interpolation_weights, self.num_siblings = z(torch.float32), z(torch.int32)
+        self.empty_i = torch.empty(0, dtype=torch.int32, device=device)
+        self.empty_f = torch.empty(0, dtype=torch.float32, device=device)
+
+    def params(self):
+        return [self.means3D, self.scales, self.rotations, self.opacities, self.shs]
+
+    def zero_grad(self):
+        for p in self.params():
+            p.grad = None
+
+
+class DeviceCamera:
+    def __init__(self, cam, device="cuda"):
+        self.W, self.H = cam.W, cam.H
+        self.tanfovx, self.tanfovy = cam.tanfovx, cam.tanfovy
+        self.viewmatrix = torch.tensor(cam.world_view_transform, device=device)
+        self.projmatrix = torch.tensor(cam.full_proj_transform, device=device)
+        self.campos = torch.tensor(cam.camera_center, device=device)
+        self.campos_cpu = torch.tensor(cam.camera_center)
+
+
+def lod_cut(scene, cam, threshold):
+    """-> number of cut Gaussians; fills scene.render_indices/parent_indices/interpolation_weights/num_siblings."""
+    zeros3 = torch.zeros(3)
+    n = expand_to_size(scene.nodes, scene.boxes, threshold, cam.campos, zeros3, scene.render_indices,
+                       scene.parent_indices, scene.nodes_for_render)
+    get_interpolation_weights(scene.nodes_for_render[:n], threshold, scene.nodes, scene.boxes, cam.campos_cpu, zeros3,
+                              scene.interpolation_weights, scene.num_siblings)
+    return n
+
+
+def interpolate_cut(scene, n):
+    """The gather + parent lerp of render_post (interp_python=True), in PyTorch ops so
+    autograd scatters the gradients back to the full-size leaves (no skybox rows here)."""
+    idx = scene.render_indices[:n].long()
+    par = scene.parent_indices[:n].long()
+    par = torch.where(par < 0, idx, par)             # the root has no parent: t == 1 there
+    t = scene.interpolation_weights[:n].unsqueeze(1)
+    u = 1.0 - t
+    means = t * scene.means3D[idx] + u * scene.means3D[par]
+    scales = t * scene.scales[idx] + u * scene.scales[par]
+    shs = t.unsqueeze(2) * scene.shs[idx] + u.unsqueeze(2) * scene.shs[par]
+    q_c = scene.rotations[idx]
+    q_p = scene.rotations[par]
+    sign = torch.where((q_c * q_p).sum(1, keepdim=True) < 0, -1.0, 1.0)     # quaternion sign alignment
+    rots = t * q_c + u * (q_p * sign)
+    opac = t * scene.opacities[idx] + u * scene.opacities[par]
+    return means.contiguous(), scales.contiguous(), rots.contiguous(), opac.contiguous(), shs.contiguous()
+
+
+def make_settings(scene, cam, bg, sh_degree, ts=None, kids=None, do_depth=False, debug=False):
+    return GaussianRasterizationSettings(
+        image_height=cam.H, image_width=cam.W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=bg, scale_modifier=1.0,
+        viewmatrix=cam.viewmatrix, projmatrix=cam.projmatrix, sh_degree=sh_degree, campos=cam.campos,
+        prefiltered=False, debug=debug, render_indices=scene.empty_i, parent_indices=scene.empty_i,
+        interpolation_weights=ts if ts is not None else scene.empty_f,
+        num_node_kids=kids if kids is not None else scene.empty_i, do_depth=do_depth)
+
+
+def render_flat(scene, cam, bg, sh_degree=3):
+    """`render()` of the reference minus exposure/clamp (flat chunk training, config #2)."""
+    rs = make_settings(scene, cam, bg, sh_degree)
+    means2D = torch.zeros_like(scene.means3D, requires_grad=scene.means3D.requires_grad)
+    img, radii, _ = GaussianRasterizer(rs)(means3D=scene.means3D, means2D=means2D, shs=scene.shs, colors_precomp=None,
+                                           opacities=scene.opacities, scales=scene.scales, rotations=scene.rotations,
+                                           cov3D_precomp=None)
+    return img, radii
+
+
+def render_hier(scene, cam, bg, threshold, sh_degree=3):
+    """`render_post()` of the reference (hierarchy post-optimisation, config #3)."""
+    n = lod_cut(scene, cam, threshold)
+    means, scales, rots, opac, shs = interpolate_cut(scene, n)
+    rs = make_settings(scene, cam, bg, sh_degree, ts=scene.interpolation_weights, kids=scene.num_siblings)
+    means2D = torch.zeros_like(means, requires_grad=means.requires_grad)
+    img, radii, _ = GaussianRasterizer(rs)(means3D=means, means2D=means2D, shs=shs, colors_precomp=None,
+                                           opacities=opac, scales=scales, rotations=rots, cov3D_precomp=None)
+    return img, radii, n
+
+
+def l1_step(scene, cam, bg, gt, threshold=None, sh_degree=3):
+    """forward + L1 loss + backward; returns the loss tensor (device) and bookkeeping."""
+    scene.zero_grad()
+    if scene.hier:
+        img, radii, n = render_hier(scene, cam, bg, threshold, sh_degree)
+    else:
+        img, radii = render_flat(scene, cam, bg, sh_degree)
+        n = scene.means3D.shape[0]
+    loss = (img - gt).abs().mean()
+    loss.backward()
+    return loss, radii, n
+
+
+def fov_threshold(tau, cam):
+    """render_hierarchy.py:55-56"""
+    return (2 * (tau + 0.5)) * cam.tanfovx / (0.5 * cam.W)

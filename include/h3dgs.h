@@ -83,7 +83,9 @@ typedef struct h3dgs_raster_args {
 
 /* Forward: K1 preprocess -> scan -> duplicateWithKeys -> radix sort -> tile ranges
  * -> record gather -> per-tile blend.  Outputs: out_color [3,H,W], out_radii [P]
- * (int32), out_invdepth [1,H,W] (written only when do_depth).  The three state
+ * (int32), out_invdepth [1,H,W] (written only when do_depth).  With shard_count > 1 the
+ * image outputs use the packed shard layout [owned tile row][channel][16][W] (rows
+ * beyond H inside the last tile row are not written).  The three state
  * buffers obtained from `alloc` must be kept alive and passed to backward.
  * num_rendered [host] receives D = sum of tiles touched. */
 int h3dgs_rasterize_forward(const h3dgs_raster_args* args, h3dgs_alloc_fn alloc, void* alloc_user,
@@ -101,6 +103,9 @@ int h3dgs_rasterize_backward(const h3dgs_raster_args* args, const int32_t* radii
                              float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh, float* dL_dcolors_precomp,
                              float* dL_dopacities, float* dL_dscales, float* dL_drotations, float* dL_dcov3D,
                              void* scratch /* >= h3dgs_backward_scratch_bytes(P) device bytes */,
+                             int phases /* 3 = whole backward; 1 = per-tile replay only (fills `scratch` with the
+                                           [P][10] 2D-space sums); 2 = per-Gaussian chain rule only (consumes it).
+                                           The multi-GPU mode all-reduces `scratch` between 1 and 2. */,
                              void* stream);
 size_t h3dgs_backward_scratch_bytes(int32_t P);
 
@@ -113,7 +118,7 @@ typedef struct h3dgs_state_view {
     const float* depths;              /* [P] view-space z (key low 32 bits)                    */
     const uint32_t* tiles_touched;    /* [P]                                                    */
     const uint32_t* point_offsets;    /* [P] inclusive scan                                     */
-    const float* records;             /* [P][12] x,y,conic.xyz,opacity | t,k-bits,r,g | b,invdepth,pad,pad */
+    const float* records;             /* [P][12] x,y,conic.x,conic.y | conic.z,opacity,t,k-bits | r,g,b,invdepth */
     const uint64_t* keys_sorted;      /* [D] (tile << 32) | depth bits                          */
     const uint32_t* point_list;       /* [D] Gaussian index, sorted                             */
     const uint32_t* ranges;           /* [tiles][2]                                             */
@@ -141,6 +146,20 @@ int h3dgs_get_interpolation_weights(int32_t n, const int32_t* node_indices, floa
                                     float viewpoint_x, float viewpoint_y, float viewpoint_z,
                                     float viewdir_x, float viewdir_y, float viewdir_z,
                                     float* ts, int32_t* num_kids, void* stream);
+
+/* ---- per-stage device timing (bench.py roofline) ----
+ * When enabled, every stage launch is bracketed by two cudaEvents recorded on the stream
+ * the kernel is launched on; h3dgs_profile_read synchronises them and returns the summed
+ * device time and the number of launches of that stage since the last reset. */
+enum {
+    H3DGS_STAGE_PREPROCESS = 0, H3DGS_STAGE_SCAN, H3DGS_STAGE_DUPLICATE, H3DGS_STAGE_SORT, H3DGS_STAGE_RANGES,
+    H3DGS_STAGE_GATHER, H3DGS_STAGE_RENDER_FWD, H3DGS_STAGE_RENDER_BWD, H3DGS_STAGE_PREPROCESS_BWD,
+    H3DGS_STAGE_LOD_CUT, H3DGS_STAGE_LOD_WEIGHTS, H3DGS_STAGE_COUNT
+};
+int h3dgs_profile_enable(int on);
+int h3dgs_profile_reset(void);
+int h3dgs_profile_read(int stage, double* total_ms, int64_t* launches);
+const char* h3dgs_stage_name(int stage);
 
 const char* h3dgs_last_error(void);
 int h3dgs_version(void);
