@@ -73,6 +73,13 @@ static int check_args(const h3dgs_raster_args* a) {
     if ((a->interpolation_weights == nullptr) != (a->num_node_kids == nullptr)) {
         set_error("interpolation_weights and num_node_kids must be given together"); return H3DGS_EINVAL;
     }
+    if ((a->render_indices == nullptr) != (a->parent_indices == nullptr)) {
+        set_error("render_indices and parent_indices must be given together"); return H3DGS_EINVAL;
+    }
+    if (a->render_indices && (!a->interpolation_weights || a->num_source <= 0 || a->colors_precomp || a->cov3D_precomp)) {
+        set_error("render_indices needs interpolation_weights/num_node_kids, num_source > 0 and SH + scale/rotation inputs");
+        return H3DGS_EINVAL;
+    }
     if (a->shard_count > 1 && (a->shard_index < 0 || a->shard_index >= a->shard_count)) {
         set_error("bad tile shard %d/%d", a->shard_index, a->shard_count); return H3DGS_EINVAL;
     }
@@ -191,6 +198,15 @@ extern "C" int h3dgs_rasterize_backward(const h3dgs_raster_args* a, const int32_
         if (rc) return rc;
     }
     if (!(phases & 2)) return H3DGS_OK;
+    if (a->render_indices) {
+        // scatter mode: gradients have num_source rows and must start from zero
+        const size_t N = (size_t)a->num_source;
+        H3_CUDA(cudaMemsetAsync(dL_dmeans3D, 0, N * 3 * sizeof(float), s));
+        H3_CUDA(cudaMemsetAsync(dL_dopacities, 0, N * sizeof(float), s));
+        H3_CUDA(cudaMemsetAsync(dL_dsh, 0, N * (size_t)a->sh_coeffs * 3 * sizeof(float), s));
+        H3_CUDA(cudaMemsetAsync(dL_dscales, 0, N * 3 * sizeof(float), s));
+        H3_CUDA(cudaMemsetAsync(dL_drotations, 0, N * 4 * sizeof(float), s));
+    }
     return launch_preprocess_backward(b, radii, (const Record*)(geom + gl.records), accum, dL_dmeans3D, dL_dmeans2D,
                                       dL_dsh, dL_dcolors_precomp, dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D, s);
 }

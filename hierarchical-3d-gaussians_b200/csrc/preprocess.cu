@@ -44,7 +44,8 @@ preprocess_kernel(int P, int deg, int M, const float* __restrict__ means3D, cons
                   float scale_mod, const float* __restrict__ rots, const float* __restrict__ opacities,
                   const float* __restrict__ shs, const float* __restrict__ cov3D_precomp,
                   const float* __restrict__ colors_precomp, const float* __restrict__ ts,
-                  const int* __restrict__ kids, const float* __restrict__ view, const float* __restrict__ proj,
+                  const int* __restrict__ kids, const int* __restrict__ ridx, const int* __restrict__ pidx,
+                  const float* __restrict__ view, const float* __restrict__ proj,
                   const float* __restrict__ campos, int W, int H, float tanx, float tany, float fx, float fy,
                   int shard_count, int shard_index,
                   int* __restrict__ radii, float* __restrict__ depths, uint32_t* __restrict__ tiles_touched,
@@ -58,7 +59,19 @@ preprocess_kernel(int P, int deg, int M, const float* __restrict__ means3D, cons
     if (i >= P) return;
 
     int out_radius = 0; uint32_t out_tiles = 0;
-    const float px_ = means3D[3 * i], py_ = means3D[3 * i + 1], pz_ = means3D[3 * i + 2];
+    // in-kernel cut gather + parent lerp: x = t*x[c] + (1-t)*x[p], evaluated as two rounded
+    // products and one rounded sum (bit-identical to the PyTorch expression of render_post)
+    int c = i, p = i;
+    float t = 1.0f, u = 0.0f;
+    if (ridx) {
+        c = ridx[i]; p = pidx[i]; if (p < 0) p = c;
+        t = ts[i]; u = 1.0f - t;
+    }
+    const bool lerp = ridx != nullptr && u != 0.0f;
+#define LERP(a, b) (lerp ? (t * (a) + u * (b)) : (a))
+    const float px_ = LERP(means3D[3 * c], means3D[3 * p]);
+    const float py_ = LERP(means3D[3 * c + 1], means3D[3 * p + 1]);
+    const float pz_ = LERP(means3D[3 * c + 2], means3D[3 * p + 2]);
     const float* m = s_view;
     const float vx = m[0] * px_ + m[4] * py_ + m[8] * pz_ + m[12];
     const float vy = m[1] * px_ + m[5] * py_ + m[9] * pz_ + m[13];
@@ -74,9 +87,16 @@ preprocess_kernel(int P, int deg, int M, const float* __restrict__ means3D, cons
         float cov6[6];
         if (cov3D_precomp) {
 #pragma unroll
-            for (int k = 0; k < 6; k++) cov6[k] = cov3D_precomp[6 * i + k];
+            for (int k = 0; k < 6; k++) cov6[k] = cov3D_precomp[6 * c + k];
         } else {
-            const float4 qq = *reinterpret_cast<const float4*>(rots + 4 * i);
+            float4 qq = *reinterpret_cast<const float4*>(rots + 4 * c);
+            if (lerp) {
+                float4 qp = *reinterpret_cast<const float4*>(rots + 4 * p);
+                const float dot = qq.x * qp.x + qq.y * qp.y + qq.z * qp.z + qq.w * qp.w;
+                if (dot < 0.f) { qp.x = -qp.x; qp.y = -qp.y; qp.z = -qp.z; qp.w = -qp.w; }
+                qq.x = t * qq.x + u * qp.x; qq.y = t * qq.y + u * qp.y;
+                qq.z = t * qq.z + u * qp.z; qq.w = t * qq.w + u * qp.w;
+            }
             const float r = qq.x, x = qq.y, y = qq.z, z = qq.w;
             float R[3][3];
             R[0][0] = 1.f - 2.f * (y * y + z * z); R[0][1] = 2.f * (x * y - r * z); R[0][2] = 2.f * (x * z + r * y);
@@ -85,7 +105,7 @@ preprocess_kernel(int P, int deg, int M, const float* __restrict__ means3D, cons
             float Mm[3][3];
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                const float s = scale_mod * scales[3 * i + k];
+                const float s = scale_mod * LERP(scales[3 * c + k], scales[3 * p + k]);
 #pragma unroll
                 for (int j = 0; j < 3; j++) Mm[k][j] = s * R[j][k];
             }
@@ -141,18 +161,24 @@ preprocess_kernel(int P, int deg, int M, const float* __restrict__ means3D, cons
                 float rgb[3];
                 uint32_t clampbits = 0;
                 if (colors_precomp) {
-                    rgb[0] = colors_precomp[3 * i]; rgb[1] = colors_precomp[3 * i + 1]; rgb[2] = colors_precomp[3 * i + 2];
+                    rgb[0] = colors_precomp[3 * c]; rgb[1] = colors_precomp[3 * c + 1]; rgb[2] = colors_precomp[3 * c + 2];
                 } else {
                     float dx = px_ - s_cam[0], dy = py_ - s_cam[1], dz = pz_ - s_cam[2];
                     const float len = sqrtf(dx * dx + dy * dy + dz * dz);
                     dx /= len; dy /= len; dz /= len;
                     const float x = dx, y = dy, z = dz;
-                    float c[48];
+                    float c_[48];
                     const int need = 3 * (deg + 1) * (deg + 1);
-                    load_sh<48>(shs + (size_t)i * M * 3, M * 3, need, c);
+                    load_sh<48>(shs + (size_t)c * M * 3, M * 3, need, c_);
+                    if (lerp) {
+                        float cp[48];
+                        load_sh<48>(shs + (size_t)p * M * 3, M * 3, need, cp);
+#pragma unroll
+                        for (int k = 0; k < 48; k++) if (k < need) c_[k] = t * c_[k] + u * cp[k];
+                    }
 #pragma unroll
                     for (int ch = 0; ch < 3; ch++) {
-#define S(k) c[(k) * 3 + ch]
+#define S(k) c_[(k) * 3 + ch]
                         float r = kSH_C0 * S(0);
                         if (deg > 0) {
                             r = r - kSH_C1 * y * S(1) + kSH_C1 * z * S(2) - kSH_C1 * x * S(3);
@@ -177,9 +203,9 @@ preprocess_kernel(int P, int deg, int M, const float* __restrict__ means3D, cons
                 }
                 Record rec;
                 rec.a = make_float4(ix, iy, conx, cony);
-                const float t = ts ? ts[i] : 1.0f;
+                const float tt = ts ? ts[i] : 1.0f;
                 const uint32_t k = kids ? (uint32_t)kids[i] : 1u;
-                rec.b = make_float4(conz, opacities[i], t, __uint_as_float((k & 0xFFFFFFu) | clampbits));
+                rec.b = make_float4(conz, LERP(opacities[c], opacities[p]), tt, __uint_as_float((k & 0xFFFFFFu) | clampbits));
                 rec.c = make_float4(rgb[0], rgb[1], rgb[2], 1.0f / vz);
                 records[i] = rec;
                 depths[i] = vz;
@@ -191,6 +217,7 @@ preprocess_kernel(int P, int deg, int M, const float* __restrict__ means3D, cons
             }
         }
     }
+#undef LERP
     radii[i] = out_radius;
     tiles_touched[i] = out_tiles;
 }
@@ -204,7 +231,8 @@ int launch_preprocess(const h3dgs_raster_args& a, int32_t* radii, float* depths,
     ProfScope prof(H3DGS_STAGE_PREPROCESS, s);
     preprocess_kernel<<<blocks, threads, 0, s>>>(a.P, a.sh_degree, a.sh_coeffs, a.means3D, a.scales, a.scale_modifier,
                                                  a.rotations, a.opacities, a.shs, a.cov3D_precomp, a.colors_precomp,
-                                                 a.interpolation_weights, a.num_node_kids, a.viewmatrix, a.projmatrix,
+                                                 a.interpolation_weights, a.num_node_kids, a.render_indices, a.parent_indices,
+                                                 a.viewmatrix, a.projmatrix,
                                                  a.campos, a.image_width, a.image_height, a.tanfovx, a.tanfovy, fx, fy,
                                                  a.shard_count > 0 ? a.shard_count : 1, a.shard_count > 0 ? a.shard_index : 0,
                                                  radii, depths, tiles_touched, records);

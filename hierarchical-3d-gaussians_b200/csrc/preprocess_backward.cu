@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(256)
 preprocess_backward_kernel(int P, int deg, int M, const float* __restrict__ means3D, const float* __restrict__ scales,
                            float scale_mod, const float* __restrict__ rots, const float* __restrict__ shs,
                            const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp,
+                           const float* __restrict__ ts, const int* __restrict__ ridx, const int* __restrict__ pidx,
                            const float* __restrict__ view, const float* __restrict__ proj,
                            const float* __restrict__ campos, int W, int H, float tanx, float tany, float fx, float fy,
                            int use_depth, const int* __restrict__ radii, const Record* __restrict__ records,
@@ -45,8 +46,9 @@ preprocess_backward_kernel(int P, int deg, int M, const float* __restrict__ mean
     const int SH3 = M * 3;
 
     if (radii[i] <= 0) {
-        store_zero(dL_dmeans3D + 3 * i, 3);
         store_zero(dL_dmeans2D + 3 * i, 3);
+        if (ridx) return;                    // scatter mode: full-size gradients are pre-zeroed
+        store_zero(dL_dmeans3D + 3 * i, 3);
         dL_dopacities[i] = 0.f;
         if (dL_dsh) {
             float* o = dL_dsh + (size_t)i * SH3;
@@ -64,7 +66,19 @@ preprocess_backward_kernel(int P, int deg, int M, const float* __restrict__ mean
     const float* ac = accum + (size_t)i * kAccum;
     const float g_mx = ac[0], g_my = ac[1], dcx = ac[2], dcy = ac[3], dcz = ac[4], g_op = ac[5];
     const float g_r = ac[6], g_g = ac[7], g_b = ac[8], g_iv = ac[9];
-    const float mx = means3D[3 * i], my = means3D[3 * i + 1], mz = means3D[3 * i + 2];
+    // gather + parent lerp exactly as the forward did (preprocess.cu)
+    int c = i, p = i;
+    float t = 1.0f, u = 0.0f;
+    if (ridx) {
+        c = ridx[i]; p = pidx[i]; if (p < 0) p = c;
+        t = ts[i]; u = 1.0f - t;
+    }
+    const bool lerp = ridx != nullptr && u != 0.0f;
+#define LERP(a, b) (lerp ? __fadd_rn(__fmul_rn(t, (a)), __fmul_rn(u, (b))) : (a))
+    const float mx = LERP(means3D[3 * c], means3D[3 * p]);
+    const float my = LERP(means3D[3 * c + 1], means3D[3 * p + 1]);
+    const float mz = LERP(means3D[3 * c + 2], means3D[3 * p + 2]);
+    float qsign = 1.0f;
 
     // cov3D (recomputed: cheaper than a 24-B round trip through HBM)
     double cov6[6];
@@ -72,16 +86,23 @@ preprocess_backward_kernel(int P, int deg, int M, const float* __restrict__ mean
     double qr = 1., qx = 0., qy = 0., qz = 0.;
     if (cov3D_precomp) {
 #pragma unroll
-        for (int k = 0; k < 6; k++) cov6[k] = cov3D_precomp[6 * i + k];
+        for (int k = 0; k < 6; k++) cov6[k] = cov3D_precomp[6 * c + k];
     } else {
-        const float4 qq = *reinterpret_cast<const float4*>(rots + 4 * i);
+        float4 qq = *reinterpret_cast<const float4*>(rots + 4 * c);
+        if (lerp) {
+            float4 qp = *reinterpret_cast<const float4*>(rots + 4 * p);
+            const float dot = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(qq.x, qp.x), __fmul_rn(qq.y, qp.y)), __fmul_rn(qq.z, qp.z)), __fmul_rn(qq.w, qp.w));
+            if (dot < 0.f) qsign = -1.0f;
+            qq.x = LERP(qq.x, qsign * qp.x); qq.y = LERP(qq.y, qsign * qp.y);
+            qq.z = LERP(qq.z, qsign * qp.z); qq.w = LERP(qq.w, qsign * qp.w);
+        }
         qr = qq.x; qx = qq.y; qy = qq.z; qz = qq.w;
         R[0][0] = 1. - 2. * (qy * qy + qz * qz); R[0][1] = 2. * (qx * qy - qr * qz); R[0][2] = 2. * (qx * qz + qr * qy);
         R[1][0] = 2. * (qx * qy + qr * qz); R[1][1] = 1. - 2. * (qx * qx + qz * qz); R[1][2] = 2. * (qy * qz - qr * qx);
         R[2][0] = 2. * (qx * qz - qr * qy); R[2][1] = 2. * (qy * qz + qr * qx); R[2][2] = 1. - 2. * (qx * qx + qy * qy);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            sc[k] = (double)scale_mod * (double)scales[3 * i + k];
+            sc[k] = (double)scale_mod * (double)LERP(scales[3 * c + k], scales[3 * p + k]);
 #pragma unroll
             for (int j = 0; j < 3; j++) Mm[k][j] = sc[k] * R[j][k];
         }
@@ -169,37 +190,53 @@ preprocess_backward_kernel(int P, int deg, int M, const float* __restrict__ mean
         dmean[2] += (q[8] * m_w - q[11] * mul1) * g_mx + (q[9] * m_w - q[11] * mul2) * g_my;
     }
     dL_dmeans2D[3 * i] = g_mx; dL_dmeans2D[3 * i + 1] = g_my; dL_dmeans2D[3 * i + 2] = 0.f;
-    dL_dopacities[i] = g_op;
+    // EMIT: direct store (flat / pre-gathered inputs) or t / (1-t) scatter into the full-size
+    // gradients (red.global.add; a parent row is shared by its k children)
+#define EMIT(ptr, width, k, val)                                                           \
+    do {                                                                                   \
+        const float v__ = (val);                                                           \
+        if (!ridx) (ptr)[(size_t)i * (width) + (k)] = v__;                                 \
+        else {                                                                             \
+            atomicAdd((ptr) + (size_t)c * (width) + (k), t * v__);                         \
+            if (lerp) atomicAdd((ptr) + (size_t)p * (width) + (k), u * v__);               \
+        }                                                                                  \
+    } while (0)
+    EMIT(dL_dopacities, 1, 0, g_op);
 
     // ---- K9b: colour -> SH and view direction ----
     if (colors_precomp) {
-        if (dL_dcolors) { dL_dcolors[3 * i] = g_r; dL_dcolors[3 * i + 1] = g_g; dL_dcolors[3 * i + 2] = g_b; }
+        if (dL_dcolors) { dL_dcolors[3 * c] = g_r; dL_dcolors[3 * c + 1] = g_g; dL_dcolors[3 * c + 2] = g_b; }
     } else {
         const uint32_t kb = __float_as_uint(records[i].b.w);
         const float dRGB[3] = {(kb >> 24) & 1u ? 0.f : g_r, (kb >> 25) & 1u ? 0.f : g_g, (kb >> 26) & 1u ? 0.f : g_b};
         const float d0x = mx - s_cam[0], d0y = my - s_cam[1], d0z = mz - s_cam[2];
         const float len = sqrtf(d0x * d0x + d0y * d0y + d0z * d0z);
         const float x = d0x / len, y = d0y / len, z = d0z / len;
-        const float* sh = shs + (size_t)i * SH3;
+        const float* sh = shs + (size_t)c * SH3;
+        const float* shp = shs + (size_t)p * SH3;
         float* dsh = dL_dsh + (size_t)i * SH3;
         float out[48];
         float ddx = 0.f, ddy = 0.f, ddz = 0.f;
         const int ncoef = (deg + 1) * (deg + 1);
-        float c[48];
+        float c_[48];
         if ((SH3 & 3) == 0) {
 #pragma unroll
             for (int k = 0; k < 12; k++)
                 if (4 * k < 3 * ncoef) {
-                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(sh) + k);
-                    c[4 * k] = t4.x; c[4 * k + 1] = t4.y; c[4 * k + 2] = t4.z; c[4 * k + 3] = t4.w;
+                    float4 t4 = __ldg(reinterpret_cast<const float4*>(sh) + k);
+                    if (lerp) {
+                        const float4 p4 = __ldg(reinterpret_cast<const float4*>(shp) + k);
+                        t4.x = LERP(t4.x, p4.x); t4.y = LERP(t4.y, p4.y); t4.z = LERP(t4.z, p4.z); t4.w = LERP(t4.w, p4.w);
+                    }
+                    c_[4 * k] = t4.x; c_[4 * k + 1] = t4.y; c_[4 * k + 2] = t4.z; c_[4 * k + 3] = t4.w;
                 }
         } else {
 #pragma unroll
-            for (int k = 0; k < 48; k++) if (k < 3 * ncoef) c[k] = __ldg(sh + k);
+            for (int k = 0; k < 48; k++) if (k < 3 * ncoef) c_[k] = LERP(__ldg(sh + k), __ldg(shp + k));
         }
 #pragma unroll
         for (int k = 0; k < 48; k++) out[k] = 0.f;
-#define S(k, ch) c[(k) * 3 + (ch)]
+#define S(k, ch) c_[(k) * 3 + (ch)]
 #define DS(k, ch) out[(k) * 3 + (ch)]
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
@@ -240,7 +277,15 @@ preprocess_backward_kernel(int P, int deg, int M, const float* __restrict__ mean
         }
 #undef S
 #undef DS
-        if ((SH3 & 3) == 0) {
+        if (ridx) {
+            // only the active coefficients carry gradient; the rest of the row stays zero
+#pragma unroll
+            for (int k = 0; k < 48; k++)
+                if (k < 3 * ncoef) {
+                    atomicAdd(dL_dsh + (size_t)c * SH3 + k, t * out[k]);
+                    if (lerp) atomicAdd(dL_dsh + (size_t)p * SH3 + k, u * out[k]);
+                }
+        } else if ((SH3 & 3) == 0) {
 #pragma unroll
             for (int k = 0; k < 12; k++)
                 if (4 * k < SH3) reinterpret_cast<float4*>(dsh)[k] = make_float4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
@@ -254,13 +299,13 @@ preprocess_backward_kernel(int P, int deg, int M, const float* __restrict__ mean
         dmean[1] += (-d0x * d0y * ddx + (sum2 - d0y * d0y) * ddy - d0z * d0y * ddz) * invsum32;
         dmean[2] += (-d0x * d0z * ddx - d0y * d0z * ddy + (sum2 - d0z * d0z) * ddz) * invsum32;
     }
-    dL_dmeans3D[3 * i] = (float)dmean[0]; dL_dmeans3D[3 * i + 1] = (float)dmean[1]; dL_dmeans3D[3 * i + 2] = (float)dmean[2];
+    EMIT(dL_dmeans3D, 3, 0, (float)dmean[0]); EMIT(dL_dmeans3D, 3, 1, (float)dmean[1]); EMIT(dL_dmeans3D, 3, 2, (float)dmean[2]);
 
     // ---- K9c: cov3D -> scale, rotation ----
     if (cov3D_precomp) {
         if (dL_dcov3D) {
 #pragma unroll
-            for (int k = 0; k < 6; k++) dL_dcov3D[6 * i + k] = (float)g6[k];
+            for (int k = 0; k < 6; k++) dL_dcov3D[6 * c + k] = (float)g6[k];
         }
     } else {
         const double dS[3][3] = {{g6[0], 0.5 * g6[1], 0.5 * g6[2]}, {0.5 * g6[1], g6[3], 0.5 * g6[4]}, {0.5 * g6[2], 0.5 * g6[4], g6[5]}};
@@ -271,7 +316,7 @@ preprocess_backward_kernel(int P, int deg, int M, const float* __restrict__ mean
             for (int j = 0; j < 3; j++) dM[k][j] = 2.0 * (Mm[k][0] * dS[0][j] + Mm[k][1] * dS[1][j] + Mm[k][2] * dS[2][j]);
 #pragma unroll
         for (int k = 0; k < 3; k++)
-            dL_dscales[3 * i + k] = (float)((double)scale_mod * (R[0][k] * dM[k][0] + R[1][k] * dM[k][1] + R[2][k] * dM[k][2]));
+            EMIT(dL_dscales, 3, k, (float)((double)scale_mod * (R[0][k] * dM[k][0] + R[1][k] * dM[k][1] + R[2][k] * dM[k][2])));
         double dR[3][3];
 #pragma unroll
         for (int j = 0; j < 3; j++)
@@ -282,12 +327,23 @@ preprocess_backward_kernel(int P, int deg, int M, const float* __restrict__ mean
         dq.y = (float)(2 * qy * (dR[0][1] + dR[1][0]) + 2 * qz * (dR[0][2] + dR[2][0]) + 2 * qr * (dR[2][1] - dR[1][2]) - 4 * qx * (dR[1][1] + dR[2][2]));
         dq.z = (float)(2 * qx * (dR[0][1] + dR[1][0]) + 2 * qr * (dR[0][2] - dR[2][0]) + 2 * qz * (dR[1][2] + dR[2][1]) - 4 * qy * (dR[0][0] + dR[2][2]));
         dq.w = (float)(2 * qr * (dR[1][0] - dR[0][1]) + 2 * qx * (dR[0][2] + dR[2][0]) + 2 * qy * (dR[1][2] + dR[2][1]) - 4 * qz * (dR[0][0] + dR[1][1]));
-        *reinterpret_cast<float4*>(dL_drots + 4 * i) = dq;
+        if (!ridx) *reinterpret_cast<float4*>(dL_drots + 4 * i) = dq;
+        else {
+            atomicAdd(dL_drots + 4 * (size_t)c + 0, t * dq.x); atomicAdd(dL_drots + 4 * (size_t)c + 1, t * dq.y);
+            atomicAdd(dL_drots + 4 * (size_t)c + 2, t * dq.z); atomicAdd(dL_drots + 4 * (size_t)c + 3, t * dq.w);
+            if (lerp) {
+                const float us = u * qsign;
+                atomicAdd(dL_drots + 4 * (size_t)p + 0, us * dq.x); atomicAdd(dL_drots + 4 * (size_t)p + 1, us * dq.y);
+                atomicAdd(dL_drots + 4 * (size_t)p + 2, us * dq.z); atomicAdd(dL_drots + 4 * (size_t)p + 3, us * dq.w);
+            }
+        }
         if (dL_dcov3D) {
 #pragma unroll
-            for (int k = 0; k < 6; k++) dL_dcov3D[6 * i + k] = (float)g6[k];
+            for (int k = 0; k < 6; k++) dL_dcov3D[6 * c + k] = (float)g6[k];
         }
     }
+#undef EMIT
+#undef LERP
 }
 
 int launch_preprocess_backward(const h3dgs_raster_args& a, const int32_t* radii, const Record* records,
@@ -300,7 +356,7 @@ int launch_preprocess_backward(const h3dgs_raster_args& a, const int32_t* radii,
     ProfScope prof(H3DGS_STAGE_PREPROCESS_BWD, s);
     preprocess_backward_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(
         a.P, a.sh_degree, a.sh_coeffs, a.means3D, a.scales, a.scale_modifier, a.rotations, a.shs, a.cov3D_precomp,
-        a.colors_precomp, a.viewmatrix, a.projmatrix, a.campos, a.image_width, a.image_height, a.tanfovx, a.tanfovy,
+        a.colors_precomp, a.interpolation_weights, a.render_indices, a.parent_indices, a.viewmatrix, a.projmatrix, a.campos, a.image_width, a.image_height, a.tanfovx, a.tanfovy,
         fx, fy, a.do_depth, radii, records, accum, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacities,
         dL_dscales, dL_drots, dL_dcov3D);
     H3_LAUNCHED("preprocess_backward", a.debug, s);

@@ -50,7 +50,8 @@ def _stream():
 
 def _make_args(P, means3D, sh, colors_precomp, opacities, scales, rotations, cov3D_precomp, bg, viewmatrix, projmatrix,
                campos, tanfovx, tanfovy, image_height, image_width, sh_degree, scale_modifier, prefiltered, debug,
-               interpolation_weights, num_node_kids, do_depth, shard=(1, 0)):
+               interpolation_weights, num_node_kids, do_depth, shard=(1, 0), render_indices=None,
+               parent_indices=None, num_source=0):
     a = _lib.RasterArgs()
     a.P = P
     a.sh_degree = int(sh_degree)
@@ -62,19 +63,24 @@ def _make_args(P, means3D, sh, colors_precomp, opacities, scales, rotations, cov
     a.means3D, a.shs, a.colors_precomp, a.opacities = _ptr(means3D), _ptr(sh), _ptr(colors_precomp), _ptr(opacities)
     a.scales, a.rotations, a.cov3D_precomp = _ptr(scales), _ptr(rotations), _ptr(cov3D_precomp)
     a.interpolation_weights, a.num_node_kids = _ptr(interpolation_weights), _ptr(num_node_kids)
+    a.render_indices, a.parent_indices, a.num_source = _ptr(render_indices), _ptr(parent_indices), int(num_source)
     a.shard_count, a.shard_index = int(shard[0]), int(shard[1])
     return a
 
 
 def _prep_inputs(means3D, sh, colors_precomp, opacities, scales, rotations, cov3D_precomp, bg, viewmatrix, projmatrix,
-                 campos, interpolation_weights, num_node_kids, render_indices):
-    if render_indices is not None and render_indices.numel() != 0:
-        # API surface only: every shipped call site passes empty index tensors
-        # (gaussian_renderer/__init__.py:39-42, 244-245; SURVEY.md 8a note 1).
-        raise NotImplementedError("in-kernel render_indices/parent_indices gather is not implemented; "
-                                  "gather in Python as render_post does (interp_python=True)")
+                 campos, interpolation_weights, num_node_kids, render_indices, parent_indices=None):
     means3D = _f32c(means3D, "means3D")
     P = 0 if means3D is None else means3D.shape[0]
+    ridx = pidx = None
+    if render_indices is not None and render_indices.numel() != 0:
+        # in-kernel cut gather + parent lerp (every shipped call site passes empty index tensors,
+        # gaussian_renderer/__init__.py:39-42, 244-245; this is the fused form of :199-218)
+        ridx = _i32c(render_indices, "render_indices")
+        pidx = _i32c(parent_indices, "parent_indices")
+        if pidx is None or pidx.numel() < ridx.numel():
+            raise RuntimeError("parent_indices must hold one entry per render index")
+        P = ridx.numel()
     sh = _f32c(sh, "shs"); colors_precomp = _f32c(colors_precomp, "colors_precomp")
     opacities = _f32c(opacities, "opacities")
     scales = _f32c(scales, "scales"); rotations = _f32c(rotations, "rotations")
@@ -87,7 +93,7 @@ def _prep_inputs(means3D, sh, colors_precomp, opacities, scales, rotations, cov3
     kids = _i32c(num_node_kids, "num_node_kids") if ts is not None else None
     if ts is not None and (ts.numel() < P or kids is None or kids.numel() < P):
         raise RuntimeError("interpolation_weights / num_node_kids must hold at least P entries")
-    return P, means3D, sh, colors_precomp, opacities, scales, rotations, cov3D_precomp, bg, viewmatrix, projmatrix, campos, ts, kids
+    return P, means3D, sh, colors_precomp, opacities, scales, rotations, cov3D_precomp, bg, viewmatrix, projmatrix, campos, ts, kids, ridx, pidx
 
 
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
@@ -97,12 +103,14 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     """-> (num_rendered, color[3,H,W], radii[P] i32, geomBuffer, binningBuffer, imgBuffer, invdepth[1,H,W])"""
     L = _lib.lib()
     (P, means3D, sh, colors, opacity, scales, rotations, cov3D_precomp, background, viewmatrix, projmatrix, campos,
-     ts, kids) = _prep_inputs(means3D, sh, colors, opacity, scales, rotations, cov3D_precomp, background, viewmatrix,
-                              projmatrix, campos, interpolation_weights, num_node_kids, render_indices)
+     ts, kids, ridx, pidx) = _prep_inputs(means3D, sh, colors, opacity, scales, rotations, cov3D_precomp, background,
+                                          viewmatrix, projmatrix, campos, interpolation_weights, num_node_kids,
+                                          render_indices, parent_indices)
     dev = background.device
     H, W = int(image_height), int(image_width)
     a = _make_args(P, means3D, sh, colors, opacity, scales, rotations, cov3D_precomp, background, viewmatrix, projmatrix,
-                   campos, tan_fovx, tan_fovy, H, W, degree, scale_modifier, prefiltered, debug, ts, kids, do_depth, shard)
+                   campos, tan_fovx, tan_fovy, H, W, degree, scale_modifier, prefiltered, debug, ts, kids, do_depth, shard,
+                   ridx, pidx, 0 if ridx is None else means3D.shape[0])
     if shard[0] > 1:      # packed shard layout [owned tile rows][3][16][W]
         gy = (H + 15) // 16
         rows = (gy + shard[0] - 1 - shard[1]) // shard[0]
@@ -138,25 +146,27 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, opacities, 
     """-> (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)"""
     L = _lib.lib()
     (P, means3D, sh, colors, opacities, scales, rotations, cov3D_precomp, background, viewmatrix, projmatrix, campos,
-     ts, kids) = _prep_inputs(means3D, sh, colors, opacities, scales, rotations, cov3D_precomp, background, viewmatrix,
-                              projmatrix, campos, interpolation_weights, num_node_kids, render_indices)
+     ts, kids, ridx, pidx) = _prep_inputs(means3D, sh, colors, opacities, scales, rotations, cov3D_precomp, background,
+                                          viewmatrix, projmatrix, campos, interpolation_weights, num_node_kids,
+                                          render_indices, parent_indices)
+    N = P if ridx is None else means3D.shape[0]          # rows of the gradient tensors
     dev = background.device
     H = int(image_height if image_height is not None else dL_dout_color.shape[1])
     W = int(image_width if image_width is not None else dL_dout_color.shape[2])
     a = _make_args(P, means3D, sh, colors, opacities, scales, rotations, cov3D_precomp, background, viewmatrix,
                    projmatrix, campos, tan_fovx, tan_fovy, H, W, degree, scale_modifier, False, debug, ts, kids,
-                   do_depth, shard)
+                   do_depth, shard, ridx, pidx, 0 if ridx is None else N)
     g_color = _f32c(dL_dout_color, "dL_dout_color")
     g_depth = _f32c(dL_dout_invdepth, "dL_dout_invdepth") if (do_depth and dL_dout_invdepth is not None) else None
     e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
     M = sh.shape[1] if sh is not None else 0
     if phases & 2:
-        d_means3D, d_means2D, d_opac = e(P, 3), e(P, 3), e(P, 1)
-        d_sh = e(P, M, 3) if sh is not None else e(0)
-        d_colors = e(P, 3) if colors is not None else e(0)
-        d_scales = e(P, 3) if scales is not None else e(0)
-        d_rots = e(P, 4) if rotations is not None else e(0)
-        d_cov = e(P, 6) if cov3D_precomp is not None else e(0)
+        d_means3D, d_means2D, d_opac = e(N, 3), e(P, 3), e(N, 1)
+        d_sh = e(N, M, 3) if sh is not None else e(0)
+        d_colors = e(N, 3) if colors is not None else e(0)
+        d_scales = e(N, 3) if scales is not None else e(0)
+        d_rots = e(N, 4) if rotations is not None else e(0)
+        d_cov = e(N, 6) if cov3D_precomp is not None else e(0)
     else:
         d_means3D = d_means2D = d_opac = d_sh = d_colors = d_scales = d_rots = d_cov = None
     if scratch is None:

@@ -53,6 +53,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         num_rendered, color, radii, geomBuffer, binningBuffer, imgBuffer, invdepths = _C.rasterize_gaussians(*args)
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
+        ctx.means2D_rows = means2D.shape[0]
         ctx.save_for_backward(colors_precomp, means3D, scales, rotations, cov3Ds_precomp, radii, sh, opacities,
                               geomBuffer, binningBuffer, imgBuffer)
         ctx.mark_non_differentiable(radii)
@@ -70,6 +71,10 @@ class _RasterizeGaussians(torch.autograd.Function):
                 rs.image_height, rs.image_width)
         (grad_means2D, grad_colors_precomp, grad_opacities, grad_means3D, grad_cov3Ds_precomp, grad_sh, grad_scales,
          grad_rotations) = _C.rasterize_gaussians_backward(*args)
+        if grad_means2D.shape[0] != ctx.means2D_rows:      # in-kernel gather: means2D may be the full-size sink
+            full = grad_means2D.new_zeros((ctx.means2D_rows, 3))
+            full[:grad_means2D.shape[0]] = grad_means2D
+            grad_means2D = full
         return (grad_means3D, grad_means2D, grad_sh, grad_colors_precomp, grad_opacities, grad_scales, grad_rotations,
                 grad_cov3Ds_precomp, None)
 

@@ -30,6 +30,7 @@ class RasterArgs(C.Structure):
         ("means3D", C.c_void_p), ("shs", C.c_void_p), ("colors_precomp", C.c_void_p), ("opacities", C.c_void_p),
         ("scales", C.c_void_p), ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p),
         ("interpolation_weights", C.c_void_p), ("num_node_kids", C.c_void_p),
+        ("render_indices", C.c_void_p), ("parent_indices", C.c_void_p), ("num_source", C.c_int32),
         ("shard_count", C.c_int32), ("shard_index", C.c_int32),
     ]
 

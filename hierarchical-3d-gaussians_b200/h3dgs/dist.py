@@ -99,7 +99,7 @@ class _ShardedRasterize(torch.autograd.Function):
                 rs.interpolation_weights, rs.num_node_kids, False, rs.image_height, rs.image_width)
         # phase 1: per-tile replay on the owned tiles -> partial [P,10] sums
         accum = _C.rasterize_gaussians_backward(*common, grad_img.contiguous(), None, *tail, shard=ctx.shard, phases=1)
-        reduce_accum(accum, means3D.shape[0], ctx.group)
+        reduce_accum(accum, radii.shape[0], ctx.group)
         # phase 2: per-Gaussian chain rule, replicated
         (d_means2D, _dc, d_opac, d_means3D, _dcov, d_sh, d_scales, d_rots) = _C.rasterize_gaussians_backward(
             *common, None, None, *tail, shard=ctx.shard, phases=2, scratch=accum)
@@ -112,9 +112,11 @@ class TileSharder:
 
     def render(self, scene, cam, bg, threshold=None, sh_degree=3):
         if scene.hier:
+            # fused form: the cut gather + parent lerp run inside K1/K9 (full arrays + indices)
             n = pipeline.lod_cut(scene, cam, threshold)
-            means, scales, rots, opac, shs = pipeline.interpolate_cut(scene, n)
-            rs = pipeline.make_settings(scene, cam, bg, sh_degree, ts=scene.interpolation_weights, kids=scene.num_siblings)
+            means, scales, rots, opac, shs = scene.means3D, scene.scales, scene.rotations, scene.opacities, scene.shs
+            rs = pipeline.make_settings(scene, cam, bg, sh_degree, ts=scene.interpolation_weights, kids=scene.num_siblings,
+                                        ridx=scene.render_indices[:n], pidx=scene.parent_indices[:n])
         else:
             n = scene.means3D.shape[0]
             means, scales, rots, opac, shs = scene.means3D, scene.scales, scene.rotations, scene.opacities, scene.shs

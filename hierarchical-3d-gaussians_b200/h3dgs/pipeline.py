@@ -88,11 +88,12 @@ def interpolate_cut(scene, n):
     return means.contiguous(), scales.contiguous(), rots.contiguous(), opac.contiguous(), shs.contiguous()
 
 
-def make_settings(scene, cam, bg, sh_degree, ts=None, kids=None, do_depth=False, debug=False):
+def make_settings(scene, cam, bg, sh_degree, ts=None, kids=None, do_depth=False, debug=False, ridx=None, pidx=None):
     return GaussianRasterizationSettings(
         image_height=cam.H, image_width=cam.W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=bg, scale_modifier=1.0,
         viewmatrix=cam.viewmatrix, projmatrix=cam.projmatrix, sh_degree=sh_degree, campos=cam.campos,
-        prefiltered=False, debug=debug, render_indices=scene.empty_i, parent_indices=scene.empty_i,
+        prefiltered=False, debug=debug, render_indices=ridx if ridx is not None else scene.empty_i,
+        parent_indices=pidx if pidx is not None else scene.empty_i,
         interpolation_weights=ts if ts is not None else scene.empty_f,
         num_node_kids=kids if kids is not None else scene.empty_i, do_depth=do_depth)
 
@@ -118,11 +119,25 @@ def render_hier(scene, cam, bg, threshold, sh_degree=3):
     return img, radii, n
 
 
-def l1_step(scene, cam, bg, gt, threshold=None, sh_degree=3):
+def render_hier_fused(scene, cam, bg, threshold, sh_degree=3):
+    """Same result as render_hier, but the cut gather + parent lerp (and the gradient scatter in
+    backward) run inside K1/K9 through the settings' render_indices/parent_indices fields instead
+    of ~25 PyTorch kernels with full-size temporaries."""
+    n = lod_cut(scene, cam, threshold)
+    rs = make_settings(scene, cam, bg, sh_degree, ts=scene.interpolation_weights, kids=scene.num_siblings,
+                       ridx=scene.render_indices[:n], pidx=scene.parent_indices[:n])
+    means2D = torch.zeros((n, 3), device=scene.means3D.device, requires_grad=scene.means3D.requires_grad)
+    img, radii, _ = GaussianRasterizer(rs)(means3D=scene.means3D, means2D=means2D, shs=scene.shs, colors_precomp=None,
+                                           opacities=scene.opacities, scales=scene.scales, rotations=scene.rotations,
+                                           cov3D_precomp=None)
+    return img, radii, n
+
+
+def l1_step(scene, cam, bg, gt, threshold=None, sh_degree=3, fused=True):
     """forward + L1 loss + backward; returns the loss tensor (device) and bookkeeping."""
     scene.zero_grad()
     if scene.hier:
-        img, radii, n = render_hier(scene, cam, bg, threshold, sh_degree)
+        img, radii, n = (render_hier_fused if fused else render_hier)(scene, cam, bg, threshold, sh_degree)
     else:
         img, radii = render_flat(scene, cam, bg, sh_degree)
         n = scene.means3D.shape[0]

@@ -76,10 +76,22 @@ typedef struct h3dgs_raster_args {
     /* hierarchy extras (empty tensors at the flat call sites -> NULL) */
     const float* interpolation_weights; /* t  [>=P] or NULL                                     */
     const int32_t* num_node_kids;       /* k  [>=P] or NULL                                     */
+    /* In-kernel cut gather + parent lerp (GaussianRasterizationSettings.render_indices /
+     * parent_indices; empty at the shipped call sites, SURVEY.md 8a note 1).  When
+     * render_indices != NULL the per-Gaussian inputs above are the FULL arrays with
+     * num_source rows and rendered Gaussian i (i < P) is
+     *   x = t_i * x[render_indices[i]] + (1 - t_i) * x[parent_indices[i]]
+     * for means, scales, SH, opacity and (sign-aligned, un-renormalised) rotations --
+     * exactly the arithmetic of render_post(interp_python=True),
+     * gaussian_renderer/__init__.py:199-218.  parent < 0 means "no parent" (t must be 1).
+     * Backward scatters t*g / (1-t)*g into zero-filled gradients of num_source rows. */
+    const int32_t* render_indices;      /* [P] or NULL                                          */
+    const int32_t* parent_indices;      /* [P] or NULL                                          */
+    int32_t num_source;                 /* rows of the full arrays (ignored when render_indices == NULL) */
     /* screen-tile shard for the multi-GPU mode: this call bins and renders only
      * tile rows y with (y % shard_count) == shard_index.  (1,0) = whole image. */
     int32_t shard_count, shard_index;
-} h3dgs_raster_args;
+} h3dgs_raster_args;   /* NOTE: keep hierarchical-3d-gaussians_b200/h3dgs/_lib.py::RasterArgs in sync */
 
 /* Forward: K1 preprocess -> scan -> duplicateWithKeys -> radix sort -> tile ranges
  * -> record gather -> per-tile blend.  Outputs: out_color [3,H,W], out_radii [P]

@@ -56,15 +56,59 @@ def test_hierarchy_step_matches_oracle_composition():
     assert 0 < n_ref < 12000 * 2 - 1
     scene = pipeline.Scene(h)
     dcam = pipeline.DeviceCamera(cam)
-    loss, radii, n = pipeline.l1_step(scene, dcam, torch.zeros(3, device="cuda"), torch.tensor(gt, device="cuda"), thr)
-    assert n == n_ref
+    bg0, gtd = torch.zeros(3, device="cuda"), torch.tensor(gt, device="cuda")
+    imgs = {}
+    for fused in (False, True):
+        # fused=False: the reference's PyTorch gather/lerp around the rasterizer (render_post);
+        # fused=True : the same arithmetic inside K1/K9 via settings.render_indices/parent_indices
+        loss, radii, n = pipeline.l1_step(scene, dcam, bg0, gtd, thr, fused=fused)
+        assert n == n_ref
+        assert np.array_equal(radii.cpu().numpy(), f["radii"])
+        loss_ref = np.abs(f["color"] - gt).mean()
+        assert abs(loss.item() - loss_ref) < 1e-6
+        for name, p in [("means3D", scene.means3D), ("scales", scene.scales), ("shs", scene.shs),
+                        ("opacities", scene.opacities), ("rotations", scene.rotations)]:
+            e = rel_err(p.grad.cpu().numpy(), gref[name])
+            assert e < 2e-5, (fused, name, e)          # 1e-5 rasterizer bar + fp32 lerp/scatter
+        with torch.no_grad():
+            imgs[fused] = (pipeline.render_hier_fused if fused else pipeline.render_hier)(scene, dcam, bg0, thr)[0]
+    assert torch.equal(imgs[False], imgs[True])         # bit-identical lerp arithmetic
+
+
+def test_fused_gather_lerp_matches_oracle_directly():
+    """op-level: full arrays + render_indices/parent_indices through the public API vs the oracle front-end."""
+    import torch
+    from oracle import oracle
+    from diff_gaussian_rasterization import GaussianRasterizer
+    from util import cuda_settings
+    cam = synth.make_camera(320, 200)
+    leaves = synth.cloud_v1(6000, cam, zmin=2.0, zmax=30.0, seed=2, scale_k=1.0)
+    z = leaves["means3D"][:, 2:3]
+    leaves["scales"] = (6e-3 * np.sqrt(2 * z) * np.ones((1, 3))).astype(np.float32)
+    h = synth.build_hierarchy(leaves)
+    thr = synth.tau_threshold(6.0, cam)
+    n, ri, pi, ni = oracle.expand_to_size(h["nodes"], h["boxes"], thr, cam.camera_center)
+    ts, kids = oracle.get_interpolation_weights(ni, thr, h["nodes"], h["boxes"], cam.camera_center)
+    assert (ts < 1).mean() > 0.1
+    bg = np.array([0.3, 0.2, 0.1], np.float32)
+    f = oracle.rasterize_forward(h["means3D"], h["shs"], None, h["opacities"], h["scales"], h["rotations"], None,
+                                 cam.world_view_transform, cam.full_proj_transform, cam.camera_center, bg, cam.W, cam.H,
+                                 cam.tanfovx, cam.tanfovy, ts=ts, kids=kids, render_indices=ri, parent_indices=pi)
+    gcol = synth.l1_grad(f["color"])
+    b = oracle.rasterize_backward(f, gcol)
+    rs = cuda_settings(cam, bg, ts=ts, kids=kids)._replace(render_indices=torch.tensor(ri, device="cuda"),
+                                                           parent_indices=torch.tensor(pi, device="cuda"))
+    t = lambda a: torch.tensor(a, device="cuda", requires_grad=True)
+    m, sh, op, s, r = t(h["means3D"]), t(h["shs"]), t(h["opacities"]), t(h["scales"]), t(h["rotations"])
+    m2 = torch.zeros((n, 3), device="cuda", requires_grad=True)
+    color, radii, _ = GaussianRasterizer(rs)(means3D=m, means2D=m2, shs=sh, colors_precomp=None, opacities=op, scales=s,
+                                            rotations=r, cov3D_precomp=None)
     assert np.array_equal(radii.cpu().numpy(), f["radii"])
-    loss_ref = np.abs(f["color"] - gt).mean()
-    assert abs(loss.item() - loss_ref) < 1e-6
-    for name, p in [("means3D", scene.means3D), ("scales", scene.scales), ("shs", scene.shs),
-                    ("opacities", scene.opacities), ("rotations", scene.rotations)]:
-        e = rel_err(p.grad.cpu().numpy(), gref[name])
-        assert e < 2e-5, (name, e)          # 1e-5 rasterizer bar + fp32 lerp/scatter in torch
+    assert rel_err(color.detach().cpu().numpy(), f["color"]) < 1e-5
+    (color * torch.tensor(gcol, device="cuda")).sum().backward()
+    for name, p_ in [("means3D", m), ("sh", sh), ("opacities", op), ("scales", s), ("rotations", r), ("means2D", m2)]:
+        e = rel_err(p_.grad.cpu().numpy(), b[name])
+        assert e < 1e-5, (name, e)
 
 
 def test_tile_shards_on_one_gpu_equal_unsharded():
@@ -111,7 +155,7 @@ def test_tile_shards_on_one_gpu_equal_unsharded():
         out = bwd((world, 0), states[0], g, 2, scratch=scratch)
         for a, b in zip(out, ref):
             if a.numel():
-                assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 2e-6      # only the fp32 sum order differs
+                assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-5      # only the fp32 sum order differs
 
 
 def test_full_size_frame_1080p():
