@@ -77,17 +77,39 @@ identify_tile_ranges_kernel(int64_t D, const uint64_t* __restrict__ keys, uint32
     if (i == D - 1) ranges[2 * tile + 1] = (uint32_t)D;
 }
 
-// sorted_records[j] = records[point_list[j]] : 48-B gathers out of an L2-resident
-// array, fully coalesced 48-B writes.  3 lanes per entry (one float4 each).
+// sorted_records[j] = records[point_list[j]] : 48-B gathers out of an L2-resident array.
+// One thread per entry.  While the record is in registers, derive which 16x2-pixel strips
+// (= warps of the blend CTAs) of ITS tile the entry can reach at all: alpha >= 1/255 needs
+// d^T Q d <= 2 ln(255 o), an ellipse whose y half-extent is sqrt(2 ln(255 o) * Q_xx / det Q).
+// The range is conservative (margin for fp32 rounding; the hierarchy weight only lowers
+// alpha), so skipping a strip never changes a result; it is stored in spare bits of kbits.
 __global__ void __launch_bounds__(256)
-gather_records_kernel(int64_t D, const uint32_t* __restrict__ point_list, const float4* __restrict__ records,
-                      float4* __restrict__ sorted)
+gather_records_kernel(int64_t D, const uint32_t* __restrict__ point_list, const uint64_t* __restrict__ keys, int gx,
+                      const Record* __restrict__ records, Record* __restrict__ sorted)
 {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 3 * D) return;
-    const int64_t j = t / 3; const int part = (int)(t - 3 * j);
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= D) return;
     const uint32_t g = point_list[j];
-    sorted[t] = __ldg(records + 3 * (size_t)g + part);
+    const float4* src = reinterpret_cast<const float4*>(records + g);
+    const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+    const int tile_y = (int)((uint32_t)(keys[j] >> 32) / (uint32_t)gx);
+    int lo = 0, hi = 7;
+    const float det = a.z * b.x - a.w * a.w;          // conic determinant
+    const float o255 = b.y * 255.0f;
+    if (!(o255 > 1.0f)) { lo = 1; hi = 0; }            // can never reach alpha >= 1/255
+    else if (det > 0.0f && a.z > 0.0f) {
+        const float ey = sqrtf(2.0f * logf(o255) * a.z / det) * 1.001f + 0.01f;
+        if (ey == ey && ey < 1e6f) {
+            const float rel = a.y - (float)(tile_y * kTile);
+            const int r0 = max(0, (int)ceilf(rel - ey)), r1 = min(kTile - 1, (int)floorf(rel + ey));
+            if (r1 < r0) { lo = 1; hi = 0; } else { lo = r0 >> 1; hi = r1 >> 1; }
+        }
+    }
+    const uint32_t kb = (__float_as_uint(b.w) & 0x00FFFFFFu) | ((uint32_t)lo << kStripLoShift) | ((uint32_t)hi << kStripHiShift);
+    float4* dst = reinterpret_cast<float4*>(sorted + j);
+    dst[0] = a;
+    dst[1] = make_float4(b.x, b.y, b.z, __uint_as_float(kb));
+    dst[2] = c;
 }
 
 int launch_binning(const h3dgs_raster_args& a, const int32_t* radii, const float* depths, const uint32_t* offsets,
@@ -118,8 +140,8 @@ int launch_binning(const h3dgs_raster_args& a, const int32_t* radii, const float
     identify_tile_ranges_kernel<<<(unsigned)((D + 255) / 256), 256, 0, s>>>(D, keys_s, ranges);
     H3_LAUNCHED("identify_tile_ranges", a.debug, s); }
     { ProfScope prof(H3DGS_STAGE_GATHER, s);
-    gather_records_kernel<<<(unsigned)((3 * D + 255) / 256), 256, 0, s>>>(D, vals_s, (const float4*)records,
-                                                                           (float4*)(bin + bl.sorted_records));
+    gather_records_kernel<<<(unsigned)((D + 255) / 256), 256, 0, s>>>(D, vals_s, keys_s, gx, records,
+                                                                       (Record*)(bin + bl.sorted_records));
     H3_LAUNCHED("gather_records", a.debug, s); }
     return H3DGS_OK;
 }

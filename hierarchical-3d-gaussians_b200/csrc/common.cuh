@@ -20,11 +20,15 @@ constexpr float kAlphaSkip = 1.0f / 255.0f;
 constexpr float kTStop = 0.0001f;
 constexpr float kWEps = 0.0000001f;
 constexpr int kBucket = H3DGS_BUCKET;
+constexpr uint32_t kKidsMask = 0xFFFFFu;
+constexpr int kClampShift = 20, kStripLoShift = 24, kStripHiShift = 27;
 
 // Per-Gaussian projected record: 3 x float4 = 48 B, 16-B aligned, so a batch of
 // records is one contiguous cp.async.bulk (TMA) transfer.
 //   a = {x, y, conic.x, conic.y}
-//   b = {conic.z, opacity, t, kbits}     kbits: low 24 bits = num_node_kids, bits 24..26 = SH clamp flags
+//   b = {conic.z, opacity, t, kbits}     kbits: bits 0..19 num_node_kids, 20..22 SH clamp flags; in the
+//                                        per-tile SORTED copy also 24..26 / 27..29 = first / last 16x2-pixel
+//                                        strip of the tile this entry can reach (strip culling, binning.cu)
 //   c = {r, g, b, invdepth}
 struct __align__(16) Record { float4 a, b, c; };
 static_assert(sizeof(Record) == 48, "record must be 48 bytes");
@@ -120,7 +124,7 @@ template <bool HIER>
 __device__ __forceinline__ void hier_alpha_grad(float a, float t, uint32_t kbits, float& alpha, float& dadb) {
     alpha = a; dadb = 1.0f;
     if (!HIER) return;
-    const uint32_t k = kbits & 0xFFFFFFu;
+    const uint32_t k = kbits & kKidsMask;
     if (k <= 1u || t >= 1.0f) return;
     const float ik = 1.0f / (float)k;
     const float l2 = log2f(1.0f - a);

@@ -197,7 +197,7 @@ preprocess_kernel(int P, int deg, int M, const float* __restrict__ means3D, cons
                         }
 #undef S
                         r += 0.5f;
-                        if (r < 0.f) clampbits |= (1u << (24 + ch));
+                        if (r < 0.f) clampbits |= (1u << (kClampShift + ch));
                         rgb[ch] = fmaxf(r, 0.f);
                     }
                 }
@@ -205,7 +205,7 @@ preprocess_kernel(int P, int deg, int M, const float* __restrict__ means3D, cons
                 rec.a = make_float4(ix, iy, conx, cony);
                 const float tt = ts ? ts[i] : 1.0f;
                 const uint32_t k = kids ? (uint32_t)kids[i] : 1u;
-                rec.b = make_float4(conz, LERP(opacities[c], opacities[p]), tt, __uint_as_float((k & 0xFFFFFFu) | clampbits));
+                rec.b = make_float4(conz, LERP(opacities[c], opacities[p]), tt, __uint_as_float((k & kKidsMask) | clampbits));
                 rec.c = make_float4(rgb[0], rgb[1], rgb[2], 1.0f / vz);
                 records[i] = rec;
                 depths[i] = vz;

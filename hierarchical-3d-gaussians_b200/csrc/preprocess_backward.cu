@@ -208,7 +208,7 @@ preprocess_backward_kernel(int P, int deg, int M, const float* __restrict__ mean
         if (dL_dcolors) { dL_dcolors[3 * c] = g_r; dL_dcolors[3 * c + 1] = g_g; dL_dcolors[3 * c + 2] = g_b; }
     } else {
         const uint32_t kb = __float_as_uint(records[i].b.w);
-        const float dRGB[3] = {(kb >> 24) & 1u ? 0.f : g_r, (kb >> 25) & 1u ? 0.f : g_g, (kb >> 26) & 1u ? 0.f : g_b};
+        const float dRGB[3] = {(kb >> kClampShift) & 1u ? 0.f : g_r, (kb >> (kClampShift + 1)) & 1u ? 0.f : g_g, (kb >> (kClampShift + 2)) & 1u ? 0.f : g_b};
         const float d0x = mx - s_cam[0], d0y = my - s_cam[1], d0z = mz - s_cam[2];
         const float len = sqrtf(d0x * d0x + d0y * d0y + d0z * d0z);
         const float x = d0x / len, y = d0y / len, z = d0z / len;

@@ -27,7 +27,7 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
     __shared__ __align__(8) uint64_t s_full[kFwdStages];
     __shared__ uint32_t s_max;
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const int tile_x = blockIdx.x % gx;
     const int tile_y = (blockIdx.x / gx) * shard_count + shard_index;
     const int tile = tile_y * gx + tile_x;
@@ -73,8 +73,13 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
             const Record* rec = &s_rec[st][0];
             const uint32_t base = (uint32_t)(b * kFwdBatch);
             for (int j = 0; j < cnt; j++) {
-                const float4 a = rec[j].a;
+                if ((j & 31) == 0 && j != 0 && __all_sync(0xffffffffu, done)) break;
                 const float4 bb = rec[j].b;
+                // strip culling (warp-uniform): this warp's two pixel rows are outside the
+                // entry's alpha >= 1/255 extent (binning.cu::gather_records_kernel)
+                const uint32_t kb = __float_as_uint(bb.w);
+                if (warp < (int)((kb >> kStripLoShift) & 7u) || warp > (int)((kb >> kStripHiShift) & 7u)) continue;
+                const float4 a = rec[j].a;
                 const float dx = a.x - fpx, dy = a.y - fpy;
                 const float power = -0.5f * (a.z * dx * dx + bb.x * dy * dy) - a.w * dx * dy;
                 float alpha = fminf(kAlphaCap, bb.y * fast_exp(power));
@@ -90,7 +95,6 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
                     T = test_T;
                     last = base + (uint32_t)j + 1u;
                 }
-                if ((j & 31) == 31 && __all_sync(0xffffffffu, done)) break;
             }
         }
         const int ndone = __syncthreads_count(done);
