@@ -120,17 +120,29 @@ __device__ __forceinline__ float fast_exp(float x) {
     return y;
 }
 
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// strip culling test for one entry's kbits (binning.cu::gather_records_kernel)
+__device__ __forceinline__ bool strip_hit(uint32_t kb, int warp) {
+    return warp >= (int)((kb >> kStripLoShift) & 7u) && warp <= (int)((kb >> kStripHiShift) & 7u);
+}
+
 template <bool HIER>
 __device__ __forceinline__ void hier_alpha_grad(float a, float t, uint32_t kbits, float& alpha, float& dadb) {
     alpha = a; dadb = 1.0f;
     if (!HIER) return;
     const uint32_t k = kbits & kKidsMask;
     if (k <= 1u || t >= 1.0f) return;
-    const float ik = 1.0f / (float)k;
-    const float l2 = log2f(1.0f - a);
-    const float root = exp2f(l2 * ik);
+    // (1-a)^(1/k) through MUFU.LG2 / MUFU.EX2: 1-a is in [0.01, 1], where lg2.approx is
+    // accurate to ~2^-22 absolute, i.e. ~2e-7 relative on the root
+    const float ik = __frcp_rn((float)k);
+    const float l2 = __log2f(1.0f - a);
+    const float root = fast_exp2(l2 * ik);
     alpha = t * a + (1.0f - t) * (1.0f - root);
-    dadb = t + (1.0f - t) * ik * exp2f(l2 * (ik - 1.0f));
+    dadb = t + (1.0f - t) * ik * fast_exp2(l2 * (ik - 1.0f));
 }
 template <bool HIER>
 __device__ __forceinline__ float hier_alpha(float a, float t, uint32_t kbits) {

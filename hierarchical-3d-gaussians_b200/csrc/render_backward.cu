@@ -111,6 +111,7 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
         if (DEPTH) gd = dL_dinvdepth[pix];
     }
     const float bg_dot = bg[0] * g0 + bg[1] * g1 + bg[2] * g2;
+    const int wlast = (int)__reduce_max_sync(0xffffffffu, (unsigned)last);   // nothing in this strip beyond it
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accd = 0.f;       // accum_rec
     float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, lcd = 0.f, last_alpha = 0.f;
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
@@ -120,12 +121,19 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
         mbar_wait(&s_full[st], (uint32_t)((it / kBwdStages) & 1));
         const int cnt = min(kBwdBatch, n - b * kBwdBatch);
         const Record* rec = &s_rec[st][0];
-        for (int j = cnt - 1; j >= 0; j--) {
+        // back to front; per group of 32 entries a ballot compacts the entries that can reach
+        // this warp's strip at all (see render_forward.cu)
+        for (int j0 = (cnt - 1) & ~31; j0 >= 0; j0 -= 32) {
+          const int jl = j0 + lane;
+          const bool hit = jl < cnt && (b * kBwdBatch + jl) < wlast && strip_hit(__float_as_uint(rec[jl].b.w), warp);
+          uint32_t m = __ballot_sync(0xffffffffu, hit);
+          while (m) {
+            const int top = 31 - __clz(m);
+            m &= ~(1u << top);
+            const int j = j0 + top;
             const int e = b * kBwdBatch + j;              // 0-based list position; contributor number e+1
             const float4 bb = rec[j].b;
             const uint32_t kb = __float_as_uint(bb.w);
-            // strip culling (warp-uniform), see render_forward.cu
-            if (warp < (int)((kb >> kStripLoShift) & 7u) || warp > (int)((kb >> kStripHiShift) & 7u)) continue;
             float v[10];
 #pragma unroll
             for (int k = 0; k < 10; k++) v[k] = 0.f;
@@ -142,7 +150,8 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
                     if (alpha >= kAlphaSkip) {
                         active = true;
                         const float4 c = rec[j].c;
-                        T = T / (1.f - alpha);
+                        const float rcp = __frcp_rn(1.f - alpha);     // one reciprocal serves T and the bg term
+                        T = T * rcp;
                         const float dchannel_dcolor = alpha * T;
                         float dL_dalpha = 0.f;
                         acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0; lc0 = c.x; dL_dalpha += (c.x - acc0) * g0;
@@ -156,7 +165,7 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
                         }
                         dL_dalpha *= T;
                         last_alpha = alpha;
-                        dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot;
+                        dL_dalpha += (-T_final * rcp) * bg_dot;
                         const float dL_dab = dL_dalpha * dadb;
                         const float dL_dG = bb.y * dL_dab;
                         const float gdx = G * dx, gdy = G * dy;
@@ -176,6 +185,7 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
                 if (slot >= 0 && (DEPTH || slot < 9))
                     atomicAdd(accum + (size_t)s_id[st][j] * kAccum + slot, total);
             }
+          }
         }
         __syncthreads();                      // every thread is done with stage st (records and ids)
         if (it + kBwdStages < nb) {

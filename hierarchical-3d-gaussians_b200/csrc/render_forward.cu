@@ -27,7 +27,7 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
     __shared__ __align__(8) uint64_t s_full[kFwdStages];
     __shared__ uint32_t s_max;
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile_x = blockIdx.x % gx;
     const int tile_y = (blockIdx.x / gx) * shard_count + shard_index;
     const int tile = tile_y * gx + tile_x;
@@ -65,35 +65,40 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
         mbar_wait(&s_full[st], (uint32_t)((b / kFwdStages) & 1));
         waited = b + 1;
         const int cnt = min(kFwdBatch, n - b * kFwdBatch);
-        // The body is straight-line + one short reconvergent `if`: a per-thread
-        // `continue`/`break` here leaves the warp split into fragments that each re-walk
-        // the list (measured: 18x the instructions).  A warp leaves the batch only when
-        // all of its 32 pixels are done (warp-uniform branch).
-        if (!__all_sync(0xffffffffu, done)) {
+        // Per group of 32 entries each lane tests ONE entry against this warp's 16x2-pixel
+        // strip and a ballot compacts the survivors, so culled entries cost nothing per pixel.
+        // The survivor loop is warp-uniform (same mask in every lane) and its body is
+        // straight-line + one short reconvergent `if`: a per-thread `continue`/`break` here
+        // leaves the warp split into fragments that each re-walk the list (measured: 18x the
+        // instructions).  A warp leaves the batch only when all of its 32 pixels are done.
+        {
             const Record* rec = &s_rec[st][0];
             const uint32_t base = (uint32_t)(b * kFwdBatch);
-            for (int j = 0; j < cnt; j++) {
-                if ((j & 31) == 0 && j != 0 && __all_sync(0xffffffffu, done)) break;
-                const float4 bb = rec[j].b;
-                // strip culling (warp-uniform): this warp's two pixel rows are outside the
-                // entry's alpha >= 1/255 extent (binning.cu::gather_records_kernel)
-                const uint32_t kb = __float_as_uint(bb.w);
-                if (warp < (int)((kb >> kStripLoShift) & 7u) || warp > (int)((kb >> kStripHiShift) & 7u)) continue;
-                const float4 a = rec[j].a;
-                const float dx = a.x - fpx, dy = a.y - fpy;
-                const float power = -0.5f * (a.z * dx * dx + bb.x * dy * dy) - a.w * dx * dy;
-                float alpha = fminf(kAlphaCap, bb.y * fast_exp(power));
-                alpha = hier_alpha<HIER>(alpha, bb.z, __float_as_uint(bb.w));
-                const float test_T = T * (1.0f - alpha);
-                bool valid = !done && power <= 0.0f && alpha >= kAlphaSkip;
-                if (valid && test_T < kTStop) { done = true; valid = false; }
-                if (valid) {
-                    const float4 c = rec[j].c;
-                    const float w = alpha * T;
-                    C0 += c.x * w; C1 += c.y * w; C2 += c.z * w;
-                    if (DEPTH) invd += c.w * w;
-                    T = test_T;
-                    last = base + (uint32_t)j + 1u;
+            for (int j0 = 0; j0 < cnt; j0 += 32) {
+                if (__all_sync(0xffffffffu, done)) break;
+                const int jl = j0 + lane;
+                const bool hit = jl < cnt && strip_hit(__float_as_uint(rec[jl].b.w), warp);
+                uint32_t m = __ballot_sync(0xffffffffu, hit);
+                while (m) {
+                    const int j = j0 + __ffs(m) - 1;
+                    m &= m - 1;
+                    const float4 a = rec[j].a;
+                    const float4 bb = rec[j].b;
+                    const float dx = a.x - fpx, dy = a.y - fpy;
+                    const float power = -0.5f * (a.z * dx * dx + bb.x * dy * dy) - a.w * dx * dy;
+                    float alpha = fminf(kAlphaCap, bb.y * fast_exp(power));
+                    alpha = hier_alpha<HIER>(alpha, bb.z, __float_as_uint(bb.w));
+                    const float test_T = T * (1.0f - alpha);
+                    bool valid = !done && power <= 0.0f && alpha >= kAlphaSkip;
+                    if (valid && test_T < kTStop) { done = true; valid = false; }
+                    if (valid) {
+                        const float4 c = rec[j].c;
+                        const float w = alpha * T;
+                        C0 += c.x * w; C1 += c.y * w; C2 += c.z * w;
+                        if (DEPTH) invd += c.w * w;
+                        T = test_T;
+                        last = base + (uint32_t)j + 1u;
+                    }
                 }
             }
         }
