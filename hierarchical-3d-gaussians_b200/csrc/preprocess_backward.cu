@@ -277,8 +277,19 @@ preprocess_backward_kernel(int P, int deg, int M, const float* __restrict__ mean
         }
 #undef S
 #undef DS
-        if (ridx) {
-            // only the active coefficients carry gradient; the rest of the row stays zero
+        if (ridx && (SH3 & 3) == 0) {
+            // 128-bit vector reductions (red.global.add.v4.f32, sm_90+): 12 per 192-B SH row instead
+            // of 48 scalar ones; only the active coefficients carry gradient, the rest stays zero
+#pragma unroll
+            for (int k = 0; k < 12; k++)
+                if (4 * k < 3 * ncoef) {
+                    atomicAdd(reinterpret_cast<float4*>(dL_dsh + (size_t)c * SH3) + k,
+                              make_float4(t * out[4 * k], t * out[4 * k + 1], t * out[4 * k + 2], t * out[4 * k + 3]));
+                    if (lerp)
+                        atomicAdd(reinterpret_cast<float4*>(dL_dsh + (size_t)p * SH3) + k,
+                                  make_float4(u * out[4 * k], u * out[4 * k + 1], u * out[4 * k + 2], u * out[4 * k + 3]));
+                }
+        } else if (ridx) {
 #pragma unroll
             for (int k = 0; k < 48; k++)
                 if (k < 3 * ncoef) {
@@ -329,12 +340,10 @@ preprocess_backward_kernel(int P, int deg, int M, const float* __restrict__ mean
         dq.w = (float)(2 * qr * (dR[1][0] - dR[0][1]) + 2 * qx * (dR[0][2] + dR[2][0]) + 2 * qy * (dR[1][2] + dR[2][1]) - 4 * qz * (dR[0][0] + dR[1][1]));
         if (!ridx) *reinterpret_cast<float4*>(dL_drots + 4 * i) = dq;
         else {
-            atomicAdd(dL_drots + 4 * (size_t)c + 0, t * dq.x); atomicAdd(dL_drots + 4 * (size_t)c + 1, t * dq.y);
-            atomicAdd(dL_drots + 4 * (size_t)c + 2, t * dq.z); atomicAdd(dL_drots + 4 * (size_t)c + 3, t * dq.w);
+            atomicAdd(reinterpret_cast<float4*>(dL_drots) + c, make_float4(t * dq.x, t * dq.y, t * dq.z, t * dq.w));
             if (lerp) {
                 const float us = u * qsign;
-                atomicAdd(dL_drots + 4 * (size_t)p + 0, us * dq.x); atomicAdd(dL_drots + 4 * (size_t)p + 1, us * dq.y);
-                atomicAdd(dL_drots + 4 * (size_t)p + 2, us * dq.z); atomicAdd(dL_drots + 4 * (size_t)p + 3, us * dq.w);
+                atomicAdd(reinterpret_cast<float4*>(dL_drots) + p, make_float4(us * dq.x, us * dq.y, us * dq.z, us * dq.w));
             }
         }
         if (dL_dcov3D) {

@@ -1,0 +1,65 @@
+"""GPU (needs >= 2 devices; skipped otherwise): the tile-sharded step over NCCL reproduces the
+single-GPU step -- image bit-identical (same per-tile order), gradients to fp32 sum order."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, out):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "hierarchical-3d-gaussians_b200")); sys.path.insert(0, os.path.join(root, "tests"))
+    import torch
+    import torch.distributed as dist
+    from h3dgs import synth, pipeline, dist as hd
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = f"cuda:{rank}"
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    cam = synth.make_camera(640, 360)
+    leaves = synth.cloud_v1(20000, cam, zmin=2.0, zmax=40.0, seed=3, scale_k=1.0)
+    z = leaves["means3D"][:, 2:3]
+    leaves["scales"] = (5e-3 * np.sqrt(2.0 * z) * np.ones((1, 3))).astype(np.float32)
+    h = synth.build_hierarchy(leaves)
+    thr = synth.tau_threshold(6.0, cam)
+    scene = pipeline.Scene(h, device=dev)
+    dcam = pipeline.DeviceCamera(cam, device=dev)
+    bg = torch.tensor([0.1, 0.2, 0.3], device=dev)
+    gt = torch.rand((3, cam.H, cam.W), generator=torch.Generator().manual_seed(1)).to(dev)
+    loss1, radii1, n1 = pipeline.l1_step(scene, dcam, bg, gt, thr)
+    g1 = [p.grad.clone() for p in scene.params()]
+    with torch.no_grad():
+        img1 = pipeline.render_hier_fused(scene, dcam, bg, thr)[0]
+    sh = hd.TileSharder(world, rank, dev)
+    loss2, radii2, n2 = sh.l1_step(scene, dcam, bg, gt, thr)
+    g2 = [p.grad.clone() for p in scene.params()]
+    with torch.no_grad():
+        img2 = sh.render(scene, dcam, bg, thr)[0]
+    ok = n1 == n2 and torch.equal(radii1, radii2) and torch.equal(img1, img2) and abs(loss1.item() - loss2.item()) < 1e-7
+    errs = [float((a - b).abs().max() / a.abs().max().clamp_min(1e-30)) for a, b in zip(g1, g2)]
+    ok = ok and max(errs) < 1e-5
+    res = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(res, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        torch.save((bool(res.item() == 1.0), errs), out)
+    dist.barrier(); dist.destroy_process_group()
+
+
+def test_tile_sharded_step_equals_single_gpu(tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = min(torch.cuda.device_count(), 4)
+    out = str(tmp_path / "r.pt")
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    ok, errs = torch.load(out)
+    assert ok, errs
