@@ -64,7 +64,10 @@ preprocess_backward_kernel(int P, int deg, int M, const float* __restrict__ mean
 
     const float* v = s_view;
     const float* ac = accum + (size_t)i * kAccum;
-    const float g_mx = ac[0], g_my = ac[1], dcx = ac[2], dcy = ac[3], dcz = ac[4], g_op = ac[5];
+    // the per-tile replay leaves its constant factors to us: d(pixel)/d(ndc) = 0.5 W, 0.5 H and the
+    // -1/2 of the quadratic form
+    const float g_mx = ac[0] * (0.5f * W), g_my = ac[1] * (0.5f * H);
+    const float dcx = -0.5f * ac[2], dcy = -0.5f * ac[3], dcz = -0.5f * ac[4], g_op = ac[5];
     const float g_r = ac[6], g_g = ac[7], g_b = ac[8], g_iv = ac[9];
     // gather + parent lerp exactly as the forward did (preprocess.cu)
     int c = i, p = i;

@@ -112,9 +112,7 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
     }
     const float bg_dot = bg[0] * g0 + bg[1] * g1 + bg[2] * g2;
     const int wlast = (int)__reduce_max_sync(0xffffffffu, (unsigned)last);   // nothing in this strip beyond it
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, accd = 0.f;       // accum_rec
-    float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, lcd = 0.f, last_alpha = 0.f;
-    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+    float acc_s = 0.f, last_cg = 0.f, last_alpha = 0.f;          // (accum_rec . g), (last colour . g)
 
     for (int it = 0; it < nb; it++) {
         const int st = it % kBwdStages, b = nb - 1 - it;
@@ -134,53 +132,48 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
             const int e = b * kBwdBatch + j;              // 0-based list position; contributor number e+1
             const float4 bb = rec[j].b;
             const uint32_t kb = __float_as_uint(bb.w);
-            float v[10];
-#pragma unroll
-            for (int k = 0; k < 10; k++) v[k] = 0.f;
-            bool active = false;
+            // decisions exactly as the forward took them; everything after is branch-free so that
+            // invalid lanes contribute exact zeros (masked G / weights), no per-value predication
+            float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f, dadb = 1.f;
+            bool valid = false;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
             if (e < last) {
-                const float4 a = rec[j].a;
-                const float dx = a.x - fpx, dy = a.y - fpy;
+                a = rec[j].a;
+                dx = a.x - fpx; dy = a.y - fpy;
                 const float power = -0.5f * (a.z * dx * dx + bb.x * dy * dy) - a.w * dx * dy;
                 if (power <= 0.0f) {
-                    const float G = fast_exp(power);
+                    G = fast_exp(power);
                     const float abase = fminf(kAlphaCap, bb.y * G);
-                    float alpha, dadb;
                     hier_alpha_grad<HIER>(abase, bb.z, kb, alpha, dadb);
-                    if (alpha >= kAlphaSkip) {
-                        active = true;
-                        const float4 c = rec[j].c;
-                        const float rcp = __frcp_rn(1.f - alpha);     // one reciprocal serves T and the bg term
-                        T = T * rcp;
-                        const float dchannel_dcolor = alpha * T;
-                        float dL_dalpha = 0.f;
-                        acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0; lc0 = c.x; dL_dalpha += (c.x - acc0) * g0;
-                        acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1; lc1 = c.y; dL_dalpha += (c.y - acc1) * g1;
-                        acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2; lc2 = c.z; dL_dalpha += (c.z - acc2) * g2;
-                        v[6] = dchannel_dcolor * g0; v[7] = dchannel_dcolor * g1; v[8] = dchannel_dcolor * g2;
-                        if (DEPTH) {
-                            accd = last_alpha * lcd + (1.f - last_alpha) * accd; lcd = c.w;
-                            dL_dalpha += (c.w - accd) * gd;
-                            v[9] = dchannel_dcolor * gd;
-                        }
-                        dL_dalpha *= T;
-                        last_alpha = alpha;
-                        dL_dalpha += (-T_final * rcp) * bg_dot;
-                        const float dL_dab = dL_dalpha * dadb;
-                        const float dL_dG = bb.y * dL_dab;
-                        const float gdx = G * dx, gdy = G * dy;
-                        const float dG_ddelx = -gdx * a.z - gdy * a.w;
-                        const float dG_ddely = -gdy * bb.x - gdx * a.w;
-                        v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                        v[1] = dL_dG * dG_ddely * ddely_dy;
-                        v[2] = -0.5f * gdx * dx * dL_dG;
-                        v[3] = -0.5f * gdx * dy * dL_dG;
-                        v[4] = -0.5f * gdy * dy * dL_dG;
-                        v[5] = G * dL_dab;
-                    }
+                    valid = alpha >= kAlphaSkip;
                 }
             }
-            if (__any_sync(0xffffffffu, active)) {
+            if (!__any_sync(0xffffffffu, valid)) continue;            // warp-uniform
+            if (!valid) { G = 0.f; alpha = 0.f; }
+            const float4 c = rec[j].c;
+            // scalar form of the accum_rec recurrence: only (accum_rec . g) is ever needed
+            float cg = c.x * g0 + c.y * g1 + c.z * g2;
+            if (DEPTH) cg += c.w * gd;
+            const float rcp = __frcp_rn(1.f - alpha);                 // one reciprocal serves T and the bg term
+            const float Tn = T * rcp;
+            const float as_n = last_alpha * last_cg + (1.f - last_alpha) * acc_s;
+            const float w = valid ? alpha * Tn : 0.f;                 // dchannel_dcolor
+            const float dL_dalpha = (cg - as_n) * Tn - (T_final * rcp) * bg_dot;
+            const float dL_dab = valid ? dL_dalpha * dadb : 0.f;
+            if (valid) { T = Tn; acc_s = as_n; last_cg = cg; last_alpha = alpha; }
+            const float dL_dG = bb.y * dL_dab;
+            const float gdx = G * dx, gdy = G * dy;
+            float v[10];
+            // constant factors (0.5 W, 0.5 H, -0.5) are applied once per Gaussian in preprocess_backward
+            v[0] = dL_dG * (-gdx * a.z - gdy * a.w);
+            v[1] = dL_dG * (-gdy * bb.x - gdx * a.w);
+            v[2] = gdx * dx * dL_dG;
+            v[3] = gdx * dy * dL_dG;
+            v[4] = gdy * dy * dL_dG;
+            v[5] = G * dL_dab;
+            v[6] = w * g0; v[7] = w * g1; v[8] = w * g2;
+            v[9] = DEPTH ? w * gd : 0.f;
+            {
                 const float total = transpose_reduce10(v, lane);
                 if (slot >= 0 && (DEPTH || slot < 9))
                     atomicAdd(accum + (size_t)s_id[st][j] * kAccum + slot, total);
