@@ -172,6 +172,7 @@ def cpu_step_fn(arrays, cams, frac):
 
 def run_cpu_arm(arrays, cams, steps, warmup, frac, budget_s=25.0):
     from oracle import oracle
+    oracle.set_threads(os.cpu_count() or 1)          # torchrun exports OMP_NUM_THREADS=1
     step = cpu_step_fn(arrays, cams, frac)
     for i in range(warmup):
         step(i)
@@ -187,6 +188,53 @@ def run_cpu_arm(arrays, cams, steps, warmup, frac, budget_s=25.0):
     return dict(ms_per_sample_step=dt * 1e3, value=1.0 / (dt * frac), steps_run=done, cores=oracle.num_threads())
 
 
+def time_classic(scene, cam, bg, thr, hier, stage_ms, iters=10):
+    """Times baseline/classic/libclassic.so (one index gather per thread per round, one pixel per
+    thread, one global atomic per pixel per gradient value -- the formulation of the 3DGS paper; the
+    reference's own kernels are absent) on the SAME binned state as our blend kernels."""
+    import ctypes as C
+    import torch
+    from h3dgs import pipeline
+    from diff_gaussian_rasterization import _C as rc
+    lib = C.CDLL(os.path.join(ROOT, "baseline", "classic", "libclassic.so"))
+    with torch.no_grad():
+        if hier:
+            n = pipeline.lod_cut(scene, cam, thr)
+            m, s, r, o, sh = pipeline.interpolate_cut(scene, n)
+        else:
+            m, s, r, o, sh = scene.means3D, scene.scales, scene.rotations, scene.opacities, scene.shs
+            n = m.shape[0]
+        D, color, radii, gb, bb, ib, _ = rc.rasterize_gaussians(bg, m, None, o, s, r, 1.0, None, cam.viewmatrix,
+                                                                cam.projmatrix, cam.tanfovx, cam.tanfovy, cam.H, cam.W,
+                                                                sh, 3, cam.campos, False, False)
+        sv = rc.state_view(n, cam.W, cam.H, D, gb, bb, ib)
+        ptr = lambda t: C.c_void_p(t.data_ptr())
+        out = torch.empty_like(color); fT = torch.empty((cam.H, cam.W), device=color.device)
+        nc = torch.empty((cam.H, cam.W), dtype=torch.int32, device=color.device)
+        g = torch.sign(color - torch.rand_like(color)) / color.numel()
+        accum = torch.zeros((n, 10), device=color.device)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        fwd = lambda: lib.classic_render_forward(cam.W, cam.H, ptr(sv["ranges"]), ptr(sv["point_list"]), ptr(sv["records"]),
+                                                 ptr(bg), ptr(out), ptr(fT), ptr(nc), st)
+        bwd = lambda: lib.classic_render_backward(cam.W, cam.H, ptr(sv["ranges"]), ptr(sv["point_list"]), ptr(sv["records"]),
+                                                  ptr(bg), ptr(fT), ptr(nc), ptr(g), ptr(accum), st)
+        res = {}
+        for name, fn in (("render_forward", fwd), ("render_backward", bwd)):
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            res[name + "_ms"] = e0.elapsed_time(e1) / iters
+        res["image_max_abs_diff_vs_ours"] = float((out - color).abs().max().item())
+        res["ours_ms"] = {k: stage_ms.get(k) for k in ("render_forward", "render_backward", "gather_records")}
+        res["note"] = ("classic = stand-in for the absent reference kernels (paper formulation, flat alpha, no "
+                       "hierarchy weight); ours includes the record materialisation (gather_records) it relies on")
+    return res
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -197,6 +245,8 @@ def main():
     ap.add_argument("--workload", default="hier3m", choices=["hier3m", "flat1m", "tiny"])
     ap.add_argument("--cpu-frac", type=int, default=16, help="CPU arm renders every k-th cut Gaussian")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--classic", action="store_true",
+                    help="also time the classic-formulation blend kernels (baseline/classic) on the same binned state")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -358,6 +408,8 @@ def main():
                                        "see profiles/ for the ncu pipe utilisation"}
             out["step_roofline"] = {"alg_bytes_per_image": ab["total"], "achieved_gbs": ab["total"] / (ms_step * 1e-3) / 1e9,
                                     "frac_of_hbm_peak": ab["total"] / (ms_step * 1e-3) / 1e9 / peak}
+        if world == 1 and args.classic:
+            out["classic_blend"] = time_classic(scene, dcams[0], bg, thr[0] if hier else None, hier, stage_ms)
         if world == 1 and not args.no_cpu_baseline:
             r = run_cpu_arm(arrays, cams, 2, 0, args.cpu_frac, budget_s=25.0)
             out["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",

@@ -715,6 +715,15 @@ void oracle_interpolation_weights(int n, const int* node_indices, float target, 
     }
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU legs of bench.py ask for all host cores explicitly */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
