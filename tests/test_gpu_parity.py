@@ -153,3 +153,60 @@ def test_mark_visible():
     rs = cuda_settings(cam, bg)
     vis = GaussianRasterizer(rs).markVisible(torch.tensor(sc["means3D"], device="cuda")).cpu().numpy()
     assert np.array_equal(vis, sc["means3D"][:, 2] > 0.2)      # identity view matrix
+
+
+@pytest.mark.parametrize("W,H", [(8, 8), (15, 33), (3840, 2160)])
+def test_odd_and_large_image_sizes(W, H):
+    """Images smaller than one tile, ragged borders, and a 4K frame (32 400 tiles)."""
+    P = 400 if W < 100 else 60000
+    cam, sc, ts, kids, bg = make_scene(P, W, H, seed=13, scale_k=6e-3 if W < 100 else 1.5e-3)
+    f, b, gcol, gdep = oracle_run(cam, sc, bg)
+    out, g, st = cuda_run(cam, sc, bg, gcol, gdep)
+    check_integer_artefacts(f, out, st)
+    check_image(f, out, st)
+    check_grads(b, g, ["means3D", "means2D", "sh", "opacities", "scales", "rotations"])
+
+
+def test_hierarchy_weight_with_depth_and_opacity_above_one():
+    """hierarchy mode + inverse depth together; abs-activation opacities up to 1.4 (alpha cap 0.99 active)."""
+    cam, sc, ts, kids, bg = make_scene(3000, 200, 150, mode="hier", seed=14)
+    assert sc["opacities"].max() > 1.0
+    f, b, gcol, gdep = oracle_run(cam, sc, bg, ts, kids, do_depth=True)
+    out, g, st = cuda_run(cam, sc, bg, gcol, gdep, ts, kids, do_depth=True)
+    check_integer_artefacts(f, out, st)
+    check_image(f, out, st, do_depth=True)
+    check_grads(b, g, ["means3D", "means2D", "sh", "opacities", "scales", "rotations"])
+
+
+def test_equal_depths_keep_index_order():
+    """Ties in the depth key must come out in Gaussian-index order (stable sort + in-order emission)."""
+    cam, sc, ts, kids, bg = make_scene(2000, 160, 120, seed=15)
+    sc["means3D"][:, 2] = np.float32(5.0)            # identical view-space depth for every Gaussian
+    f, b, gcol, gdep = oracle_run(cam, sc, bg)
+    out, g, st = cuda_run(cam, sc, bg, gcol, gdep)
+    check_integer_artefacts(f, out, st)
+    pl = st["point_list"]; keys = st["keys_sorted"].view(np.uint64)
+    same_tile = (keys[1:] >> np.uint64(32)) == (keys[:-1] >> np.uint64(32))
+    assert (pl[1:][same_tile] > pl[:-1][same_tile]).all()
+    check_image(f, out, st)
+
+
+def test_debug_flag_and_error_reporting():
+    import torch
+    from diff_gaussian_rasterization import _C
+    from h3dgs import _lib
+    from util import cuda_settings
+    cam, sc, ts, kids, bg = make_scene(500, 64, 48, seed=16)
+    f, b, gcol, gdep = oracle_run(cam, sc, bg, backward=False)
+    rs = cuda_settings(cam, bg, debug=True)
+    t = lambda a: torch.tensor(a, device="cuda")
+    n, color, radii, *_ = _C.rasterize_gaussians(rs.bg, t(sc["means3D"]), None, t(sc["opacities"]), t(sc["scales"]),
+                                                 t(sc["rotations"]), 1.0, None, rs.viewmatrix, rs.projmatrix, rs.tanfovx,
+                                                 rs.tanfovy, cam.H, cam.W, t(sc["shs"]), 3, rs.campos, False, True)
+    assert n == f["num_rendered"]
+    # a bad argument combination comes back as an exception carrying the library's message, not a crash
+    with pytest.raises(RuntimeError, match="sh_degree"):
+        _C.rasterize_gaussians(rs.bg, t(sc["means3D"]), None, t(sc["opacities"]), t(sc["scales"]), t(sc["rotations"]), 1.0,
+                               None, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, cam.H, cam.W,
+                               t(sc["shs"][:, :4].copy()), 3, rs.campos, False, False)
+    assert _lib.launch_count() > 0
