@@ -136,12 +136,17 @@ __device__ __forceinline__ void hier_alpha_grad(float a, float t, uint32_t kbits
     if (!HIER) return;
     const uint32_t k = kbits & kKidsMask;
     if (k <= 1u || t >= 1.0f) return;
-    // (1-a)^(1/k) through MUFU.LG2 / MUFU.EX2: 1-a is in [0.01, 1], where lg2.approx is
-    // accurate to ~2^-22 absolute, i.e. ~2e-7 relative on the root
+    // 1 - (1-a)^(1/k) = -expm1(log1p(-a)/k).  Near the 1/255 skip threshold a is small and the
+    // direct form cancels catastrophically (abs error ~2e-7 on a value ~4e-3 moves the skip
+    // decision for 100x more pixels than in flat mode), so small a uses the two series
+    // (relative error < 1e-7); larger a goes through MUFU.LG2 / MUFU.EX2.
     const float ik = __frcp_rn((float)k);
     const float l2 = __log2f(1.0f - a);
-    const float root = fast_exp2(l2 * ik);
-    alpha = t * a + (1.0f - t) * (1.0f - root);
+    const float L = -a * (1.0f + a * (0.5f + a * (0.33333334f + a * (0.25f + a * 0.2f))));
+    const float y = L * ik;
+    const float omr_series = -y * (1.0f + y * (0.5f + y * (0.16666667f + y * 0.041666668f)));
+    const float omr = a < 0.0625f ? omr_series : 1.0f - fast_exp2(l2 * ik);
+    alpha = t * a + (1.0f - t) * omr;
     dadb = t + (1.0f - t) * ik * fast_exp2(l2 * (ik - 1.0f));
 }
 template <bool HIER>

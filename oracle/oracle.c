@@ -283,7 +283,9 @@ long oracle_bin(int P, int W, int H, const float* depths, const int* radii, cons
  * rows of gaussian_renderer/__init__.py:232-234 rely on that). */
 static inline float hier_alpha(float a, float t, int k) {
     if (k <= 1 || t >= 1.0f) return a;
-    return t * a + (1.0f - t) * (1.0f - powf(1.0f - a, 1.0f / (float)k));
+    /* 1 - (1-a)^(1/k) evaluated as -expm1(log1p(-a)/k): the direct form cancels for the small a
+     * that sit at the 1/255 skip threshold and would make the skip decision itself noisy */
+    return t * a + (1.0f - t) * (-expm1f(log1pf(-a) / (float)k));
 }
 static inline float hier_dalpha(float a, float t, int k) {
     if (k <= 1 || t >= 1.0f) return 1.0f;

@@ -7,7 +7,7 @@ the published algorithm (oracle/oracle.c)."""
 import numpy as np
 import pytest
 
-from util import make_scene, oracle_run, cuda_run, rel_err
+from util import make_scene, oracle_run, cuda_run, rel_err, assert_image_close
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
@@ -30,12 +30,12 @@ def check_integer_artefacts(f, out, st):
 
 
 def check_image(f, out, st, do_depth=False):
-    assert rel_err(out["color"], f["color"]) < TOL
+    assert_image_close(out["color"], f["color"])
     assert np.abs(st["final_T"] - f["final_T"]).max() < 1e-5
     # n_contrib depends on exp(): allow a vanishing fraction of threshold flips
     assert (st["n_contrib"].astype(np.uint32) != f["n_contrib"]).mean() < 2e-3
     if do_depth:
-        assert rel_err(out["invdepth"], f["invdepth"]) < TOL
+        assert_image_close(out["invdepth"], f["invdepth"], "invdepth")
 
 
 def check_grads(b, g, names):

@@ -98,3 +98,21 @@ def rel_err(a, b):
     """norm-wise relative error max|a-b| / max|b|"""
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+TOL = 1e-5
+
+
+def assert_image_close(a, b, what="color"):
+    """1e-5 relative (norm-wise) on every pixel, except that an alpha landing within fp32 rounding of
+    the 1/255 skip threshold may flip one contribution (<= 1/255 * T * c): such pixels must be
+    vanishingly rare (< 1e-5 of all pixels) and bounded by 1.5/255."""
+    d = np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64))
+    scale = max(np.abs(b).max(), 1e-30)
+    bad = d > TOL * scale
+    assert bad.mean() < 1e-5, (what, float(bad.mean()), float(d.max()))
+    assert d.max() < 1.5 / 255 * max(scale, 1.0), (what, float(d.max()))
+    if a.size < 200000:                       # small images: no flip expected at all
+        assert not bad.any(), (what, float(d.max() / scale))
+
+
