@@ -31,7 +31,7 @@ def check_integer_artefacts(f, out, st):
 
 def check_image(f, out, st, do_depth=False):
     assert_image_close(out["color"], f["color"])
-    assert np.abs(st["final_T"] - f["final_T"]).max() < 1e-5
+    assert_image_close(st["final_T"], f["final_T"], "final_T")
     # n_contrib depends on exp(): allow a vanishing fraction of threshold flips
     assert (st["n_contrib"].astype(np.uint32) != f["n_contrib"]).mean() < 2e-3
     if do_depth:
