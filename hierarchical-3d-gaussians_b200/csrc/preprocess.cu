@@ -40,20 +40,19 @@ __device__ __forceinline__ void load_sh(const float* __restrict__ p, int row_flo
 }
 
 __global__ void __launch_bounds__(256)
-preprocess_kernel(int P, int deg, int M, const float* __restrict__ means3D, const float* __restrict__ scales,
+preprocess_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ scales,
                   float scale_mod, const float* __restrict__ rots, const float* __restrict__ opacities,
-                  const float* __restrict__ shs, const float* __restrict__ cov3D_precomp,
+                  const float* __restrict__ cov3D_precomp,
                   const float* __restrict__ colors_precomp, const float* __restrict__ ts,
                   const int* __restrict__ kids, const int* __restrict__ ridx, const int* __restrict__ pidx,
                   const float* __restrict__ view, const float* __restrict__ proj,
-                  const float* __restrict__ campos, int W, int H, float tanx, float tany, float fx, float fy,
+                  int W, int H, float tanx, float tany, float fx, float fy,
                   int shard_count, int shard_index,
                   int* __restrict__ radii, float* __restrict__ depths, uint32_t* __restrict__ tiles_touched,
                   Record* __restrict__ records)
 {
-    __shared__ float s_view[16], s_proj[16], s_cam[3];
+    __shared__ float s_view[16], s_proj[16];
     if (threadIdx.x < 16) { s_view[threadIdx.x] = view[threadIdx.x]; s_proj[threadIdx.x] = proj[threadIdx.x]; }
-    if (threadIdx.x < 3) s_cam[threadIdx.x] = campos[threadIdx.x];
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
@@ -158,48 +157,12 @@ preprocess_kernel(int P, int deg, int M, const float* __restrict__ means3D, cons
             const int rmaxy = min(gy, max(0, (int)((iy + rad + kTile - 1) / kTile)));
             const int area = (rmaxx - rminx) * (rmaxy - rminy);
             if (area != 0) {
-                float rgb[3];
-                uint32_t clampbits = 0;
+                // colour: precomputed colours are copied here; SH colours are filled in by
+                // preprocess_color_kernel (separate launch: keeps this kernel at high occupancy)
+                float rgb[3] = {0.f, 0.f, 0.f};
+                const uint32_t clampbits = 0;
                 if (colors_precomp) {
                     rgb[0] = colors_precomp[3 * c]; rgb[1] = colors_precomp[3 * c + 1]; rgb[2] = colors_precomp[3 * c + 2];
-                } else {
-                    float dx = px_ - s_cam[0], dy = py_ - s_cam[1], dz = pz_ - s_cam[2];
-                    const float len = sqrtf(dx * dx + dy * dy + dz * dz);
-                    dx /= len; dy /= len; dz /= len;
-                    const float x = dx, y = dy, z = dz;
-                    float c_[48];
-                    const int need = 3 * (deg + 1) * (deg + 1);
-                    load_sh<48>(shs + (size_t)c * M * 3, M * 3, need, c_);
-                    if (lerp) {
-                        float cp[48];
-                        load_sh<48>(shs + (size_t)p * M * 3, M * 3, need, cp);
-#pragma unroll
-                        for (int k = 0; k < 48; k++) if (k < need) c_[k] = t * c_[k] + u * cp[k];
-                    }
-#pragma unroll
-                    for (int ch = 0; ch < 3; ch++) {
-#define S(k) c_[(k) * 3 + ch]
-                        float r = kSH_C0 * S(0);
-                        if (deg > 0) {
-                            r = r - kSH_C1 * y * S(1) + kSH_C1 * z * S(2) - kSH_C1 * x * S(3);
-                            if (deg > 1) {
-                                const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-                                r = r + kSH_C2[0] * xy * S(4) + kSH_C2[1] * yz * S(5) + kSH_C2[2] * (2.0f * zz - xx - yy) * S(6)
-                                      + kSH_C2[3] * xz * S(7) + kSH_C2[4] * (xx - yy) * S(8);
-                                if (deg > 2) {
-                                    r = r + kSH_C3[0] * y * (3.0f * xx - yy) * S(9) + kSH_C3[1] * xy * z * S(10)
-                                          + kSH_C3[2] * y * (4.0f * zz - xx - yy) * S(11)
-                                          + kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * S(12)
-                                          + kSH_C3[4] * x * (4.0f * zz - xx - yy) * S(13)
-                                          + kSH_C3[5] * z * (xx - yy) * S(14) + kSH_C3[6] * x * (xx - 3.0f * yy) * S(15);
-                                }
-                            }
-                        }
-#undef S
-                        r += 0.5f;
-                        if (r < 0.f) clampbits |= (1u << (kClampShift + ch));
-                        rgb[ch] = fmaxf(r, 0.f);
-                    }
                 }
                 Record rec;
                 rec.a = make_float4(ix, iy, conx, cony);
@@ -222,6 +185,88 @@ preprocess_kernel(int P, int deg, int M, const float* __restrict__ means3D, cons
     tiles_touched[i] = out_tiles;
 }
 
+// K1b: SH -> RGB for the visible Gaussians only (192 B/row, x2 on lerped rows): reads the same
+// (lerped) mean as K1a, writes record.c.xyz and the three SH clamp flags.
+__global__ void __launch_bounds__(256)
+preprocess_color_kernel(int P, int deg, int M, const float* __restrict__ means3D, const float* __restrict__ shs,
+                        const float* __restrict__ ts, const int* __restrict__ ridx, const int* __restrict__ pidx,
+                        const float* __restrict__ campos, const int* __restrict__ radii, Record* __restrict__ records)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    if (radii[i] <= 0) return;
+    int c = i, p = i;
+    float t = 1.0f, u = 0.0f;
+    if (ridx) {
+        c = ridx[i]; p = pidx[i]; if (p < 0) p = c;
+        t = ts[i]; u = 1.0f - t;
+    }
+    const bool lerp = ridx != nullptr && u != 0.0f;
+#define LERP(a, b) (lerp ? (t * (a) + u * (b)) : (a))
+    const int need = 3 * (deg + 1) * (deg + 1);
+    float c_[48];
+    {
+        const float* pc = shs + (size_t)c * M * 3;
+        const float* pp = shs + (size_t)p * M * 3;
+        if (((M * 3) & 3) == 0) {
+#pragma unroll
+            for (int k = 0; k < 12; k++)
+                if (4 * k < need) {
+                    float4 v = __ldg(reinterpret_cast<const float4*>(pc) + k);
+                    if (lerp) {
+                        const float4 w = __ldg(reinterpret_cast<const float4*>(pp) + k);
+                        v.x = t * v.x + u * w.x; v.y = t * v.y + u * w.y; v.z = t * v.z + u * w.z; v.w = t * v.w + u * w.w;
+                    }
+                    c_[4 * k] = v.x; c_[4 * k + 1] = v.y; c_[4 * k + 2] = v.z; c_[4 * k + 3] = v.w;
+                }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 48; k++)
+                if (k < need) c_[k] = lerp ? t * __ldg(pc + k) + u * __ldg(pp + k) : __ldg(pc + k);
+        }
+    }
+    const float px_ = LERP(means3D[3 * c], means3D[3 * p]);
+    const float py_ = LERP(means3D[3 * c + 1], means3D[3 * p + 1]);
+    const float pz_ = LERP(means3D[3 * c + 2], means3D[3 * p + 2]);
+#undef LERP
+    float dx = px_ - campos[0], dy = py_ - campos[1], dz = pz_ - campos[2];
+    const float len = sqrtf(dx * dx + dy * dy + dz * dz);
+    dx /= len; dy /= len; dz /= len;
+    const float x = dx, y = dy, z = dz;
+    float rgb[3];
+    uint32_t clampbits = 0;
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+#define S(k) c_[(k) * 3 + ch]
+        float r = kSH_C0 * S(0);
+        if (deg > 0) {
+            r = r - kSH_C1 * y * S(1) + kSH_C1 * z * S(2) - kSH_C1 * x * S(3);
+            if (deg > 1) {
+                const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                r = r + kSH_C2[0] * xy * S(4) + kSH_C2[1] * yz * S(5) + kSH_C2[2] * (2.0f * zz - xx - yy) * S(6)
+                      + kSH_C2[3] * xz * S(7) + kSH_C2[4] * (xx - yy) * S(8);
+                if (deg > 2) {
+                    r = r + kSH_C3[0] * y * (3.0f * xx - yy) * S(9) + kSH_C3[1] * xy * z * S(10)
+                          + kSH_C3[2] * y * (4.0f * zz - xx - yy) * S(11)
+                          + kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * S(12)
+                          + kSH_C3[4] * x * (4.0f * zz - xx - yy) * S(13)
+                          + kSH_C3[5] * z * (xx - yy) * S(14) + kSH_C3[6] * x * (xx - 3.0f * yy) * S(15);
+                }
+            }
+        }
+#undef S
+        r += 0.5f;
+        if (r < 0.f) clampbits |= (1u << (kClampShift + ch));
+        rgb[ch] = fmaxf(r, 0.f);
+    }
+    float* rc = reinterpret_cast<float*>(&records[i].c);
+    rc[0] = rgb[0]; rc[1] = rgb[1]; rc[2] = rgb[2];
+    if (clampbits) {
+        uint32_t* kb = reinterpret_cast<uint32_t*>(&records[i].b) + 3;
+        *kb = *kb | clampbits;
+    }
+}
+
 int launch_preprocess(const h3dgs_raster_args& a, int32_t* radii, float* depths, uint32_t* tiles_touched,
                       Record* records, cudaStream_t s)
 {
@@ -229,17 +274,21 @@ int launch_preprocess(const h3dgs_raster_args& a, int32_t* radii, float* depths,
     const float fx = a.image_width / (2.0f * a.tanfovx), fy = a.image_height / (2.0f * a.tanfovy);
     const int threads = 256, blocks = (a.P + threads - 1) / threads;
     ProfScope prof(H3DGS_STAGE_PREPROCESS, s);
-    preprocess_kernel<<<blocks, threads, 0, s>>>(a.P, a.sh_degree, a.sh_coeffs, a.means3D, a.scales, a.scale_modifier,
-                                                 a.rotations, a.opacities, a.shs, a.cov3D_precomp, a.colors_precomp,
-                                                 a.interpolation_weights, a.num_node_kids, a.render_indices, a.parent_indices,
-                                                 a.viewmatrix, a.projmatrix,
-                                                 a.campos, a.image_width, a.image_height, a.tanfovx, a.tanfovy, fx, fy,
+    preprocess_kernel<<<blocks, threads, 0, s>>>(a.P, a.means3D, a.scales, a.scale_modifier, a.rotations, a.opacities,
+                                                 a.cov3D_precomp, a.colors_precomp, a.interpolation_weights,
+                                                 a.num_node_kids, a.render_indices, a.parent_indices, a.viewmatrix,
+                                                 a.projmatrix, a.image_width, a.image_height, a.tanfovx, a.tanfovy, fx, fy,
                                                  a.shard_count > 0 ? a.shard_count : 1, a.shard_count > 0 ? a.shard_index : 0,
                                                  radii, depths, tiles_touched, records);
     H3_LAUNCHED("preprocess", a.debug, s);
+    if (!a.colors_precomp) {
+        preprocess_color_kernel<<<blocks, threads, 0, s>>>(a.P, a.sh_degree, a.sh_coeffs, a.means3D, a.shs,
+                                                           a.interpolation_weights, a.render_indices, a.parent_indices,
+                                                           a.campos, radii, records);
+        H3_LAUNCHED("preprocess_color", a.debug, s);
+    }
     return H3DGS_OK;
 }
-
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
                                     uint8_t* __restrict__ present)
 {

@@ -7,7 +7,9 @@
 // DFMA per Gaussian are free in an HBM-bound stream.  One thread per Gaussian; a pure HBM
 // stream: reads 40 B accum + 44 B params + 192 B SH, writes 248 B of gradients.
 // Every output row is written (zeros for culled Gaussians) so the caller never
-// pays a separate memset pass over the gradient tensors.
+// pays a separate memset pass over the gradient tensors.  Two launches -- the fp64 covariance
+// chain (preprocess_backward_kernel) and the SH part (sh_backward_kernel) -- because fused they
+// needed 189 registers (11 % warp occupancy, latency-bound at a third of the DRAM roofline).
 #include "common.cuh"
 
 namespace h3dgs {
@@ -24,7 +26,7 @@ __device__ __forceinline__ void store_zero(float* p, int n) {
     for (int k = 0; k < n; k++) p[k] = 0.f;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 preprocess_backward_kernel(int P, int deg, int M, const float* __restrict__ means3D, const float* __restrict__ scales,
                            float scale_mod, const float* __restrict__ rots, const float* __restrict__ shs,
                            const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp,
@@ -37,24 +39,17 @@ preprocess_backward_kernel(int P, int deg, int M, const float* __restrict__ mean
                            float* __restrict__ dL_dopacities, float* __restrict__ dL_dscales,
                            float* __restrict__ dL_drots, float* __restrict__ dL_dcov3D)
 {
-    __shared__ float s_view[16], s_proj[16], s_cam[3];
+    __shared__ float s_view[16], s_proj[16];
     if (threadIdx.x < 16) { s_view[threadIdx.x] = view[threadIdx.x]; s_proj[threadIdx.x] = proj[threadIdx.x]; }
-    if (threadIdx.x < 3) s_cam[threadIdx.x] = campos[threadIdx.x];
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
-    const int SH3 = M * 3;
 
     if (radii[i] <= 0) {
         store_zero(dL_dmeans2D + 3 * i, 3);
         if (ridx) return;                    // scatter mode: full-size gradients are pre-zeroed
         store_zero(dL_dmeans3D + 3 * i, 3);
         dL_dopacities[i] = 0.f;
-        if (dL_dsh) {
-            float* o = dL_dsh + (size_t)i * SH3;
-            if ((SH3 & 3) == 0) { for (int k = 0; k < SH3 / 4; k++) reinterpret_cast<float4*>(o)[k] = make_float4(0, 0, 0, 0); }
-            else store_zero(o, SH3);
-        }
         if (dL_dcolors) store_zero(dL_dcolors + 3 * i, 3);
         if (dL_dscales) store_zero(dL_dscales + 3 * i, 3);
         if (dL_drots) store_zero(dL_drots + 4 * i, 4);
@@ -206,113 +201,8 @@ preprocess_backward_kernel(int P, int deg, int M, const float* __restrict__ mean
     } while (0)
     EMIT(dL_dopacities, 1, 0, g_op);
 
-    // ---- K9b: colour -> SH and view direction ----
-    if (colors_precomp) {
-        if (dL_dcolors) { dL_dcolors[3 * c] = g_r; dL_dcolors[3 * c + 1] = g_g; dL_dcolors[3 * c + 2] = g_b; }
-    } else {
-        const uint32_t kb = __float_as_uint(records[i].b.w);
-        const float dRGB[3] = {(kb >> kClampShift) & 1u ? 0.f : g_r, (kb >> (kClampShift + 1)) & 1u ? 0.f : g_g, (kb >> (kClampShift + 2)) & 1u ? 0.f : g_b};
-        const float d0x = mx - s_cam[0], d0y = my - s_cam[1], d0z = mz - s_cam[2];
-        const float len = sqrtf(d0x * d0x + d0y * d0y + d0z * d0z);
-        const float x = d0x / len, y = d0y / len, z = d0z / len;
-        const float* sh = shs + (size_t)c * SH3;
-        const float* shp = shs + (size_t)p * SH3;
-        float* dsh = dL_dsh + (size_t)i * SH3;
-        float out[48];
-        float ddx = 0.f, ddy = 0.f, ddz = 0.f;
-        const int ncoef = (deg + 1) * (deg + 1);
-        float c_[48];
-        if ((SH3 & 3) == 0) {
-#pragma unroll
-            for (int k = 0; k < 12; k++)
-                if (4 * k < 3 * ncoef) {
-                    float4 t4 = __ldg(reinterpret_cast<const float4*>(sh) + k);
-                    if (lerp) {
-                        const float4 p4 = __ldg(reinterpret_cast<const float4*>(shp) + k);
-                        t4.x = LERP(t4.x, p4.x); t4.y = LERP(t4.y, p4.y); t4.z = LERP(t4.z, p4.z); t4.w = LERP(t4.w, p4.w);
-                    }
-                    c_[4 * k] = t4.x; c_[4 * k + 1] = t4.y; c_[4 * k + 2] = t4.z; c_[4 * k + 3] = t4.w;
-                }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 48; k++) if (k < 3 * ncoef) c_[k] = LERP(__ldg(sh + k), __ldg(shp + k));
-        }
-#pragma unroll
-        for (int k = 0; k < 48; k++) out[k] = 0.f;
-#define S(k, ch) c_[(k) * 3 + (ch)]
-#define DS(k, ch) out[(k) * 3 + (ch)]
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-            const float g = dRGB[ch];
-            float dx_ = 0.f, dy_ = 0.f, dz_ = 0.f;
-            DS(0, ch) = bSH_C0 * g;
-            if (deg > 0) {
-                DS(1, ch) = -bSH_C1 * y * g; DS(2, ch) = bSH_C1 * z * g; DS(3, ch) = -bSH_C1 * x * g;
-                dx_ = -bSH_C1 * S(3, ch); dy_ = -bSH_C1 * S(1, ch); dz_ = bSH_C1 * S(2, ch);
-                if (deg > 1) {
-                    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-                    DS(4, ch) = bSH_C2[0] * xy * g; DS(5, ch) = bSH_C2[1] * yz * g;
-                    DS(6, ch) = bSH_C2[2] * (2.f * zz - xx - yy) * g;
-                    DS(7, ch) = bSH_C2[3] * xz * g; DS(8, ch) = bSH_C2[4] * (xx - yy) * g;
-                    dx_ += bSH_C2[0] * y * S(4, ch) + bSH_C2[2] * 2.f * -x * S(6, ch) + bSH_C2[3] * z * S(7, ch) + bSH_C2[4] * 2.f * x * S(8, ch);
-                    dy_ += bSH_C2[0] * x * S(4, ch) + bSH_C2[1] * z * S(5, ch) + bSH_C2[2] * 2.f * -y * S(6, ch) + bSH_C2[4] * 2.f * -y * S(8, ch);
-                    dz_ += bSH_C2[1] * y * S(5, ch) + bSH_C2[2] * 2.f * 2.f * z * S(6, ch) + bSH_C2[3] * x * S(7, ch);
-                    if (deg > 2) {
-                        DS(9, ch) = bSH_C3[0] * y * (3.f * xx - yy) * g;
-                        DS(10, ch) = bSH_C3[1] * xy * z * g;
-                        DS(11, ch) = bSH_C3[2] * y * (4.f * zz - xx - yy) * g;
-                        DS(12, ch) = bSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy) * g;
-                        DS(13, ch) = bSH_C3[4] * x * (4.f * zz - xx - yy) * g;
-                        DS(14, ch) = bSH_C3[5] * z * (xx - yy) * g;
-                        DS(15, ch) = bSH_C3[6] * x * (xx - 3.f * yy) * g;
-                        dx_ += bSH_C3[0] * S(9, ch) * 3.f * 2.f * xy + bSH_C3[1] * S(10, ch) * yz + bSH_C3[2] * S(11, ch) * -2.f * xy
-                             + bSH_C3[3] * S(12, ch) * -3.f * 2.f * xz + bSH_C3[4] * S(13, ch) * (-3.f * xx + 4.f * zz - yy)
-                             + bSH_C3[5] * S(14, ch) * 2.f * xz + bSH_C3[6] * S(15, ch) * 3.f * (xx - yy);
-                        dy_ += bSH_C3[0] * S(9, ch) * 3.f * (xx - yy) + bSH_C3[1] * S(10, ch) * xz + bSH_C3[2] * S(11, ch) * (-3.f * yy + 4.f * zz - xx)
-                             + bSH_C3[3] * S(12, ch) * -3.f * 2.f * yz + bSH_C3[4] * S(13, ch) * -2.f * xy
-                             + bSH_C3[5] * S(14, ch) * -2.f * yz + bSH_C3[6] * S(15, ch) * -3.f * 2.f * xy;
-                        dz_ += bSH_C3[1] * S(10, ch) * xy + bSH_C3[2] * S(11, ch) * 4.f * 2.f * yz + bSH_C3[3] * S(12, ch) * 3.f * (2.f * zz - xx - yy)
-                             + bSH_C3[4] * S(13, ch) * 4.f * 2.f * xz + bSH_C3[5] * S(14, ch) * (xx - yy);
-                    }
-                }
-            }
-            ddx += dx_ * g; ddy += dy_ * g; ddz += dz_ * g;
-        }
-#undef S
-#undef DS
-        if (ridx && (SH3 & 3) == 0) {
-            // 128-bit vector reductions (red.global.add.v4.f32, sm_90+): 12 per 192-B SH row instead
-            // of 48 scalar ones; only the active coefficients carry gradient, the rest stays zero
-#pragma unroll
-            for (int k = 0; k < 12; k++)
-                if (4 * k < 3 * ncoef) {
-                    atomicAdd(reinterpret_cast<float4*>(dL_dsh + (size_t)c * SH3) + k,
-                              make_float4(t * out[4 * k], t * out[4 * k + 1], t * out[4 * k + 2], t * out[4 * k + 3]));
-                    if (lerp)
-                        atomicAdd(reinterpret_cast<float4*>(dL_dsh + (size_t)p * SH3) + k,
-                                  make_float4(u * out[4 * k], u * out[4 * k + 1], u * out[4 * k + 2], u * out[4 * k + 3]));
-                }
-        } else if (ridx) {
-#pragma unroll
-            for (int k = 0; k < 48; k++)
-                if (k < 3 * ncoef) {
-                    atomicAdd(dL_dsh + (size_t)c * SH3 + k, t * out[k]);
-                    if (lerp) atomicAdd(dL_dsh + (size_t)p * SH3 + k, u * out[k]);
-                }
-        } else if ((SH3 & 3) == 0) {
-#pragma unroll
-            for (int k = 0; k < 12; k++)
-                if (4 * k < SH3) reinterpret_cast<float4*>(dsh)[k] = make_float4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 48; k++) if (k < SH3) dsh[k] = out[k];
-        }
-        const float sum2 = d0x * d0x + d0y * d0y + d0z * d0z;
-        const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
-        dmean[0] += ((sum2 - d0x * d0x) * ddx - d0y * d0x * ddy - d0z * d0x * ddz) * invsum32;
-        dmean[1] += (-d0x * d0y * ddx + (sum2 - d0y * d0y) * ddy - d0z * d0y * ddz) * invsum32;
-        dmean[2] += (-d0x * d0z * ddx - d0y * d0z * ddy + (sum2 - d0z * d0z) * ddz) * invsum32;
-    }
+    // ---- K9b (SH -> coefficients and view direction) lives in sh_backward_kernel ----
+    if (colors_precomp && dL_dcolors) { dL_dcolors[3 * c] = g_r; dL_dcolors[3 * c + 1] = g_g; dL_dcolors[3 * c + 2] = g_b; }
     EMIT(dL_dmeans3D, 3, 0, (float)dmean[0]); EMIT(dL_dmeans3D, 3, 1, (float)dmean[1]); EMIT(dL_dmeans3D, 3, 2, (float)dmean[2]);
 
     // ---- K9c: cov3D -> scale, rotation ----
@@ -358,6 +248,148 @@ preprocess_backward_kernel(int P, int deg, int M, const float* __restrict__ mean
 #undef LERP
 }
 
+// K9b: dL/dcolour -> dL/dSH (basis x dL/dRGB, no intermediate array) and, through the view
+// direction, an ADDITIVE term of dL/dmean (runs after preprocess_backward_kernel on the stream).
+__global__ void __launch_bounds__(128)
+sh_backward_kernel(int P, int deg, int M, const float* __restrict__ means3D, const float* __restrict__ shs,
+                   const float* __restrict__ ts, const int* __restrict__ ridx, const int* __restrict__ pidx,
+                   const float* __restrict__ campos, const int* __restrict__ radii, const Record* __restrict__ records,
+                   const float* __restrict__ accum, float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dsh)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const int SH3 = M * 3;
+    if (radii[i] <= 0) {
+        if (!ridx) {                                   // scatter mode: full-size gradients are pre-zeroed
+            float* o = dL_dsh + (size_t)i * SH3;
+            if ((SH3 & 3) == 0) { for (int k = 0; k < SH3 / 4; k++) reinterpret_cast<float4*>(o)[k] = make_float4(0, 0, 0, 0); }
+            else store_zero(o, SH3);
+        }
+        return;
+    }
+    int c = i, p = i;
+    float t = 1.0f, u = 0.0f;
+    if (ridx) {
+        c = ridx[i]; p = pidx[i]; if (p < 0) p = c;
+        t = ts[i]; u = 1.0f - t;
+    }
+    const bool lerp = ridx != nullptr && u != 0.0f;
+#define LERP(a, b) (lerp ? __fadd_rn(__fmul_rn(t, (a)), __fmul_rn(u, (b))) : (a))
+    const float mx = LERP(means3D[3 * c], means3D[3 * p]);
+    const float my = LERP(means3D[3 * c + 1], means3D[3 * p + 1]);
+    const float mz = LERP(means3D[3 * c + 2], means3D[3 * p + 2]);
+    const float* ac = accum + (size_t)i * kAccum;
+    const uint32_t kb = __float_as_uint(records[i].b.w);
+    const float dRGB[3] = {(kb >> kClampShift) & 1u ? 0.f : ac[6], (kb >> (kClampShift + 1)) & 1u ? 0.f : ac[7],
+                           (kb >> (kClampShift + 2)) & 1u ? 0.f : ac[8]};
+    const float d0x = mx - campos[0], d0y = my - campos[1], d0z = mz - campos[2];
+    const float len = sqrtf(d0x * d0x + d0y * d0y + d0z * d0z);
+    const float x = d0x / len, y = d0y / len, z = d0z / len;
+    const int ncoef = (deg + 1) * (deg + 1);
+    // SH basis and its derivatives w.r.t. the unit direction (coefficient-major rows [k][3])
+    float B[16], Bx[16], By[16], Bz[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) { B[k] = 0.f; Bx[k] = 0.f; By[k] = 0.f; Bz[k] = 0.f; }
+    B[0] = bSH_C0;
+    if (deg > 0) {
+        B[1] = -bSH_C1 * y; B[2] = bSH_C1 * z; B[3] = -bSH_C1 * x;
+        By[1] = -bSH_C1; Bz[2] = bSH_C1; Bx[3] = -bSH_C1;
+        if (deg > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            B[4] = bSH_C2[0] * xy; B[5] = bSH_C2[1] * yz; B[6] = bSH_C2[2] * (2.f * zz - xx - yy);
+            B[7] = bSH_C2[3] * xz; B[8] = bSH_C2[4] * (xx - yy);
+            Bx[4] = bSH_C2[0] * y; By[4] = bSH_C2[0] * x;
+            By[5] = bSH_C2[1] * z; Bz[5] = bSH_C2[1] * y;
+            Bx[6] = bSH_C2[2] * 2.f * -x; By[6] = bSH_C2[2] * 2.f * -y; Bz[6] = bSH_C2[2] * 2.f * 2.f * z;
+            Bx[7] = bSH_C2[3] * z; Bz[7] = bSH_C2[3] * x;
+            Bx[8] = bSH_C2[4] * 2.f * x; By[8] = bSH_C2[4] * 2.f * -y;
+            if (deg > 2) {
+                B[9] = bSH_C3[0] * y * (3.f * xx - yy); B[10] = bSH_C3[1] * xy * z;
+                B[11] = bSH_C3[2] * y * (4.f * zz - xx - yy); B[12] = bSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+                B[13] = bSH_C3[4] * x * (4.f * zz - xx - yy); B[14] = bSH_C3[5] * z * (xx - yy);
+                B[15] = bSH_C3[6] * x * (xx - 3.f * yy);
+                Bx[9] = bSH_C3[0] * 3.f * 2.f * xy;   By[9] = bSH_C3[0] * 3.f * (xx - yy);
+                Bx[10] = bSH_C3[1] * yz;              By[10] = bSH_C3[1] * xz;               Bz[10] = bSH_C3[1] * xy;
+                Bx[11] = bSH_C3[2] * -2.f * xy;       By[11] = bSH_C3[2] * (-3.f * yy + 4.f * zz - xx); Bz[11] = bSH_C3[2] * 4.f * 2.f * yz;
+                Bx[12] = bSH_C3[3] * -3.f * 2.f * xz; By[12] = bSH_C3[3] * -3.f * 2.f * yz;  Bz[12] = bSH_C3[3] * 3.f * (2.f * zz - xx - yy);
+                Bx[13] = bSH_C3[4] * (-3.f * xx + 4.f * zz - yy); By[13] = bSH_C3[4] * -2.f * xy; Bz[13] = bSH_C3[4] * 4.f * 2.f * xz;
+                Bx[14] = bSH_C3[5] * 2.f * xz;        By[14] = bSH_C3[5] * -2.f * yz;        Bz[14] = bSH_C3[5] * (xx - yy);
+                Bx[15] = bSH_C3[6] * 3.f * (xx - yy); By[15] = bSH_C3[6] * -3.f * 2.f * xy;
+            }
+        }
+    }
+    // one pass over the row in 128-bit pieces: float e = 3k + ch.  dL/d(dir) needs the (lerped) coefficients,
+    // dL/dSH[k][ch] = B[k] * dRGB[ch] is emitted straight away
+    float ddx = 0.f, ddy = 0.f, ddz = 0.f;
+    const float* shc = shs + (size_t)c * SH3;
+    const float* shp = shs + (size_t)p * SH3;
+    float* dshi = dL_dsh + (size_t)i * SH3;
+    if ((SH3 & 3) == 0) {
+#pragma unroll
+        for (int q = 0; q < 12; q++) {
+            if (4 * q < SH3) {
+                float o4[4] = {0.f, 0.f, 0.f, 0.f};
+                if (4 * q < 3 * ncoef) {
+                    float4 v = __ldg(reinterpret_cast<const float4*>(shc) + q);
+                    if (lerp) {
+                        const float4 w = __ldg(reinterpret_cast<const float4*>(shp) + q);
+                        v.x = LERP(v.x, w.x); v.y = LERP(v.y, w.y); v.z = LERP(v.z, w.z); v.w = LERP(v.w, w.w);
+                    }
+                    const float sv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        const int e = 4 * q + r, k = e / 3, ch = e - 3 * k;      // compile-time after unrolling
+                        const float g = dRGB[ch];
+                        o4[r] = B[k] * g;
+                        ddx += Bx[k] * sv[r] * g; ddy += By[k] * sv[r] * g; ddz += Bz[k] * sv[r] * g;
+                    }
+                }
+                if (!ridx) reinterpret_cast<float4*>(dshi)[q] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+                else if (4 * q < 3 * ncoef) {
+                    // 128-bit vector reductions (red.global.add.v4.f32): 12 per 192-B row
+                    atomicAdd(reinterpret_cast<float4*>(dL_dsh + (size_t)c * SH3) + q, make_float4(t * o4[0], t * o4[1], t * o4[2], t * o4[3]));
+                    if (lerp) atomicAdd(reinterpret_cast<float4*>(dL_dsh + (size_t)p * SH3) + q, make_float4(u * o4[0], u * o4[1], u * o4[2], u * o4[3]));
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 48; e++) {
+            if (e < SH3) {
+                const int k = e / 3, ch = e - 3 * k;
+                float o = 0.f;
+                if (e < 3 * ncoef) {
+                    const float sv = LERP(__ldg(shc + e), __ldg(shp + e));
+                    const float g = dRGB[ch];
+                    o = B[k] * g;
+                    ddx += Bx[k] * sv * g; ddy += By[k] * sv * g; ddz += Bz[k] * sv * g;
+                }
+                if (!ridx) dshi[e] = o;
+                else if (e < 3 * ncoef) {
+                    atomicAdd(dL_dsh + (size_t)c * SH3 + e, t * o);
+                    if (lerp) atomicAdd(dL_dsh + (size_t)p * SH3 + e, u * o);
+                }
+            }
+        }
+    }
+    const float sum2 = d0x * d0x + d0y * d0y + d0z * d0z;
+    const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+    const float dm0 = ((sum2 - d0x * d0x) * ddx - d0y * d0x * ddy - d0z * d0x * ddz) * invsum32;
+    const float dm1 = (-d0x * d0y * ddx + (sum2 - d0y * d0y) * ddy - d0z * d0y * ddz) * invsum32;
+    const float dm2 = (-d0x * d0z * ddx - d0y * d0z * ddy + (sum2 - d0z * d0z) * ddz) * invsum32;
+    if (!ridx) {       // row i belongs to this thread; preprocess_backward_kernel already stored its part
+        dL_dmeans3D[3 * i] += dm0; dL_dmeans3D[3 * i + 1] += dm1; dL_dmeans3D[3 * i + 2] += dm2;
+    } else {
+        atomicAdd(dL_dmeans3D + 3 * (size_t)c + 0, t * dm0); atomicAdd(dL_dmeans3D + 3 * (size_t)c + 1, t * dm1);
+        atomicAdd(dL_dmeans3D + 3 * (size_t)c + 2, t * dm2);
+        if (lerp) {
+            atomicAdd(dL_dmeans3D + 3 * (size_t)p + 0, u * dm0); atomicAdd(dL_dmeans3D + 3 * (size_t)p + 1, u * dm1);
+            atomicAdd(dL_dmeans3D + 3 * (size_t)p + 2, u * dm2);
+        }
+    }
+#undef LERP
+}
+
 int launch_preprocess_backward(const h3dgs_raster_args& a, const int32_t* radii, const Record* records,
                                const float* accum, float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh,
                                float* dL_dcolors, float* dL_dopacities, float* dL_dscales, float* dL_drots,
@@ -366,12 +398,18 @@ int launch_preprocess_backward(const h3dgs_raster_args& a, const int32_t* radii,
     if (a.P == 0) return H3DGS_OK;
     const float fx = a.image_width / (2.0f * a.tanfovx), fy = a.image_height / (2.0f * a.tanfovy);
     ProfScope prof(H3DGS_STAGE_PREPROCESS_BWD, s);
-    preprocess_backward_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(
+    preprocess_backward_kernel<<<(a.P + 127) / 128, 128, 0, s>>>(
         a.P, a.sh_degree, a.sh_coeffs, a.means3D, a.scales, a.scale_modifier, a.rotations, a.shs, a.cov3D_precomp,
         a.colors_precomp, a.interpolation_weights, a.render_indices, a.parent_indices, a.viewmatrix, a.projmatrix, a.campos, a.image_width, a.image_height, a.tanfovx, a.tanfovy,
         fx, fy, a.do_depth, radii, records, accum, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacities,
         dL_dscales, dL_drots, dL_dcov3D);
     H3_LAUNCHED("preprocess_backward", a.debug, s);
+    if (!a.colors_precomp) {
+        sh_backward_kernel<<<(a.P + 127) / 128, 128, 0, s>>>(a.P, a.sh_degree, a.sh_coeffs, a.means3D, a.shs,
+                                                             a.interpolation_weights, a.render_indices, a.parent_indices,
+                                                             a.campos, radii, records, accum, dL_dmeans3D, dL_dsh);
+        H3_LAUNCHED("sh_backward", a.debug, s);
+    }
     return H3DGS_OK;
 }
 
