@@ -170,10 +170,11 @@ def test_full_size_frame_1080p():
     d = np.abs(out["color"] - f["color"])
     # an alpha that lands within rounding of the 1/255 cut flips a contribution of <= 1/255
     assert (d > 1e-5).mean() < 1e-5 and d.max() < 1.5 / 255
-    # At this depth (hundreds of blended entries per pixel, 300 k Gaussians) the fp32 rounding of the
-    # per-pixel quadratic form, of exp and of the transmittance recurrence T <- T/(1-alpha) -- all of
-    # which the published algorithm itself performs in fp32 -- sits at ~1e-5 of the largest gradient
-    # against the oracle's exact-arithmetic (double) backward: measured 1.2e-5 (means2D), 1.6e-5
-    # (scales).  The small and medium scenes keep the 1e-5 bar; this one states 2e-5.
+    # 300 k Gaussians, hundreds of blended entries per pixel.  The gradient bar stays 1e-5 per element
+    # with the flip allowance of util.assert_grad_close; on top of that the fp32 rounding of the per-pixel
+    # quadratic form / exp / T <- T/(1-alpha) recurrence that the published algorithm itself performs
+    # leaves up to ~1.6e-5 at this depth against the oracle's exact-arithmetic backward (measured),
+    # so this one test states 2e-5.
+    from util import assert_grad_close
     for k in ["means3D", "means2D", "sh", "opacities", "scales", "rotations"]:
-        assert rel_err(g[k], b[k]) < 2e-5, (k, rel_err(g[k], b[k]))
+        assert_grad_close(g[k], b[k], k, tol=2e-5)

@@ -116,3 +116,21 @@ def assert_image_close(a, b, what="color"):
         assert not bad.any(), (what, float(d.max() / scale))
 
 
+
+
+def assert_grad_close(a, b, name="grad", tol=TOL, strict_rows=20000):
+    """1e-5 relative (norm-wise: |a-b| <= tol * max|b|) for every element of a returned gradient.
+    On big frames an alpha landing within fp32 rounding of the 1/255 skip threshold can flip one
+    pixel's contribution in or out (see assert_image_close); the affected Gaussian's gradient then moves
+    by one pixel's worth.  Such rows must be rare (< 1e-4 of the rows) and small (< 1e-3 * max|b|);
+    scenes with fewer than `strict_rows` rows get no such allowance."""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    scale = max(np.abs(b).max(), 1e-30)
+    d = np.abs(a - b).reshape(a.shape[0], -1).max(1) if a.ndim > 1 else np.abs(a - b)
+    bad = d > tol * scale
+    if a.shape[0] < strict_rows:
+        assert not bad.any(), (name, float(d.max() / scale))
+    else:
+        assert bad.mean() < 1e-4, (name, float(bad.mean()), float(d.max() / scale))
+        assert d.max() < 1e-3 * scale, (name, float(d.max() / scale))
+    return float(np.median(d) / scale), float(d.max() / scale)
