@@ -76,7 +76,8 @@ def alg_bytes(P, V, D, hier):
     that must produce/consume it, fp32/i32, sort idealised as one read + one write)."""
     Px, T = W * H, ((W + 15) // 16) * ((H + 15) // 16)
     b = {
-        "preprocess": 44 * P + 8 * P + 192 * V + 40 * V + (8 * P if hier else 0),
+        "preprocess": 44 * P + 8 * P + 40 * V + (8 * P if hier else 0),
+        "preprocess_color": 192 * V,
         "scan": 8 * P,
         "duplicate_with_keys": 12 * D,
         "radix_sort": 24 * D,
@@ -84,7 +85,8 @@ def alg_bytes(P, V, D, hier):
         "gather_records": 0,                       # implementation choice (TMA staging), not algorithmic
         "render_forward": 40 * D + 20 * Px,
         "render_backward": 40 * D + 36 * D + 32 * Px,
-        "preprocess_backward": (36 + 44 + 192 + 40) * V + 248 * V,
+        "preprocess_backward": (36 + 44 + 40) * V + 56 * V,
+        "sh_backward": 192 * V + 192 * V,
     }
     b["total"] = sum(b.values())
     return b

@@ -56,6 +56,24 @@ static void prof_drain() {
     g_prof_pending.clear();
 }
 
+// ---- side stream: zero-filling the full-size gradients (0.7 GB in scatter mode, pure DRAM
+// traffic) overlaps the issue-bound per-tile replay instead of preceding the chain rule ----
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static SideStream g_side[64];
+static int side_stream(SideStream** out) {
+    int dev = 0;
+    H3_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return H3DGS_EINVAL; }
+    SideStream& ss = g_side[dev];
+    if (!ss.s) {
+        H3_CUDA(cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking));
+        H3_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+        H3_CUDA(cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming));
+    }
+    *out = &ss;
+    return H3DGS_OK;
+}
+
 static int check_args(const h3dgs_raster_args* a) {
     if (!a) { set_error("args is NULL"); return H3DGS_EINVAL; }
     if (a->P < 0 || a->image_width <= 0 || a->image_height <= 0) { set_error("bad sizes P=%d W=%d H=%d", a->P, a->image_width, a->image_height); return H3DGS_EINVAL; }
@@ -109,7 +127,8 @@ extern "C" int h3dgs_profile_read(int stage, double* total_ms, int64_t* launches
 }
 extern "C" const char* h3dgs_stage_name(int stage) {
     static const char* names[H3DGS_STAGE_COUNT] = {"preprocess", "scan", "duplicate_with_keys", "radix_sort", "identify_tile_ranges",
-        "gather_records", "render_forward", "render_backward", "preprocess_backward", "lod_cut", "lod_weights"};
+        "gather_records", "render_forward", "render_backward", "preprocess_backward", "lod_cut", "lod_weights",
+        "preprocess_color", "sh_backward"};
     return (stage >= 0 && stage < H3DGS_STAGE_COUNT) ? names[stage] : "?";
 }
 extern "C" const char* h3dgs_last_error(void) { return g_err; }
@@ -140,6 +159,22 @@ extern "C" int h3dgs_rasterize_forward(const h3dgs_raster_args* a, h3dgs_alloc_f
 
     rc = launch_preprocess(*a, out_radii, depths, tiles, records, s);
     if (rc) return rc;
+    // SH -> RGB only feeds record.c (read again by gather_records): run it on the side stream,
+    // overlapped with the scan, the num_rendered round trip, key emission and the sort
+    SideStream* ss = nullptr;
+    const bool side_color = !a->colors_precomp && P > 0 && !a->debug;
+    if (side_color) {
+        rc = side_stream(&ss);
+        if (rc) return rc;
+        H3_CUDA(cudaEventRecord(ss->fork, s));
+        H3_CUDA(cudaStreamWaitEvent(ss->s, ss->fork, 0));
+        rc = launch_preprocess_color(*a, out_radii, records, ss->s);
+        if (rc) return rc;
+        H3_CUDA(cudaEventRecord(ss->join, ss->s));
+    } else {
+        rc = launch_preprocess_color(*a, out_radii, records, s);
+        if (rc) return rc;
+    }
     rc = launch_scan(tiles, offsets, P, geom + gl.scan_temp, gl.scan_temp_bytes, s, a->debug);
     if (rc) return rc;
     // The reference API sizes the binning buffer from num_rendered: one D2H + sync.
@@ -154,6 +189,7 @@ extern "C" int h3dgs_rasterize_forward(const h3dgs_raster_args* a, h3dgs_alloc_f
     uint8_t* bin = (uint8_t*)alloc(user, 1, bl.total);
     if (!bin) { set_error("alloc callback returned NULL"); return H3DGS_ENOMEM; }
     uint32_t* ranges = (uint32_t*)(img + il.ranges);
+    if (side_color) H3_CUDA(cudaStreamWaitEvent(s, ss->join, 0));      // colours are needed from gather_records on
     rc = launch_binning(*a, out_radii, depths, offsets, records, D, bin, bl, ranges, s);
     if (rc) return rc;
     rc = launch_render_forward(*a, ranges, (const Record*)(bin + bl.sorted_records), out_color, out_invdepth,
@@ -171,7 +207,7 @@ extern "C" int h3dgs_rasterize_backward(const h3dgs_raster_args* a, const int32_
 {
     int rc = check_args(a);
     if (rc) return rc;
-    if (a->P == 0) return H3DGS_OK;
+    if (a->P == 0) return H3DGS_OK;                      // nothing rendered: all outputs have zero rows
     if (!geom_state || !binning_state || !image_state || ((phases & 1) && !dL_dcolor) || !scratch || !radii) {
         set_error("backward: missing saved state / scratch"); return H3DGS_EINVAL;
     }
@@ -189,6 +225,23 @@ extern "C" int h3dgs_rasterize_backward(const h3dgs_raster_args* a, const int32_
     float* accum = (float*)scratch;
     h3dgs_raster_args b = *a;
     if (!dL_dinvdepth && (phases & 1)) b.do_depth = 0;
+    bool zero_joined = true;
+    SideStream* ss = nullptr;
+    if ((phases & 2) && a->render_indices) {
+        // scatter mode: gradients have num_source rows and must start from zero
+        rc = side_stream(&ss);
+        if (rc) return rc;
+        const size_t N = (size_t)a->num_source;
+        H3_CUDA(cudaEventRecord(ss->fork, s));              // outputs may still be in use by earlier work on s
+        H3_CUDA(cudaStreamWaitEvent(ss->s, ss->fork, 0));
+        H3_CUDA(cudaMemsetAsync(dL_dmeans3D, 0, N * 3 * sizeof(float), ss->s));
+        H3_CUDA(cudaMemsetAsync(dL_dopacities, 0, N * sizeof(float), ss->s));
+        H3_CUDA(cudaMemsetAsync(dL_dsh, 0, N * (size_t)a->sh_coeffs * 3 * sizeof(float), ss->s));
+        H3_CUDA(cudaMemsetAsync(dL_dscales, 0, N * 3 * sizeof(float), ss->s));
+        H3_CUDA(cudaMemsetAsync(dL_drotations, 0, N * 4 * sizeof(float), ss->s));
+        H3_CUDA(cudaEventRecord(ss->join, ss->s));
+        zero_joined = false;
+    }
     if (phases & 1) H3_CUDA(cudaMemsetAsync(accum, 0, (size_t)a->P * kAccum * sizeof(float), s));
     if (D > 0 && (phases & 1)) {
         rc = launch_render_backward(b, (const uint32_t*)(img + il.ranges), (const Record*)(bin + bl.sorted_records),
@@ -198,17 +251,26 @@ extern "C" int h3dgs_rasterize_backward(const h3dgs_raster_args* a, const int32_
         if (rc) return rc;
     }
     if (!(phases & 2)) return H3DGS_OK;
-    if (a->render_indices) {
-        // scatter mode: gradients have num_source rows and must start from zero
-        const size_t N = (size_t)a->num_source;
-        H3_CUDA(cudaMemsetAsync(dL_dmeans3D, 0, N * 3 * sizeof(float), s));
-        H3_CUDA(cudaMemsetAsync(dL_dopacities, 0, N * sizeof(float), s));
-        H3_CUDA(cudaMemsetAsync(dL_dsh, 0, N * (size_t)a->sh_coeffs * 3 * sizeof(float), s));
-        H3_CUDA(cudaMemsetAsync(dL_dscales, 0, N * 3 * sizeof(float), s));
-        H3_CUDA(cudaMemsetAsync(dL_drotations, 0, N * 4 * sizeof(float), s));
+    if (!zero_joined && !a->debug && !a->colors_precomp) {
+        // scatter mode: every output is an atomic reduction, so the SH kernel (side stream, right
+        // after its zero-fill) and the covariance kernel (main stream) run concurrently
+        H3_CUDA(cudaEventRecord(ss->fork, s));                           // accum is complete at this point of s
+        H3_CUDA(cudaStreamWaitEvent(ss->s, ss->fork, 0));
+        rc = launch_sh_backward(b, radii, (const Record*)(geom + gl.records), accum, dL_dmeans3D, dL_dsh, ss->s);
+        if (rc) return rc;
+        H3_CUDA(cudaStreamWaitEvent(s, ss->join, 0));                    // zero-fill done before our own reductions
+        H3_CUDA(cudaEventRecord(ss->join, ss->s));
+        rc = launch_preprocess_backward(b, radii, (const Record*)(geom + gl.records), accum, dL_dmeans3D, dL_dmeans2D,
+                                        dL_dsh, dL_dcolors_precomp, dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D, s);
+        if (rc) return rc;
+        H3_CUDA(cudaStreamWaitEvent(s, ss->join, 0));
+        return H3DGS_OK;
     }
-    return launch_preprocess_backward(b, radii, (const Record*)(geom + gl.records), accum, dL_dmeans3D, dL_dmeans2D,
-                                      dL_dsh, dL_dcolors_precomp, dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D, s);
+    if (!zero_joined) H3_CUDA(cudaStreamWaitEvent(s, ss->join, 0));
+    rc = launch_preprocess_backward(b, radii, (const Record*)(geom + gl.records), accum, dL_dmeans3D, dL_dmeans2D,
+                                    dL_dsh, dL_dcolors_precomp, dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D, s);
+    if (rc) return rc;
+    return launch_sh_backward(b, radii, (const Record*)(geom + gl.records), accum, dL_dmeans3D, dL_dsh, s);
 }
 
 extern "C" int h3dgs_state_layout(int32_t P, int32_t W, int32_t H, int64_t D, const void* geom_state,

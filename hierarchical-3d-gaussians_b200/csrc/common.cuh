@@ -90,6 +90,9 @@ extern int64_t g_launches;
 // ---- stage entry points (one per .cu file) ----
 int launch_preprocess(const h3dgs_raster_args& a, int32_t* radii, float* depths, uint32_t* tiles_touched,
                       Record* records, cudaStream_t s);
+int launch_preprocess_color(const h3dgs_raster_args& a, const int32_t* radii, Record* records, cudaStream_t s);
+int launch_sh_backward(const h3dgs_raster_args& a, const int32_t* radii, const Record* records, const float* accum,
+                       float* dL_dmeans3D, float* dL_dsh, cudaStream_t s);
 int launch_scan(const uint32_t* in, uint32_t* out, int n, void* temp, size_t temp_bytes, cudaStream_t s, bool debug);
 size_t scan_temp_bytes(int n);
 size_t sort_temp_bytes(int64_t n);

@@ -281,12 +281,18 @@ int launch_preprocess(const h3dgs_raster_args& a, int32_t* radii, float* depths,
                                                  a.shard_count > 0 ? a.shard_count : 1, a.shard_count > 0 ? a.shard_index : 0,
                                                  radii, depths, tiles_touched, records);
     H3_LAUNCHED("preprocess", a.debug, s);
-    if (!a.colors_precomp) {
-        preprocess_color_kernel<<<blocks, threads, 0, s>>>(a.P, a.sh_degree, a.sh_coeffs, a.means3D, a.shs,
-                                                           a.interpolation_weights, a.render_indices, a.parent_indices,
-                                                           a.campos, radii, records);
-        H3_LAUNCHED("preprocess_color", a.debug, s);
-    }
+    return H3DGS_OK;
+}
+
+int launch_preprocess_color(const h3dgs_raster_args& a, const int32_t* radii, Record* records, cudaStream_t s)
+{
+    if (a.P == 0 || a.colors_precomp) return H3DGS_OK;
+    const int threads = 256, blocks = (a.P + threads - 1) / threads;
+    ProfScope prof(H3DGS_STAGE_PREPROCESS_COLOR, s);
+    preprocess_color_kernel<<<blocks, threads, 0, s>>>(a.P, a.sh_degree, a.sh_coeffs, a.means3D, a.shs,
+                                                       a.interpolation_weights, a.render_indices, a.parent_indices,
+                                                       a.campos, radii, records);
+    H3_LAUNCHED("preprocess_color", a.debug, s);
     return H3DGS_OK;
 }
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,

@@ -404,12 +404,18 @@ int launch_preprocess_backward(const h3dgs_raster_args& a, const int32_t* radii,
         fx, fy, a.do_depth, radii, records, accum, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacities,
         dL_dscales, dL_drots, dL_dcov3D);
     H3_LAUNCHED("preprocess_backward", a.debug, s);
-    if (!a.colors_precomp) {
-        sh_backward_kernel<<<(a.P + 127) / 128, 128, 0, s>>>(a.P, a.sh_degree, a.sh_coeffs, a.means3D, a.shs,
-                                                             a.interpolation_weights, a.render_indices, a.parent_indices,
-                                                             a.campos, radii, records, accum, dL_dmeans3D, dL_dsh);
-        H3_LAUNCHED("sh_backward", a.debug, s);
-    }
+    return H3DGS_OK;
+}
+
+int launch_sh_backward(const h3dgs_raster_args& a, const int32_t* radii, const Record* records, const float* accum,
+                       float* dL_dmeans3D, float* dL_dsh, cudaStream_t s)
+{
+    if (a.P == 0 || a.colors_precomp) return H3DGS_OK;
+    ProfScope prof(H3DGS_STAGE_SH_BACKWARD, s);
+    sh_backward_kernel<<<(a.P + 127) / 128, 128, 0, s>>>(a.P, a.sh_degree, a.sh_coeffs, a.means3D, a.shs,
+                                                         a.interpolation_weights, a.render_indices, a.parent_indices,
+                                                         a.campos, radii, records, accum, dL_dmeans3D, dL_dsh);
+    H3_LAUNCHED("sh_backward", a.debug, s);
     return H3DGS_OK;
 }
 

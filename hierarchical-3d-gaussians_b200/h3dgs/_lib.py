@@ -92,7 +92,7 @@ def launch_count():
     return int(lib().h3dgs_launch_count())
 
 
-STAGES = 11
+STAGES = 13
 
 
 def profile_enable(on=True):
