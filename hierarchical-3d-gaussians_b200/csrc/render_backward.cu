@@ -1,10 +1,10 @@
 // render_backward.cu -- K7: per-tile gradient replay (replaces BACKWARD::render).
 // Semantics per oracle/oracle.c::oracle_render_backward.
 //
-// v1 ("pixel-parallel"): one CTA per tile, records streamed back-to-front with the
-// same TMA double buffer as the forward; per-entry partials are reduced over the 32
-// pixels of a warp with shuffles and lane 0 issues one red.global.add per value --
-// 32x fewer atomics than the classic one-atomic-per-pixel formulation.
+// One CTA (128 threads, two pixels each) per tile, records streamed back-to-front with the same TMA
+// double buffer as the forward; per-entry partials of a warp's 64 pixels are reduced with a
+// transpose-reduce (12 shuffles for 10 values) and 10 lanes issue ONE red.global.add for the warp --
+// 64x fewer atomics than the classic one-atomic-per-pixel formulation.
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -50,8 +50,60 @@ __device__ __forceinline__ float transpose_reduce10(const float (&v)[10], int la
     return d;
 }
 
+constexpr int kBwdThreads = 128;      // two vertically adjacent pixels per thread (see render_forward.cu)
+
+// per-pixel replay state
+struct PixState {
+    float T, acc_s, last_cg, last_alpha;   // transmittance, (accum_rec . g), (last colour . g), last alpha
+};
+
+// alpha of one pixel for entry (a, bb), with exactly the forward's decisions
+template <bool HIER>
+__device__ __forceinline__ bool pixel_alpha(const float4& a, const float4& bb, uint32_t kb, float dx, float dy, bool in_list,
+                                            float& G, float& alpha, float& dadb)
+{
+    G = 0.f; alpha = 0.f; dadb = 1.f;
+    bool valid = false;
+    const float power = -0.5f * (a.z * dx * dx + bb.x * dy * dy) - a.w * dx * dy;
+    if (in_list && power <= 0.0f) {
+        G = fast_exp(power);
+        const float abase = fminf(kAlphaCap, bb.y * G);
+        hier_alpha_grad<HIER>(abase, bb.z, kb, alpha, dadb);
+        valid = alpha >= kAlphaSkip;
+    }
+    if (!valid) { G = 0.f; alpha = 0.f; }
+    return valid;
+}
+
+// One pixel's contribution of entry (a, bb, c) to the 10 per-Gaussian sums; branch-free so that an
+// invalid pixel (G = alpha = 0) adds exact zeros.
+template <bool DEPTH>
+__device__ __forceinline__ void pixel_grad(const float4& a, const float4& bb, float dx, float dy, bool valid, float G,
+                                           float alpha, float dadb, float cg, float T_final, float bg_dot, float g0,
+                                           float g1, float g2, float gd, PixState& st, float (&v)[10])
+{
+    const float rcp = __frcp_rn(1.f - alpha);                 // one reciprocal serves T and the bg term
+    const float Tn = st.T * rcp;
+    const float as_n = st.last_alpha * st.last_cg + (1.f - st.last_alpha) * st.acc_s;
+    const float w = valid ? alpha * Tn : 0.f;                 // dchannel_dcolor
+    const float dL_dalpha = (cg - as_n) * Tn - (T_final * rcp) * bg_dot;
+    const float dL_dab = valid ? dL_dalpha * dadb : 0.f;
+    if (valid) { st.T = Tn; st.acc_s = as_n; st.last_cg = cg; st.last_alpha = alpha; }
+    const float dL_dG = bb.y * dL_dab;
+    const float gdx = G * dx, gdy = G * dy;
+    // constant factors (0.5 W, 0.5 H, -0.5) are applied once per Gaussian in preprocess_backward
+    v[0] += dL_dG * (-gdx * a.z - gdy * a.w);
+    v[1] += dL_dG * (-gdy * bb.x - gdx * a.w);
+    v[2] += gdx * dx * dL_dG;
+    v[3] += gdx * dy * dL_dG;
+    v[4] += gdy * dy * dL_dG;
+    v[5] += G * dL_dab;
+    v[6] += w * g0; v[7] += w * g1; v[8] += w * g2;
+    if (DEPTH) v[9] += w * gd;
+}
+
 template <bool HIER, bool DEPTH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kBwdThreads)
 render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, const uint2* __restrict__ ranges,
                        const Record* __restrict__ sorted, const uint32_t* __restrict__ point_list,
                        const float* __restrict__ bg, const float* __restrict__ final_T,
@@ -80,8 +132,10 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
     // handles batch b = nb-1-it (back to front).
     auto stage_ids = [&](int it) {
         const int b = nb - 1 - it, st = it % kBwdStages;
-        const int e = b * kBwdBatch + tid;
-        if (e < n) s_id[st][tid] = ids[e];
+        for (int k = tid; k < kBwdBatch; k += kBwdThreads) {
+            const int e = b * kBwdBatch + k;
+            if (e < n) s_id[st][k] = ids[e];
+        }
     };
     for (int it = 0; it < kBwdStages && it < nb; it++) stage_ids(it);
     if (tid == 0) {
@@ -98,21 +152,20 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
     if (tid == 0)
         for (int it = 0; it < kBwdStages && it < nb; it++) issue(it);
 
-    const int px = tile_x * kTile + (tid & 15), py = tile_y * kTile + (tid >> 4);
-    const bool inside = px < W && py < H;
-    const float fpx = (float)px, fpy = (float)py;
-    const size_t pix = (size_t)py * W + px, plane = (size_t)H * W;
-    const float T_final = inside ? final_T[pix] : 0.f;
-    float T = T_final;
-    const int last = inside ? (int)n_contrib[pix] : 0;
-    float g0 = 0.f, g1 = 0.f, g2 = 0.f, gd = 0.f;
-    if (inside) {
-        g0 = dL_dcolor[pix]; g1 = dL_dcolor[plane + pix]; g2 = dL_dcolor[2 * plane + pix];
-        if (DEPTH) gd = dL_dinvdepth[pix];
-    }
-    const float bg_dot = bg[0] * g0 + bg[1] * g1 + bg[2] * g2;
-    const int wlast = (int)__reduce_max_sync(0xffffffffu, (unsigned)last);   // nothing in this strip beyond it
-    float acc_s = 0.f, last_cg = 0.f, last_alpha = 0.f;          // (accum_rec . g), (last colour . g)
+    const int px = tile_x * kTile + (lane & 15);
+    const int py0 = tile_y * kTile + 4 * warp + 2 * (lane >> 4), py1 = py0 + 1;
+    const bool in0 = px < W && py0 < H, in1 = px < W && py1 < H;
+    const float fpx = (float)px, fpy0 = (float)py0, fpy1 = (float)py1;
+    const size_t pix0 = (size_t)py0 * W + px, pix1 = (size_t)py1 * W + px, plane = (size_t)H * W;
+    const float Tf0 = in0 ? final_T[pix0] : 0.f, Tf1 = in1 ? final_T[pix1] : 0.f;
+    PixState st0 = {Tf0, 0.f, 0.f, 0.f}, st1 = {Tf1, 0.f, 0.f, 0.f};
+    const int last0 = in0 ? (int)n_contrib[pix0] : 0, last1 = in1 ? (int)n_contrib[pix1] : 0;
+    float ga0 = 0.f, ga1 = 0.f, ga2 = 0.f, gad = 0.f, gb0 = 0.f, gb1 = 0.f, gb2 = 0.f, gbd = 0.f;
+    if (in0) { ga0 = dL_dcolor[pix0]; ga1 = dL_dcolor[plane + pix0]; ga2 = dL_dcolor[2 * plane + pix0]; if (DEPTH) gad = dL_dinvdepth[pix0]; }
+    if (in1) { gb0 = dL_dcolor[pix1]; gb1 = dL_dcolor[plane + pix1]; gb2 = dL_dcolor[2 * plane + pix1]; if (DEPTH) gbd = dL_dinvdepth[pix1]; }
+    const float bgd0 = bg[0] * ga0 + bg[1] * ga1 + bg[2] * ga2, bgd1 = bg[0] * gb0 + bg[1] * gb1 + bg[2] * gb2;
+    const int wlast = (int)__reduce_max_sync(0xffffffffu, (unsigned)max(last0, last1));   // nothing in these strips beyond it
+    const int s_lo = 2 * warp, s_hi = 2 * warp + 1;
 
     for (int it = 0; it < nb; it++) {
         const int st = it % kBwdStages, b = nb - 1 - it;
@@ -120,65 +173,40 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
         const int cnt = min(kBwdBatch, n - b * kBwdBatch);
         const Record* rec = &s_rec[st][0];
         // back to front; per group of 32 entries a ballot compacts the entries that can reach
-        // this warp's strip at all (see render_forward.cu)
+        // this warp's strips at all (see render_forward.cu)
         for (int j0 = (cnt - 1) & ~31; j0 >= 0; j0 -= 32) {
-          const int jl = j0 + lane;
-          const bool hit = jl < cnt && (b * kBwdBatch + jl) < wlast && strip_hit(__float_as_uint(rec[jl].b.w), warp);
-          uint32_t m = __ballot_sync(0xffffffffu, hit);
-          while (m) {
-            const int top = 31 - __clz(m);
-            m &= ~(1u << top);
-            const int j = j0 + top;
-            const int e = b * kBwdBatch + j;              // 0-based list position; contributor number e+1
-            const float4 bb = rec[j].b;
-            const uint32_t kb = __float_as_uint(bb.w);
-            // decisions exactly as the forward took them; everything after is branch-free so that
-            // invalid lanes contribute exact zeros (masked G / weights), no per-value predication
-            float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f, dadb = 1.f;
-            bool valid = false;
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e < last) {
-                a = rec[j].a;
-                dx = a.x - fpx; dy = a.y - fpy;
-                const float power = -0.5f * (a.z * dx * dx + bb.x * dy * dy) - a.w * dx * dy;
-                if (power <= 0.0f) {
-                    G = fast_exp(power);
-                    const float abase = fminf(kAlphaCap, bb.y * G);
-                    hier_alpha_grad<HIER>(abase, bb.z, kb, alpha, dadb);
-                    valid = alpha >= kAlphaSkip;
-                }
+            const int jl = j0 + lane;
+            bool hit = false;
+            if (jl < cnt && (b * kBwdBatch + jl) < wlast) {
+                const uint32_t kbl = __float_as_uint(rec[jl].b.w);
+                hit = (int)((kbl >> kStripHiShift) & 7u) >= s_lo && (int)((kbl >> kStripLoShift) & 7u) <= s_hi;
             }
-            if (!__any_sync(0xffffffffu, valid)) continue;            // warp-uniform
-            if (!valid) { G = 0.f; alpha = 0.f; }
-            const float4 c = rec[j].c;
-            // scalar form of the accum_rec recurrence: only (accum_rec . g) is ever needed
-            float cg = c.x * g0 + c.y * g1 + c.z * g2;
-            if (DEPTH) cg += c.w * gd;
-            const float rcp = __frcp_rn(1.f - alpha);                 // one reciprocal serves T and the bg term
-            const float Tn = T * rcp;
-            const float as_n = last_alpha * last_cg + (1.f - last_alpha) * acc_s;
-            const float w = valid ? alpha * Tn : 0.f;                 // dchannel_dcolor
-            const float dL_dalpha = (cg - as_n) * Tn - (T_final * rcp) * bg_dot;
-            const float dL_dab = valid ? dL_dalpha * dadb : 0.f;
-            if (valid) { T = Tn; acc_s = as_n; last_cg = cg; last_alpha = alpha; }
-            const float dL_dG = bb.y * dL_dab;
-            const float gdx = G * dx, gdy = G * dy;
-            float v[10];
-            // constant factors (0.5 W, 0.5 H, -0.5) are applied once per Gaussian in preprocess_backward
-            v[0] = dL_dG * (-gdx * a.z - gdy * a.w);
-            v[1] = dL_dG * (-gdy * bb.x - gdx * a.w);
-            v[2] = gdx * dx * dL_dG;
-            v[3] = gdx * dy * dL_dG;
-            v[4] = gdy * dy * dL_dG;
-            v[5] = G * dL_dab;
-            v[6] = w * g0; v[7] = w * g1; v[8] = w * g2;
-            v[9] = DEPTH ? w * gd : 0.f;
-            {
+            uint32_t m = __ballot_sync(0xffffffffu, hit);
+            while (m) {
+                const int top = 31 - __clz(m);
+                m &= ~(1u << top);
+                const int j = j0 + top;
+                const int e = b * kBwdBatch + j;              // 0-based list position; contributor number e+1
+                const float4 a = rec[j].a;
+                const float4 bb = rec[j].b;
+                const uint32_t kb = __float_as_uint(bb.w);
+                const float dx = a.x - fpx, dy0 = a.y - fpy0, dy1 = a.y - fpy1;
+                float G0, al0, dd0, G1, al1, dd1;
+                const bool v0 = pixel_alpha<HIER>(a, bb, kb, dx, dy0, e < last0, G0, al0, dd0);
+                const bool v1 = pixel_alpha<HIER>(a, bb, kb, dx, dy1, e < last1, G1, al1, dd1);
+                if (!__any_sync(0xffffffffu, v0 || v1)) continue;            // warp-uniform
+                const float4 c = rec[j].c;
+                float cg0 = c.x * ga0 + c.y * ga1 + c.z * ga2, cg1 = c.x * gb0 + c.y * gb1 + c.z * gb2;
+                if (DEPTH) { cg0 += c.w * gad; cg1 += c.w * gbd; }
+                float v[10];
+#pragma unroll
+                for (int k = 0; k < 10; k++) v[k] = 0.f;
+                pixel_grad<DEPTH>(a, bb, dx, dy0, v0, G0, al0, dd0, cg0, Tf0, bgd0, ga0, ga1, ga2, gad, st0, v);
+                pixel_grad<DEPTH>(a, bb, dx, dy1, v1, G1, al1, dd1, cg1, Tf1, bgd1, gb0, gb1, gb2, gbd, st1, v);
                 const float total = transpose_reduce10(v, lane);
                 if (slot >= 0 && (DEPTH || slot < 9))
                     atomicAdd(accum + (size_t)s_id[st][j] * kAccum + slot, total);
             }
-          }
         }
         __syncthreads();                      // every thread is done with stage st (records and ids)
         if (it + kBwdStages < nb) {
@@ -200,7 +228,7 @@ int launch_render_backward(const h3dgs_raster_args& a, const uint32_t* ranges, c
     if (rows <= 0 || gx <= 0) return H3DGS_OK;
     const bool hier = a.interpolation_weights != nullptr;
     const bool depth = a.do_depth != 0 && dL_dinvdepth != nullptr;
-    const dim3 grid(gx * rows), block(256);
+    const dim3 grid(gx * rows), block(kBwdThreads);
     ProfScope prof(H3DGS_STAGE_RENDER_BWD, s);
 #define LAUNCH(HI, DE)                                                                                          \
     render_backward_kernel<HI, DE><<<grid, block, 0, s>>>(W, H, gx, sc, si, (const uint2*)ranges, sorted_records, \

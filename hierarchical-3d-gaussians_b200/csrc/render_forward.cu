@@ -1,7 +1,7 @@
 // render_forward.cu -- K6: per-tile front-to-back alpha blend (replaces FORWARD::render).
 // Semantics per oracle/oracle.c::oracle_render_forward.
 //
-// B200 design: one CTA per 16x16 tile.  The tile's depth-sorted records were
+// B200 design: one CTA (128 threads, two pixels each) per 16x16 tile.  The tile's depth-sorted records were
 // materialised contiguously by binning.cu, so a batch of 256 records is ONE 12 KB
 // cp.async.bulk (TMA) transfer into shared memory, double-buffered behind an
 // mbarrier; no thread spends registers or LSU issue slots on staging.  Every pixel
@@ -16,8 +16,14 @@ namespace h3dgs {
 constexpr int kFwdBatch = 256;
 constexpr int kFwdStages = 2;
 
+// Two vertically adjacent pixels per thread: CTA = 128 threads = 4 warps, warp w owns pixel rows
+// 4w..4w+3 (lanes 0-15: rows 4w,4w+1; lanes 16-31: rows 4w+2,4w+3), i.e. the 16x2 strips 2w and 2w+1.
+// The entry's record, its dx terms, the survivor loop and (in backward) the warp reduction are
+// shared by the two pixels.
+constexpr int kFwdThreads = 128;
+
 template <bool HIER, bool DEPTH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kFwdThreads)
 render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, const uint2* __restrict__ ranges,
                       const Record* __restrict__ sorted, const float* __restrict__ bg, float* __restrict__ out_color,
                       float* __restrict__ out_invdepth, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
@@ -52,12 +58,15 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
     }
     issued = min(kFwdStages, nb);
 
-    const int px = tile_x * kTile + (tid & 15), py = tile_y * kTile + (tid >> 4);
-    const bool inside = px < W && py < H;
-    const float fpx = (float)px, fpy = (float)py;
-    bool done = !inside;
-    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f, invd = 0.f;
-    uint32_t last = 0;
+    const int px = tile_x * kTile + (lane & 15);
+    const int py0 = tile_y * kTile + 4 * warp + 2 * (lane >> 4), py1 = py0 + 1;
+    const bool in0 = px < W && py0 < H, in1 = px < W && py1 < H;
+    const float fpx = (float)px, fpy0 = (float)py0, fpy1 = (float)py1;
+    bool done0 = !in0, done1 = !in1;
+    float T0 = 1.0f, T1 = 1.0f;
+    float Ca0 = 0.f, Ca1 = 0.f, Ca2 = 0.f, Cb0 = 0.f, Cb1 = 0.f, Cb2 = 0.f, inv0 = 0.f, inv1 = 0.f;
+    uint32_t last0 = 0, last1 = 0;
+    const int s_lo = 2 * warp, s_hi = 2 * warp + 1;        // the two 16x2 strips this warp covers
 
     int waited = 0;
     for (int b = 0; b < nb; b++) {
@@ -65,45 +74,64 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
         mbar_wait(&s_full[st], (uint32_t)((b / kFwdStages) & 1));
         waited = b + 1;
         const int cnt = min(kFwdBatch, n - b * kFwdBatch);
-        // Per group of 32 entries each lane tests ONE entry against this warp's 16x2-pixel
-        // strip and a ballot compacts the survivors, so culled entries cost nothing per pixel.
-        // The survivor loop is warp-uniform (same mask in every lane) and its body is
-        // straight-line + one short reconvergent `if`: a per-thread `continue`/`break` here
-        // leaves the warp split into fragments that each re-walk the list (measured: 18x the
-        // instructions).  A warp leaves the batch only when all of its 32 pixels are done.
+        // Per group of 32 entries each lane tests ONE entry against this warp's strips and a ballot
+        // compacts the survivors, so culled entries cost nothing per pixel.  The survivor loop is
+        // warp-uniform (same mask in every lane) and its body is straight-line + short reconvergent
+        // `if`s: a per-thread `continue`/`break` here leaves the warp split into fragments that each
+        // re-walk the list (measured: 18x the instructions).  A warp leaves the batch only when all of
+        // its 64 pixels are done.
         {
             const Record* rec = &s_rec[st][0];
             const uint32_t base = (uint32_t)(b * kFwdBatch);
             for (int j0 = 0; j0 < cnt; j0 += 32) {
-                if (__all_sync(0xffffffffu, done)) break;
+                if (__all_sync(0xffffffffu, done0 && done1)) break;
                 const int jl = j0 + lane;
-                const bool hit = jl < cnt && strip_hit(__float_as_uint(rec[jl].b.w), warp);
+                bool hit = false;
+                if (jl < cnt) {
+                    const uint32_t kb = __float_as_uint(rec[jl].b.w);
+                    hit = (int)((kb >> kStripHiShift) & 7u) >= s_lo && (int)((kb >> kStripLoShift) & 7u) <= s_hi;
+                }
                 uint32_t m = __ballot_sync(0xffffffffu, hit);
                 while (m) {
                     const int j = j0 + __ffs(m) - 1;
                     m &= m - 1;
                     const float4 a = rec[j].a;
                     const float4 bb = rec[j].b;
-                    const float dx = a.x - fpx, dy = a.y - fpy;
-                    const float power = -0.5f * (a.z * dx * dx + bb.x * dy * dy) - a.w * dx * dy;
-                    float alpha = fminf(kAlphaCap, bb.y * fast_exp(power));
-                    alpha = hier_alpha<HIER>(alpha, bb.z, __float_as_uint(bb.w));
-                    const float test_T = T * (1.0f - alpha);
-                    bool valid = !done && power <= 0.0f && alpha >= kAlphaSkip;
-                    if (valid && test_T < kTStop) { done = true; valid = false; }
-                    if (valid) {
+                    const uint32_t kb = __float_as_uint(bb.w);
+                    const float dx = a.x - fpx, dy0 = a.y - fpy0, dy1 = a.y - fpy1;
+                    const float qx = a.z * dx * dx, qxy = a.w * dx;
+                    const float pw0 = -0.5f * (qx + bb.x * dy0 * dy0) - qxy * dy0;
+                    const float pw1 = -0.5f * (qx + bb.x * dy1 * dy1) - qxy * dy1;
+                    float al0 = fminf(kAlphaCap, bb.y * fast_exp(pw0));
+                    float al1 = fminf(kAlphaCap, bb.y * fast_exp(pw1));
+                    al0 = hier_alpha<HIER>(al0, bb.z, kb);
+                    al1 = hier_alpha<HIER>(al1, bb.z, kb);
+                    const float tT0 = T0 * (1.0f - al0), tT1 = T1 * (1.0f - al1);
+                    bool v0 = !done0 && pw0 <= 0.0f && al0 >= kAlphaSkip;
+                    bool v1 = !done1 && pw1 <= 0.0f && al1 >= kAlphaSkip;
+                    if (v0 && tT0 < kTStop) { done0 = true; v0 = false; }
+                    if (v1 && tT1 < kTStop) { done1 = true; v1 = false; }
+                    if (v0 || v1) {
                         const float4 c = rec[j].c;
-                        const float w = alpha * T;
-                        C0 += c.x * w; C1 += c.y * w; C2 += c.z * w;
-                        if (DEPTH) invd += c.w * w;
-                        T = test_T;
-                        last = base + (uint32_t)j + 1u;
+                        const uint32_t idx = base + (uint32_t)j + 1u;
+                        if (v0) {
+                            const float w = al0 * T0;
+                            Ca0 += c.x * w; Ca1 += c.y * w; Ca2 += c.z * w;
+                            if (DEPTH) inv0 += c.w * w;
+                            T0 = tT0; last0 = idx;
+                        }
+                        if (v1) {
+                            const float w = al1 * T1;
+                            Cb0 += c.x * w; Cb1 += c.y * w; Cb2 += c.z * w;
+                            if (DEPTH) inv1 += c.w * w;
+                            T1 = tT1; last1 = idx;
+                        }
                     }
                 }
             }
         }
-        const int ndone = __syncthreads_count(done);
-        if (ndone == 256) break;
+        const int ndone = __syncthreads_count(done0 && done1);
+        if (ndone == kFwdThreads) break;
         if (b + kFwdStages < nb) {
             if (tid == 0) {
                 const int nb2 = b + kFwdStages;
@@ -118,7 +146,9 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
     if (tid == 0)
         for (int b = waited; b < issued; b++) mbar_wait(&s_full[b % kFwdStages], (uint32_t)((b / kFwdStages) & 1));
 
-    if (inside) {
+    const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
+    auto store = [&](bool inside, int py, float T, float c0, float c1, float c2, float invd, uint32_t last) {
+        if (!inside) return;
         const size_t pix = (size_t)py * W + px;
         final_T[pix] = T;
         n_contrib[pix] = last;
@@ -128,20 +158,18 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
             const size_t local_row = blockIdx.x / gx;
             const size_t o = ((local_row * 3) * kTile + (size_t)(py & (kTile - 1))) * W + px;
             const size_t cs = (size_t)kTile * W;
-            out_color[o] = C0 + T * bg[0];
-            out_color[o + cs] = C1 + T * bg[1];
-            out_color[o + 2 * cs] = C2 + T * bg[2];
+            out_color[o] = c0 + T * bg0; out_color[o + cs] = c1 + T * bg1; out_color[o + 2 * cs] = c2 + T * bg2;
             if (DEPTH) out_invdepth[(local_row * kTile + (size_t)(py & (kTile - 1))) * W + px] = invd;
         } else {
             const size_t plane = (size_t)H * W;
-            out_color[pix] = C0 + T * bg[0];
-            out_color[plane + pix] = C1 + T * bg[1];
-            out_color[2 * plane + pix] = C2 + T * bg[2];
+            out_color[pix] = c0 + T * bg0; out_color[plane + pix] = c1 + T * bg1; out_color[2 * plane + pix] = c2 + T * bg2;
             if (DEPTH) out_invdepth[pix] = invd;
         }
-    }
-    const uint32_t wmax = __reduce_max_sync(0xffffffffu, last);
-    if ((tid & 31) == 0) atomicMax(&s_max, wmax);
+    };
+    store(in0, py0, T0, Ca0, Ca1, Ca2, inv0, last0);
+    store(in1, py1, T1, Cb0, Cb1, Cb2, inv1, last1);
+    const uint32_t wmax = __reduce_max_sync(0xffffffffu, max(last0, last1));
+    if (lane == 0) atomicMax(&s_max, wmax);
     __syncthreads();
     if (tid == 0) tile_max_contrib[tile] = s_max;
 }
@@ -157,7 +185,7 @@ int launch_render_forward(const h3dgs_raster_args& a, const uint32_t* ranges, co
     if (rows <= 0 || gx <= 0) return H3DGS_OK;
     const bool hier = a.interpolation_weights != nullptr;
     const bool depth = a.do_depth != 0;
-    const dim3 grid(gx * rows), block(256);
+    const dim3 grid(gx * rows), block(kFwdThreads);
     ProfScope prof(H3DGS_STAGE_RENDER_FWD, s);
 #define LAUNCH(HI, DE)                                                                                         \
     render_forward_kernel<HI, DE><<<grid, block, 0, s>>>(W, H, gx, sc, si, (const uint2*)ranges, sorted_records, \
