@@ -104,7 +104,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -353,13 +353,15 @@ def main():
             ms = float(t.item())
         return ms
 
-    for i in range(args.warmup):
-        step(i)
-    torch.cuda.synchronize()
-
+    # the clock sampler (nvidia-smi) starts BEFORE the warm-up: its NVML start-up stalls the GPU for
+    # milliseconds and must not land inside the timed region
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(1.0)
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
     _lib.profile_reset(); _lib.profile_enable(True)
     l0 = _lib.launch_count()
     stats = []

