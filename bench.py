@@ -342,7 +342,7 @@ def main():
             if not resident:
                 loss_host = loss.item()          # D2H read of the step's result
             if collect is not None:
-                collect.append((n, radii))
+                collect.append(n)            # ints only: holding tensors here would defeat the caching allocator
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -371,16 +371,15 @@ def main():
     ms_e2e = timed(args.steps, False)
     clocks = sampler.stop() if rank == 0 else None
 
-    # bookkeeping for the roofline: P (cut), V, D averaged over the timed steps
-    Pm = float(np.mean([s[0] for s in stats]))
-    Vm = float(np.mean([int((s[1] > 0).sum().item()) for s in stats[:N_VIEWS]]))
+    # bookkeeping for the roofline (untimed pass over the views): P (cut), V, D
+    from diff_gaussian_rasterization import _C as rc
+    Pm = float(np.mean(stats))
+    Vs, Ds = [], []
+    for i in range(N_VIEWS):
+        loss, radii, n = step(i)
+        Vs.append(int((radii > 0).sum().item())); Ds.append(rc.last_num_rendered())
+    Vm, Dm = float(np.mean(Vs)), float(np.mean(Ds))
     stage_ms = {k: (v[0] / max(v[1], 1)) for k, v in prof.items() if v[1] > 0}
-    Dm = None
-    try:
-        from diff_gaussian_rasterization import _C as rc
-        Dm = float(rc.last_num_rendered())
-    except Exception:
-        pass
 
     if rank == 0:
         ms_step = ms_total / args.steps
