@@ -391,7 +391,7 @@ def main():
                "e2e": {"value": 1000.0 / (ms_e2e / args.steps), "unit": UNIT,
                        "h2d_bytes_per_step": 3 * H * W * 4 + 16 * 4 * 2 + 3 * 4, "d2h_bytes_per_step": 4},
                "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
-               "counts": {"P_cut": Pm, "V": Vm, "D": Dm, "N_all": int(scene.means3D.shape[0])}}
+               "counts": {"P_cut": Pm, "V": Vm, "D_rank0": Dm, "N_all": int(scene.means3D.shape[0])}}
         # roofline of the dominant kernel
         peaks = {}
         try:
@@ -402,13 +402,22 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         if stage_ms and Dm:
             dom = max((k for k in stage_ms if k not in ("lod_cut", "lod_weights")), key=lambda k: stage_ms[k])
-            ab = alg_bytes(Pm, Vm, Dm / max(world, 1) if dom.startswith("render") else Dm, hier)
+            # Dm is THIS rank's num_rendered: with tile sharding every rank bins ~D/world entries
+            ab = alg_bytes(Pm, Vm, Dm, hier)
             achieved = ab[dom] / (stage_ms[dom] * 1e-3) / 1e9
+            traffic = None
+            try:   # DRAM bytes of this kernel from the committed `ncu --set full` capture (per launch)
+                tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+                if tr.get("workload") == args.workload and world == 1:
+                    traffic = tr["kernels"].get(dom, {}).get("dram_bytes")
+            except Exception:
+                pass
             out["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                               "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                               "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                                "alg_bytes_per_launch": ab[dom], "kernel_ms": stage_ms[dom],
                                "note": "the blend kernels are FP32-issue-bound, not HBM-bound (SURVEY.md 8d); "
                                        "see profiles/ for the ncu pipe utilisation"}
+            ab = alg_bytes(Pm, Vm, Dm * world, hier)       # whole frame
             out["step_roofline"] = {"alg_bytes_per_image": ab["total"], "achieved_gbs": ab["total"] / (ms_step * 1e-3) / 1e9,
                                     "frac_of_hbm_peak": ab["total"] / (ms_step * 1e-3) / 1e9 / peak}
         if world == 1 and args.classic:
