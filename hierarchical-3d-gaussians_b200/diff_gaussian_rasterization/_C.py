@@ -51,7 +51,7 @@ def _stream():
 def _make_args(P, means3D, sh, colors_precomp, opacities, scales, rotations, cov3D_precomp, bg, viewmatrix, projmatrix,
                campos, tanfovx, tanfovy, image_height, image_width, sh_degree, scale_modifier, prefiltered, debug,
                interpolation_weights, num_node_kids, do_depth, shard=(1, 0), render_indices=None,
-               parent_indices=None, num_source=0):
+               parent_indices=None, num_source=0, grad_rows=(0, 0)):
     a = _lib.RasterArgs()
     a.P = P
     a.sh_degree = int(sh_degree)
@@ -65,6 +65,7 @@ def _make_args(P, means3D, sh, colors_precomp, opacities, scales, rotations, cov
     a.interpolation_weights, a.num_node_kids = _ptr(interpolation_weights), _ptr(num_node_kids)
     a.render_indices, a.parent_indices, a.num_source = _ptr(render_indices), _ptr(parent_indices), int(num_source)
     a.shard_count, a.shard_index = int(shard[0]), int(shard[1])
+    a.grad_row_begin, a.grad_row_end = int(grad_rows[0]), int(grad_rows[1])
     return a
 
 
@@ -142,7 +143,7 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, opacities, 
                                  dL_dout_invdepth, sh, degree, campos, geomBuffer, num_rendered, binningBuffer,
                                  imageBuffer, debug, render_indices=None, parent_indices=None,
                                  interpolation_weights=None, num_node_kids=None, do_depth=False, image_height=None,
-                                 image_width=None, shard=(1, 0), phases=3, scratch=None, grads=None):
+                                 image_width=None, shard=(1, 0), phases=3, scratch=None, grad_rows=(0, 0)):
     """-> (dL_dmeans2D, dL_dcolors, dL_dopacity, dL_dmeans3D, dL_dcov3D, dL_dsh, dL_dscales, dL_drotations)"""
     L = _lib.lib()
     (P, means3D, sh, colors, opacities, scales, rotations, cov3D_precomp, background, viewmatrix, projmatrix, campos,
@@ -155,10 +156,12 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, opacities, 
     W = int(image_width if image_width is not None else dL_dout_color.shape[2])
     a = _make_args(P, means3D, sh, colors, opacities, scales, rotations, cov3D_precomp, background, viewmatrix,
                    projmatrix, campos, tan_fovx, tan_fovy, H, W, degree, scale_modifier, False, debug, ts, kids,
-                   do_depth, shard, ridx, pidx, 0 if ridx is None else N)
+                   do_depth, shard, ridx, pidx, 0 if ridx is None else N, grad_rows)
     g_color = _f32c(dL_dout_color, "dL_dout_color")
     g_depth = _f32c(dL_dout_invdepth, "dL_dout_invdepth") if (do_depth and dL_dout_invdepth is not None) else None
-    e = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+    # a row block leaves the other rows untouched: start them from zero
+    e = (lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)) if grad_rows[1] > grad_rows[0] else \
+        (lambda *s: torch.empty(s, dtype=torch.float32, device=dev))
     M = sh.shape[1] if sh is not None else 0
     if phases & 2:
         d_means3D, d_means2D, d_opac = e(N, 3), e(P, 3), e(N, 1)

@@ -32,6 +32,7 @@ class RasterArgs(C.Structure):
         ("interpolation_weights", C.c_void_p), ("num_node_kids", C.c_void_p),
         ("render_indices", C.c_void_p), ("parent_indices", C.c_void_p), ("num_source", C.c_int32),
         ("shard_count", C.c_int32), ("shard_index", C.c_int32),
+        ("grad_row_begin", C.c_int32), ("grad_row_end", C.c_int32),
     ]
 
 

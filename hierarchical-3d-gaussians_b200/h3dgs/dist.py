@@ -8,9 +8,10 @@ Per frame, with G ranks and replicated parameters:
   * forward exchange : ONE all-gather of the packed per-rank slabs [rows][3][16][W];
   * the loss is evaluated on the full image on every rank (replicated), so no second
     image exchange is needed for dL/dcolor;
-  * backward exchange: ONE sum-reduction of the [P,10] 2D-space gradient sums (40 B per
+  * backward exchange: ONE reduce-scatter of the [P,10] 2D-space gradient sums (40 B per
     Gaussian, taken BEFORE the per-Gaussian chain rule: 6x less traffic than reducing the
-    248 B of final gradients), then K8/K9 run replicated.
+    248 B of final gradients); K8/K9 then run on each rank's own row block only, so the
+    parameter gradients come out sharded by rendered row (sum over ranks = the full gradient).
 G == 1 never touches torch.distributed.
 """
 import torch
@@ -68,10 +69,28 @@ def gather_image(packed, H, W, world, group=None):
     return unpack(flat.view((world, rpr) + tuple(slab.shape[1:])), H, W, world)
 
 
-def reduce_accum(accum_bytes, P, group=None):
-    """ONE sum-reduction of the [P,10] fp32 2D-space gradient sums held in the backward scratch."""
-    acc = accum_bytes.view(torch.float32)[: P * 10]
-    dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+def row_block(P, world, rank):
+    """rendered rows [begin, end) whose gradients rank `rank` finishes (equal blocks, last ones may be short)."""
+    chunk = (P + world - 1) // world
+    return min(rank * chunk, P), min((rank + 1) * chunk, P)
+
+
+def accum_scratch(P, world, device):
+    """backward scratch holding world equal row blocks of the [P][10] sums (tail rows zero)."""
+    chunk = (P + world - 1) // world
+    return torch.zeros((max(world * chunk, 1) * 10,), dtype=torch.float32, device=device).view(torch.uint8)
+
+
+def reduce_accum(accum_bytes, P, world, rank, group=None):
+    """ONE reduction of the [P,10] fp32 2D-space gradient sums: a reduce-scatter by row block on NCCL
+    (in place: every rank keeps the complete sums of ITS rows only); backends without reduce-scatter
+    (gloo, CPU tests) fall back to an all-reduce, of which only the own block is consumed."""
+    chunk = (P + world - 1) // world
+    acc = accum_bytes.view(torch.float32)[: world * chunk * 10]
+    if dist.get_backend(group) == "nccl":
+        dist.reduce_scatter_tensor(acc[rank * chunk * 10:(rank + 1) * chunk * 10], acc, op=dist.ReduceOp.SUM, group=group)
+    else:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
     return accum_bytes
 
 
@@ -97,12 +116,16 @@ class _ShardedRasterize(torch.autograd.Function):
                   rs.projmatrix, rs.tanfovx, rs.tanfovy)
         tail = (shs, rs.sh_degree, rs.campos, gb, ctx.n, bb, ib, rs.debug, rs.render_indices, rs.parent_indices,
                 rs.interpolation_weights, rs.num_node_kids, False, rs.image_height, rs.image_width)
+        world, rank = ctx.shard
+        P = radii.shape[0]
         # phase 1: per-tile replay on the owned tiles -> partial [P,10] sums
-        accum = _C.rasterize_gaussians_backward(*common, grad_img.contiguous(), None, *tail, shard=ctx.shard, phases=1)
-        reduce_accum(accum, radii.shape[0], ctx.group)
-        # phase 2: per-Gaussian chain rule, replicated
+        accum = _C.rasterize_gaussians_backward(*common, grad_img.contiguous(), None, *tail, shard=ctx.shard, phases=1,
+                                                scratch=accum_scratch(P, world, radii.device))
+        # ONE reduce-scatter by row block; phase 2 (per-Gaussian chain rule) only on the own block:
+        # the returned gradients are SHARDED by rendered row (complete for the own block, zero elsewhere)
+        reduce_accum(accum, P, world, rank, ctx.group)
         (d_means2D, _dc, d_opac, d_means3D, _dcov, d_sh, d_scales, d_rots) = _C.rasterize_gaussians_backward(
-            *common, None, None, *tail, shard=ctx.shard, phases=2, scratch=accum)
+            *common, None, None, *tail, shard=ctx.shard, phases=2, scratch=accum, grad_rows=row_block(P, world, rank))
         return d_means3D, d_sh, d_opac, d_scales, d_rots, None, None, None, None
 
 

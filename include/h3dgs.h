@@ -91,6 +91,10 @@ typedef struct h3dgs_raster_args {
     /* screen-tile shard for the multi-GPU mode: this call bins and renders only
      * tile rows y with (y % shard_count) == shard_index.  (1,0) = whole image. */
     int32_t shard_count, shard_index;
+    /* Backward phase 2 (per-Gaussian chain rule) only for rendered rows [grad_row_begin, grad_row_end);
+     * (0, 0) = all rows.  The multi-GPU mode reduce-scatters the [P][10] sums and lets every rank finish
+     * only its own row block, so the final gradients come out sharded by rendered row. */
+    int32_t grad_row_begin, grad_row_end;
 } h3dgs_raster_args;   /* NOTE: keep hierarchical-3d-gaussians_b200/h3dgs/_lib.py::RasterArgs in sync */
 
 /* Forward: K1 preprocess -> scan -> duplicateWithKeys -> radix sort -> tile ranges

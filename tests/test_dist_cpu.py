@@ -29,12 +29,15 @@ def _worker(rank, world, port, H, W, out):
     img = hd.gather_image(packed, H, W, world)
     ok_img = torch.equal(img, full)
     # gradient sums: each rank holds a partial [P,10]; padded scratch like the C-ABI's
-    P = 1000
+    P = 1001                                  # not a multiple of the world size
     parts = torch.rand((world, P, 10), generator=g)
-    scratch = torch.zeros((P * 10 * 4 + 256,), dtype=torch.uint8)
+    scratch = hd.accum_scratch(P, world, "cpu")
     scratch.view(torch.float32)[: P * 10] = parts[rank].flatten()
-    hd.reduce_accum(scratch, P)
-    ok_acc = torch.allclose(scratch.view(torch.float32)[: P * 10].view(P, 10), parts.sum(0), rtol=1e-6, atol=1e-7)
+    hd.reduce_accum(scratch, P, world, rank)
+    lo, hi = hd.row_block(P, world, rank)
+    ok_acc = torch.allclose(scratch.view(torch.float32)[lo * 10: hi * 10].view(hi - lo, 10), parts.sum(0)[lo:hi],
+                            rtol=1e-6, atol=1e-7)
+    ok_acc = ok_acc and sum(b[1] - b[0] for b in (hd.row_block(P, world, r) for r in range(world))) == P
     if rank == 0:
         torch.save((ok_img, ok_acc), out)
     dist.barrier(); dist.destroy_process_group()

@@ -41,6 +41,8 @@ def _worker(rank, world, port, out):
     sh = hd.TileSharder(world, rank, dev)
     loss2, radii2, n2 = sh.l1_step(scene, dcam, bg, gt, thr)
     g2 = [p.grad.clone() for p in scene.params()]
+    for t_ in g2:                              # gradients come back sharded by rendered row: their sum is the full gradient
+        dist.all_reduce(t_, op=dist.ReduceOp.SUM)
     with torch.no_grad():
         img2 = sh.render(scene, dcam, bg, thr)[0]
     ok = n1 == n2 and torch.equal(radii1, radii2) and torch.equal(img1, img2) and abs(loss1.item() - loss2.item()) < 1e-7
