@@ -159,12 +159,14 @@ def rasterize_gaussians_backward(background, means3D, radii, colors, opacities, 
                    do_depth, shard, ridx, pidx, 0 if ridx is None else N, grad_rows)
     g_color = _f32c(dL_dout_color, "dL_dout_color")
     g_depth = _f32c(dL_dout_invdepth, "dL_dout_invdepth") if (do_depth and dL_dout_invdepth is not None) else None
-    # a row block leaves the other rows untouched: start them from zero
-    e = (lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)) if grad_rows[1] > grad_rows[0] else \
+    # a row block leaves the other rows untouched: start them from zero (in scatter mode the library
+    # zero-fills the full-size gradients itself, overlapped on its side stream)
+    e = (lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)) if (grad_rows[1] > grad_rows[0] and ridx is None) else \
         (lambda *s: torch.empty(s, dtype=torch.float32, device=dev))
     M = sh.shape[1] if sh is not None else 0
     if phases & 2:
-        d_means3D, d_means2D, d_opac = e(N, 3), e(P, 3), e(N, 1)
+        d_means3D, d_opac = e(N, 3), e(N, 1)
+        d_means2D = torch.zeros((P, 3), dtype=torch.float32, device=dev) if grad_rows[1] > grad_rows[0] else e(P, 3)
         d_sh = e(N, M, 3) if sh is not None else e(0)
         d_colors = e(N, 3) if colors is not None else e(0)
         d_scales = e(N, 3) if scales is not None else e(0)
