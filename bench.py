@@ -308,12 +308,14 @@ def main():
     gts_host = [torch.rand((3, H, W), generator=g).pin_memory() for _ in range(N_VIEWS)]
     gts_dev = [t.to(dev) for t in gts_host]
     sharder = hdist.TileSharder(world, rank, dev) if world > 1 else None
+    copy_stream = torch.cuda.Stream(device=dev)
 
     host_cams = [(torch.tensor(c.world_view_transform).pin_memory(), torch.tensor(c.full_proj_transform).pin_memory(),
                   torch.tensor(c.camera_center).pin_memory()) for c in cams]
 
     def step(i, resident=True):
         v = i % N_VIEWS
+        ready = None
         if resident:
             cam, gt = dcams[v], gts_dev[v]
         else:       # e2e: this step's camera and target come from pinned host memory
@@ -324,11 +326,16 @@ def main():
             cam.projmatrix = host_cams[v][1].to(dev, non_blocking=True)
             cam.campos = host_cams[v][2].to(dev, non_blocking=True)
             cam.campos_cpu = host_cams[v][2]
-            gt = gts_host[v].to(dev, non_blocking=True)
+            # the 25 MB target is only needed at the loss: upload it on a copy stream, overlapped with
+            # this step's LOD cut and forward pass
+            with torch.cuda.stream(copy_stream):
+                gt = gts_host[v].to(dev, non_blocking=True)
+                ready = torch.cuda.Event(); ready.record(copy_stream)
+            gt.record_stream(torch.cuda.current_stream())
         if sharder is None:
-            loss, radii, n = pipeline.l1_step(scene, cam, bg, gt, thr[v] if hier else None)
+            loss, radii, n = pipeline.l1_step(scene, cam, bg, gt, thr[v] if hier else None, gt_ready=ready)
         else:
-            loss, radii, n = sharder.l1_step(scene, cam, bg, gt, thr[v] if hier else None)
+            loss, radii, n = sharder.l1_step(scene, cam, bg, gt, thr[v] if hier else None, gt_ready=ready)
         return loss, radii, n
 
     def timed(nsteps, resident, collect=None):

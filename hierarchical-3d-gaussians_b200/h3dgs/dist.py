@@ -147,9 +147,11 @@ class TileSharder:
         img, radii = _ShardedRasterize.apply(means, shs, opac, scales, rots, rs, self.world, self.rank, self.group)
         return img, radii, n
 
-    def l1_step(self, scene, cam, bg, gt, threshold=None, sh_degree=3):
+    def l1_step(self, scene, cam, bg, gt, threshold=None, sh_degree=3, gt_ready=None):
         scene.zero_grad()
         img, radii, n = self.render(scene, cam, bg, threshold, sh_degree)
+        if gt_ready is not None:
+            torch.cuda.current_stream().wait_event(gt_ready)
         loss = (img - gt).abs().mean()
         loss.backward()
         return loss, radii, n

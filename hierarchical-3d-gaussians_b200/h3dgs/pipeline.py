@@ -133,14 +133,17 @@ def render_hier_fused(scene, cam, bg, threshold, sh_degree=3):
     return img, radii, n
 
 
-def l1_step(scene, cam, bg, gt, threshold=None, sh_degree=3, fused=True):
-    """forward + L1 loss + backward; returns the loss tensor (device) and bookkeeping."""
+def l1_step(scene, cam, bg, gt, threshold=None, sh_degree=3, fused=True, gt_ready=None):
+    """forward + L1 loss + backward; returns the loss tensor (device) and bookkeeping.
+    gt_ready: optional CUDA event after which `gt` (uploaded on another stream) may be read."""
     scene.zero_grad()
     if scene.hier:
         img, radii, n = (render_hier_fused if fused else render_hier)(scene, cam, bg, threshold, sh_degree)
     else:
         img, radii = render_flat(scene, cam, bg, sh_degree)
         n = scene.means3D.shape[0]
+    if gt_ready is not None:
+        torch.cuda.current_stream().wait_event(gt_ready)
     loss = (img - gt).abs().mean()
     loss.backward()
     return loss, radii, n
