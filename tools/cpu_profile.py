@@ -1,6 +1,6 @@
 """scratch: CPU-side profile of the step (GPU box)"""
 import os, sys, cProfile, pstats, io
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "hierarchical-3d-gaussians_b200"))
 import torch, bench
 from h3dgs import pipeline, synth

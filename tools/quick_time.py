@@ -1,6 +1,6 @@
 """scratch: quick timing of the stages on the GPU box (not the bench)."""
 import sys, os, time
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "hierarchical-3d-gaussians_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
 from h3dgs import synth

@@ -1,6 +1,6 @@
 """scratch: where does the non-kernel time of a step go? (GPU box)"""
 import os, sys, time
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "hierarchical-3d-gaussians_b200"))
 import numpy as np, torch
 import bench
