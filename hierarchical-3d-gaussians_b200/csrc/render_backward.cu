@@ -82,7 +82,7 @@ __device__ __forceinline__ void pixel_grad(const float4& a, const float4& bb, fl
                                            float alpha, float dadb, float cg, float T_final, float bg_dot, float g0,
                                            float g1, float g2, float gd, PixState& st, float (&v)[10])
 {
-    const float rcp = __frcp_rn(1.f - alpha);                 // one reciprocal serves T and the bg term
+    const float rcp = fast_rcp(1.f - alpha);                   // one reciprocal serves T and the bg term
     const float Tn = st.T * rcp;
     const float as_n = st.last_alpha * st.last_cg + (1.f - st.last_alpha) * st.acc_s;
     const float w = valid ? alpha * Tn : 0.f;                 // dchannel_dcolor
