@@ -78,11 +78,12 @@ identify_tile_ranges_kernel(int64_t D, const uint64_t* __restrict__ keys, uint32
 }
 
 // sorted_records[j] = records[point_list[j]] : 48-B gathers out of an L2-resident array.
-// One thread per entry.  While the record is in registers, derive which 16x2-pixel strips
-// (= warps of the blend CTAs) of ITS tile the entry can reach at all: alpha >= 1/255 needs
-// d^T Q d <= 2 ln(255 o), an ellipse whose y half-extent is sqrt(2 ln(255 o) * Q_xx / det Q).
-// The range is conservative (margin for fp32 rounding; the hierarchy weight only lowers
-// alpha), so skipping a strip never changes a result; it is stored in spare bits of kbits.
+// One thread per entry.  While the record is in registers, derive which of the four 8x8-pixel
+// quadrants (= warps of the blend CTAs) of ITS tile the entry can reach at all: alpha >= 1/255
+// needs d^T Q d <= 2 ln(255 o), an ellipse whose half-extents are sqrt(2 ln(255 o) * Q_yy / det Q) in
+// x and sqrt(2 ln(255 o) * Q_xx / det Q) in y.  The box is conservative (margin for fp32 rounding;
+// the hierarchy weight only lowers alpha), so skipping a quadrant never changes a result; the
+// 4-bit mask is stored in spare bits of kbits.
 __global__ void __launch_bounds__(256)
 gather_records_kernel(int64_t D, const uint32_t* __restrict__ point_list, const uint64_t* __restrict__ keys, int gx,
                       const Record* __restrict__ records, Record* __restrict__ sorted)
@@ -92,20 +93,26 @@ gather_records_kernel(int64_t D, const uint32_t* __restrict__ point_list, const 
     const uint32_t g = point_list[j];
     const float4* src = reinterpret_cast<const float4*>(records + g);
     const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
-    const int tile_y = (int)((uint32_t)(keys[j] >> 32) / (uint32_t)gx);
-    int lo = 0, hi = 7;
+    const uint32_t tile = (uint32_t)(keys[j] >> 32);
+    const int tile_y = (int)(tile / (uint32_t)gx), tile_x = (int)(tile - (uint32_t)tile_y * (uint32_t)gx);
+    uint32_t mask = 0xFu;
     const float det = a.z * b.x - a.w * a.w;          // conic determinant
     const float o255 = b.y * 255.0f;
-    if (!(o255 > 1.0f)) { lo = 1; hi = 0; }            // can never reach alpha >= 1/255
-    else if (det > 0.0f && a.z > 0.0f) {
-        const float ey = sqrtf(2.0f * logf(o255) * a.z / det) * 1.001f + 0.01f;
-        if (ey == ey && ey < 1e6f) {
-            const float rel = a.y - (float)(tile_y * kTile);
-            const int r0 = max(0, (int)ceilf(rel - ey)), r1 = min(kTile - 1, (int)floorf(rel + ey));
-            if (r1 < r0) { lo = 1; hi = 0; } else { lo = r0 >> 1; hi = r1 >> 1; }
+    if (!(o255 > 1.0f)) mask = 0u;                     // can never reach alpha >= 1/255
+    else if (det > 0.0f && a.z > 0.0f && b.x > 0.0f) {
+        const float s = 2.0f * logf(o255) / det;
+        const float ex = sqrtf(s * b.x) * 1.001f + 0.01f, ey = sqrtf(s * a.z) * 1.001f + 0.01f;
+        if (ex == ex && ey == ey && ex < 1e6f && ey < 1e6f) {
+            const float rx = a.x - (float)(tile_x * kTile), ry = a.y - (float)(tile_y * kTile);
+            // pixel columns / rows [lo, hi] inside the tile that the box covers
+            const int x0 = (int)ceilf(rx - ex), x1 = (int)floorf(rx + ex);
+            const int y0 = (int)ceilf(ry - ey), y1 = (int)floorf(ry + ey);
+            const uint32_t mx = (x0 <= 7 && x1 >= 0 ? 1u : 0u) | (x0 <= 15 && x1 >= 8 ? 2u : 0u);
+            const uint32_t my = (y0 <= 7 && y1 >= 0 ? 1u : 0u) | (y0 <= 15 && y1 >= 8 ? 2u : 0u);
+            mask = ((my & 1u) ? mx : 0u) | ((my & 2u) ? (mx << 2) : 0u);
         }
     }
-    const uint32_t kb = (__float_as_uint(b.w) & 0x00FFFFFFu) | ((uint32_t)lo << kStripLoShift) | ((uint32_t)hi << kStripHiShift);
+    const uint32_t kb = (__float_as_uint(b.w) & 0x00FFFFFFu) | (mask << kQuadShift);
     float4* dst = reinterpret_cast<float4*>(sorted + j);
     dst[0] = a;
     dst[1] = make_float4(b.x, b.y, b.z, __uint_as_float(kb));

@@ -21,14 +21,14 @@ constexpr float kTStop = 0.0001f;
 constexpr float kWEps = 0.0000001f;
 constexpr int kBucket = H3DGS_BUCKET;
 constexpr uint32_t kKidsMask = 0xFFFFFu;
-constexpr int kClampShift = 20, kStripLoShift = 24, kStripHiShift = 27;
+constexpr int kClampShift = 20, kQuadShift = 24;
 
 // Per-Gaussian projected record: 3 x float4 = 48 B, 16-B aligned, so a batch of
 // records is one contiguous cp.async.bulk (TMA) transfer.
 //   a = {x, y, conic.x, conic.y}
 //   b = {conic.z, opacity, t, kbits}     kbits: bits 0..19 num_node_kids, 20..22 SH clamp flags; in the
-//                                        per-tile SORTED copy also 24..26 / 27..29 = first / last 16x2-pixel
-//                                        strip of the tile this entry can reach (strip culling, binning.cu)
+//                                        per-tile SORTED copy also bits 24..27 = mask of the tile's four 8x8-pixel
+//                                        quadrants this entry can reach (quadrant culling, binning.cu)
 //   c = {r, g, b, invdepth}
 struct __align__(16) Record { float4 a, b, c; };
 static_assert(sizeof(Record) == 48, "record must be 48 bytes");
@@ -135,9 +135,11 @@ __device__ __forceinline__ float fast_exp2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// strip culling test for one entry's kbits (binning.cu::gather_records_kernel)
-__device__ __forceinline__ bool strip_hit(uint32_t kb, int warp) {
-    return warp >= (int)((kb >> kStripLoShift) & 7u) && warp <= (int)((kb >> kStripHiShift) & 7u);
+// Pixel layout of the blend kernels: CTA = 128 threads = 4 warps; warp q owns the 8x8 quadrant
+// (q & 1, q >> 1) of the 16x16 tile; lane l owns column (l & 7) and the two rows 2*(l >> 3), +1.
+__device__ __forceinline__ void quad_pixel(int tile_x, int tile_y, int warp, int lane, int& px, int& py0) {
+    px = tile_x * kTile + 8 * (warp & 1) + (lane & 7);
+    py0 = tile_y * kTile + 8 * (warp >> 1) + 2 * (lane >> 3);
 }
 
 template <bool HIER>

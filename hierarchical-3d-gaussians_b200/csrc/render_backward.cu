@@ -152,8 +152,9 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
     if (tid == 0)
         for (int it = 0; it < kBwdStages && it < nb; it++) issue(it);
 
-    const int px = tile_x * kTile + (lane & 15);
-    const int py0 = tile_y * kTile + 4 * warp + 2 * (lane >> 4), py1 = py0 + 1;
+    int px, py0;
+    quad_pixel(tile_x, tile_y, warp, lane, px, py0);
+    const int py1 = py0 + 1;
     const bool in0 = px < W && py0 < H, in1 = px < W && py1 < H;
     const float fpx = (float)px, fpy0 = (float)py0, fpy1 = (float)py1;
     const size_t pix0 = (size_t)py0 * W + px, pix1 = (size_t)py1 * W + px, plane = (size_t)H * W;
@@ -164,8 +165,8 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
     if (in0) { ga0 = dL_dcolor[pix0]; ga1 = dL_dcolor[plane + pix0]; ga2 = dL_dcolor[2 * plane + pix0]; if (DEPTH) gad = dL_dinvdepth[pix0]; }
     if (in1) { gb0 = dL_dcolor[pix1]; gb1 = dL_dcolor[plane + pix1]; gb2 = dL_dcolor[2 * plane + pix1]; if (DEPTH) gbd = dL_dinvdepth[pix1]; }
     const float bgd0 = bg[0] * ga0 + bg[1] * ga1 + bg[2] * ga2, bgd1 = bg[0] * gb0 + bg[1] * gb1 + bg[2] * gb2;
-    const int wlast = (int)__reduce_max_sync(0xffffffffu, (unsigned)max(last0, last1));   // nothing in these strips beyond it
-    const int s_lo = 2 * warp, s_hi = 2 * warp + 1;
+    const int wlast = (int)__reduce_max_sync(0xffffffffu, (unsigned)max(last0, last1));   // nothing in this quadrant beyond it
+    const uint32_t qbit = 1u << (kQuadShift + warp);
 
     for (int it = 0; it < nb; it++) {
         const int st = it % kBwdStages, b = nb - 1 - it;
@@ -173,14 +174,10 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
         const int cnt = min(kBwdBatch, n - b * kBwdBatch);
         const Record* rec = &s_rec[st][0];
         // back to front; per group of 32 entries a ballot compacts the entries that can reach
-        // this warp's strips at all (see render_forward.cu)
+        // this warp's quadrant at all (see render_forward.cu)
         for (int j0 = (cnt - 1) & ~31; j0 >= 0; j0 -= 32) {
             const int jl = j0 + lane;
-            bool hit = false;
-            if (jl < cnt && (b * kBwdBatch + jl) < wlast) {
-                const uint32_t kbl = __float_as_uint(rec[jl].b.w);
-                hit = (int)((kbl >> kStripHiShift) & 7u) >= s_lo && (int)((kbl >> kStripLoShift) & 7u) <= s_hi;
-            }
+            const bool hit = jl < cnt && (b * kBwdBatch + jl) < wlast && (__float_as_uint(rec[jl].b.w) & qbit) != 0u;
             uint32_t m = __ballot_sync(0xffffffffu, hit);
             while (m) {
                 const int top = 31 - __clz(m);

@@ -16,8 +16,8 @@ namespace h3dgs {
 constexpr int kFwdBatch = 256;
 constexpr int kFwdStages = 2;
 
-// Two vertically adjacent pixels per thread: CTA = 128 threads = 4 warps, warp w owns pixel rows
-// 4w..4w+3 (lanes 0-15: rows 4w,4w+1; lanes 16-31: rows 4w+2,4w+3), i.e. the 16x2 strips 2w and 2w+1.
+// Two vertically adjacent pixels per thread: CTA = 128 threads = 4 warps, warp q owns one 8x8-pixel
+// quadrant of the tile (common.cuh::quad_pixel).
 // The entry's record, its dx terms, the survivor loop and (in backward) the warp reduction are
 // shared by the two pixels.
 constexpr int kFwdThreads = 128;
@@ -58,15 +58,16 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
     }
     issued = min(kFwdStages, nb);
 
-    const int px = tile_x * kTile + (lane & 15);
-    const int py0 = tile_y * kTile + 4 * warp + 2 * (lane >> 4), py1 = py0 + 1;
+    int px, py0;
+    quad_pixel(tile_x, tile_y, warp, lane, px, py0);
+    const int py1 = py0 + 1;
     const bool in0 = px < W && py0 < H, in1 = px < W && py1 < H;
     const float fpx = (float)px, fpy0 = (float)py0, fpy1 = (float)py1;
     bool done0 = !in0, done1 = !in1;
     float T0 = 1.0f, T1 = 1.0f;
     float Ca0 = 0.f, Ca1 = 0.f, Ca2 = 0.f, Cb0 = 0.f, Cb1 = 0.f, Cb2 = 0.f, inv0 = 0.f, inv1 = 0.f;
     uint32_t last0 = 0, last1 = 0;
-    const int s_lo = 2 * warp, s_hi = 2 * warp + 1;        // the two 16x2 strips this warp covers
+    const uint32_t qbit = 1u << (kQuadShift + warp);        // this warp's quadrant in the entries' reach mask
 
     int waited = 0;
     for (int b = 0; b < nb; b++) {
@@ -74,7 +75,7 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
         mbar_wait(&s_full[st], (uint32_t)((b / kFwdStages) & 1));
         waited = b + 1;
         const int cnt = min(kFwdBatch, n - b * kFwdBatch);
-        // Per group of 32 entries each lane tests ONE entry against this warp's strips and a ballot
+        // Per group of 32 entries each lane tests ONE entry against this warp's quadrant and a ballot
         // compacts the survivors, so culled entries cost nothing per pixel.  The survivor loop is
         // warp-uniform (same mask in every lane) and its body is straight-line + short reconvergent
         // `if`s: a per-thread `continue`/`break` here leaves the warp split into fragments that each
@@ -86,11 +87,7 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
             for (int j0 = 0; j0 < cnt; j0 += 32) {
                 if (__all_sync(0xffffffffu, done0 && done1)) break;
                 const int jl = j0 + lane;
-                bool hit = false;
-                if (jl < cnt) {
-                    const uint32_t kb = __float_as_uint(rec[jl].b.w);
-                    hit = (int)((kb >> kStripHiShift) & 7u) >= s_lo && (int)((kb >> kStripLoShift) & 7u) <= s_hi;
-                }
+                const bool hit = jl < cnt && (__float_as_uint(rec[jl].b.w) & qbit) != 0u;
                 uint32_t m = __ballot_sync(0xffffffffu, hit);
                 while (m) {
                     const int j = j0 + __ffs(m) - 1;
