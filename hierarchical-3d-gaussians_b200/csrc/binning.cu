@@ -80,10 +80,10 @@ identify_tile_ranges_kernel(int64_t D, const uint64_t* __restrict__ keys, uint32
 // sorted_records[j] = records[point_list[j]] : 48-B gathers out of an L2-resident array.
 // One thread per entry.  While the record is in registers, derive which of the four 8x8-pixel
 // quadrants (= warps of the blend CTAs) of ITS tile the entry can reach at all: alpha >= 1/255
-// needs d^T Q d <= 2 ln(255 o), an ellipse whose half-extents are sqrt(2 ln(255 o) * Q_yy / det Q) in
-// x and sqrt(2 ln(255 o) * Q_xx / det Q) in y.  The box is conservative (margin for fp32 rounding;
-// the hierarchy weight only lowers alpha), so skipping a quadrant never changes a result; the
-// 4-bit mask is stored in spare bits of kbits.
+// needs q(d) = d^T Q d <= 2 ln(255 o); the exact minimum of the convex q over the quadrant's rectangle of
+// pixel centres (0 if the mean is inside, else attained on an edge) is compared with that bound.  The
+// test is conservative (margin for fp32 rounding; the hierarchy weight only lowers alpha), so skipping
+// a quadrant never changes a result; the 4-bit mask is stored in spare bits of kbits.
 __global__ void __launch_bounds__(256)
 gather_records_kernel(int64_t D, const uint32_t* __restrict__ point_list, const uint64_t* __restrict__ keys, int gx,
                       const Record* __restrict__ records, Record* __restrict__ sorted)
@@ -96,20 +96,39 @@ gather_records_kernel(int64_t D, const uint32_t* __restrict__ point_list, const 
     const uint32_t tile = (uint32_t)(keys[j] >> 32);
     const int tile_y = (int)(tile / (uint32_t)gx), tile_x = (int)(tile - (uint32_t)tile_y * (uint32_t)gx);
     uint32_t mask = 0xFu;
-    const float det = a.z * b.x - a.w * a.w;          // conic determinant
+    const float A = a.z, B = a.w, C = b.x;             // conic: q(d) = A dx^2 + 2 B dx dy + C dy^2 = -2 power
+    const float det = A * C - B * B;
     const float o255 = b.y * 255.0f;
     if (!(o255 > 1.0f)) mask = 0u;                     // can never reach alpha >= 1/255
-    else if (det > 0.0f && a.z > 0.0f && b.x > 0.0f) {
-        const float s = 2.0f * logf(o255) / det;
-        const float ex = sqrtf(s * b.x) * 1.001f + 0.01f, ey = sqrtf(s * a.z) * 1.001f + 0.01f;
-        if (ex == ex && ey == ey && ex < 1e6f && ey < 1e6f) {
-            const float rx = a.x - (float)(tile_x * kTile), ry = a.y - (float)(tile_y * kTile);
-            // pixel columns / rows [lo, hi] inside the tile that the box covers
-            const int x0 = (int)ceilf(rx - ex), x1 = (int)floorf(rx + ex);
-            const int y0 = (int)ceilf(ry - ey), y1 = (int)floorf(ry + ey);
-            const uint32_t mx = (x0 <= 7 && x1 >= 0 ? 1u : 0u) | (x0 <= 15 && x1 >= 8 ? 2u : 0u);
-            const uint32_t my = (y0 <= 7 && y1 >= 0 ? 1u : 0u) | (y0 <= 15 && y1 >= 8 ? 2u : 0u);
-            mask = ((my & 1u) ? mx : 0u) | ((my & 2u) ? (mx << 2) : 0u);
+    else if (det > 0.0f && A > 0.0f && C > 0.0f) {
+        // alpha >= 1/255  <=>  q(d) <= 2 ln(255 o): compare the exact minimum of q over each quadrant's
+        // rectangle of pixel centres with that bound (conservative margin for fp32 rounding)
+        const float bound = 2.0f * logf(o255) * 1.002f + 1e-3f;
+        const float rx = a.x - (float)(tile_x * kTile), ry = a.y - (float)(tile_y * kTile);
+        if (bound == bound && rx == rx && ry == ry) {
+            mask = 0u;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                // rectangle of pixel centres relative to the mean: dx in [x0, x1], dy in [y0, y1]
+                const float x0 = (float)(8 * (q & 1)) - rx, x1 = x0 + 7.0f;
+                const float y0 = (float)(8 * (q >> 1)) - ry, y1 = y0 + 7.0f;
+                float qmin;
+                if (x0 <= 0.f && x1 >= 0.f && y0 <= 0.f && y1 >= 0.f) qmin = 0.f;      // the mean is inside
+                else {
+                    qmin = 3.0e38f;
+                    // vertical edges dx = xe: minimise over dy (dy* = -B xe / C, clamped)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const float xe = e ? x1 : x0;
+                        const float dy = fminf(y1, fmaxf(y0, -B * xe / C));
+                        qmin = fminf(qmin, A * xe * xe + 2.0f * B * xe * dy + C * dy * dy);
+                        const float ye = e ? y1 : y0;
+                        const float dx = fminf(x1, fmaxf(x0, -B * ye / A));
+                        qmin = fminf(qmin, A * dx * dx + 2.0f * B * dx * ye + C * ye * ye);
+                    }
+                }
+                if (!(qmin > bound)) mask |= 1u << q;
+            }
         }
     }
     const uint32_t kb = (__float_as_uint(b.w) & 0x00FFFFFFu) | (mask << kQuadShift);
