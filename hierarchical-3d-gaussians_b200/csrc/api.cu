@@ -157,10 +157,16 @@ extern "C" int h3dgs_rasterize_forward(const h3dgs_raster_args* a, h3dgs_alloc_f
     uint32_t* offsets = (uint32_t*)(geom + gl.offsets);
     Record* records = (Record*)(geom + gl.records);
 
-    rc = launch_preprocess(*a, out_radii, depths, tiles, records, s);
+    // per-tile histogram (filled by K1) -> ranges; its memset also covers ScanInfo
+    uint32_t* tile_count = (uint32_t*)(img + il.tile_count);
+    ScanInfo* info = (ScanInfo*)(img + il.scan_info);
+    uint32_t* ranges = (uint32_t*)(img + il.ranges);
+    const int gxy = ((a->image_width + kTile - 1) / kTile) * ((a->image_height + kTile - 1) / kTile);
+    H3_CUDA(cudaMemsetAsync(tile_count, 0, (size_t)gxy * sizeof(uint32_t), s));
+    rc = launch_preprocess(*a, out_radii, depths, tiles, records, tile_count, s);
     if (rc) return rc;
-    // SH -> RGB only feeds record.c (read again by gather_records): run it on the side stream,
-    // overlapped with the scan, the num_rendered round trip, key emission and the sort
+    // SH -> RGB only feeds record.c (read again by the record gather): run it on the side stream,
+    // overlapped with the tile scan, the num_rendered round trip and key emission
     SideStream* ss = nullptr;
     const bool side_color = !a->colors_precomp && P > 0 && !a->debug;
     if (side_color) {
@@ -175,23 +181,29 @@ extern "C" int h3dgs_rasterize_forward(const h3dgs_raster_args* a, h3dgs_alloc_f
         rc = launch_preprocess_color(*a, out_radii, records, s);
         if (rc) return rc;
     }
-    rc = launch_scan(tiles, offsets, P, geom + gl.scan_temp, gl.scan_temp_bytes, s, a->debug);
+    rc = launch_tile_scan(*a, tile_count, ranges, info, s);
     if (rc) return rc;
     // The reference API sizes the binning buffer from num_rendered: one D2H + sync.
-    uint32_t D32 = 0;
-    if (P > 0) {
-        H3_CUDA(cudaMemcpyAsync(&D32, offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        H3_CUDA(cudaStreamSynchronize(s));
-    }
-    const int64_t D = (int64_t)D32;
+    ScanInfo hinfo = {0, 0};
+    H3_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(ScanInfo), cudaMemcpyDeviceToHost, s));
+    H3_CUDA(cudaStreamSynchronize(s));
+    const int64_t D = (int64_t)hinfo.D;
     if (num_rendered) *num_rendered = D;
     const BinLayout bl = bin_layout(D);
     uint8_t* bin = (uint8_t*)alloc(user, 1, bl.total);
     if (!bin) { set_error("alloc callback returned NULL"); return H3DGS_ENOMEM; }
-    uint32_t* ranges = (uint32_t*)(img + il.ranges);
-    if (side_color) H3_CUDA(cudaStreamWaitEvent(s, ss->join, 0));      // colours are needed from gather_records on
-    rc = launch_binning(*a, out_radii, depths, offsets, records, D, bin, bl, ranges, s);
-    if (rc) return rc;
+    if (hinfo.max_count <= (uint32_t)kTileSortCap) {
+        if (side_color) H3_CUDA(cudaStreamWaitEvent(s, ss->join, 0));  // colours are needed by the record gather
+        rc = launch_tile_binning(*a, out_radii, depths, records, D, hinfo.max_count, bin, bl, ranges, tile_count, s);
+        if (rc) return rc;
+    } else {
+        // a tile list too long for the shared-memory sort: global stable radix sort (CUB), same order
+        rc = launch_scan(tiles, offsets, P, geom + gl.scan_temp, gl.scan_temp_bytes, s, a->debug);
+        if (rc) return rc;
+        if (side_color) H3_CUDA(cudaStreamWaitEvent(s, ss->join, 0));
+        rc = launch_binning(*a, out_radii, depths, offsets, records, D, bin, bl, ranges, s);
+        if (rc) return rc;
+    }
     rc = launch_render_forward(*a, ranges, (const Record*)(bin + bl.sorted_records), out_color, out_invdepth,
                                (float*)(img + il.final_T), (uint32_t*)(img + il.n_contrib),
                                (uint32_t*)(img + il.tile_max_contrib), s);

@@ -77,24 +77,9 @@ identify_tile_ranges_kernel(int64_t D, const uint64_t* __restrict__ keys, uint32
     if (i == D - 1) ranges[2 * tile + 1] = (uint32_t)D;
 }
 
-// sorted_records[j] = records[point_list[j]] : 48-B gathers out of an L2-resident array.
-// One thread per entry.  While the record is in registers, derive which of the four 8x8-pixel
-// quadrants (= warps of the blend CTAs) of ITS tile the entry can reach at all: alpha >= 1/255
-// needs q(d) = d^T Q d <= 2 ln(255 o); the exact minimum of the convex q over the quadrant's rectangle of
-// pixel centres (0 if the mean is inside, else attained on an edge) is compared with that bound.  The
-// test is conservative (margin for fp32 rounding; the hierarchy weight only lowers alpha), so skipping
-// a quadrant never changes a result; the 4-bit mask is stored in spare bits of kbits.
-__global__ void __launch_bounds__(256)
-gather_records_kernel(int64_t D, const uint32_t* __restrict__ point_list, const uint64_t* __restrict__ keys, int gx,
-                      const Record* __restrict__ records, Record* __restrict__ sorted)
+// Which of the four 8x8-pixel quadrants of tile (tile_x, tile_y) can entry (a, b) reach at all?
+__device__ __forceinline__ uint32_t quadrant_mask(const float4& a, const float4& b, int tile_x, int tile_y)
 {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= D) return;
-    const uint32_t g = point_list[j];
-    const float4* src = reinterpret_cast<const float4*>(records + g);
-    const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
-    const uint32_t tile = (uint32_t)(keys[j] >> 32);
-    const int tile_y = (int)(tile / (uint32_t)gx), tile_x = (int)(tile - (uint32_t)tile_y * (uint32_t)gx);
     uint32_t mask = 0xFu;
     const float A = a.z, B = a.w, C = b.x;             // conic: q(d) = A dx^2 + 2 B dx dy + C dy^2 = -2 power
     const float det = A * C - B * B;
@@ -131,11 +116,154 @@ gather_records_kernel(int64_t D, const uint32_t* __restrict__ point_list, const 
             }
         }
     }
+    return mask;
+}
+
+// sorted_records[j] = records[point_list[j]] : 48-B gathers out of an L2-resident array.
+// One thread per entry.  While the record is in registers, derive which of the four 8x8-pixel
+// quadrants (= warps of the blend CTAs) of ITS tile the entry can reach at all: alpha >= 1/255
+// needs q(d) = d^T Q d <= 2 ln(255 o); the exact minimum of the convex q over the quadrant's rectangle of
+// pixel centres (0 if the mean is inside, else attained on an edge) is compared with that bound.  The
+// test is conservative (margin for fp32 rounding; the hierarchy weight only lowers alpha), so skipping
+// a quadrant never changes a result; the 4-bit mask is stored in spare bits of kbits.
+__global__ void __launch_bounds__(256)
+gather_records_kernel(int64_t D, const uint32_t* __restrict__ point_list, const uint64_t* __restrict__ keys, int gx,
+                      const Record* __restrict__ records, Record* __restrict__ sorted)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= D) return;
+    const uint32_t g = point_list[j];
+    const float4* src = reinterpret_cast<const float4*>(records + g);
+    const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+    const uint32_t tile = (uint32_t)(keys[j] >> 32);
+    const int tile_y = (int)(tile / (uint32_t)gx), tile_x = (int)(tile - (uint32_t)tile_y * (uint32_t)gx);
+    const uint32_t mask = quadrant_mask(a, b, tile_x, tile_y);
     const uint32_t kb = (__float_as_uint(b.w) & 0x00FFFFFFu) | (mask << kQuadShift);
     float4* dst = reinterpret_cast<float4*>(sorted + j);
     dst[0] = a;
     dst[1] = make_float4(b.x, b.y, b.z, __uint_as_float(kb));
     dst[2] = c;
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-tile path (default): K1 has left a per-tile histogram.  (1) one CTA scans it into
+// ranges[T] and reports D and the longest list; (2) every Gaussian drops (depth bits, idx) into
+// its tiles' segments (slot claimed with an atomic -- order inside a segment is arbitrary);
+// (3) one CTA per tile sorts its segment in shared memory by the 64-bit key (depth bits, idx)
+// -- exactly the order of a stable sort on depth over emission-in-index-order -- and, while the
+// index is in registers, gathers the 48-B record and its quadrant-reach mask.  HBM traffic:
+// 8 D (emit) + 8 D (read) + 12 D (keys/list out) + 96 D (records) instead of ~7 x 24 D for the
+// global radix sort plus the separate gather.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges, ScanInfo* __restrict__ info)
+{
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry, s_max;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_carry = 0; s_max = 0; }
+    __syncthreads();
+    uint32_t local_max = 0;
+    for (int base = 0; base < T; base += 1024) {
+        const int t = base + tid;
+        const uint32_t cnt = t < T ? tile_count[t] : 0u;
+        local_max = max(local_max, cnt);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += v; }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t start = s_carry + (warp ? s_warp[warp - 1] : 0u) + incl - cnt;
+        if (t < T) ranges[t] = cnt ? make_uint2(start, start + cnt) : make_uint2(0u, 0u);   // empty tiles: (0,0)
+        __syncthreads();
+        if (tid == 1023) s_carry = start + cnt;
+        __syncthreads();
+    }
+    local_max = __reduce_max_sync(0xffffffffu, local_max);
+    if (lane == 0) atomicMax(&s_max, local_max);
+    __syncthreads();
+    if (tid == 0) { info->D = s_carry; info->max_count = s_max; }
+}
+
+__global__ void __launch_bounds__(256)
+emit_to_tiles_kernel(int P, int W, int H, int shard_count, int shard_index, const int* __restrict__ radii,
+                     const float* __restrict__ depths, const Record* __restrict__ records,
+                     const uint2* __restrict__ ranges, uint32_t* __restrict__ tile_count, uint2* __restrict__ pairs)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const int rad = radii[i];
+    if (rad <= 0) return;
+    const float4 a = records[i].a;
+    const float ix = a.x, iy = a.y;
+    const int gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
+    const int rminx = min(gx, max(0, (int)((ix - rad) / kTile)));
+    const int rminy = min(gy, max(0, (int)((iy - rad) / kTile)));
+    const int rmaxx = min(gx, max(0, (int)((ix + rad + kTile - 1) / kTile)));
+    const int rmaxy = min(gy, max(0, (int)((iy + rad + kTile - 1) / kTile)));
+    const uint32_t dbits = __float_as_uint(depths[i]);
+    for (int y = rminy; y < rmaxy; y++) {
+        if (shard_count > 1 && (y % shard_count) != shard_index) continue;
+        for (int x = rminx; x < rmaxx; x++) {
+            const int tile = y * gx + x;
+            const uint32_t slot = atomicSub(tile_count + tile, 1u) - 1u;       // the histogram doubles as the cursor
+            pairs[ranges[tile].x + slot] = make_uint2((uint32_t)i, dbits);      // little-endian u64 = depth << 32 | idx
+        }
+    }
+}
+
+// one CTA per tile: bitonic sort of (depth bits << 32 | idx) in shared memory, then gather
+__global__ void __launch_bounds__(256)
+tile_sort_gather_kernel(int gx, int rows, int shard_count, int shard_index, const uint2* __restrict__ ranges,
+                        const uint64_t* __restrict__ pairs, const Record* __restrict__ records,
+                        uint64_t* __restrict__ keys_sorted, uint32_t* __restrict__ point_list,
+                        Record* __restrict__ sorted)
+{
+    extern __shared__ uint64_t s_key[];
+    const int tid = threadIdx.x;
+    const int tile_x = blockIdx.x % gx;
+    const int tile_y = (blockIdx.x / gx) * shard_count + shard_index;
+    const uint32_t tile = (uint32_t)(tile_y * gx + tile_x);
+    const uint2 range = ranges[tile];
+    const int n = (int)(range.y - range.x);
+    if (n == 0) return;
+    int m = 32;
+    while (m < n) m <<= 1;
+    for (int k = tid; k < m; k += 256) s_key[k] = k < n ? pairs[range.x + k] : 0xFFFFFFFFFFFFFFFFull;
+    __syncthreads();
+    for (int size = 2; size <= m; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int k = tid; k < (m >> 1); k += 256) {
+                const int lo = 2 * k - (k & (stride - 1));             // index of the lower partner
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const uint64_t x = s_key[lo], y = s_key[hi];
+                if ((x > y) == up) { s_key[lo] = y; s_key[hi] = x; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int k = tid; k < n; k += 256) {
+        const uint64_t key = s_key[k];
+        const uint32_t g = (uint32_t)key, dbits = (uint32_t)(key >> 32);
+        const size_t pos = (size_t)range.x + k;
+        keys_sorted[pos] = ((uint64_t)tile << 32) | dbits;
+        point_list[pos] = g;
+        const float4* src = reinterpret_cast<const float4*>(records + g);
+        const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+        const uint32_t kb = (__float_as_uint(b.w) & 0x00FFFFFFu) | (quadrant_mask(a, b, tile_x, tile_y) << kQuadShift);
+        float4* dst = reinterpret_cast<float4*>(sorted + pos);
+        dst[0] = a;
+        dst[1] = make_float4(b.x, b.y, b.z, __uint_as_float(kb));
+        dst[2] = c;
+    }
 }
 
 int launch_binning(const h3dgs_raster_args& a, const int32_t* radii, const float* depths, const uint32_t* offsets,
@@ -172,6 +300,47 @@ int launch_binning(const h3dgs_raster_args& a, const int32_t* radii, const float
     return H3DGS_OK;
 }
 
+int launch_tile_scan(const h3dgs_raster_args& a, const uint32_t* tile_count, uint32_t* ranges, ScanInfo* info,
+                     cudaStream_t s)
+{
+    const int gx = (a.image_width + kTile - 1) / kTile, gy = (a.image_height + kTile - 1) / kTile;
+    ProfScope prof(H3DGS_STAGE_SCAN, s);
+    tile_scan_kernel<<<1, 1024, 0, s>>>(gx * gy, tile_count, (uint2*)ranges, info);
+    H3_LAUNCHED("tile_scan", a.debug, s);
+    return H3DGS_OK;
+}
+
+int launch_tile_binning(const h3dgs_raster_args& a, const int32_t* radii, const float* depths, const Record* records,
+                        int64_t D, uint32_t max_count, uint8_t* bin, const BinLayout& bl, const uint32_t* ranges,
+                        uint32_t* tile_count, cudaStream_t s)
+{
+    if (D == 0 || a.P == 0) return H3DGS_OK;
+    const int W = a.image_width, H = a.image_height;
+    const int gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
+    const int sc = a.shard_count > 0 ? a.shard_count : 1, si = a.shard_count > 0 ? a.shard_index : 0;
+    const int rows = (gy + sc - 1 - si) / sc;
+    uint2* pairs = (uint2*)(bin + bl.keys_unsorted);
+    { ProfScope prof(H3DGS_STAGE_DUPLICATE, s);
+    emit_to_tiles_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a.P, W, H, sc, si, radii, depths, records, (const uint2*)ranges,
+                                                           tile_count, pairs);
+    H3_LAUNCHED("emit_to_tiles", a.debug, s); }
+    int m = 32;
+    while (m < (int)max_count) m <<= 1;
+    const size_t smem = (size_t)m * sizeof(uint64_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        H3_CUDA(cudaFuncSetAttribute(tile_sort_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kTileSortCap * (int)sizeof(uint64_t)));
+        attr_set = true;
+    }
+    { ProfScope prof(H3DGS_STAGE_SORT, s);
+    tile_sort_gather_kernel<<<gx * rows, 256, smem, s>>>(gx, rows, sc, si, (const uint2*)ranges, (const uint64_t*)pairs, records,
+                                                         (uint64_t*)(bin + bl.keys_sorted), (uint32_t*)(bin + bl.vals_sorted),
+                                                         (Record*)(bin + bl.sorted_records));
+    H3_LAUNCHED("tile_sort_gather", a.debug, s); }
+    return H3DGS_OK;
+}
+
 GeomLayout geom_layout(int P) {
     GeomLayout l; size_t o = 0; const size_t n = (size_t)(P > 0 ? P : 1);
     l.depths = o; o = align_up(o + n * 4);
@@ -203,7 +372,8 @@ ImgLayout img_layout(int W, int H) {
     l.n_contrib = o; o = align_up(o + px * 4);
     l.ranges = o; o = align_up(o + tiles * 8);
     l.tile_max_contrib = o; o = align_up(o + tiles * 4);
-    l.bucket_offsets = o; o = align_up(o + (tiles + 1) * 4);
+    l.tile_count = o; o = align_up(o + tiles * 4);
+    l.scan_info = o; o = align_up(o + sizeof(ScanInfo));
     l.total = o;
     return l;
 }

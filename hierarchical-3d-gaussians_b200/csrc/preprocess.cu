@@ -49,7 +49,7 @@ preprocess_kernel(int P, const float* __restrict__ means3D, const float* __restr
                   int W, int H, float tanx, float tany, float fx, float fy,
                   int shard_count, int shard_index,
                   int* __restrict__ radii, float* __restrict__ depths, uint32_t* __restrict__ tiles_touched,
-                  Record* __restrict__ records)
+                  Record* __restrict__ records, uint32_t* __restrict__ tile_count)
 {
     __shared__ float s_view[16], s_proj[16];
     if (threadIdx.x < 16) { s_view[threadIdx.x] = view[threadIdx.x]; s_proj[threadIdx.x] = proj[threadIdx.x]; }
@@ -177,6 +177,11 @@ preprocess_kernel(int P, const float* __restrict__ means3D, const float* __restr
                 const int rows = (rmaxy + shard_count - 1 - shard_index) / shard_count
                                - (rminy + shard_count - 1 - shard_index) / shard_count;
                 out_tiles = (uint32_t)(rows * (rmaxx - rminx));
+                // per-tile histogram for the per-tile sort (binning.cu): replaces the scan over P
+                for (int y = rminy; y < rmaxy; y++) {
+                    if (shard_count > 1 && (y % shard_count) != shard_index) continue;
+                    for (int x = rminx; x < rmaxx; x++) atomicAdd(tile_count + (y * gx + x), 1u);
+                }
             }
         }
     }
@@ -268,7 +273,7 @@ preprocess_color_kernel(int P, int deg, int M, const float* __restrict__ means3D
 }
 
 int launch_preprocess(const h3dgs_raster_args& a, int32_t* radii, float* depths, uint32_t* tiles_touched,
-                      Record* records, cudaStream_t s)
+                      Record* records, uint32_t* tile_count, cudaStream_t s)
 {
     if (a.P == 0) return H3DGS_OK;
     const float fx = a.image_width / (2.0f * a.tanfovx), fy = a.image_height / (2.0f * a.tanfovy);
@@ -279,7 +284,7 @@ int launch_preprocess(const h3dgs_raster_args& a, int32_t* radii, float* depths,
                                                  a.num_node_kids, a.render_indices, a.parent_indices, a.viewmatrix,
                                                  a.projmatrix, a.image_width, a.image_height, a.tanfovx, a.tanfovy, fx, fy,
                                                  a.shard_count > 0 ? a.shard_count : 1, a.shard_count > 0 ? a.shard_index : 0,
-                                                 radii, depths, tiles_touched, records);
+                                                 radii, depths, tiles_touched, records, tile_count);
     H3_LAUNCHED("preprocess", a.debug, s);
     return H3DGS_OK;
 }

@@ -208,3 +208,17 @@ def test_debug_flag_and_error_reporting():
                                None, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, cam.H, cam.W,
                                t(sc["shs"][:, :4].copy()), 3, rs.campos, False, False)
     assert _lib.launch_count() > 0
+
+
+def test_tile_lists_longer_than_the_shared_memory_sort():
+    """> 8192 entries in one tile: the per-tile shared-memory sort hands over to the global radix sort;
+    keys, order and image must still match the oracle exactly."""
+    cam, sc, ts, kids, bg = make_scene(9500, 48, 32, seed=17, zmin=1.0, zmax=3.0, scale_k=0.5)
+    sc["means3D"][:, :2] *= 0.2                                  # everything lands on the few tiles
+    sc["opacities"][:] = 0.02
+    f, b, gcol, gdep = oracle_run(cam, sc, bg)
+    assert (f["ranges"][:, 1] - f["ranges"][:, 0]).max() > 8192
+    out, g, st = cuda_run(cam, sc, bg, gcol, gdep)
+    check_integer_artefacts(f, out, st)
+    check_image(f, out, st)
+    check_grads(b, g, ["means3D", "means2D", "sh", "opacities", "scales", "rotations"])
