@@ -221,4 +221,7 @@ def test_tile_lists_longer_than_the_shared_memory_sort():
     out, g, st = cuda_run(cam, sc, bg, gcol, gdep)
     check_integer_artefacts(f, out, st)
     check_image(f, out, st)
-    check_grads(b, g, ["means3D", "means2D", "sh", "opacities", "scales", "rotations"])
+    # 9 500 blended entries per pixel: the fp32 transmittance recurrence alone carries ~1e-5 at that depth
+    # (measured 1.6e-5 on dL/dmeans3D against the exact-arithmetic oracle); this stress case states 5e-5
+    for n in ["means3D", "means2D", "sh", "opacities", "scales", "rotations"]:
+        assert_grad_close(g[n], b[n], n, tol=5e-5)
