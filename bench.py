@@ -78,11 +78,11 @@ def alg_bytes(P, V, D, hier):
     b = {
         "preprocess": 44 * P + 8 * P + 40 * V + (8 * P if hier else 0),
         "preprocess_color": 192 * V,
-        "scan": 8 * P,
-        "duplicate_with_keys": 12 * D,
-        "radix_sort": 24 * D,
-        "identify_tile_ranges": 8 * D + 8 * T,
-        "gather_records": 0,                       # implementation choice (TMA staging), not algorithmic
+        "scan": 8 * P,                             # per-tile path: 8 T (tile histogram scan)
+        "key_emission": 12 * D,
+        "sort": 24 * D,                            # per-tile path: fused with the record gather (tile_sort_gather)
+        "identify_tile_ranges": 8 * D + 8 * T,     # fallback path only
+        "gather_records": 0,                       # fallback path only; implementation choice (TMA staging)
         "render_forward": 40 * D + 20 * Px,
         "render_backward": 40 * D + 36 * D + 32 * Px,
         "preprocess_backward": (36 + 44 + 40) * V + 56 * V,

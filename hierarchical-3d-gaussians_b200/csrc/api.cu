@@ -126,7 +126,7 @@ extern "C" int h3dgs_profile_read(int stage, double* total_ms, int64_t* launches
     return H3DGS_OK;
 }
 extern "C" const char* h3dgs_stage_name(int stage) {
-    static const char* names[H3DGS_STAGE_COUNT] = {"preprocess", "scan", "duplicate_with_keys", "radix_sort", "identify_tile_ranges",
+    static const char* names[H3DGS_STAGE_COUNT] = {"preprocess", "scan", "key_emission", "sort", "identify_tile_ranges",
         "gather_records", "render_forward", "render_backward", "preprocess_backward", "lod_cut", "lod_weights",
         "preprocess_color", "sh_backward"};
     return (stage >= 0 && stage < H3DGS_STAGE_COUNT) ? names[stage] : "?";

@@ -19,7 +19,6 @@ constexpr float kAlphaCap = 0.99f;
 constexpr float kAlphaSkip = 1.0f / 255.0f;
 constexpr float kTStop = 0.0001f;
 constexpr float kWEps = 0.0000001f;
-constexpr int kBucket = H3DGS_BUCKET;
 constexpr uint32_t kKidsMask = 0xFFFFFu;
 constexpr int kClampShift = 20, kQuadShift = 24;
 

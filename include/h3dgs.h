@@ -38,7 +38,6 @@ extern "C" {
 
 #define H3DGS_VERSION 1
 #define H3DGS_TILE 16            /* 16x16-pixel tiles                                         */
-#define H3DGS_BUCKET 32          /* entries per backward bucket (one warp lane per entry)     */
 
 #define H3DGS_OK 0
 #define H3DGS_EINVAL (-1)        /* bad argument combination (shs xor colors, scales xor cov) */

@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     assert l.h3dgs_version() == 1
     assert l.h3dgs_backward_scratch_bytes(1000) >= 1000 * 10 * 4
     assert l.h3dgs_expand_scratch_bytes(1000) > 0
-    assert l.h3dgs_stage_name(6) == b"render_forward"
+    assert l.h3dgs_stage_name(6) == b"render_forward" and l.h3dgs_stage_name(3) == b"sort"
 
 
 def test_ctypes_struct_mirrors_header():
