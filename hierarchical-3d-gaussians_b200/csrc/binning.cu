@@ -219,8 +219,11 @@ emit_to_tiles_kernel(int P, int W, int H, int shard_count, int shard_index, cons
     }
 }
 
-// one CTA per tile: bitonic sort of (depth bits << 32 | idx) in shared memory, then gather
-__global__ void __launch_bounds__(256)
+// one CTA per tile: bitonic sort of (depth bits << 32 | idx) in shared memory, then gather.
+// 128 threads: a typical list (a few hundred entries, m = 512) gives each thread two comparators per
+// stage (ILP) and halves the warps that meet at each of the 45 barriers.
+constexpr int kSortThreads = 128;
+__global__ void __launch_bounds__(kSortThreads)
 tile_sort_gather_kernel(int gx, int rows, int shard_count, int shard_index, const uint2* __restrict__ ranges,
                         const uint64_t* __restrict__ pairs, const Record* __restrict__ records,
                         uint64_t* __restrict__ keys_sorted, uint32_t* __restrict__ point_list,
@@ -236,11 +239,11 @@ tile_sort_gather_kernel(int gx, int rows, int shard_count, int shard_index, cons
     if (n == 0) return;
     int m = 32;
     while (m < n) m <<= 1;
-    for (int k = tid; k < m; k += 256) s_key[k] = k < n ? pairs[range.x + k] : 0xFFFFFFFFFFFFFFFFull;
+    for (int k = tid; k < m; k += kSortThreads) s_key[k] = k < n ? pairs[range.x + k] : 0xFFFFFFFFFFFFFFFFull;
     __syncthreads();
     for (int size = 2; size <= m; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int k = tid; k < (m >> 1); k += 256) {
+            for (int k = tid; k < (m >> 1); k += kSortThreads) {
                 const int lo = 2 * k - (k & (stride - 1));             // index of the lower partner
                 const int hi = lo + stride;
                 const bool up = (lo & size) == 0;
@@ -250,7 +253,7 @@ tile_sort_gather_kernel(int gx, int rows, int shard_count, int shard_index, cons
             __syncthreads();
         }
     }
-    for (int k = tid; k < n; k += 256) {
+    for (int k = tid; k < n; k += kSortThreads) {
         const uint64_t key = s_key[k];
         const uint32_t g = (uint32_t)key, dbits = (uint32_t)(key >> 32);
         const size_t pos = (size_t)range.x + k;
@@ -334,7 +337,7 @@ int launch_tile_binning(const h3dgs_raster_args& a, const int32_t* radii, const 
         attr_set = true;
     }
     { ProfScope prof(H3DGS_STAGE_SORT, s);
-    tile_sort_gather_kernel<<<gx * rows, 256, smem, s>>>(gx, rows, sc, si, (const uint2*)ranges, (const uint64_t*)pairs, records,
+    tile_sort_gather_kernel<<<gx * rows, kSortThreads, smem, s>>>(gx, rows, sc, si, (const uint2*)ranges, (const uint64_t*)pairs, records,
                                                          (uint64_t*)(bin + bl.keys_sorted), (uint32_t*)(bin + bl.vals_sorted),
                                                          (Record*)(bin + bl.sorted_records));
     H3_LAUNCHED("tile_sort_gather", a.debug, s); }
