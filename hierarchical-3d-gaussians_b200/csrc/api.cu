@@ -206,7 +206,7 @@ extern "C" int h3dgs_rasterize_forward(const h3dgs_raster_args* a, h3dgs_alloc_f
     }
     rc = launch_render_forward(*a, ranges, (const Record*)(bin + bl.sorted_records), out_color, out_invdepth,
                                (float*)(img + il.final_T), (uint32_t*)(img + il.n_contrib),
-                               (uint32_t*)(img + il.tile_max_contrib), (uint32_t*)(bin + bl.active), bl.active_words, s);
+                               (uint32_t*)(img + il.tile_max_contrib), s);
     return rc;
 }
 
@@ -257,8 +257,7 @@ extern "C" int h3dgs_rasterize_backward(const h3dgs_raster_args* a, const int32_
     if (phases & 1) H3_CUDA(cudaMemsetAsync(accum, 0, (size_t)a->P * kAccum * sizeof(float), s));
     if (D > 0 && (phases & 1)) {
         rc = launch_render_backward(b, (const uint32_t*)(img + il.ranges), (const Record*)(bin + bl.sorted_records),
-                                    (const uint32_t*)(bin + bl.vals_sorted), (const uint32_t*)(bin + bl.active),
-                                    bl.active_words, (const float*)(img + il.final_T),
+                                    (const uint32_t*)(bin + bl.vals_sorted), (const float*)(img + il.final_T),
                                     (const uint32_t*)(img + il.n_contrib), (const uint32_t*)(img + il.tile_max_contrib),
                                     dL_dcolor, dL_dinvdepth, accum, s);
         if (rc) return rc;

@@ -40,9 +40,8 @@ struct GeomLayout {
     size_t scan_temp_bytes;
 };
 struct BinLayout {
-    size_t keys_unsorted, keys_sorted, vals_unsorted, vals_sorted, sort_temp, sorted_records, active, total;
+    size_t keys_unsorted, keys_sorted, vals_unsorted, vals_sorted, sort_temp, sorted_records, total;
     size_t sort_temp_bytes;
-    size_t active_words;      // words per quadrant of the "blended at least one pixel" bitmap (bit = list position)
 };
 struct ImgLayout {
     size_t final_T, n_contrib, ranges, tile_max_contrib, tile_count, scan_info, total;
@@ -110,10 +109,9 @@ int launch_binning(const h3dgs_raster_args& a, const int32_t* radii, const float
                    cudaStream_t s);
 int launch_render_forward(const h3dgs_raster_args& a, const uint32_t* ranges, const Record* sorted_records,
                           float* out_color, float* out_invdepth, float* final_T, uint32_t* n_contrib,
-                          uint32_t* tile_max_contrib, uint32_t* active, size_t active_words, cudaStream_t s);
+                          uint32_t* tile_max_contrib, cudaStream_t s);
 int launch_render_backward(const h3dgs_raster_args& a, const uint32_t* ranges, const Record* sorted_records,
-                           const uint32_t* point_list, const uint32_t* active, size_t active_words,
-                           const float* final_T, const uint32_t* n_contrib,
+                           const uint32_t* point_list, const float* final_T, const uint32_t* n_contrib,
                            const uint32_t* tile_max_contrib, const float* dL_dcolor, const float* dL_dinvdepth,
                            float* accum /*[P][10] zeroed*/, cudaStream_t s);
 int launch_preprocess_backward(const h3dgs_raster_args& a, const int32_t* radii, const Record* records,

@@ -106,7 +106,6 @@ template <bool HIER, bool DEPTH>
 __global__ void __launch_bounds__(kBwdThreads)
 render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, const uint2* __restrict__ ranges,
                        const Record* __restrict__ sorted, const uint32_t* __restrict__ point_list,
-                       const uint32_t* __restrict__ active, size_t active_words,
                        const float* __restrict__ bg, const float* __restrict__ final_T,
                        const uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ tile_max_contrib,
                        const float* __restrict__ dL_dcolor, const float* __restrict__ dL_dinvdepth,
@@ -167,6 +166,7 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
     if (in1) { gb0 = dL_dcolor[pix1]; gb1 = dL_dcolor[plane + pix1]; gb2 = dL_dcolor[2 * plane + pix1]; if (DEPTH) gbd = dL_dinvdepth[pix1]; }
     const float bgd0 = bg[0] * ga0 + bg[1] * ga1 + bg[2] * ga2, bgd1 = bg[0] * gb0 + bg[1] * gb1 + bg[2] * gb2;
     const int wlast = (int)__reduce_max_sync(0xffffffffu, (unsigned)max(last0, last1));   // nothing in this quadrant beyond it
+    const uint32_t qbit = 1u << (kQuadShift + warp);
 
     for (int it = 0; it < nb; it++) {
         const int st = it % kBwdStages, b = nb - 1 - it;
@@ -177,12 +177,7 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
         // this warp's quadrant at all (see render_forward.cu)
         for (int j0 = (cnt - 1) & ~31; j0 >= 0; j0 -= 32) {
             const int jl = j0 + lane;
-            // the forward left one bit per (quadrant, list position): was the entry blended by any pixel?
-            bool hit = false;
-            if (jl < cnt && (b * kBwdBatch + jl) < wlast) {
-                const uint32_t pos = range.x + (uint32_t)(b * kBwdBatch + jl);
-                hit = (__ldg(active + (size_t)warp * active_words + (pos >> 5)) >> (pos & 31u)) & 1u;
-            }
+            const bool hit = jl < cnt && (b * kBwdBatch + jl) < wlast && (__float_as_uint(rec[jl].b.w) & qbit) != 0u;
             uint32_t m = __ballot_sync(0xffffffffu, hit);
             while (m) {
                 const int top = 31 - __clz(m);
@@ -219,8 +214,7 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
 }
 
 int launch_render_backward(const h3dgs_raster_args& a, const uint32_t* ranges, const Record* sorted_records,
-                           const uint32_t* point_list, const uint32_t* active, size_t active_words,
-                           const float* final_T, const uint32_t* n_contrib,
+                           const uint32_t* point_list, const float* final_T, const uint32_t* n_contrib,
                            const uint32_t* tile_max_contrib, const float* dL_dcolor, const float* dL_dinvdepth,
                            float* accum, cudaStream_t s)
 {
@@ -235,7 +229,7 @@ int launch_render_backward(const h3dgs_raster_args& a, const uint32_t* ranges, c
     ProfScope prof(H3DGS_STAGE_RENDER_BWD, s);
 #define LAUNCH(HI, DE)                                                                                          \
     render_backward_kernel<HI, DE><<<grid, block, 0, s>>>(W, H, gx, sc, si, (const uint2*)ranges, sorted_records, \
-                                                          point_list, active, active_words, a.bg, final_T, n_contrib, tile_max_contrib, \
+                                                          point_list, a.bg, final_T, n_contrib, tile_max_contrib, \
                                                           dL_dcolor, dL_dinvdepth, accum)
     if (hier) { if (depth) LAUNCH(true, true); else LAUNCH(true, false); }
     else      { if (depth) LAUNCH(false, true); else LAUNCH(false, false); }

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(kFwdThreads)
 render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, const uint2* __restrict__ ranges,
                       const Record* __restrict__ sorted, const float* __restrict__ bg, float* __restrict__ out_color,
                       float* __restrict__ out_invdepth, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
-                      uint32_t* __restrict__ tile_max_contrib, uint32_t* __restrict__ active, size_t active_words)
+                      uint32_t* __restrict__ tile_max_contrib)
 {
     __shared__ __align__(128) Record s_rec[kFwdStages][kFwdBatch];
     __shared__ __align__(8) uint64_t s_full[kFwdStages];
@@ -89,10 +89,8 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
                 const int jl = j0 + lane;
                 const bool hit = jl < cnt && (__float_as_uint(rec[jl].b.w) & qbit) != 0u;
                 uint32_t m = __ballot_sync(0xffffffffu, hit);
-                uint32_t blended = 0;        // bit k: entry j0 + k was blended by at least one pixel of this quadrant
                 while (m) {
-                    const int bit = __ffs(m) - 1;
-                    const int j = j0 + bit;
+                    const int j = j0 + __ffs(m) - 1;
                     m &= m - 1;
                     const float4 a = rec[j].a;
                     const float4 bb = rec[j].b;
@@ -110,7 +108,6 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
                     bool v1 = !done1 && pw1 <= 0.0f && al1 >= kAlphaSkip;
                     if (v0 && tT0 < kTStop) { done0 = true; v0 = false; }
                     if (v1 && tT1 < kTStop) { done1 = true; v1 = false; }
-                    if (__any_sync(0xffffffffu, v0 || v1)) blended |= 1u << bit;
                     if (v0 || v1) {
                         const float4 c = rec[j].c;
                         const uint32_t idx = base + (uint32_t)j + 1u;
@@ -127,15 +124,6 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
                             T1 = tT1; last1 = idx;
                         }
                     }
-                }
-                // Remember which entries this quadrant really blended: the backward replay visits only
-                // those (bitmap indexed by list position; tiles share boundary words, hence atomicOr)
-                if (blended && lane == 0) {
-                    const uint32_t pos = range.x + base + (uint32_t)j0;
-                    uint32_t* w = active + (size_t)warp * active_words + (pos >> 5);
-                    const uint32_t sh = pos & 31u;
-                    atomicOr(w, blended << sh);
-                    if (sh && (blended >> (32u - sh))) atomicOr(w + 1, blended >> (32u - sh));
                 }
             }
         }
@@ -185,7 +173,7 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
 
 int launch_render_forward(const h3dgs_raster_args& a, const uint32_t* ranges, const Record* sorted_records,
                           float* out_color, float* out_invdepth, float* final_T, uint32_t* n_contrib,
-                          uint32_t* tile_max_contrib, uint32_t* active, size_t active_words, cudaStream_t s)
+                          uint32_t* tile_max_contrib, cudaStream_t s)
 {
     const int W = a.image_width, H = a.image_height;
     const int gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
@@ -195,12 +183,11 @@ int launch_render_forward(const h3dgs_raster_args& a, const uint32_t* ranges, co
     const bool hier = a.interpolation_weights != nullptr;
     const bool depth = a.do_depth != 0;
     const dim3 grid(gx * rows), block(kFwdThreads);
-    H3_CUDA(cudaMemsetAsync(active, 0, 4 * active_words * sizeof(uint32_t), s));
     ProfScope prof(H3DGS_STAGE_RENDER_FWD, s);
 #define LAUNCH(HI, DE)                                                                                         \
     render_forward_kernel<HI, DE><<<grid, block, 0, s>>>(W, H, gx, sc, si, (const uint2*)ranges, sorted_records, \
                                                          a.bg, out_color, out_invdepth, final_T, n_contrib,      \
-                                                         tile_max_contrib, active, active_words)
+                                                         tile_max_contrib)
     if (hier) { if (depth) LAUNCH(true, true); else LAUNCH(true, false); }
     else      { if (depth) LAUNCH(false, true); else LAUNCH(false, false); }
 #undef LAUNCH
