@@ -330,12 +330,9 @@ int launch_tile_binning(const h3dgs_raster_args& a, const int32_t* radii, const 
     int m = 32;
     while (m < (int)max_count) m <<= 1;
     const size_t smem = (size_t)m * sizeof(uint64_t);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (smem > 48 * 1024)     // per device, idempotent: only the rare long lists need the opt-in
         H3_CUDA(cudaFuncSetAttribute(tile_sort_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      kTileSortCap * (int)sizeof(uint64_t)));
-        attr_set = true;
-    }
     { ProfScope prof(H3DGS_STAGE_SORT, s);
     tile_sort_gather_kernel<<<gx * rows, kSortThreads, smem, s>>>(gx, rows, sc, si, (const uint2*)ranges, (const uint64_t*)pairs, records,
                                                          (uint64_t*)(bin + bl.keys_sorted), (uint32_t*)(bin + bl.vals_sorted),

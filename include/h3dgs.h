@@ -132,7 +132,7 @@ int h3dgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
 typedef struct h3dgs_state_view {
     const float* depths;              /* [P] view-space z (key low 32 bits)                    */
     const uint32_t* tiles_touched;    /* [P]                                                    */
-    const uint32_t* point_offsets;    /* [P] inclusive scan                                     */
+    const uint32_t* point_offsets;    /* [P] inclusive scan (filled only by the global-sort fallback)*/
     const float* records;             /* [P][12] x,y,conic.x,conic.y | conic.z,opacity,t,k-bits | r,g,b,invdepth */
     const uint64_t* keys_sorted;      /* [D] (tile << 32) | depth bits                          */
     const uint32_t* point_list;       /* [D] Gaussian index, sorted                             */
