@@ -178,3 +178,59 @@ def test_full_size_frame_1080p():
     from util import assert_grad_close
     for k in ["means3D", "means2D", "sh", "opacities", "scales", "rotations"]:
         assert_grad_close(g[k], b[k], k, tol=2e-5)
+
+
+def test_config2_size_properties_1M_gaussians_1080p():
+    """BASELINE.json configs[1] at full size (1M flat Gaussians, 1920x1080, SH-3), where the CPU oracle is too
+    slow to be the checker: size-independent properties of the path instead -- the binned lists are a
+    tile-major, depth-sorted partition of exactly sum(tiles_touched) entries; per-pixel state is consistent
+    with them; the backward is linear in dL/dcolor."""
+    import torch
+    from diff_gaussian_rasterization import _C
+    cam = synth.make_camera(1920, 1080)
+    sc = synth.cloud_v1(1_000_000, cam, sh_degree=3, seed=0)
+    t = lambda a: torch.tensor(a, device="cuda")
+    m, sh, op, s, r = t(sc["means3D"]), t(sc["shs"]), t(sc["opacities"]), t(sc["scales"]), t(sc["rotations"])
+    bg = torch.tensor([0.2, 0.3, 0.4], device="cuda")
+    vm, pm, cp = t(cam.world_view_transform), t(cam.full_proj_transform), t(cam.camera_center)
+    n, color, radii, gb, bb, ib, _ = _C.rasterize_gaussians(bg, m, None, op, s, r, 1.0, None, vm, pm, cam.tanfovx, cam.tanfovy,
+                                                            cam.H, cam.W, sh, 3, cp, False, False)
+    sv = _C.state_view(m.shape[0], cam.W, cam.H, n, gb, bb, ib)
+    tiles_touched = sv["tiles_touched"].long()
+    assert int(tiles_touched.sum()) == n and int(((radii > 0) != (tiles_touched > 0)).sum()) == 0
+    keys = sv["keys_sorted"]                                   # int64 view of (tile << 32 | depth bits): all positive
+    assert bool((keys[1:] >= keys[:-1]).all())                 # tile-major, depth-sorted
+    tile_of = (keys >> 32)
+    ranges = sv["ranges"].long()
+    T = ranges.shape[0]
+    counts = torch.bincount(tile_of, minlength=T)
+    assert bool(((ranges[:, 1] - ranges[:, 0]) == counts).all())
+    nz = counts > 0
+    starts = torch.cumsum(counts, 0) - counts
+    assert bool((ranges[nz, 0] == starts[nz]).all()) and int(ranges[:, 1].max()) == n
+    pl = sv["point_list"].long()
+    assert bool((radii[pl] > 0).all())
+    depth_bits = sv["depths"].view(torch.int32).long()
+    assert bool(((keys & 0xFFFFFFFF) == depth_bits[pl]).all())
+    # per-pixel state
+    gx = (cam.W + 15) // 16
+    ys, xs = torch.meshgrid(torch.arange(cam.H, device="cuda"), torch.arange(cam.W, device="cuda"), indexing="ij")
+    tl = (ys // 16) * gx + xs // 16
+    assert bool((sv["n_contrib"].long() <= counts[tl]).all())
+    fT = sv["final_T"]
+    assert bool(((fT >= 0) & (fT <= 1)).all()) and bool(torch.isfinite(color).all())
+    assert bool((color >= 0).all())                            # colours are clamped at 0, bg >= 0
+    # linearity of the backward in dL/dcolor
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    g1 = (torch.rand(color.shape, device="cuda", generator=gen) - 0.5) / color.numel()
+    g2 = (torch.rand(color.shape, device="cuda", generator=gen) - 0.5) / color.numel()
+
+    def bwd(g):
+        out = _C.rasterize_gaussians_backward(bg, m, radii, None, op, s, r, 1.0, None, vm, pm, cam.tanfovx, cam.tanfovy, g,
+                                              None, sh, 3, cp, gb, n, bb, ib, False, None, None, None, None, False,
+                                              cam.H, cam.W)
+        return [o for o in out if o.numel()]
+    a, b, ab = bwd(g1), bwd(g2), bwd(g1 + 2.0 * g2)
+    for x, y, z in zip(a, b, ab):
+        ref = x + 2.0 * y
+        assert float((z - ref).abs().max() / ref.abs().max().clamp_min(1e-30)) < 2e-5
