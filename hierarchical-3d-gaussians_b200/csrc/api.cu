@@ -74,6 +74,16 @@ static int side_stream(SideStream** out) {
     return H3DGS_OK;
 }
 
+static void* g_pinned[64] = {nullptr};
+int pinned_scratch(void** out) {
+    int dev = 0;
+    H3_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return H3DGS_EINVAL; }
+    if (!g_pinned[dev]) H3_CUDA(cudaHostAlloc(&g_pinned[dev], 64, cudaHostAllocDefault));
+    *out = g_pinned[dev];
+    return H3DGS_OK;
+}
+
 static int check_args(const h3dgs_raster_args* a) {
     if (!a) { set_error("args is NULL"); return H3DGS_EINVAL; }
     if (a->P < 0 || a->image_width <= 0 || a->image_height <= 0) { set_error("bad sizes P=%d W=%d H=%d", a->P, a->image_width, a->image_height); return H3DGS_EINVAL; }
@@ -184,9 +194,12 @@ extern "C" int h3dgs_rasterize_forward(const h3dgs_raster_args* a, h3dgs_alloc_f
     rc = launch_tile_scan(*a, tile_count, ranges, info, s);
     if (rc) return rc;
     // The reference API sizes the binning buffer from num_rendered: one D2H + sync.
-    ScanInfo hinfo = {0, 0};
-    H3_CUDA(cudaMemcpyAsync(&hinfo, info, sizeof(ScanInfo), cudaMemcpyDeviceToHost, s));
+    void* pin = nullptr;
+    rc = pinned_scratch(&pin);
+    if (rc) return rc;
+    H3_CUDA(cudaMemcpyAsync(pin, info, sizeof(ScanInfo), cudaMemcpyDeviceToHost, s));
     H3_CUDA(cudaStreamSynchronize(s));
+    const ScanInfo hinfo = *static_cast<const ScanInfo*>(pin);
     const int64_t D = (int64_t)hinfo.D;
     if (num_rendered) *num_rendered = D;
     const BinLayout bl = bin_layout(D);

@@ -64,6 +64,10 @@ struct ProfScope {
     ~ProfScope() { prof_end(stage, s); }
 };
 
+// 64-B pinned host scratch per device for the small D2H read-backs (num_rendered, cut size): a
+// pageable destination makes cudaMemcpyAsync stage through the driver (api.cu)
+int pinned_scratch(void** out);
+
 // error plumbing (api.cu)
 void set_error(const char* fmt, ...);
 extern int64_t g_launches;

@@ -127,10 +127,11 @@ extern "C" int h3dgs_expand_to_size(int32_t N, const int32_t* nodes, const float
     put_render_indices_kernel<<<blocks, 256, 0, s>>>(N, nodes, counts, offsets, render_indices, parent_indices,
                                                      nodes_for_render_indices);
     H3_LAUNCHED("put_render_indices", 0, s); }
-    int total = 0;
-    H3_CUDA(cudaMemcpyAsync(&total, offsets + (N - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
+    void* pin = nullptr;
+    if (int rc = pinned_scratch(&pin)) return rc;
+    H3_CUDA(cudaMemcpyAsync(pin, offsets + (N - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
     H3_CUDA(cudaStreamSynchronize(s));
-    return total;
+    return *static_cast<const int*>(pin);
 }
 
 extern "C" int h3dgs_get_interpolation_weights(int32_t n, const int32_t* node_indices, float target_size,
