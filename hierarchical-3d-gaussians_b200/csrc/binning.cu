@@ -209,13 +209,27 @@ emit_to_tiles_kernel(int P, int W, int H, int shard_count, int shard_index, cons
     const int rmaxx = min(gx, max(0, (int)((ix + rad + kTile - 1) / kTile)));
     const int rmaxy = min(gy, max(0, (int)((iy + rad + kTile - 1) / kTile)));
     const uint32_t dbits = __float_as_uint(depths[i]);
-    for (int y = rminy; y < rmaxy; y++) {
-        if (shard_count > 1 && (y % shard_count) != shard_index) continue;
-        for (int x = rminx; x < rmaxx; x++) {
-            const int tile = y * gx + x;
-            const uint32_t slot = atomicSub(tile_count + tile, 1u) - 1u;       // the histogram doubles as the cursor
-            pairs[ranges[tile].x + slot] = make_uint2((uint32_t)i, dbits);      // little-endian u64 = depth << 32 | idx
+    // The slot claims return a value, so each costs a full L2 round trip: walk the rect as a flat index
+    // and keep four independent claims (then four range loads, then four stores) in flight per thread.
+    const int w = rmaxx - rminx, area = w * (rmaxy - rminy);
+    for (int t0 = 0; t0 < area; t0 += 4) {
+        int tl[4]; uint32_t sl[4], st[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            tl[k] = -1;
+            const int t = t0 + k;
+            if (t < area) {
+                const int y = rminy + t / w, x = rminx + t % w;
+                if (shard_count <= 1 || (y % shard_count) == shard_index) tl[k] = y * gx + x;
+            }
         }
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (tl[k] >= 0) sl[k] = atomicSub(tile_count + tl[k], 1u) - 1u;   // histogram doubles as cursor
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (tl[k] >= 0) st[k] = ranges[tl[k]].x;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (tl[k] >= 0) pairs[st[k] + sl[k]] = make_uint2((uint32_t)i, dbits);   // little-endian u64 = depth << 32 | idx
     }
 }
 
