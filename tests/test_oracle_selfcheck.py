@@ -96,3 +96,45 @@ def test_integer_artefacts_are_consistent():
     ys, xs = np.mgrid[0:64, 0:80]
     tl = (ys // 16) * gx + xs // 16
     assert (f["n_contrib"] <= (f["ranges"][tl, 1] - f["ranges"][tl, 0])).all()
+
+
+def test_fused_gather_lerp_oracle_matches_torch_autograd():
+    """The oracle front-end's cut gather + parent lerp (+ t/(1-t) gradient scatter to the full-size arrays)
+    against PyTorch ops written as in gaussian_renderer/__init__.py:199-218, differentiated by autograd."""
+    cam = synth.make_camera(96, 64)
+    leaves = synth.cloud_v1(160, cam, zmin=2.0, zmax=10.0, seed=4, scale_k=1.0)
+    z = leaves["means3D"][:, 2:3]
+    leaves["scales"] = (3e-2 * np.sqrt(z) * np.ones((1, 3))).astype(np.float32)
+    h = synth.build_hierarchy(leaves)
+    thr = synth.tau_threshold(6.0, cam)
+    n, ri, pi, ni = oracle.expand_to_size(h["nodes"], h["boxes"], thr, cam.camera_center)
+    ts, kids = oracle.get_interpolation_weights(ni, thr, h["nodes"], h["boxes"], cam.camera_center)
+    assert 0 < n < h["nodes"].shape[0] and (ts < 1).any()
+    bg = np.array([0.1, 0.2, 0.3], np.float32)
+    f = oracle.rasterize_forward(h["means3D"], h["shs"], None, h["opacities"], h["scales"], h["rotations"], None,
+                                 cam.world_view_transform, cam.full_proj_transform, cam.camera_center, bg, cam.W, cam.H,
+                                 cam.tanfovx, cam.tanfovy, ts=ts, kids=kids, render_indices=ri, parent_indices=pi)
+    gcol = synth.l1_grad(f["color"])
+    b = oracle.rasterize_backward(f, gcol)
+    T = lambda a: torch.tensor(a, dtype=torch.float64)
+    full = {k: T(h[k]).requires_grad_(True) for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+    idx = torch.tensor(ri, dtype=torch.long); par = torch.tensor(np.where(pi < 0, ri, pi), dtype=torch.long)
+    t = T(ts).unsqueeze(1); u = 1 - t
+    means = t * full["means3D"][idx] + u * full["means3D"][par]
+    scales = t * full["scales"][idx] + u * full["scales"][par]
+    shs = t.unsqueeze(2) * full["shs"][idx] + u.unsqueeze(2) * full["shs"][par]
+    parents = full["rotations"][par]
+    rots = full["rotations"][idx]
+    dots = torch.bmm(rots.unsqueeze(1), parents.unsqueeze(2)).flatten()
+    parents = torch.where((dots < 0).unsqueeze(1), -parents, parents)
+    rot = t * rots + u * parents
+    opac = t * full["opacities"][idx] + u * full["opacities"][par]
+    col, radii, _ = torch_splat.splat(means, shs, None, opac, scales, rot, None, T(cam.world_view_transform),
+                                      T(cam.full_proj_transform), T(cam.camera_center), T(bg), cam.W, cam.H, cam.tanfovx,
+                                      cam.tanfovy, ts=T(ts), kids=torch.tensor(kids))
+    (col * T(gcol)).sum().backward()
+    assert (radii.numpy() == f["radii"]).all()
+    assert np.abs(col.detach().numpy() - f["color"]).max() < 5e-6
+    for k, name in [("means3D", "means3D"), ("shs", "sh"), ("opacities", "opacities"), ("scales", "scales"),
+                    ("rotations", "rotations")]:
+        assert _rel(full[k].grad.numpy(), b[name]) < 1e-4, k
