@@ -162,6 +162,17 @@ int h3dgs_get_interpolation_weights(int32_t n, const int32_t* node_indices, floa
                                     float viewdir_x, float viewdir_y, float viewdir_z,
                                     float* ts, int32_t* num_kids, void* stream);
 
+/* ---- fused L1 + SSIM loss (replaces utils/loss_utils.py:17-63 as used in
+ * train_post.py:134-140: loss = (1-l) * L1 + l * (1 - SSIM), 11x11 Gaussian window, sigma 1.5) ----
+ * forward: sums[0] = sum |img-gt|, sums[1] = sum of the SSIM map (device doubles, zeroed here);
+ *          maps [3][C,H,W] (ds/dmu1, ds/dE11, ds/dE12) are written when non-NULL (needed by backward).
+ * backward: dL_dimg = coeffs[0] * sign(img-gt) + coeffs[1] * d(sum ssim)/d img ; coeffs is a DEVICE
+ *          pointer to two floats so that the upstream gradient never has to visit the host. */
+int h3dgs_l1_ssim_forward(int32_t C, int32_t H, int32_t W, const float* img, const float* gt, double* sums,
+                          float* maps, void* stream);
+int h3dgs_l1_ssim_backward(int32_t C, int32_t H, int32_t W, const float* img, const float* gt, const float* maps,
+                           const float* coeffs, float* dL_dimg, void* stream);
+
 /* ---- per-stage device timing (bench.py roofline) ----
  * When enabled, every stage launch is bracketed by two cudaEvents recorded on the stream
  * the kernel is launched on; h3dgs_profile_read synchronises them and returns the summed

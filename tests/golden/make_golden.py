@@ -76,3 +76,18 @@ for i in range(6):
                      full=full.numpy(), center=center.numpy()))
 np.savez(os.path.join(HERE, "camera.npz"), **{f"{k}_{i}": np.asarray(c[k]) for i, c in enumerate(cams) for k in c})
 print("golden written")
+
+# ---- L1 + SSIM loss (utils/loss_utils.py:17-63, combined as train_post.py:134-140) ----
+from utils.loss_utils import l1_loss, ssim          # noqa: E402
+gl = torch.Generator().manual_seed(99)
+for name, (C_, H_, W_) in {"a": (3, 37, 53), "b": (3, 16, 16), "c": (1, 70, 9)}.items():
+    img = torch.rand(C_, H_, W_, generator=gl).requires_grad_(True)
+    gt = (img.detach() * 0.7 + 0.3 * torch.rand(C_, H_, W_, generator=gl)).clamp(0, 1)
+    lam = 0.2
+    Ll1 = l1_loss(img, gt)
+    s = ssim(img, gt)
+    loss = (1.0 - lam) * Ll1 + lam * (1.0 - s)
+    loss.backward()
+    np.savez(os.path.join(HERE, f"loss_{name}.npz"), img=img.detach().numpy(), gt=gt.numpy(), lam=lam,
+             l1=Ll1.item(), ssim=s.item(), loss=loss.item(), grad=img.grad.numpy())
+print("loss golden written")
