@@ -11,7 +11,7 @@ def test_library_exports_every_declared_symbol():
     from h3dgs import _lib
     l = _lib.lib()
     hdr = open(os.path.join(ROOT, "include", "h3dgs.h")).read()
-    declared = set(re.findall(r"\b(h3dgs_[a-z_]+)\s*\(", hdr)) - {"h3dgs_alloc_fn"}
+    declared = set(re.findall(r"\b(h3dgs_[a-z0-9_]+)\s*\(", hdr)) - {"h3dgs_alloc_fn"}
     assert declared, "no declarations parsed"
     for name in sorted(declared):
         assert hasattr(l, name), name
