@@ -16,7 +16,7 @@ EXPORTS = [
     "h3dgs_state_layout", "h3dgs_expand_to_size", "h3dgs_expand_scratch_bytes", "h3dgs_get_interpolation_weights",
     "h3dgs_last_error", "h3dgs_version", "h3dgs_launch_count",
     "h3dgs_profile_enable", "h3dgs_profile_reset", "h3dgs_profile_read", "h3dgs_stage_name",
-    "h3dgs_l1_ssim_forward", "h3dgs_l1_ssim_backward",
+    "h3dgs_l1_ssim_forward", "h3dgs_l1_ssim_backward", "h3dgs_sparse_adam",
 ]
 
 
@@ -82,6 +82,9 @@ def lib():
     l.h3dgs_l1_ssim_forward.argtypes = [C.c_int32] * 3 + [C.c_void_p] * 5
     l.h3dgs_l1_ssim_backward.restype = C.c_int
     l.h3dgs_l1_ssim_backward.argtypes = [C.c_int32] * 3 + [C.c_void_p] * 6
+    l.h3dgs_sparse_adam.restype = C.c_int
+    l.h3dgs_sparse_adam.argtypes = [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_void_p]
     l.h3dgs_profile_read.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     l.h3dgs_stage_name.restype = C.c_char_p
     _lib = l

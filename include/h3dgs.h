@@ -173,6 +173,14 @@ int h3dgs_l1_ssim_forward(int32_t C, int32_t H, int32_t W, const float* img, con
 int h3dgs_l1_ssim_backward(int32_t C, int32_t H, int32_t W, const float* img, const float* gt, const float* maps,
                            const float* coeffs, float* dL_dimg, void* stream);
 
+/* ---- sparse Adam (replaces scene/OurAdam.py:249-337 as driven by train_single.py:170-178) ----
+ * In-place Adam update of the rows listed in relevant[num_relevant] (int64 row indices) of one parameter
+ * tensor viewed as [rows, width]; `step` is the 1-based step count of that tensor (the reference
+ * increments it on every call, whatever the rows).  amsgrad off, weight_decay 0, minimise. */
+int h3dgs_sparse_adam(int64_t num_relevant, int32_t width, const int64_t* relevant, float* param, const float* grad,
+                      float* exp_avg, float* exp_avg_sq, double lr, double beta1, double beta2, double eps, int64_t step,
+                      void* stream);
+
 /* ---- per-stage device timing (bench.py roofline) ----
  * When enabled, every stage launch is bracketed by two cudaEvents recorded on the stream
  * the kernel is launched on; h3dgs_profile_read synchronises them and returns the summed

@@ -91,3 +91,37 @@ for name, (C_, H_, W_) in {"a": (3, 37, 53), "b": (3, 16, 16), "c": (1, 70, 9)}.
     np.savez(os.path.join(HERE, f"loss_{name}.npz"), img=img.detach().numpy(), gt=gt.numpy(), lam=lam,
              l1=Ll1.item(), ssim=s.item(), loss=loss.item(), grad=img.grad.numpy())
 print("loss golden written")
+
+# ---- sparse Adam (scene/OurAdam.py:249-337 via Adam.step(relevant), as driven by train_single.py:170-178) ----
+import importlib.util                                   # noqa: E402
+_spec = importlib.util.spec_from_file_location("ref_OurAdam", os.path.join(REF, "scene", "OurAdam.py"))
+_mod = importlib.util.module_from_spec(_spec); _spec.loader.exec_module(_mod)
+# the reference targets an older torch: this private Optimizer hook was renamed since; it does no arithmetic
+if not hasattr(_mod.Adam, "_cuda_graph_capture_health_check"):
+    _mod.Adam._cuda_graph_capture_health_check = lambda self: None
+ga = torch.Generator().manual_seed(7)
+Nrows = 500
+params = [torch.randn(Nrows, 3, generator=ga), torch.randn(Nrows, 15, 3, generator=ga), torch.rand(Nrows, 1, generator=ga)]
+p0 = [p.clone().numpy() for p in params]
+plist = [torch.nn.Parameter(p.clone()) for p in params]
+lrs = [1.6e-4, 1.25e-4, 0.05]
+opt = _mod.Adam([{"params": [p], "lr": lr} for p, lr in zip(plist, lrs)], lr=0.0, eps=1e-15)
+steps = []
+for it in range(4):
+    rel = torch.nonzero(torch.rand(Nrows, generator=ga) < 0.3).flatten().long()
+    grads = [torch.randn(p.shape, generator=ga) * 1e-3 for p in plist]
+    for p, g_ in zip(plist, grads):
+        p.grad = g_.clone()
+    opt.step(rel)
+    steps.append(dict(rel=rel.numpy(), grads=[g_.numpy() for g_ in grads], after=[p.detach().clone().numpy() for p in plist]))
+out = {"lrs": np.array(lrs), "eps": 1e-15, "n_steps": len(steps)}
+for i, p in enumerate(p0):
+    out[f"p0_{i}"] = p
+for s_i, st in enumerate(steps):
+    out[f"rel_{s_i}"] = st["rel"]
+    for i in range(3):
+        out[f"grad_{s_i}_{i}"] = st["grads"][i]; out[f"after_{s_i}_{i}"] = st["after"][i]
+st_ = opt.state[plist[0]]
+out["exp_avg_0"] = st_["exp_avg"].numpy(); out["exp_avg_sq_0"] = st_["exp_avg_sq"].numpy()
+np.savez(os.path.join(HERE, "sparse_adam.npz"), **out)
+print("sparse adam golden written")
