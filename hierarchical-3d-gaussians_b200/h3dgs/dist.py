@@ -136,10 +136,10 @@ class TileSharder:
     def render(self, scene, cam, bg, threshold=None, sh_degree=3):
         if scene.hier:
             # fused form: the cut gather + parent lerp run inside K1/K9 (full arrays + indices)
-            n = pipeline.lod_cut(scene, cam, threshold)
+            n, P = pipeline.fused_cut(scene, cam, threshold)
             means, scales, rots, opac, shs = scene.means3D, scene.scales, scene.rotations, scene.opacities, scene.shs
             rs = pipeline.make_settings(scene, cam, bg, sh_degree, ts=scene.interpolation_weights, kids=scene.num_siblings,
-                                        ridx=scene.render_indices[:n], pidx=scene.parent_indices[:n])
+                                        ridx=scene.render_indices[:P], pidx=scene.parent_indices[:P])
         else:
             n = scene.means3D.shape[0]
             means, scales, rots, opac, shs = scene.means3D, scene.scales, scene.rotations, scene.opacities, scene.shs

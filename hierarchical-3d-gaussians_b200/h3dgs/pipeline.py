@@ -32,6 +32,10 @@ class Scene:
         self.shs = t(arrays["shs"]).requires_grad_(requires_grad)
         self.hier = "nodes" in arrays
         N = self.means3D.shape[0]
+        # skybox rows sit after the hierarchy rows and are rendered on every step
+        # (gaussian_renderer/__init__.py:220-234); the LOD scratch covers them (train_post.py:59-63)
+        self.skybox_points = int(arrays.get("skybox_points", 0))
+        self.skybox_inds = torch.arange(N - self.skybox_points, N, dtype=torch.int32, device=device)
         if self.hier:
             self.nodes = t(arrays["nodes"])
             self.boxes = t(arrays["boxes"])
@@ -71,7 +75,8 @@ def lod_cut(scene, cam, threshold):
 
 def interpolate_cut(scene, n):
     """The gather + parent lerp of render_post (interp_python=True), in PyTorch ops so
-    autograd scatters the gradients back to the full-size leaves (no skybox rows here)."""
+    autograd scatters the gradients back to the full-size leaves; skybox rows are appended
+    un-interpolated (:220-229)."""
     idx = scene.render_indices[:n].long()
     par = scene.parent_indices[:n].long()
     par = torch.where(par < 0, idx, par)             # the root has no parent: t == 1 there
@@ -85,6 +90,10 @@ def interpolate_cut(scene, n):
     sign = torch.where((q_c * q_p).sum(1, keepdim=True) < 0, -1.0, 1.0)     # quaternion sign alignment
     rots = t * q_c + u * (q_p * sign)
     opac = t * scene.opacities[idx] + u * scene.opacities[par]
+    if scene.skybox_points:
+        sky = scene.skybox_inds.long()
+        means, scales, rots = torch.cat((means, scene.means3D[sky])), torch.cat((scales, scene.scales[sky])), torch.cat((rots, scene.rotations[sky]))
+        opac, shs = torch.cat((opac, scene.opacities[sky])), torch.cat((shs, scene.shs[sky]))
     return means.contiguous(), scales.contiguous(), rots.contiguous(), opac.contiguous(), shs.contiguous()
 
 
@@ -96,6 +105,14 @@ def make_settings(scene, cam, bg, sh_degree, ts=None, kids=None, do_depth=False,
         parent_indices=pidx if pidx is not None else scene.empty_i,
         interpolation_weights=ts if ts is not None else scene.empty_f,
         num_node_kids=kids if kids is not None else scene.empty_i, do_depth=do_depth)
+
+
+def _skybox_weights(scene, n):
+    """t = 1, kids = 1 for the skybox rows that follow the cut (gaussian_renderer/__init__.py:232-234)."""
+    S = scene.skybox_points
+    if S:
+        scene.interpolation_weights[n:n + S] = 1.0
+        scene.num_siblings[n:n + S] = 1
 
 
 def render_flat(scene, cam, bg, sh_degree=3):
@@ -112,6 +129,7 @@ def render_hier(scene, cam, bg, threshold, sh_degree=3):
     """`render_post()` of the reference (hierarchy post-optimisation, config #3)."""
     n = lod_cut(scene, cam, threshold)
     means, scales, rots, opac, shs = interpolate_cut(scene, n)
+    _skybox_weights(scene, n)
     rs = make_settings(scene, cam, bg, sh_degree, ts=scene.interpolation_weights, kids=scene.num_siblings)
     means2D = torch.zeros_like(means, requires_grad=means.requires_grad)
     img, radii, _ = GaussianRasterizer(rs)(means3D=means, means2D=means2D, shs=shs, colors_precomp=None,
@@ -119,14 +137,27 @@ def render_hier(scene, cam, bg, threshold, sh_degree=3):
     return img, radii, n
 
 
+def fused_cut(scene, cam, threshold):
+    """LOD cut for the fused form -> (n cut rows, P rows to rasterize): the skybox rows follow the
+    cut in render_indices/parent_indices as their own parents with t = 1, kids = 1."""
+    n = lod_cut(scene, cam, threshold)
+    S = scene.skybox_points
+    if S:
+        scene.render_indices[n:n + S] = scene.skybox_inds
+        scene.parent_indices[n:n + S] = scene.skybox_inds
+        _skybox_weights(scene, n)
+    return n, n + S
+
+
 def render_hier_fused(scene, cam, bg, threshold, sh_degree=3):
     """Same result as render_hier, but the cut gather + parent lerp (and the gradient scatter in
     backward) run inside K1/K9 through the settings' render_indices/parent_indices fields instead
-    of ~25 PyTorch kernels with full-size temporaries."""
-    n = lod_cut(scene, cam, threshold)
+    of ~25 PyTorch kernels with full-size temporaries.  Skybox rows are appended to
+    the cut as indices that are their own parent with t = 1 (x = 1*x exactly, as in render_post)."""
+    n, P = fused_cut(scene, cam, threshold)
     rs = make_settings(scene, cam, bg, sh_degree, ts=scene.interpolation_weights, kids=scene.num_siblings,
-                       ridx=scene.render_indices[:n], pidx=scene.parent_indices[:n])
-    means2D = torch.zeros((n, 3), device=scene.means3D.device, requires_grad=scene.means3D.requires_grad)
+                       ridx=scene.render_indices[:P], pidx=scene.parent_indices[:P])
+    means2D = torch.zeros((P, 3), device=scene.means3D.device, requires_grad=scene.means3D.requires_grad)
     img, radii, _ = GaussianRasterizer(rs)(means3D=scene.means3D, means2D=means2D, shs=scene.shs, colors_precomp=None,
                                            opacities=scene.opacities, scales=scene.scales, rotations=scene.rotations,
                                            cov3D_precomp=None)

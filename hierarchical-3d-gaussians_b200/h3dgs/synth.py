@@ -229,6 +229,28 @@ def build_hierarchy(leaves):
                 opacities=opac.astype(np.float32)[:, None], shs=shs.astype(np.float32), nodes=nodes, boxes=boxes)
 
 
+def append_skybox(h, S, radius=200.0, sh_degree=3, seed=5):
+    """Append S far "skybox" Gaussians after the hierarchy rows, the layout render_post expects
+    (gaussian_renderer/__init__.py:220-223: the last `skybox_points` rows of the parameter tensors,
+    rendered every step with t = 1, kids = 1).  nodes/boxes are unchanged (the skybox is not in the tree)."""
+    g = np.random.default_rng(seed)
+    d = g.standard_normal((S, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    K = h["shs"].shape[1]
+    shs = np.zeros((S, K, 3), np.float32)
+    shs[:, 0] = (g.uniform(0.1, 0.9, (S, 3)) - 0.5) / 0.28209479177387814
+    if K > 1:
+        shs[:, 1:] = 0.05 * g.standard_normal((S, K - 1, 3))
+    q = g.standard_normal((S, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    sky = dict(means3D=(radius * d).astype(np.float32),
+               scales=(radius * 0.03 * np.exp(0.3 * g.standard_normal((S, 3)))).astype(np.float32),
+               rotations=q.astype(np.float32), opacities=g.uniform(0.3, 0.9, (S, 1)).astype(np.float32), shs=shs)
+    out = dict(h)
+    for k, v in sky.items():
+        out[k] = np.concatenate([h[k], v])
+    out["skybox_points"] = S
+    return out
+
+
 def tau_threshold(tau, cam):
     """render_hierarchy.py:55-56"""
     return (2 * (tau + 0.5)) * cam.tanfovx / (0.5 * cam.W)

@@ -16,6 +16,11 @@ def _oracle_hier_step(h, cam, thr, gt):
     n, ri, pi, ni = oracle.expand_to_size(h["nodes"], h["boxes"], thr, cam.camera_center)
     ts, kids = oracle.get_interpolation_weights(ni, thr, h["nodes"], h["boxes"], cam.camera_center)
     pi = np.where(pi < 0, ri, pi)
+    S = int(h.get("skybox_points", 0))
+    if S:                       # skybox rows follow the cut: own parent, t = 1, kids = 1 (render_post :220-234)
+        sky = np.arange(h["means3D"].shape[0] - S, h["means3D"].shape[0], dtype=ri.dtype)
+        ri, pi = np.concatenate([ri, sky]), np.concatenate([pi, sky])
+        ts, kids = np.concatenate([ts, np.ones(S, ts.dtype)]), np.concatenate([kids, np.ones(S, kids.dtype)])
     t = ts[:, None]
     lerp = lambda a: (t.reshape((-1,) + (1,) * (a.ndim - 1)) * a[ri] + (1 - t).reshape((-1,) + (1,) * (a.ndim - 1)) * a[pi]).astype(np.float32)
     qc, qp = h["rotations"][ri], h["rotations"][pi]
@@ -73,6 +78,40 @@ def test_hierarchy_step_matches_oracle_composition():
         with torch.no_grad():
             imgs[fused] = (pipeline.render_hier_fused if fused else pipeline.render_hier)(scene, dcam, bg0, thr)[0]
     assert torch.equal(imgs[False], imgs[True])         # bit-identical lerp arithmetic
+
+
+def test_skybox_rows_follow_the_cut():
+    """render_post appends the model's last `skybox_points` rows to every cut with t = 1, kids = 1
+    (gaussian_renderer/__init__.py:220-234); both the PyTorch-op form and the fused index form."""
+    import torch
+    from h3dgs import pipeline
+    cam = synth.make_camera(400, 240)
+    leaves = synth.cloud_v1(5000, cam, zmin=2.0, zmax=30.0, seed=7, scale_k=1.0)
+    z = leaves["means3D"][:, 2:3]
+    leaves["scales"] = (5e-3 * np.sqrt(2.0 * z) * np.ones((1, 3))).astype(np.float32)
+    h = synth.append_skybox(synth.build_hierarchy(leaves), 300)
+    thr = synth.tau_threshold(6.0, cam)
+    gt = np.random.default_rng(4).uniform(0, 1, (3, cam.H, cam.W)).astype(np.float32)
+    n_ref, f, gref = _oracle_hier_step(h, cam, thr, gt)
+    S = h["skybox_points"]
+    assert (f["radii"][n_ref:] > 0).sum() > 10            # some of the sky is in view
+    scene = pipeline.Scene(h)
+    dcam = pipeline.DeviceCamera(cam)
+    bg0, gtd = torch.zeros(3, device="cuda"), torch.tensor(gt, device="cuda")
+    imgs = {}
+    for fused in (False, True):
+        loss, radii, n = pipeline.l1_step(scene, dcam, bg0, gtd, thr, fused=fused)
+        assert n == n_ref and radii.shape[0] == n + S
+        assert np.array_equal(radii.cpu().numpy(), f["radii"])
+        assert abs(loss.item() - np.abs(f["color"] - gt).mean()) < 1e-6
+        for name, p in [("means3D", scene.means3D), ("scales", scene.scales), ("shs", scene.shs),
+                        ("opacities", scene.opacities), ("rotations", scene.rotations)]:
+            e = rel_err(p.grad.cpu().numpy(), gref[name])
+            assert e < 2e-5, (fused, name, e)
+            assert p.grad[-S:].abs().sum() > 0              # the skybox rows receive gradients
+        with torch.no_grad():
+            imgs[fused] = (pipeline.render_hier_fused if fused else pipeline.render_hier)(scene, dcam, bg0, thr)[0]
+    assert torch.equal(imgs[False], imgs[True])
 
 
 def test_fused_gather_lerp_matches_oracle_directly():

@@ -65,3 +65,33 @@ def test_weights_range_and_monotone_cut(hier):
         assert (pi[ni != 0] == h["nodes"][h["nodes"][ni[ni != 0], 1], 2]).all()
         sizes.append(n)
     assert all(a >= b for a, b in zip(sizes, sizes[1:])) and sizes[0] > sizes[-1]
+
+
+def test_skybox_rows_as_indices_equal_appended_rows():
+    """The fused form renders the skybox by appending its row indices (own parent, t = 1) to the cut;
+    render_post appends the gathered rows themselves (gaussian_renderer/__init__.py:220-234).
+    Both must be the same arithmetic: 1*x + 0*x == x."""
+    from oracle import oracle
+    from test_gpu_pipeline import _oracle_hier_step
+    cam = synth.make_camera(400, 240)
+    leaves = synth.cloud_v1(5000, cam, zmin=2.0, zmax=30.0, seed=7, scale_k=1.0)
+    z = leaves["means3D"][:, 2:3]
+    leaves["scales"] = (5e-3 * np.sqrt(2.0 * z) * np.ones((1, 3))).astype(np.float32)
+    h = synth.append_skybox(synth.build_hierarchy(leaves), 300)
+    S, N = h["skybox_points"], h["means3D"].shape[0]
+    thr = synth.tau_threshold(6.0, cam)
+    gt = np.random.default_rng(4).uniform(0, 1, (3, cam.H, cam.W)).astype(np.float32)
+    n, f, grads = _oracle_hier_step(h, cam, thr, gt)                 # appended-rows form
+    assert f["radii"].shape[0] == n + S and (f["radii"][n:] > 0).sum() > 10
+    assert np.abs(grads["means3D"][-S:]).sum() > 0 and np.abs(grads["shs"][-S:]).sum() > 0
+    _, ri, pi, ni = oracle.expand_to_size(h["nodes"], h["boxes"], thr, cam.camera_center)
+    ts, kids = oracle.get_interpolation_weights(ni, thr, h["nodes"], h["boxes"], cam.camera_center)
+    sky = np.arange(N - S, N, dtype=ri.dtype)
+    g = oracle.rasterize_forward(h["means3D"], h["shs"], None, h["opacities"], h["scales"], h["rotations"], None,
+                                 cam.world_view_transform, cam.full_proj_transform, cam.camera_center,
+                                 np.zeros(3, np.float32), cam.W, cam.H, cam.tanfovx, cam.tanfovy,
+                                 ts=np.concatenate([ts, np.ones(S, ts.dtype)]),
+                                 kids=np.concatenate([kids, np.ones(S, kids.dtype)]),
+                                 render_indices=np.concatenate([ri, sky]), parent_indices=np.concatenate([pi, sky]))
+    assert np.array_equal(g["radii"], f["radii"])
+    assert np.array_equal(g["color"], f["color"])
