@@ -129,8 +129,13 @@ def render_hier(scene, cam, bg, threshold, sh_degree=3):
     """`render_post()` of the reference (hierarchy post-optimisation, config #3)."""
     n = lod_cut(scene, cam, threshold)
     means, scales, rots, opac, shs = interpolate_cut(scene, n)
-    _skybox_weights(scene, n)
-    rs = make_settings(scene, cam, bg, sh_degree, ts=scene.interpolation_weights, kids=scene.num_siblings)
+    ts = scene.interpolation_weights
+    if scene.skybox_points:
+        # a copy, as in render_post (:232): autograd holds a view of the cut's weights for the lerp backward
+        ts = ts.clone()
+        ts[n:n + scene.skybox_points] = 1.0
+        scene.num_siblings[n:n + scene.skybox_points] = 1
+    rs = make_settings(scene, cam, bg, sh_degree, ts=ts, kids=scene.num_siblings)
     means2D = torch.zeros_like(means, requires_grad=means.requires_grad)
     img, radii, _ = GaussianRasterizer(rs)(means3D=means, means2D=means2D, shs=shs, colors_precomp=None,
                                            opacities=opac, scales=scales, rotations=rots, cov3D_precomp=None)
