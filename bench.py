@@ -247,6 +247,9 @@ def main():
     ap.add_argument("--workload", default="hier3m", choices=["hier3m", "flat1m", "tiny"])
     ap.add_argument("--cpu-frac", type=int, default=16, help="CPU arm renders every k-th cut Gaussian")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="hierarchy workloads: the sync-free step replayed from CUDA graphs (h3dgs.graphstep) instead of "
+                         "the call-by-call public API; same kernels, no host round trips inside the step")
     ap.add_argument("--classic", action="store_true",
                     help="also time the classic-formulation blend kernels (baseline/classic) on the same binned state")
     args = ap.parse_args()
@@ -313,7 +316,52 @@ def main():
     host_cams = [(torch.tensor(c.world_view_transform).pin_memory(), torch.tensor(c.full_proj_transform).pin_memory(),
                   torch.tensor(c.camera_center).pin_memory()) for c in cams]
 
+    gs = None
+    if args.graph:
+        if not hier:
+            raise SystemExit("--graph drives the hierarchy step (LOD cut + fused gather/lerp)")
+        from h3dgs.graphstep import GraphedStep
+        c0 = cams[0]
+        mk = lambda **kw: GraphedStep(scene, W, H, c0.tanfovx, c0.tanfovy, bg, thr[0], world=world, rank=rank, **kw)
+        # capacities: one eager sync-free pass over the views with generous sizes, then +15 % head room
+        # (rows and entries) and the next power of two (longest tile list)
+        probe = mk(bin_capacity=1 << 23, sort_capacity=8192, capture=False)
+        need = {"rows": 0, "D": 0, "longest_list": 0}
+        for v in range(N_VIEWS):
+            probe.step(dcams[v], gts_dev[v])
+            st = probe.status()
+            if st["overflow"]:
+                raise SystemExit(f"--graph: view {v} does not fit the probe capacities: {st}")
+            need = {k: max(need[k], st[k]) for k in need}
+        del probe
+        torch.cuda.empty_cache()
+        rows_cap = min(int(need["rows"] * 1.15) + 1, scene.means3D.shape[0])
+        if world > 1:       # the row blocks of the reduce-scatter must agree on every rank
+            t = torch.tensor([rows_cap], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); rows_cap = int(t.item())
+        sort_cap = 32
+        while sort_cap < min(int(need["longest_list"] * 1.25), 8192):
+            sort_cap *= 2
+        gs = mk(row_capacity=rows_cap, bin_capacity=int(need["D"] * 1.15) + 1, sort_capacity=sort_cap, capture=False)
+        gs.set_camera(dcams[0]); gs.gt.copy_(gts_dev[0])
+        gs.capture()
+        config["graph"] = {"row_capacity": rows_cap, "bin_capacity": gs.bin_capacity, "sort_capacity": sort_cap,
+                           "library_launches_per_step": int(gs.launches_per_step)}
+
+    def step_graph(i, resident=True):
+        v = i % N_VIEWS
+        ready = gs.upload_target(gts_dev[v] if resident else gts_host[v], copy_stream)
+        if resident:
+            gs.set_camera(dcams[v])
+        else:
+            gs.view.copy_(host_cams[v][0].reshape(16), non_blocking=True)
+            gs.proj.copy_(host_cams[v][1].reshape(16), non_blocking=True)
+            gs.campos.copy_(host_cams[v][2], non_blocking=True)
+        gs.step(gt_ready=ready)
+        return gs.status_dev[0], gs.radii, -1
+
     def step(i, resident=True):
+        if gs is not None:
+            return step_graph(i, resident)
         v = i % N_VIEWS
         ready = None
         if resident:
@@ -385,11 +433,28 @@ def main():
 
     # bookkeeping for the roofline (untimed pass over the views): P (cut), V, D
     from diff_gaussian_rasterization import _C as rc
-    Pm = float(np.mean(stats))
     Vs, Ds = [], []
-    for i in range(N_VIEWS):
-        loss, radii, n = step(i)
-        Vs.append(int((radii > 0).sum().item())); Ds.append(rc.last_num_rendered())
+    if gs is None:
+        Pm = float(np.mean(stats))
+        for i in range(N_VIEWS):
+            loss, radii, n = step(i)
+            Vs.append(int((radii > 0).sum().item())); Ds.append(rc.last_num_rendered())
+    else:
+        # graph replays bypass the library's stage events and launch counter: the same sync-free step,
+        # run eagerly once per view, gives the per-stage device times; every view must have fitted
+        launches = gs.launches_per_step * args.steps
+        graphs, gs.graph_a, gs.graph_b = (gs.graph_a, gs.graph_b), None, None
+        _lib.profile_reset(); _lib.profile_enable(True)
+        Ps = []
+        for i in range(N_VIEWS):
+            step(i)
+            st = gs.status()
+            if st["overflow"]:
+                raise SystemExit(f"--graph: view {i} overflowed the capacities {config['graph']}: {st}; timed result invalid")
+            Ps.append(st["rows"]); Ds.append(st["D"]); Vs.append(int((gs.radii > 0).sum().item()))
+        prof = _lib.profile_read(); _lib.profile_enable(False)
+        gs.graph_a, gs.graph_b = graphs
+        Pm = float(np.mean(Ps))
     Vm, Dm = float(np.mean(Vs)), float(np.mean(Ds))
     stage_ms = {k: (v[0] / max(v[1], 1)) for k, v in prof.items() if v[1] > 0}
 
@@ -401,7 +466,8 @@ def main():
                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                "clocks": clocks, "gpu_launches": int(launches),
                "e2e": {"value": 1000.0 / (ms_e2e / args.steps), "unit": UNIT,
-                       "h2d_bytes_per_step": 3 * H * W * 4 + 16 * 4 * 2 + 3 * 4, "d2h_bytes_per_step": 4},
+                       "h2d_bytes_per_step": 3 * H * W * 4 + 16 * 4 * 2 + 3 * 4,
+                       "d2h_bytes_per_step": 8 if gs is not None else 4},
                "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
                "counts": {"P_cut": Pm, "V": Vm, "D_rank0": Dm, "N_all": int(scene.means3D.shape[0])}}
         # roofline of the dominant kernel

@@ -156,7 +156,8 @@ gather_records_kernel(int64_t D, const uint32_t* __restrict__ point_list, const 
 // global radix sort plus the separate gather.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
-tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges, ScanInfo* __restrict__ info)
+tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges, ScanInfo* __restrict__ info,
+                 uint32_t cap_entries, uint32_t cap_list)
 {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry, s_max;
@@ -189,18 +190,24 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restri
     local_max = __reduce_max_sync(0xffffffffu, local_max);
     if (lane == 0) atomicMax(&s_max, local_max);
     __syncthreads();
-    if (tid == 0) { info->D = s_carry; info->max_count = s_max; }
+    // capacity mode (cap_entries > 0): a frame that does not fit is turned into an empty one
+    const bool overflow = cap_entries != 0u && (s_carry > cap_entries || s_max > cap_list);
+    if (tid == 0) { info->D = s_carry; info->max_count = s_max; info->overflow = overflow ? 1u : 0u; }
+    if (overflow)
+        for (int t = tid; t < T; t += 1024) ranges[t] = make_uint2(0u, 0u);
 }
 
 __global__ void __launch_bounds__(256)
 emit_to_tiles_kernel(int P, int W, int H, int shard_count, int shard_index, const int* __restrict__ radii,
                      const float* __restrict__ depths, const Record* __restrict__ records,
-                     const uint2* __restrict__ ranges, uint32_t* __restrict__ tile_count, uint2* __restrict__ pairs)
+                     const uint2* __restrict__ ranges, const ScanInfo* __restrict__ info,
+                     uint32_t* __restrict__ tile_count, uint2* __restrict__ pairs)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     const int rad = radii[i];
     if (rad <= 0) return;
+    if (info->overflow) return;                  // capacity mode: the segments would not fit `pairs`
     const float4 a = records[i].a;
     const float ix = a.x, iy = a.y;
     const int gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
@@ -318,18 +325,18 @@ int launch_binning(const h3dgs_raster_args& a, const int32_t* radii, const float
 }
 
 int launch_tile_scan(const h3dgs_raster_args& a, const uint32_t* tile_count, uint32_t* ranges, ScanInfo* info,
-                     cudaStream_t s)
+                     uint32_t cap_entries, uint32_t cap_list, cudaStream_t s)
 {
     const int gx = (a.image_width + kTile - 1) / kTile, gy = (a.image_height + kTile - 1) / kTile;
     ProfScope prof(H3DGS_STAGE_SCAN, s);
-    tile_scan_kernel<<<1, 1024, 0, s>>>(gx * gy, tile_count, (uint2*)ranges, info);
+    tile_scan_kernel<<<1, 1024, 0, s>>>(gx * gy, tile_count, (uint2*)ranges, info, cap_entries, cap_list);
     H3_LAUNCHED("tile_scan", a.debug, s);
     return H3DGS_OK;
 }
 
 int launch_tile_binning(const h3dgs_raster_args& a, const int32_t* radii, const float* depths, const Record* records,
                         int64_t D, uint32_t max_count, uint8_t* bin, const BinLayout& bl, const uint32_t* ranges,
-                        uint32_t* tile_count, cudaStream_t s)
+                        const ScanInfo* info, uint32_t* tile_count, cudaStream_t s)
 {
     if (D == 0 || a.P == 0) return H3DGS_OK;
     const int W = a.image_width, H = a.image_height;
@@ -339,7 +346,7 @@ int launch_tile_binning(const h3dgs_raster_args& a, const int32_t* radii, const 
     uint2* pairs = (uint2*)(bin + bl.keys_unsorted);
     { ProfScope prof(H3DGS_STAGE_DUPLICATE, s);
     emit_to_tiles_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a.P, W, H, sc, si, radii, depths, records, (const uint2*)ranges,
-                                                           tile_count, pairs);
+                                                           info, tile_count, pairs);
     H3_LAUNCHED("emit_to_tiles", a.debug, s); }
     int m = 32;
     while (m < (int)max_count) m <<= 1;

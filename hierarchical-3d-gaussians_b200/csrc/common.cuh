@@ -46,8 +46,10 @@ struct BinLayout {
 struct ImgLayout {
     size_t final_T, n_contrib, ranges, tile_max_contrib, tile_count, scan_info, total;
 };
-// written by tile_scan_kernel, read back by the host (the one num_rendered round trip)
-struct ScanInfo { uint32_t D, max_count; };
+// written by tile_scan_kernel; read back by the host in exact mode (the one num_rendered round trip).
+// overflow: capacity mode only -- the frame does not fit (bin_capacity, sort_capacity); all ranges are
+// emptied and key emission is skipped, so every later stage is a no-op for this frame.
+struct ScanInfo { uint32_t D, max_count, overflow; };
 // largest per-tile list the shared-memory sort handles; bigger lists fall back to the global CUB sort
 constexpr int kTileSortCap = 8192;
 
@@ -98,10 +100,10 @@ extern int64_t g_launches;
 int launch_preprocess(const h3dgs_raster_args& a, int32_t* radii, float* depths, uint32_t* tiles_touched,
                       Record* records, uint32_t* tile_count, cudaStream_t s);
 int launch_tile_scan(const h3dgs_raster_args& a, const uint32_t* tile_count, uint32_t* ranges, ScanInfo* info,
-                     cudaStream_t s);
+                     uint32_t cap_entries, uint32_t cap_list, cudaStream_t s);
 int launch_tile_binning(const h3dgs_raster_args& a, const int32_t* radii, const float* depths, const Record* records,
                         int64_t D, uint32_t max_count, uint8_t* bin, const BinLayout& bl, const uint32_t* ranges,
-                        uint32_t* tile_count, cudaStream_t s);
+                        const ScanInfo* info, uint32_t* tile_count, cudaStream_t s);
 int launch_preprocess_color(const h3dgs_raster_args& a, const int32_t* radii, Record* records, cudaStream_t s);
 int launch_sh_backward(const h3dgs_raster_args& a, const int32_t* radii, const Record* records, const float* accum,
                        float* dL_dmeans3D, float* dL_dsh, cudaStream_t s);

@@ -63,7 +63,9 @@ preprocess_kernel(int P, const float* __restrict__ means3D, const float* __restr
     int c = i, p = i;
     float t = 1.0f, u = 0.0f;
     if (ridx) {
-        c = ridx[i]; p = pidx[i]; if (p < 0) p = c;
+        c = ridx[i];
+        if (c < 0) { radii[i] = 0; tiles_touched[i] = 0; return; }   // tail after a device-side LOD cut (h3dgs_lod_cut)
+        p = pidx[i]; if (p < 0) p = c;
         t = ts[i]; u = 1.0f - t;
     }
     const bool lerp = ridx != nullptr && u != 0.0f;
