@@ -28,10 +28,11 @@ __device__ __forceinline__ float node_size(const float4* __restrict__ boxes, int
 
 __global__ void __launch_bounds__(256)
 mark_nodes_kernel(int N, const int* __restrict__ nodes, const float4* __restrict__ boxes, float target,
-                  const float* __restrict__ viewpoint, int* __restrict__ counts)
+                  const float* __restrict__ target_dev, const float* __restrict__ viewpoint, int* __restrict__ counts)
 {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
+    if (target_dev) target = *target_dev;
     const float vx = viewpoint[0], vy = viewpoint[1], vz = viewpoint[2];
     const int* nd = nodes + 7 * (size_t)n;
     const int depth = nd[0], parent = nd[1], cl = nd[3], cm = nd[4];
@@ -97,12 +98,13 @@ interpolation_weights_kernel(int n, const int* __restrict__ node_indices, float 
 // emitting thread already holds the node and its parent -- plus the count for the consumer.
 __global__ void __launch_bounds__(256)
 put_cut_kernel(int N, const int* __restrict__ nodes, const float4* __restrict__ boxes, float target,
-               const float* __restrict__ viewpoint, const int* __restrict__ counts, const int* __restrict__ offsets,
+               const float* __restrict__ target_dev, const float* __restrict__ viewpoint, const int* __restrict__ counts, const int* __restrict__ offsets,
                int* __restrict__ render_indices, int* __restrict__ parent_indices, int* __restrict__ nodes_of_render,
                float* __restrict__ ts, int* __restrict__ kids, int* __restrict__ total)
 {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
+    if (target_dev) target = *target_dev;
     if (n == N - 1) *total = offsets[N - 1];
     const int count = counts[n];
     if (count == 0) return;
@@ -150,7 +152,7 @@ extern "C" int h3dgs_expand_to_size(int32_t N, const int32_t* nodes, const float
     size_t temp_bytes = expand_scan_bytes(N);
     const int blocks = (N + 255) / 256;
     { ProfScope prof(H3DGS_STAGE_LOD_CUT, s);
-    mark_nodes_kernel<<<blocks, 256, 0, s>>>(N, nodes, (const float4*)boxes, target_size, viewpoint, counts);
+    mark_nodes_kernel<<<blocks, 256, 0, s>>>(N, nodes, (const float4*)boxes, target_size, nullptr, viewpoint, counts);
     H3_LAUNCHED("mark_nodes", 0, s);
     H3_CUDA(cub::DeviceScan::InclusiveSum(temp, temp_bytes, counts, offsets, N, s));
     H3_LAUNCHED("expand_scan", 0, s);
@@ -165,7 +167,7 @@ extern "C" int h3dgs_expand_to_size(int32_t N, const int32_t* nodes, const float
 }
 
 extern "C" int h3dgs_lod_cut(int32_t N, const int32_t* nodes, const float* boxes, float target_size,
-                             const float* viewpoint, int32_t* render_indices, int32_t* parent_indices,
+                             const float* target_size_dev, const float* viewpoint, int32_t* render_indices, int32_t* parent_indices,
                              int32_t* nodes_for_render_indices, float* ts, int32_t* num_kids, int32_t* count,
                              void* scratch, void* stream)
 {
@@ -182,11 +184,11 @@ extern "C" int h3dgs_lod_cut(int32_t N, const int32_t* nodes, const float* boxes
     ProfScope prof(H3DGS_STAGE_LOD_CUT, s);
     // rows after the cut: index -1 = "skip" for the rasterizer (the head is overwritten below)
     H3_CUDA(cudaMemsetAsync(render_indices, 0xFF, (size_t)N * sizeof(int32_t), s));
-    mark_nodes_kernel<<<blocks, 256, 0, s>>>(N, nodes, (const float4*)boxes, target_size, viewpoint, counts);
+    mark_nodes_kernel<<<blocks, 256, 0, s>>>(N, nodes, (const float4*)boxes, target_size, target_size_dev, viewpoint, counts);
     H3_LAUNCHED("mark_nodes", 0, s);
     H3_CUDA(cub::DeviceScan::InclusiveSum(temp, temp_bytes, counts, offsets, N, s));
     H3_LAUNCHED("expand_scan", 0, s);
-    put_cut_kernel<<<blocks, 256, 0, s>>>(N, nodes, (const float4*)boxes, target_size, viewpoint, counts, offsets,
+    put_cut_kernel<<<blocks, 256, 0, s>>>(N, nodes, (const float4*)boxes, target_size, target_size_dev, viewpoint, counts, offsets,
                                           render_indices, parent_indices, nodes_for_render_indices, ts, num_kids, count);
     H3_LAUNCHED("put_cut", 0, s);
     return H3DGS_OK;

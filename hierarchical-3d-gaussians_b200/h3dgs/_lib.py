@@ -81,7 +81,7 @@ def lib():
     l.h3dgs_get_interpolation_weights.argtypes = [C.c_int32, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p] + \
         [C.c_float] * 6 + [C.c_void_p, C.c_void_p, C.c_void_p]
     l.h3dgs_lod_cut.restype = C.c_int
-    l.h3dgs_lod_cut.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_float] + [C.c_void_p] * 10
+    l.h3dgs_lod_cut.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_float] + [C.c_void_p] * 11
     l.h3dgs_l1_ssim_forward.restype = C.c_int
     l.h3dgs_l1_ssim_forward.argtypes = [C.c_int32] * 3 + [C.c_void_p] * 5
     l.h3dgs_l1_ssim_backward.restype = C.c_int

@@ -35,8 +35,9 @@ def _ptr(t):
 
 
 class GraphedStep:
-    """scene: pipeline.Scene with a hierarchy.  camera-independent sizes (W, H, tanfov) and the LOD
-    threshold are fixed per instance (they are launch constants inside the graphs)."""
+    """scene: pipeline.Scene with a hierarchy.  The camera-independent sizes (W, H, tanfov) are fixed per
+    instance (launch constants inside the graphs); camera, target and LOD threshold are device-resident
+    inputs that change between replays (set_camera, upload_target / step(gt=), set_threshold)."""
 
     def __init__(self, scene, W, H, tanfovx, tanfovy, bg, threshold, sh_degree=3, row_capacity=None,
                  bin_capacity=1 << 22, sort_capacity=4096, world=1, rank=0, group=None, capture=True):
@@ -61,6 +62,7 @@ class GraphedStep:
         self.view, self.proj, self.campos = f(16), f(16), f(3)
         self.bg = bg.to(dev).float().contiguous()
         self.gt = f(3, H, W)
+        self.threshold_dev = torch.full((1,), self.threshold, dtype=torch.float32, device=dev)   # read by the cut kernels
         # static outputs
         self.count = torch.zeros(1, dtype=torch.int32, device=dev)
         self.radii = torch.zeros(self.P, dtype=torch.int32, device=dev)
@@ -129,7 +131,7 @@ class GraphedStep:
         if self.N > self.N_nodes:
             sc.render_indices[self.N_nodes:].fill_(-1)  # the library marks [n, N_nodes); these are the skybox slots beyond
         _lib.check(L.h3dgs_lod_cut(self.N_nodes, sc.nodes.data_ptr(), sc.boxes.data_ptr(), self.threshold,
-                                   self.campos.data_ptr(), sc.render_indices.data_ptr(), sc.parent_indices.data_ptr(),
+                                   self.threshold_dev.data_ptr(), self.campos.data_ptr(), sc.render_indices.data_ptr(), sc.parent_indices.data_ptr(),
                                    sc.nodes_for_render.data_ptr(), sc.interpolation_weights.data_ptr(),
                                    sc.num_siblings.data_ptr(), self.count.data_ptr(), self.lod_scratch.data_ptr(),
                                    self._stream()))
@@ -191,6 +193,11 @@ class GraphedStep:
         self.view.copy_(cam.viewmatrix.reshape(16), non_blocking=True)
         self.proj.copy_(cam.projmatrix.reshape(16), non_blocking=True)
         self.campos.copy_(cam.campos.reshape(3), non_blocking=True)
+
+    def set_threshold(self, threshold):
+        """A new LOD threshold for the next step (train_post.py:66-74 draws one per step)."""
+        self.threshold = float(threshold)
+        self.threshold_dev.fill_(self.threshold)
 
     def upload_target(self, src, stream):
         """Copy this step's target (device tensor or pinned host tensor) into the static buffer on

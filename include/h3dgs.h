@@ -180,8 +180,11 @@ int h3dgs_get_interpolation_weights(int32_t n, const int32_t* node_indices, floa
  * pass with the same arithmetic, nothing returned to the host.  Outputs as the two calls above
  * (render_indices, parent_indices, nodes_for_render_indices, ts, num_kids: first n entries); in addition
  * render_indices[n .. N) = -1 (rows the rasterizer skips when handed P = N) and *count [device] = n.
+ * target_size_dev, when not NULL, is a device float that overrides target_size: train_post.py:66-74 draws a
+ * new threshold every step, and a value read on the device can change between replays of a captured graph.
  * scratch as for h3dgs_expand_to_size. */
-int h3dgs_lod_cut(int32_t N, const int32_t* nodes, const float* boxes, float target_size, const float* viewpoint,
+int h3dgs_lod_cut(int32_t N, const int32_t* nodes, const float* boxes, float target_size, const float* target_size_dev,
+                  const float* viewpoint,
                   int32_t* render_indices, int32_t* parent_indices, int32_t* nodes_for_render_indices,
                   float* ts, int32_t* num_kids, int32_t* count, void* scratch, void* stream);
 

@@ -46,7 +46,8 @@ def test_device_lod_cut_equals_the_two_call_api(tau):
     count = torch.zeros(1, dtype=torch.int32, device="cuda")
     L = _lib.lib()
     scratch = torch.empty(int(L.h3dgs_expand_scratch_bytes(N)), dtype=torch.uint8, device="cuda")
-    _lib.check(L.h3dgs_lod_cut(N, nodes.data_ptr(), boxes.data_ptr(), thr, vp.data_ptr(), r2.data_ptr(), p2.data_ptr(),
+    thr_dev = torch.full((1,), thr, dtype=torch.float32, device="cuda")
+    _lib.check(L.h3dgs_lod_cut(N, nodes.data_ptr(), boxes.data_ptr(), -1.0, thr_dev.data_ptr(), vp.data_ptr(), r2.data_ptr(), p2.data_ptr(),
                                nn2.data_ptr(), ts2.data_ptr(), kids2.data_ptr(), count.data_ptr(), scratch.data_ptr(),
                                torch.cuda.current_stream().cuda_stream))
     assert int(count.item()) == n and n > 0
@@ -100,6 +101,13 @@ def test_sync_free_step_equals_exact_step(skybox, capture):
         for k, ref in grads.items():
             e = rel_err(gs.grads[k].cpu().numpy(), ref.cpu().numpy())
             assert e < 2e-6, (v, k, e)               # same partial sums, different atomic order
+    # a new LOD threshold between replays (train_post.py:66-74 draws one per step): it lives on the device
+    thr2 = synth.tau_threshold(15.0, cam)
+    loss, radii, n, grads, img, D = _exact_step(scene, dcams[0], bg, gts[0], thr2)
+    gs.set_threshold(thr2)
+    gs.step(dcams[0], gts[0])
+    st = gs.status()
+    assert not st["overflow"] and st["rows"] == n + skybox and st["D"] == D and torch.equal(gs.image, img)
 
 
 def test_capacity_overflow_is_flagged_and_harmless():
