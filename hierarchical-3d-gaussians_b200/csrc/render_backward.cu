@@ -2,7 +2,8 @@
 // Semantics per oracle/oracle.c::oracle_render_backward.
 //
 // One CTA (128 threads, two pixels each) per tile, records streamed back-to-front with the same TMA
-// double buffer as the forward; per-entry partials of a warp's 64 pixels are reduced with a
+// double buffer as the forward; the arithmetic of a thread's two pixels runs on packed FP32x2
+// instructions (one FFMA2 / FMUL2 / FADD2 serves both: the kernel is issue-bound); per-entry partials of a warp's 64 pixels are reduced with a
 // transpose-reduce (12 shuffles for 10 values) and 10 lanes issue ONE red.global.add for the warp --
 // 64x fewer atomics than the classic one-atomic-per-pixel formulation.
 #include "common.cuh"
@@ -52,54 +53,49 @@ __device__ __forceinline__ float transpose_reduce10(const float (&v)[10], int la
 
 constexpr int kBwdThreads = 128;      // two vertically adjacent pixels per thread (see render_forward.cu)
 
-// per-pixel replay state
-struct PixState {
-    float T, acc_s, last_cg, last_alpha;   // transmittance, (accum_rec . g), (last colour . g), last alpha
-};
+// Replay state of the thread's two pixels, packed {pixel 0, pixel 1} (common.cuh "packed FP32 pairs"):
+// T = transmittance in front of the current entry, acc = (colour accumulated behind it) . dL/dC.
+// The classic formulation defers the update of acc by one contributor (last_alpha, last_color); the
+// equivalent immediate form  acc <- acc + alpha (c.g - acc),  T <- T / (1 - alpha)  is the identity for
+// alpha = 0, so a pixel that does not take the entry needs no selects to keep its state.
+struct PairState { f2 T, acc; };
 
-// alpha of one pixel for entry (a, bb), with exactly the forward's decisions
-template <bool HIER>
-__device__ __forceinline__ bool pixel_alpha(const float4& a, const float4& bb, uint32_t kb, float dx, float dy, bool in_list,
-                                            float& G, float& alpha, float& dadb)
+// Contribution of entry (a, bb) at the thread's two pixels to the 10 per-Gaussian sums.  G and alpha
+// are zero for a pixel that does not take the entry: every term below then is an exact zero
+// (each carries a factor G or alpha, the other factors are finite) and its state is unchanged.
+template <bool HIER, bool DEPTH>
+__device__ __forceinline__ void pair_grad(const float4& a, const float4& bb, float dx, f2 d, f2 G, f2 alpha, f2 dadb,
+                                          f2 cg, f2 T_final, f2 neg_bg_dot, f2 g0, f2 g1, f2 g2, f2 gd,
+                                          PairState& st, float (&v)[10])
 {
-    G = 0.f; alpha = 0.f; dadb = 1.f;
-    bool valid = false;
-    const float power = -0.5f * (a.z * dx * dx + bb.x * dy * dy) - a.w * dx * dy;
-    if (in_list && power <= 0.0f) {
-        G = fast_exp(power);
-        const float abase = fminf(kAlphaCap, bb.y * G);
-        hier_alpha_grad<HIER>(abase, bb.z, kb, alpha, dadb);
-        valid = alpha >= kAlphaSkip;
-    }
-    if (!valid) { G = 0.f; alpha = 0.f; }
-    return valid;
-}
-
-// One pixel's contribution of entry (a, bb, c) to the 10 per-Gaussian sums; branch-free so that an
-// invalid pixel (G = alpha = 0) adds exact zeros.
-template <bool DEPTH>
-__device__ __forceinline__ void pixel_grad(const float4& a, const float4& bb, float dx, float dy, bool valid, float G,
-                                           float alpha, float dadb, float cg, float T_final, float bg_dot, float g0,
-                                           float g1, float g2, float gd, PixState& st, float (&v)[10])
-{
-    const float rcp = fast_rcp(1.f - alpha);                   // one reciprocal serves T and the bg term
-    const float Tn = st.T * rcp;
-    const float as_n = st.last_alpha * st.last_cg + (1.f - st.last_alpha) * st.acc_s;
-    const float w = valid ? alpha * Tn : 0.f;                 // dchannel_dcolor
-    const float dL_dalpha = (cg - as_n) * Tn - (T_final * rcp) * bg_dot;
-    const float dL_dab = valid ? dL_dalpha * dadb : 0.f;
-    if (valid) { st.T = Tn; st.acc_s = as_n; st.last_cg = cg; st.last_alpha = alpha; }
-    const float dL_dG = bb.y * dL_dab;
-    const float gdx = G * dx, gdy = G * dy;
+    // one reciprocal of (1 - alpha) serves T and the background term: MUFU.RCP + one Newton step
+    // (exactly 1 for alpha = 0)
+    const f2 oma = sub2(bc(1.0f), alpha);
+    float o0, o1; upk(oma, o0, o1);
+    float r0, r1;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(o0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(o1));
+    const f2 r = pk(r0, r1);
+    const f2 rcp = mul2(r, sub2(bc(2.0f), mul2(oma, r)));
+    const f2 Tn = mul2(st.T, rcp);
+    const f2 diff = sub2(cg, st.acc);
+    const f2 dL_dalpha = fma2(mul2(T_final, rcp), neg_bg_dot, mul2(diff, Tn));
+    const f2 dL_dab = HIER ? mul2(dL_dalpha, dadb) : dL_dalpha;
+    const f2 w = mul2(alpha, Tn);                                              // dchannel_dcolor
+    st.T = Tn;
+    st.acc = fma2(alpha, diff, st.acc);
+    const f2 dL_dG = mul2(bc(bb.y), dL_dab);
+    const f2 gdx = mul2(G, bc(dx)), gdy = mul2(G, d);
+    const f2 qx = mul2(gdx, dL_dG), qy = mul2(gdy, dL_dG);
     // constant factors (0.5 W, 0.5 H, -0.5) are applied once per Gaussian in preprocess_backward
-    v[0] += dL_dG * (-gdx * a.z - gdy * a.w);
-    v[1] += dL_dG * (-gdy * bb.x - gdx * a.w);
-    v[2] += gdx * dx * dL_dG;
-    v[3] += gdx * dy * dL_dG;
-    v[4] += gdy * dy * dL_dG;
-    v[5] += G * dL_dab;
-    v[6] += w * g0; v[7] += w * g1; v[8] += w * g2;
-    if (DEPTH) v[9] += w * gd;
+    v[0] = hsum(fma2(qy, bc(-a.w), mul2(qx, bc(-a.z))));                      // dL_dG (-gdx cx - gdy cy)
+    v[1] = hsum(fma2(qx, bc(-a.w), mul2(qy, bc(-bb.x))));                     // dL_dG (-gdy cz - gdx cy)
+    v[2] = hsum(qx) * dx;
+    v[3] = hsum(mul2(qx, d));
+    v[4] = hsum(mul2(qy, d));
+    v[5] = hsum(mul2(G, dL_dab));
+    v[6] = hsum(mul2(w, g0)); v[7] = hsum(mul2(w, g1)); v[8] = hsum(mul2(w, g2));
+    v[9] = DEPTH ? hsum(mul2(w, gd)) : 0.f;
 }
 
 template <bool HIER, bool DEPTH>
@@ -156,15 +152,18 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
     quad_pixel(tile_x, tile_y, warp, lane, px, py0);
     const int py1 = py0 + 1;
     const bool in0 = px < W && py0 < H, in1 = px < W && py1 < H;
-    const float fpx = (float)px, fpy0 = (float)py0, fpy1 = (float)py1;
+    const float fpx = (float)px;
+    const f2 nfpy = pk(-(float)py0, -(float)py1);
     const size_t pix0 = (size_t)py0 * W + px, pix1 = (size_t)py1 * W + px, plane = (size_t)H * W;
     const float Tf0 = in0 ? final_T[pix0] : 0.f, Tf1 = in1 ? final_T[pix1] : 0.f;
-    PixState st0 = {Tf0, 0.f, 0.f, 0.f}, st1 = {Tf1, 0.f, 0.f, 0.f};
+    const f2 Tf = pk(Tf0, Tf1);
+    PairState ps = {Tf, bc(0.f)};
     const int last0 = in0 ? (int)n_contrib[pix0] : 0, last1 = in1 ? (int)n_contrib[pix1] : 0;
     float ga0 = 0.f, ga1 = 0.f, ga2 = 0.f, gad = 0.f, gb0 = 0.f, gb1 = 0.f, gb2 = 0.f, gbd = 0.f;
     if (in0) { ga0 = dL_dcolor[pix0]; ga1 = dL_dcolor[plane + pix0]; ga2 = dL_dcolor[2 * plane + pix0]; if (DEPTH) gad = dL_dinvdepth[pix0]; }
     if (in1) { gb0 = dL_dcolor[pix1]; gb1 = dL_dcolor[plane + pix1]; gb2 = dL_dcolor[2 * plane + pix1]; if (DEPTH) gbd = dL_dinvdepth[pix1]; }
-    const float bgd0 = bg[0] * ga0 + bg[1] * ga1 + bg[2] * ga2, bgd1 = bg[0] * gb0 + bg[1] * gb1 + bg[2] * gb2;
+    const f2 g0 = pk(ga0, gb0), g1 = pk(ga1, gb1), g2 = pk(ga2, gb2), gd = pk(gad, gbd);
+    const f2 neg_bgd = pk(-(bg[0] * ga0 + bg[1] * ga1 + bg[2] * ga2), -(bg[0] * gb0 + bg[1] * gb1 + bg[2] * gb2));
     const int wlast = (int)__reduce_max_sync(0xffffffffu, (unsigned)max(last0, last1));   // nothing in this quadrant beyond it
     const uint32_t qbit = 1u << (kQuadShift + warp);
 
@@ -187,19 +186,24 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
                 const float4 a = rec[j].a;
                 const float4 bb = rec[j].b;
                 const uint32_t kb = __float_as_uint(bb.w);
-                const float dx = a.x - fpx, dy0 = a.y - fpy0, dy1 = a.y - fpy1;
-                float G0, al0, dd0, G1, al1, dd1;
-                const bool v0 = pixel_alpha<HIER>(a, bb, kb, dx, dy0, e < last0, G0, al0, dd0);
-                const bool v1 = pixel_alpha<HIER>(a, bb, kb, dx, dy1, e < last1, G1, al1, dd1);
+                const float dx = a.x - fpx;
+                // alpha of the two pixels with exactly the forward's arithmetic and decisions
+                f2 d, G, al, dadb;
+                const f2 pw = pair_power(a, bb, dx, nfpy, d);
+                pair_gauss(pw, bb.y, G, al);
+                pair_hier_alpha<HIER, true>(al, bb.z, kb, al, dadb);
+                float pw0, pw1, al0, al1;
+                upk(pw, pw0, pw1); upk(al, al0, al1);
+                const bool v0 = e < last0 && pw0 <= 0.0f && al0 >= kAlphaSkip;
+                const bool v1 = e < last1 && pw1 <= 0.0f && al1 >= kAlphaSkip;
                 if (!__any_sync(0xffffffffu, v0 || v1)) continue;            // warp-uniform
+                G = sel2(v0, v1, G, bc(0.f));
+                al = sel2(v0, v1, al, bc(0.f));
                 const float4 c = rec[j].c;
-                float cg0 = c.x * ga0 + c.y * ga1 + c.z * ga2, cg1 = c.x * gb0 + c.y * gb1 + c.z * gb2;
-                if (DEPTH) { cg0 += c.w * gad; cg1 += c.w * gbd; }
+                f2 cg = fma2(bc(c.z), g2, fma2(bc(c.y), g1, mul2(bc(c.x), g0)));
+                if (DEPTH) cg = fma2(bc(c.w), gd, cg);
                 float v[10];
-#pragma unroll
-                for (int k = 0; k < 10; k++) v[k] = 0.f;
-                pixel_grad<DEPTH>(a, bb, dx, dy0, v0, G0, al0, dd0, cg0, Tf0, bgd0, ga0, ga1, ga2, gad, st0, v);
-                pixel_grad<DEPTH>(a, bb, dx, dy1, v1, G1, al1, dd1, cg1, Tf1, bgd1, gb0, gb1, gb2, gbd, st1, v);
+                pair_grad<HIER, DEPTH>(a, bb, dx, d, G, al, dadb, cg, Tf, neg_bgd, g0, g1, g2, gd, ps, v);
                 const float total = transpose_reduce10(v, lane);
                 if (slot >= 0 && (DEPTH || slot < 9))
                     atomicAdd(accum + (size_t)s_id[st][j] * kAccum + slot, total);
