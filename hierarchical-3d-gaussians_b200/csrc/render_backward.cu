@@ -53,51 +53,6 @@ __device__ __forceinline__ float transpose_reduce10(const float (&v)[10], int la
 
 constexpr int kBwdThreads = 128;      // two vertically adjacent pixels per thread (see render_forward.cu)
 
-// Replay state of the thread's two pixels, packed {pixel 0, pixel 1} (common.cuh "packed FP32 pairs"):
-// T = transmittance in front of the current entry, acc = (colour accumulated behind it) . dL/dC.
-// The classic formulation defers the update of acc by one contributor (last_alpha, last_color); the
-// equivalent immediate form  acc <- acc + alpha (c.g - acc),  T <- T / (1 - alpha)  is the identity for
-// alpha = 0, so a pixel that does not take the entry needs no selects to keep its state.
-struct PairState { f2 T, acc; };
-
-// Contribution of entry (a, bb) at the thread's two pixels to the 10 per-Gaussian sums.  G and alpha
-// are zero for a pixel that does not take the entry: every term below then is an exact zero
-// (each carries a factor G or alpha, the other factors are finite) and its state is unchanged.
-template <bool HIER, bool DEPTH>
-__device__ __forceinline__ void pair_grad(const float4& a, const float4& bb, float dx, f2 d, f2 G, f2 alpha, f2 dadb,
-                                          f2 cg, f2 T_final, f2 neg_bg_dot, f2 g0, f2 g1, f2 g2, f2 gd,
-                                          PairState& st, float (&v)[10])
-{
-    // one reciprocal of (1 - alpha) serves T and the background term: MUFU.RCP + one Newton step
-    // (exactly 1 for alpha = 0)
-    const f2 oma = sub2(bc(1.0f), alpha);
-    float o0, o1; upk(oma, o0, o1);
-    float r0, r1;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(o0));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(o1));
-    const f2 r = pk(r0, r1);
-    const f2 rcp = mul2(r, sub2(bc(2.0f), mul2(oma, r)));
-    const f2 Tn = mul2(st.T, rcp);
-    const f2 diff = sub2(cg, st.acc);
-    const f2 dL_dalpha = fma2(mul2(T_final, rcp), neg_bg_dot, mul2(diff, Tn));
-    const f2 dL_dab = HIER ? mul2(dL_dalpha, dadb) : dL_dalpha;
-    const f2 w = mul2(alpha, Tn);                                              // dchannel_dcolor
-    st.T = Tn;
-    st.acc = fma2(alpha, diff, st.acc);
-    const f2 dL_dG = mul2(bc(bb.y), dL_dab);
-    const f2 gdx = mul2(G, bc(dx)), gdy = mul2(G, d);
-    const f2 qx = mul2(gdx, dL_dG), qy = mul2(gdy, dL_dG);
-    // constant factors (0.5 W, 0.5 H, -0.5) are applied once per Gaussian in preprocess_backward
-    v[0] = hsum(fma2(qy, bc(-a.w), mul2(qx, bc(-a.z))));                      // dL_dG (-gdx cx - gdy cy)
-    v[1] = hsum(fma2(qx, bc(-a.w), mul2(qy, bc(-bb.x))));                     // dL_dG (-gdy cz - gdx cy)
-    v[2] = hsum(qx) * dx;
-    v[3] = hsum(mul2(qx, d));
-    v[4] = hsum(mul2(qy, d));
-    v[5] = hsum(mul2(G, dL_dab));
-    v[6] = hsum(mul2(w, g0)); v[7] = hsum(mul2(w, g1)); v[8] = hsum(mul2(w, g2));
-    v[9] = DEPTH ? hsum(mul2(w, gd)) : 0.f;
-}
-
 template <bool HIER, bool DEPTH>
 __global__ void __launch_bounds__(kBwdThreads)
 render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, const uint2* __restrict__ ranges,

@@ -103,19 +103,12 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
                     const f2 pw = pair_power(a, bb, a.x - fpx, nfpy, d);
                     pair_gauss(pw, bb.y, G, al);
                     pair_hier_alpha<HIER, false>(al, bb.z, kb, al, unused);
-                    const f2 tT = mul2(T, sub2(bc(1.0f), al));
-                    float pw0, pw1, al0, al1, tT0, tT1;
-                    upk(pw, pw0, pw1); upk(al, al0, al1); upk(tT, tT0, tT1);
-                    bool v0 = !done0 && pw0 <= 0.0f && al0 >= kAlphaSkip;
-                    bool v1 = !done1 && pw1 <= 0.0f && al1 >= kAlphaSkip;
-                    if (v0 && tT0 < kTStop) { done0 = true; v0 = false; }
-                    if (v1 && tT1 < kTStop) { done1 = true; v1 = false; }
-                    const f2 w = sel2(v0, v1, mul2(al, T), bc(0.f));
+                    bool v0, v1;
+                    const f2 w = pair_blend(pw, al, T, done0, done1, v0, v1);
                     upk(fma2(bc(c.x), w, pk(Ca0, Cb0)), Ca0, Cb0);
                     upk(fma2(bc(c.y), w, pk(Ca1, Cb1)), Ca1, Cb1);
                     upk(fma2(bc(c.z), w, pk(Ca2, Cb2)), Ca2, Cb2);
                     if (DEPTH) upk(fma2(bc(c.w), w, pk(inv0, inv1)), inv0, inv1);
-                    T = sel2(v0, v1, tT, T);
                     const uint32_t idx = base + (uint32_t)j + 1u;
                     last0 = v0 ? idx : last0; last1 = v1 ? idx : last1;
                 }
