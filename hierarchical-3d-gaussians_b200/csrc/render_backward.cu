@@ -31,20 +31,23 @@ __device__ __forceinline__ int reduce_slot(int lane) {
 __device__ __forceinline__ float xchg_add(float keep, float send, int mask) {
     return keep + __shfl_xor_sync(0xffffffffu, send, mask);
 }
+// two exchanges whose additions share one packed FADD2
+__device__ __forceinline__ f2 xchg_add2(float keep0, float send0, float keep1, float send1, int mask) {
+    return add2(pk(keep0, keep1), pk(__shfl_xor_sync(0xffffffffu, send0, mask), __shfl_xor_sync(0xffffffffu, send1, mask)));
+}
 __device__ __forceinline__ float transpose_reduce10(const float (&v)[10], int lane) {
     const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
     float a[5];
-#pragma unroll
-    for (int k = 0; k < 5; k++) a[k] = xchg_add(b4 ? v[k + 5] : v[k], b4 ? v[k] : v[k + 5], 16);
+    upk(xchg_add2(b4 ? v[5] : v[0], b4 ? v[0] : v[5], b4 ? v[6] : v[1], b4 ? v[1] : v[6], 16), a[0], a[1]);
+    upk(xchg_add2(b4 ? v[7] : v[2], b4 ? v[2] : v[7], b4 ? v[8] : v[3], b4 ? v[3] : v[8], 16), a[2], a[3]);
+    a[4] = xchg_add(b4 ? v[9] : v[4], b4 ? v[4] : v[9], 16);
     // 5 -> (3 | 2)
     float b[3];
-    b[0] = xchg_add(b3 ? a[3] : a[0], b3 ? a[0] : a[3], 8);
-    b[1] = xchg_add(b3 ? a[4] : a[1], b3 ? a[1] : a[4], 8);
+    upk(xchg_add2(b3 ? a[3] : a[0], b3 ? a[0] : a[3], b3 ? a[4] : a[1], b3 ? a[1] : a[4], 8), b[0], b[1]);
     b[2] = xchg_add(b3 ? 0.f : a[2], b3 ? a[2] : 0.f, 8);
     // 3 -> (2 | 1)
     float c[2];
-    c[0] = xchg_add(b2 ? b[2] : b[0], b2 ? b[0] : b[2], 4);
-    c[1] = xchg_add(b2 ? 0.f : b[1], b2 ? b[1] : 0.f, 4);
+    upk(xchg_add2(b2 ? b[2] : b[0], b2 ? b[0] : b[2], b2 ? 0.f : b[1], b2 ? b[1] : 0.f, 4), c[0], c[1]);
     // 2 -> (1 | 1)
     float d = xchg_add(b1 ? c[1] : c[0], b1 ? c[0] : c[1], 2);
     d += __shfl_xor_sync(0xffffffffu, d, 1);
@@ -140,18 +143,26 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
                 const int e = b * kBwdBatch + j;              // 0-based list position; contributor number e+1
                 const float4 a = rec[j].a;
                 const float4 bb = rec[j].b;
+                const uint32_t gid = s_id[st][j];             // loaded with the record: same uniform address arithmetic
                 const uint32_t kb = __float_as_uint(bb.w);
                 const float dx = a.x - fpx;
                 // alpha of the two pixels with exactly the forward's arithmetic and decisions
-                f2 d, G, al, dadb;
+                f2 d, G, al, dadb = 0;                        // dadb is only read with HIER
                 const f2 pw = pair_power(a, bb, dx, nfpy, d);
                 pair_gauss(pw, bb.y, G, al);
-                pair_hier_alpha<HIER, true>(al, bb.z, kb, al, dadb);
                 float pw0, pw1, al0, al1;
                 upk(pw, pw0, pw1); upk(al, al0, al1);
-                const bool v0 = e < last0 && pw0 <= 0.0f && al0 >= kAlphaSkip;
-                const bool v1 = e < last1 && pw1 <= 0.0f && al1 >= kAlphaSkip;
+                // the hierarchy weight only lowers alpha (1 - (1-a)^(1/k) <= a), so an entry that no pixel of
+                // the warp takes at its base alpha is skipped before that arithmetic
+                bool v0 = e < last0 && pw0 <= 0.0f && al0 >= kAlphaSkip;
+                bool v1 = e < last1 && pw1 <= 0.0f && al1 >= kAlphaSkip;
                 if (!__any_sync(0xffffffffu, v0 || v1)) continue;            // warp-uniform
+                if (HIER) {
+                    pair_hier_alpha<HIER, true>(al, bb.z, kb, al, dadb);
+                    upk(al, al0, al1);
+                    v0 = v0 && al0 >= kAlphaSkip;
+                    v1 = v1 && al1 >= kAlphaSkip;
+                }
                 G = sel2(v0, v1, G, bc(0.f));
                 al = sel2(v0, v1, al, bc(0.f));
                 const float4 c = rec[j].c;
@@ -161,7 +172,7 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
                 pair_grad<HIER, DEPTH>(a, bb, dx, d, G, al, dadb, cg, Tf, neg_bgd, g0, g1, g2, gd, ps, v);
                 const float total = transpose_reduce10(v, lane);
                 if (slot >= 0 && (DEPTH || slot < 9))
-                    atomicAdd(accum + (size_t)s_id[st][j] * kAccum + slot, total);
+                    atomicAdd(accum + (size_t)gid * kAccum + slot, total);
             }
         }
         __syncthreads();                      // every thread is done with stage st (records and ids)
