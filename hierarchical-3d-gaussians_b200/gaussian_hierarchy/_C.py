@@ -1,9 +1,11 @@
 """`gaussian_hierarchy._C`: LOD-cut ops on libh3dgs.so (sm_100a), same signatures
 as the reference's call sites (train_post.py:91-113, render_hierarchy.py:58-80).
-No CPU fallback; raises if the library is missing or a call fails."""
+No CPU fallback; raises if the library is missing or a call fails.
+`load_hierarchy` / `write_hierarchy` (scene/gaussian_model.py:24) are host-side disk IO: hier_io.py."""
 import torch
 
 from h3dgs import _lib
+from .hier_io import load_hierarchy, write_hierarchy  # noqa: F401
 
 _scratch = {}
 
