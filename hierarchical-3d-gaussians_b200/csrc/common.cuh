@@ -125,30 +125,7 @@ int launch_preprocess_backward(const h3dgs_raster_args& a, const int32_t* radii,
                                float* dL_dcolors, float* dL_dopacities, float* dL_dscales, float* dL_drots,
                                float* dL_dcov3D, cudaStream_t s);
 
-// Hierarchy transition weight on the per-pixel blending weight (UNPINNED semantics,
-// DESIGN.md "hierarchy alpha"): a' = t a + (1-t)(1 - (1-a)^(1/k)); identity for k<=1 or t>=1.
-// One definition for forward and backward so both take identical skip decisions.
 #ifdef __CUDACC__
-// exp(x) for x <= 0 as one FMUL + MUFU.EX2 (ftz: results below 2^-126 flush to 0, far
-// below the 1/255 alpha cut).  Shared by forward and backward so both see the same alpha.
-__device__ __forceinline__ float fast_exp(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
-    return y;
-}
-
-// 1/x for x in [0.01, 2^20]: MUFU.RCP + one Newton step (no range/denormal handling needed
-// here; ~1 ulp), 3 instructions instead of the ~10 of the IEEE-rounded __frcp_rn
-__device__ __forceinline__ float fast_rcp(float x) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r * (2.0f - x * r);
-}
-__device__ __forceinline__ float fast_exp2(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 // Pixel layout of the blend kernels: CTA = 128 threads = 4 warps; warp q owns the 8x8 quadrant
 // (q & 1, q >> 1) of the 16x16 tile; lane l owns column (l & 7) and the two rows 2*(l >> 3), +1.
 __device__ __forceinline__ void quad_pixel(int tile_x, int tile_y, int warp, int lane, int& px, int& py0) {
@@ -156,34 +133,13 @@ __device__ __forceinline__ void quad_pixel(int tile_x, int tile_y, int warp, int
     py0 = tile_y * kTile + 8 * (warp >> 1) + 2 * (lane >> 3);
 }
 
-template <bool HIER>
-__device__ __forceinline__ void hier_alpha_grad(float a, float t, uint32_t kbits, float& alpha, float& dadb) {
-    alpha = a; dadb = 1.0f;
-    if (!HIER) return;
-    const uint32_t k = kbits & kKidsMask;
-    if (k <= 1u || t >= 1.0f) return;
-    // 1 - (1-a)^(1/k) = -expm1(log1p(-a)/k).  Near the 1/255 skip threshold a is small and the
-    // direct form cancels catastrophically (abs error ~2e-7 on a value ~4e-3 moves the skip
-    // decision for 100x more pixels than in flat mode), so small a uses the two series
-    // (relative error < 1e-7); larger a goes through MUFU.LG2 / MUFU.EX2.
-    const float ik = fast_rcp((float)k);
-    const float l2 = __log2f(1.0f - a);
-    const float L = -a * (1.0f + a * (0.5f + a * (0.33333334f + a * (0.25f + a * 0.2f))));
-    const float y = L * ik;
-    const float omr_series = -y * (1.0f + y * (0.5f + y * (0.16666667f + y * 0.041666668f)));
-    const float omr = a < 0.0625f ? omr_series : 1.0f - fast_exp2(l2 * ik);
-    alpha = t * a + (1.0f - t) * omr;
-    dadb = t + (1.0f - t) * ik * fast_exp2(l2 * (ik - 1.0f));
-}
-template <bool HIER>
-__device__ __forceinline__ float hier_alpha(float a, float t, uint32_t kbits) {
-    float alpha, dadb;
-    hier_alpha_grad<HIER>(a, t, kbits, alpha, dadb);
-    return alpha;
-}
 #endif
 
 // accum row layout (floats): 0,1 dmean2D.xy | 2,3,4 dconic | 5 dopacity | 6,7,8 dcolor | 9 dinvdepth
 constexpr int kAccum = 10;
 
 }  // namespace h3dgs
+
+#ifdef __CUDACC__
+#include "pair_math.cuh"      // packed FP32x2 arithmetic of the blend kernels
+#endif

@@ -19,7 +19,8 @@ constexpr int kFwdStages = 2;
 // Two vertically adjacent pixels per thread: CTA = 128 threads = 4 warps, warp q owns one 8x8-pixel
 // quadrant of the tile (common.cuh::quad_pixel).
 // The entry's record, its dx terms, the survivor loop and (in backward) the warp reduction are
-// shared by the two pixels.
+// shared by the two pixels, and the per-pixel arithmetic of the pair runs on packed FP32x2
+// instructions (FFMA2 / FMUL2 / FADD2): the kernel is issue-bound, one instruction serves both pixels.
 constexpr int kFwdThreads = 128;
 
 template <bool HIER, bool DEPTH>
@@ -62,9 +63,11 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
     quad_pixel(tile_x, tile_y, warp, lane, px, py0);
     const int py1 = py0 + 1;
     const bool in0 = px < W && py0 < H, in1 = px < W && py1 < H;
-    const float fpx = (float)px, fpy0 = (float)py0, fpy1 = (float)py1;
+    const float fpx = (float)px;
+    const f2 nfpy = pk(-(float)py0, -(float)py1);
     bool done0 = !in0, done1 = !in1;
-    float T0 = 1.0f, T1 = 1.0f;
+    // packed per-pixel state {pixel 0, pixel 1} (common.cuh "packed FP32 pairs")
+    f2 T = bc(1.0f);
     float Ca0 = 0.f, Ca1 = 0.f, Ca2 = 0.f, Cb0 = 0.f, Cb1 = 0.f, Cb2 = 0.f, inv0 = 0.f, inv1 = 0.f;
     uint32_t last0 = 0, last1 = 0;
     const uint32_t qbit = 1u << (kQuadShift + warp);        // this warp's quadrant in the entries' reach mask
@@ -77,10 +80,10 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
         const int cnt = min(kFwdBatch, n - b * kFwdBatch);
         // Per group of 32 entries each lane tests ONE entry against this warp's quadrant and a ballot
         // compacts the survivors, so culled entries cost nothing per pixel.  The survivor loop is
-        // warp-uniform (same mask in every lane) and its body is straight-line + short reconvergent
-        // `if`s: a per-thread `continue`/`break` here leaves the warp split into fragments that each
-        // re-walk the list (measured: 18x the instructions).  A warp leaves the batch only when all of
-        // its 64 pixels are done.
+        // warp-uniform (same mask in every lane) and its body is straight-line: a per-thread
+        // `continue`/`break` here leaves the warp split into fragments that each re-walk the list
+        // (measured: 18x the instructions).  A pixel that does not take an entry adds w = 0.
+        // A warp leaves the batch only when all of its 64 pixels are done.
         {
             const Record* rec = &s_rec[st][0];
             const uint32_t base = (uint32_t)(b * kFwdBatch);
@@ -94,36 +97,20 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
                     m &= m - 1;
                     const float4 a = rec[j].a;
                     const float4 bb = rec[j].b;
+                    const float4 c = rec[j].c;
                     const uint32_t kb = __float_as_uint(bb.w);
-                    const float dx = a.x - fpx, dy0 = a.y - fpy0, dy1 = a.y - fpy1;
-                    const float qx = a.z * dx * dx, qxy = a.w * dx;
-                    const float pw0 = -0.5f * (qx + bb.x * dy0 * dy0) - qxy * dy0;
-                    const float pw1 = -0.5f * (qx + bb.x * dy1 * dy1) - qxy * dy1;
-                    float al0 = fminf(kAlphaCap, bb.y * fast_exp(pw0));
-                    float al1 = fminf(kAlphaCap, bb.y * fast_exp(pw1));
-                    al0 = hier_alpha<HIER>(al0, bb.z, kb);
-                    al1 = hier_alpha<HIER>(al1, bb.z, kb);
-                    const float tT0 = T0 * (1.0f - al0), tT1 = T1 * (1.0f - al1);
-                    bool v0 = !done0 && pw0 <= 0.0f && al0 >= kAlphaSkip;
-                    bool v1 = !done1 && pw1 <= 0.0f && al1 >= kAlphaSkip;
-                    if (v0 && tT0 < kTStop) { done0 = true; v0 = false; }
-                    if (v1 && tT1 < kTStop) { done1 = true; v1 = false; }
-                    if (v0 || v1) {
-                        const float4 c = rec[j].c;
-                        const uint32_t idx = base + (uint32_t)j + 1u;
-                        if (v0) {
-                            const float w = al0 * T0;
-                            Ca0 += c.x * w; Ca1 += c.y * w; Ca2 += c.z * w;
-                            if (DEPTH) inv0 += c.w * w;
-                            T0 = tT0; last0 = idx;
-                        }
-                        if (v1) {
-                            const float w = al1 * T1;
-                            Cb0 += c.x * w; Cb1 += c.y * w; Cb2 += c.z * w;
-                            if (DEPTH) inv1 += c.w * w;
-                            T1 = tT1; last1 = idx;
-                        }
-                    }
+                    f2 d, G, al, unused;
+                    const f2 pw = pair_power(a, bb, a.x - fpx, nfpy, d);
+                    pair_gauss(pw, bb.y, G, al);
+                    pair_hier_alpha<HIER, false>(al, bb.z, kb, al, unused);
+                    bool v0, v1;
+                    const f2 w = pair_blend(pw, al, T, done0, done1, v0, v1);
+                    upk(fma2(bc(c.x), w, pk(Ca0, Cb0)), Ca0, Cb0);
+                    upk(fma2(bc(c.y), w, pk(Ca1, Cb1)), Ca1, Cb1);
+                    upk(fma2(bc(c.z), w, pk(Ca2, Cb2)), Ca2, Cb2);
+                    if (DEPTH) upk(fma2(bc(c.w), w, pk(inv0, inv1)), inv0, inv1);
+                    const uint32_t idx = base + (uint32_t)j + 1u;
+                    last0 = v0 ? idx : last0; last1 = v1 ? idx : last1;
                 }
             }
         }
@@ -163,8 +150,8 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
             if (DEPTH) out_invdepth[pix] = invd;
         }
     };
-    store(in0, py0, T0, Ca0, Ca1, Ca2, inv0, last0);
-    store(in1, py1, T1, Cb0, Cb1, Cb2, inv1, last1);
+    store(in0, py0, lo(T), Ca0, Ca1, Ca2, inv0, last0);
+    store(in1, py1, hi(T), Cb0, Cb1, Cb2, inv1, last1);
     const uint32_t wmax = __reduce_max_sync(0xffffffffu, max(last0, last1));
     if (lane == 0) atomicMax(&s_max, wmax);
     __syncthreads();
