@@ -6,7 +6,8 @@
 // i.e. the 2x2 screen covariance and the gradient of its inverse -- sums of terms several orders of
 // magnitude larger than the result (~50 fp64 operations).  Measured with the host build of this header on
 // the test scenes against the double-precision oracle (norm-wise, tests/test_cov_grad_cpu.py): all-fp32
-// is off by up to 7e-6 (covariance) / 5e-6 (rotation) with the parity bar at 1e-5; with the block in fp64
+// misses the 1e-5 parity bar on the rotation gradient (1.5e-5); with only denom .. dL/dc in fp64 the
+// outputs are still off by up to 7e-6 (covariance) / 5e-6 (rotation); with the whole block in fp64
 // every output is within 2e-6, as good as the whole chain in fp64 -- which is what the kernel did before,
 // at 156 registers and ~400 DFMA per Gaussian.
 //
