@@ -8,7 +8,6 @@ size_average=True) combined as in train_post.py:134-140:
 but one CUDA kernel forward and one backward instead of 5 grouped conv2d + ~20 elementwise kernels and
 their autograd.  Gradients flow to `image` only (the ground truth is data).  No CPU fallback.
 """
-import ctypes as C
 
 import torch
 

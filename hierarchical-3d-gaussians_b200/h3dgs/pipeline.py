@@ -9,7 +9,6 @@ API the reference's scripts use:
 
 Used by bench.py and the GPU tests; nothing here touches oracle/.
 """
-import math
 
 import torch
 

@@ -10,8 +10,6 @@ utils/general_utils.py:68-114 (cov3D), gaussian_renderer/__init__.py:85-89.
 
 Only practical for small scenes (memory ~ 8 * Npix * P * ~12 bytes).
 """
-import math
-
 import torch
 
 C0 = 0.28209479177387814

@@ -50,7 +50,6 @@ def test_camera_construction_matches_reference(golden_dir):
     z = np.load(os.path.join(golden_dir, "camera.npz"))
     for i in range(6):
         W, H = 640, 480
-        import math
         fovx, fovy = float(z[f"fovx_{i}"]), float(z[f"fovy_{i}"])
         wv = synth.world2view(z[f"R_{i}"], z[f"T_{i}"]).transpose()
         pr = synth.projection(0.01, 100.0, fovx, fovy, float(z[f"primx_{i}"]), float(z[f"primy_{i}"])).transpose()
