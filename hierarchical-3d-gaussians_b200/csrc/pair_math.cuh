@@ -17,11 +17,13 @@
 #include <stdint.h>
 #define H3_PM_FN static inline
 namespace h3dgs {
+#ifndef H3_SIMT_EMU               /* stand-alone host build (tests/emul/pair_math_test.cpp); the SIMT emulator has common.cuh */
 struct float4 { float x, y, z, w; };
 constexpr float kAlphaCap = 0.99f;
 constexpr float kAlphaSkip = 1.0f / 255.0f;
 constexpr float kTStop = 0.0001f;
 constexpr uint32_t kKidsMask = 0xFFFFFu;
+#endif
 struct f2 { float lo, hi; };
 H3_PM_FN f2 pk(float lo, float hi) { return f2{lo, hi}; }
 H3_PM_FN void upk(f2 v, float& lo, float& hi) { lo = v.lo; hi = v.hi; }

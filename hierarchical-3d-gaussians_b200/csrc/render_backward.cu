@@ -147,7 +147,7 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
                 const uint32_t kb = __float_as_uint(bb.w);
                 const float dx = a.x - fpx;
                 // alpha of the two pixels with exactly the forward's arithmetic and decisions
-                f2 d, G, al, dadb = 0;                        // dadb is only read with HIER
+                f2 d, G, al, dadb = bc(1.0f);                // dadb is only read with HIER
                 const f2 pw = pair_power(a, bb, dx, nfpy, d);
                 pair_gauss(pw, bb.y, G, al);
                 float pw0, pw1, al0, al1;

@@ -1,0 +1,217 @@
+"""CPU: the library's own kernels -- the .cu sources compiled with g++ against a small SIMT emulator
+(tests/emul/: fibers for the threads of a block, rendezvous for barriers and warp collectives, memcpy for
+the TMA staging) -- driven through the same C-ABI calls as on the GPU and compared with the oracle on
+small scenes.  This is how kernel changes are checked before any GPU time is spent; it is test
+infrastructure: the product library is built by nvcc only and has no CPU path."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from h3dgs import synth
+from util import make_scene, oracle_run, rel_err
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "emul"))
+
+
+def image_close(a, b, what="color", max_flips=6):
+    """assert_image_close for the small emulated frames: an alpha within fp32 rounding of the 1/255 skip
+    threshold may flip a contribution in or out (the emulator rounds like neither the GPU's contracted
+    FMAs nor the oracle); a handful of such pixels, each bounded by one contribution, is not a defect."""
+    d = np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64))
+    scale = max(np.abs(b).max(), 1e-30)
+    bad = d > 1e-5 * scale
+    assert bad.sum() <= max_flips, (what, int(bad.sum()), float(d.max()))
+    assert d.max() < 1.5 / 255 * max(scale, 1.0), (what, float(d.max()))
+
+
+def grad_close(a, b, name, tol=1e-5, max_rows=12):
+    """assert_grad_close with the same allowance: the few rows a flipped pixel feeds (a cut row and its
+    parent in scatter mode) may move by one pixel's worth of a 1/255 contribution."""
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    scale = max(np.abs(b).max(), 1e-30)
+    d = np.abs(a - b).reshape(a.shape[0], -1).max(1)
+    bad = d > tol * scale
+    assert bad.sum() <= max_rows, (name, int(bad.sum()), float(d.max() / scale))
+    assert d.max() < 5e-3 * scale, (name, float(d.max() / scale))
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    from build_emu import build
+    from emu_api import Emu
+    return Emu(build(str(tmp_path_factory.mktemp("h3dgs_emu"))))
+
+
+def _check(emu, cam, sc, bg, ts=None, kids=None, do_depth=False, sh_degree=3, colors=None, cov=None, tol=1e-5):
+    f, b, gcol, gdep = oracle_run(cam, sc, bg, ts, kids, do_depth=do_depth, sh_degree=sh_degree, colors=colors, cov=cov)
+    a, keep = emu.args(cam, bg, sc, sh_degree=sh_degree, ts=ts, kids=kids, do_depth=do_depth, colors=colors, cov=cov)
+    fw = emu.forward(a, keep)
+    st = emu.state(a, fw)
+    assert fw["D"] == f["num_rendered"]
+    assert np.array_equal(fw["radii"], f["radii"])
+    if fw["D"]:
+        assert np.array_equal(st["point_list"], f["point_list"])
+        assert np.array_equal(st["keys_sorted"], f["keys"])
+    assert np.array_equal(st["ranges"], f["ranges"].reshape(-1, 2))
+    image_close(fw["color"], f["color"])
+    image_close(st["final_T"], f["final_T"].reshape(-1), "final_T")
+    assert (st["n_contrib"] != f["n_contrib"].reshape(-1)).mean() < 2e-3
+    if do_depth:
+        image_close(fw["invdepth"], f["invdepth"], "invdepth")
+    g = emu.backward(a, fw, gcol, gdep if do_depth else None)
+    for k in ("means3D", "means2D", "sh", "colors_precomp", "opacities", "scales", "rotations", "cov3Ds_precomp"):
+        if g.get(k) is not None and b.get(k) is not None:
+            grad_close(g[k], b[k], k, tol=tol)
+    return f, fw, st, g
+
+
+@pytest.mark.parametrize("mode,do_depth", [("flat", False), ("flat", True), ("hier", False), ("hier", True)])
+def test_forward_backward_parity(emu, mode, do_depth):
+    cam, sc, ts, kids, bg = make_scene(3000, 256, 192, mode=mode, seed=42)
+    _check(emu, cam, sc, bg, ts, kids, do_depth=do_depth)
+
+
+@pytest.mark.parametrize("deg,K", [(0, 1), (1, 4), (2, 9), (1, 16)])
+def test_sh_degrees_and_layouts(emu, deg, K):
+    cam, sc, ts, kids, bg = make_scene(1500, 160, 96, sh_degree=int(np.sqrt(K)) - 1, seed=7)
+    _check(emu, cam, sc, bg, sh_degree=deg)
+
+
+def test_precomputed_colour_and_covariance(emu):
+    from oracle import oracle
+    cam, sc, ts, kids, bg = make_scene(1500, 160, 96, seed=9)
+    colors = np.random.default_rng(1).uniform(0, 1, (1500, 3)).astype(np.float32)
+    f0 = oracle_run(cam, sc, bg, backward=False)[0]
+    _check(emu, cam, sc, bg, colors=colors, cov=f0["cov3Ds"])
+
+
+@pytest.mark.parametrize("W,H", [(8, 8), (15, 33), (100, 50)])
+def test_odd_image_sizes(emu, W, H):
+    cam, sc, ts, kids, bg = make_scene(300, W, H, seed=3, scale_k=2e-2)
+    _check(emu, cam, sc, bg)
+
+
+def test_deep_tiles_and_early_termination(emu):
+    cam, sc, ts, kids, bg = make_scene(6000, 96, 64, seed=11, scale_k=3e-2, zmax=6.0)
+    sc["opacities"] = np.clip(sc["opacities"] * 1.5, 0, 0.99).astype(np.float32)
+    f, fw, st, g = _check(emu, cam, sc, bg)
+    lens = st["ranges"][:, 1] - st["ranges"][:, 0]
+    assert lens.max() > 600                                   # several TMA batches per tile
+    assert (f["final_T"] < 1e-3).mean() > 0.2                 # early termination is exercised
+
+
+def test_tile_shards_equal_the_whole_frame(emu):
+    cam, sc, ts, kids, bg = make_scene(2500, 160, 112, mode="hier", seed=5)
+    f, b, gcol, gdep = oracle_run(cam, sc, bg, ts, kids)
+    a, keep = emu.args(cam, bg, sc, ts=ts, kids=kids)
+    full = emu.forward(a, keep)
+    gy = (cam.H + 15) // 16
+    img = np.zeros_like(full["color"])
+    acc = None
+    for r in range(3):
+        a_s, keep_s = emu.args(cam, bg, sc, ts=ts, kids=kids, shard=(3, r))
+        fw = emu.forward(a_s, keep_s)
+        rows = (gy + 3 - 1 - r) // 3
+        packed = fw["color"].reshape(-1)[: rows * 3 * 16 * cam.W].reshape(rows, 3, 16, cam.W)
+        for k in range(rows):
+            y0 = (k * 3 + r) * 16
+            h = min(16, cam.H - y0)
+            img[:, y0:y0 + h] = packed[k, :, :h]
+        g = emu.backward(a_s, fw, gcol)
+        acc = {k: v.copy() for k, v in g.items() if v is not None} if acc is None else \
+            {k: acc[k] + g[k] for k in acc}
+    assert np.array_equal(img, full["color"])                  # same per-tile arithmetic
+    for k in ("means3D", "sh", "opacities", "scales", "rotations"):
+        grad_close(acc[k], b[k], k)
+
+
+def test_fused_cut_gather_and_scatter(emu):
+    from oracle import oracle
+    cam = synth.make_camera(160, 112)
+    leaves = synth.cloud_v1(1500, cam, zmin=2.0, zmax=30.0, seed=2, scale_k=1.0)
+    z = leaves["means3D"][:, 2:3]
+    leaves["scales"] = (8e-3 * np.sqrt(2 * z) * np.ones((1, 3))).astype(np.float32)
+    h = synth.build_hierarchy(leaves)
+    thr = synth.tau_threshold(6.0, cam)
+    n, ri, pi, ni = oracle.expand_to_size(h["nodes"], h["boxes"], thr, cam.camera_center)
+    ts, kids = oracle.get_interpolation_weights(ni, thr, h["nodes"], h["boxes"], cam.camera_center)
+    assert (ts < 1).mean() > 0.05
+    bg = np.array([0.3, 0.2, 0.1], np.float32)
+    f = oracle.rasterize_forward(h["means3D"], h["shs"], None, h["opacities"], h["scales"], h["rotations"], None,
+                                 cam.world_view_transform, cam.full_proj_transform, cam.camera_center, bg, cam.W, cam.H,
+                                 cam.tanfovx, cam.tanfovy, ts=ts, kids=kids, render_indices=ri, parent_indices=pi)
+    gcol = synth.l1_grad(f["color"])
+    b = oracle.rasterize_backward(f, gcol)
+    a, keep = emu.args(cam, bg, h, ts=ts, kids=kids, ridx=ri, pidx=pi)
+    fw = emu.forward(a, keep)
+    assert np.array_equal(fw["radii"], f["radii"])
+    image_close(fw["color"], f["color"])
+    g = emu.backward(a, fw, gcol)
+    for k in ("means3D", "sh", "opacities", "scales", "rotations", "means2D"):
+        grad_close(g[k], b[k], k)
+
+
+def test_device_lod_cut_and_skipped_rows(emu):
+    """h3dgs_lod_cut = expand_to_size + get_interpolation_weights; rows after the cut are marked -1 and
+    the rasterizer handed P = capacity skips them (the sync-free step)."""
+    import ctypes as C
+    from emu_api import aligned, f32, i32, ptr
+    from oracle import oracle
+    cam = synth.make_camera(160, 112)
+    leaves = synth.cloud_v1(1200, cam, zmin=2.0, zmax=30.0, seed=4, scale_k=1.0)
+    z = leaves["means3D"][:, 2:3]
+    leaves["scales"] = (8e-3 * np.sqrt(2 * z) * np.ones((1, 3))).astype(np.float32)
+    h = synth.build_hierarchy(leaves)
+    N = h["nodes"].shape[0]
+    thr = synth.tau_threshold(6.0, cam)
+    n, ri, pi, ni = oracle.expand_to_size(h["nodes"], h["boxes"], thr, cam.camera_center)
+    ts, kids = oracle.get_interpolation_weights(ni, thr, h["nodes"], h["boxes"], cam.camera_center)
+    L = emu.L
+    nodes, boxes, vp, thr_dev = i32(h["nodes"]), f32(h["boxes"]), f32(cam.camera_center), f32([thr])
+    r2, p2, n2, k2 = (aligned(N * 4, np.int32, (N,)) for _ in range(4))
+    t2 = aligned(N * 4, np.float32, (N,))
+    count = aligned(4, np.int32, (1,))
+    scratch = aligned(L.h3dgs_expand_scratch_bytes(N))
+    emu.check(L.h3dgs_lod_cut(N, ptr(nodes), ptr(boxes), -1.0, ptr(thr_dev), ptr(vp), ptr(r2), ptr(p2), ptr(n2), ptr(t2),
+                              ptr(k2), ptr(count), ptr(scratch), None))
+    assert int(count[0]) == n
+    assert np.array_equal(r2[:n], ri) and np.array_equal(p2[:n], pi) and np.array_equal(n2[:n], ni)
+    assert np.array_equal(t2[:n].view(np.uint32), ts.view(np.uint32)) and np.array_equal(k2[:n], kids)
+    assert (r2[n:] == -1).all()
+    # the two-call API on the same library gives the same
+    r3, p3, n3 = (aligned(N * 4, np.int32, (N,)) for _ in range(3))
+    got = L.h3dgs_expand_to_size(N, ptr(nodes), ptr(boxes), thr, ptr(vp), 0.0, 0.0, 0.0, ptr(r3), ptr(p3), ptr(n3), ptr(scratch), None)
+    assert got == n and np.array_equal(r3[:n], ri)
+    # capacity-sized rasterization over the marked index array == exact rasterization of the cut
+    bg = np.array([0.1, 0.2, 0.3], np.float32)
+    a0, keep0 = emu.args(cam, bg, h, ts=ts, kids=kids, ridx=ri, pidx=pi)
+    exact = emu.forward(a0, keep0)
+    a1, keep1 = emu.args(cam, bg, h, ts=t2, kids=k2, ridx=r2, pidx=p2, P=N, bin_capacity=exact["D"] + 10, sort_capacity=4096)
+    cap = emu.forward(a1, keep1)
+    st = emu.state(a1, cap)
+    assert list(st["scan_info"]) == [exact["D"], st["scan_info"][1], 0]
+    assert np.array_equal(cap["color"], exact["color"])
+    assert np.array_equal(cap["radii"][:n], exact["radii"]) and (cap["radii"][n:] == 0).all()
+    gcol = synth.l1_grad(exact["color"])
+    g0, g1 = emu.backward(a0, exact, gcol), emu.backward(a1, cap, gcol)
+    for k in ("means3D", "sh", "opacities", "scales", "rotations"):
+        assert rel_err(g1[k], g0[k]) < 1e-6, k
+    # a frame that does not fit: flagged, background only, zero gradients
+    for kw in (dict(bin_capacity=exact["D"] // 2, sort_capacity=4096), dict(bin_capacity=exact["D"] + 10, sort_capacity=32)):
+        a2, keep2 = emu.args(cam, bg, h, ts=t2, kids=k2, ridx=r2, pidx=p2, P=N, **kw)
+        ov = emu.forward(a2, keep2)
+        s2 = emu.state(a2, ov)
+        assert s2["scan_info"][2] == 1 and s2["scan_info"][0] == exact["D"]
+        assert np.array_equal(ov["color"], np.broadcast_to(bg.reshape(3, 1, 1), ov["color"].shape))
+        g2 = emu.backward(a2, ov, gcol)
+        assert all(float(np.abs(v).sum()) == 0.0 for k, v in g2.items() if v is not None and k != "means2D")
+
+
+def test_equal_depths_and_long_lists_fall_back_to_the_global_sort(emu):
+    cam, sc, ts, kids, bg = make_scene(16000, 48, 48, seed=13, scale_k=6e-2, zmax=4.0)
+    sc["means3D"][:, 2] = np.round(sc["means3D"][:, 2] * 4) / 4       # many equal depths: order must follow the index
+    f, fw, st, g = _check(emu, cam, sc, bg, tol=5e-5)
+    assert (st["ranges"][:, 1] - st["ranges"][:, 0]).max() > 8192    # longer than the shared-memory sort handles
