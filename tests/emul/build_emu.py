@@ -22,6 +22,10 @@ def rewrite(text):
     text = re.sub(r"extern\s+__shared__\s+(\w+)\s+(\w+)\[\];", r"\1* \2 = (\1*)simt::g_dyn_smem;", text)
     text = re.sub(r"__device__\s+__constant__", "static const", text)
     text = _LAUNCH.sub(lambda m: f"SIMT_LAUNCH(({m.group(1)}), {m.group(2)})(", text)
+    # the three MUFU wrappers written in inline PTX
+    text = re.sub(r'asm\("ex2\.approx\.ftz\.f32 %0, %1;" : "=f"\((\w+)\) : "f"\((.*?)\)\);', r"\1 = exp2f(\2);", text)
+    text = re.sub(r'asm\("lg2\.approx\.ftz\.f32 %0, %1;" : "=f"\((\w+)\) : "f"\((.*?)\)\);', r"\1 = log2f(\2);", text)
+    text = re.sub(r'asm\("rcp\.approx\.ftz\.f32 %0, %1;" : "=f"\((\w+)\) : "f"\((.*?)\)\);', r"\1 = 1.0f / (\2);", text)
     return text
 
 
