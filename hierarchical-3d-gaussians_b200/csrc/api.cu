@@ -195,11 +195,11 @@ extern "C" int h3dgs_rasterize_forward(const h3dgs_raster_args* a, h3dgs_alloc_f
         if (rc) return rc;
         H3_CUDA(cudaEventRecord(ss->fork, s));
         H3_CUDA(cudaStreamWaitEvent(ss->s, ss->fork, 0));
-        rc = launch_preprocess_color(*a, out_radii, records, ss->s);
+        rc = launch_preprocess_color(*a, out_radii, tiles, records, ss->s);
         if (rc) return rc;
         H3_CUDA(cudaEventRecord(ss->join, ss->s));
     } else {
-        rc = launch_preprocess_color(*a, out_radii, records, s);
+        rc = launch_preprocess_color(*a, out_radii, tiles, records, s);
         if (rc) return rc;
     }
     const bool capacity_mode = a->bin_capacity > 0;

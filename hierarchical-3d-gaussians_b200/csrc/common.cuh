@@ -104,7 +104,8 @@ int launch_tile_scan(const h3dgs_raster_args& a, const uint32_t* tile_count, uin
 int launch_tile_binning(const h3dgs_raster_args& a, const int32_t* radii, const float* depths, const Record* records,
                         int64_t D, uint32_t max_count, uint8_t* bin, const BinLayout& bl, const uint32_t* ranges,
                         const ScanInfo* info, uint32_t* tile_count, cudaStream_t s);
-int launch_preprocess_color(const h3dgs_raster_args& a, const int32_t* radii, Record* records, cudaStream_t s);
+int launch_preprocess_color(const h3dgs_raster_args& a, const int32_t* radii, const uint32_t* tiles_touched,
+                            Record* records, cudaStream_t s);
 int launch_sh_backward(const h3dgs_raster_args& a, const int32_t* radii, const Record* records, const float* accum,
                        float* dL_dmeans3D, float* dL_dsh, cudaStream_t s);
 int launch_scan(const uint32_t* in, uint32_t* out, int n, void* temp, size_t temp_bytes, cudaStream_t s, bool debug);

@@ -94,7 +94,9 @@ typedef struct h3dgs_raster_args {
     int32_t shard_count, shard_index;
     /* Backward phase 2 (per-Gaussian chain rule) only for rendered rows [grad_row_begin, grad_row_end);
      * (0, 0) = all rows.  The multi-GPU mode reduce-scatters the [P][10] sums and lets every rank finish
-     * only its own row block, so the final gradients come out sharded by rendered row. */
+     * only its own row block, so the final gradients come out sharded by rendered row.  When the row block
+     * is also given to the FORWARD of a sharded frame, the SH colour is evaluated only for the Gaussians this
+     * rank needs: those touching its tile rows and those in its row block. */
     int32_t grad_row_begin, grad_row_end;
     /* Capacity mode -- no host synchronisation, so the call can be captured in a CUDA graph.  With
      * bin_capacity > 0 the binning state is sized for bin_capacity (tile, Gaussian) entries instead of

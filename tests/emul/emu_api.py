@@ -43,7 +43,7 @@ class Emu:
         return rc
 
     def args(self, cam, bg, sc, sh_degree=3, ts=None, kids=None, do_depth=False, ridx=None, pidx=None, shard=(1, 0),
-             colors=None, cov=None, bin_capacity=0, sort_capacity=0, P=None):
+             colors=None, cov=None, bin_capacity=0, sort_capacity=0, P=None, grad_rows=(0, 0)):
         a = _lib.RasterArgs()
         keep = dict(bg=f32(bg), view=f32(cam.world_view_transform), proj=f32(cam.full_proj_transform), campos=f32(cam.camera_center),
                     means=f32(sc["means3D"]), opac=f32(sc["opacities"]),
@@ -64,7 +64,7 @@ class Emu:
         a.interpolation_weights, a.num_node_kids = ptr(keep["ts"]), ptr(keep["kids"])
         a.render_indices, a.parent_indices, a.num_source = ptr(keep["ridx"]), ptr(keep["pidx"]), (n_src if ridx is not None else 0)
         a.shard_count, a.shard_index = shard
-        a.grad_row_begin = a.grad_row_end = 0
+        a.grad_row_begin, a.grad_row_end = int(grad_rows[0]), int(grad_rows[1])
         a.bin_capacity, a.sort_capacity = int(bin_capacity), int(sort_capacity)
         return a, keep
 
@@ -102,7 +102,9 @@ class Emu:
             out["keys_sorted"] = view(b[1], v.keys_sorted, np.uint64, D)
         return out
 
-    def backward(self, a, fwd, dL_dcolor, dL_dinvdepth=None, phases=3):
+    def backward(self, a, fwd, dL_dcolor, dL_dinvdepth=None, phases=3, scratch=None):
+        """phases / scratch as in h3dgs_rasterize_backward: 1 fills `scratch` with the [P][10] sums (returned as
+        g["scratch"]), 2 consumes it"""
         P = a.P
         N = a.num_source if a.render_indices else P
         M = a.sh_coeffs
@@ -113,7 +115,8 @@ class Emu:
                  scales=aligned(N * 12, np.float32, (N, 3)) if a.scales else None,
                  rotations=aligned(N * 16, np.float32, (N, 4)) if a.rotations else None,
                  cov3Ds_precomp=aligned(N * 24, np.float32, (N, 6)) if a.cov3D_precomp else None)
-        scratch = aligned(self.L.h3dgs_backward_scratch_bytes(P))
+        if scratch is None:
+            scratch = aligned(self.L.h3dgs_backward_scratch_bytes(P))
         gcol = f32(dL_dcolor)
         gdep = f32(dL_dinvdepth) if (a.do_depth and dL_dinvdepth is not None) else None
         b = fwd["bufs"]
@@ -121,4 +124,5 @@ class Emu:
                                                    ptr(gcol), ptr(gdep), ptr(g["means3D"]), ptr(g["means2D"]), ptr(g["sh"]),
                                                    ptr(g["colors_precomp"]), ptr(g["opacities"]), ptr(g["scales"]),
                                                    ptr(g["rotations"]), ptr(g["cov3Ds_precomp"]), ptr(scratch), int(phases), None))
+        g["scratch"] = scratch
         return g

@@ -128,6 +128,35 @@ def test_tile_shards_equal_the_whole_frame(emu):
         grad_close(acc[k], b[k], k)
 
 
+def test_sharded_frame_with_row_blocks(emu):
+    """the multi-GPU schedule on one CPU: every shard renders its tile rows (the forward knows its gradient
+    row block and skips foreign SH colours), phase 1 fills each shard's [P][10] sums, their total is what the
+    reduce-scatter delivers, phase 2 finishes each shard's own row block."""
+    cam, sc, ts, kids, bg = make_scene(2500, 160, 112, mode="hier", seed=8)
+    f, b, gcol, gdep = oracle_run(cam, sc, bg, ts, kids)
+    P, G = 2500, 3
+    chunk = (P + G - 1) // G
+    rows = [(min(r * chunk, P), min((r + 1) * chunk, P)) for r in range(G)]
+    shards = []
+    for r in range(G):
+        a, keep = emu.args(cam, bg, sc, ts=ts, kids=kids, shard=(G, r), grad_rows=rows[r])
+        fw = emu.forward(a, keep)
+        g1 = emu.backward(a, fw, gcol, phases=1)
+        shards.append((a, keep, fw, g1["scratch"].view(np.float32)[: P * 10].copy()))
+    total = sum(s[3].astype(np.float64) for s in shards).astype(np.float32)
+    out = {k: np.zeros_like(b[k]) for k in ("means3D", "sh", "opacities", "scales", "rotations", "means2D")}
+    for r, (a, keep, fw, _) in enumerate(shards):
+        from emu_api import aligned
+        scratch = aligned(emu.L.h3dgs_backward_scratch_bytes(P))
+        scratch.view(np.float32)[: P * 10] = total
+        g2 = emu.backward(a, fw, gcol, phases=2, scratch=scratch)
+        lo, hi = rows[r]
+        for k in out:
+            out[k][lo:hi] = g2[k][lo:hi]
+    for k in out:
+        grad_close(out[k], b[k], k)
+
+
 def test_fused_cut_gather_and_scatter(emu):
     from oracle import oracle
     cam = synth.make_camera(160, 112)
