@@ -22,7 +22,7 @@ struct float4 { float x, y, z, w; };
 constexpr float kAlphaCap = 0.99f;
 constexpr float kAlphaSkip = 1.0f / 255.0f;
 constexpr float kTStop = 0.0001f;
-constexpr uint32_t kKidsMask = 0xFFFFFu;
+constexpr uint32_t kSortedKidsMask = 0xFFFu;
 #endif
 struct f2 { float lo, hi; };
 H3_PM_FN f2 pk(float lo, float hi) { return f2{lo, hi}; }
@@ -91,10 +91,9 @@ H3_PM_FN void pair_gauss(f2 power, float opacity, f2& G, f2& abase) {
 // pixels than in flat mode), so small a uses the two series (relative error < 2e-7); larger a goes
 // through MUFU.LG2 / MUFU.EX2.
 template <bool HIER, bool GRAD>
-H3_PM_FN void pair_hier_alpha(f2 a, float t, uint32_t kbits, f2& alpha, f2& dadb) {
+H3_PM_FN void pair_hier_alpha(f2 a, float t, uint32_t k /* num_node_kids */, f2& alpha, f2& dadb) {
     alpha = a; dadb = bc(1.0f);
     if (!HIER) return;
-    const uint32_t k = kbits & kKidsMask;
     if (k <= 1u || t >= 1.0f) return;
     const float ik = fast_rcp((float)k), u = 1.0f - t;
     float a0, a1; upk(a, a0, a1);
@@ -121,12 +120,13 @@ H3_PM_FN void pair_hier_alpha(f2 a, float t, uint32_t kbits, f2& alpha, f2& dadb
 // T: transmittance in front of the entry.  Returns the blend weights w = alpha T (0 for a pixel that
 // does not take the entry), updates T, and reports per pixel whether it took the entry (v) and
 // whether it terminated on it (done: T (1 - alpha) < 1e-4; the entry is then NOT blended).
-H3_PM_FN f2 pair_blend(f2 pw, f2 al, f2& T, bool& done0, bool& done1, bool& v0, bool& v1) {
+// active = false: this lane has no entry in this iteration (group walk); nothing is taken, nothing terminates.
+H3_PM_FN f2 pair_blend(f2 pw, f2 al, f2& T, bool& done0, bool& done1, bool& v0, bool& v1, bool active = true) {
     const f2 tT = mul2(T, sub2(bc(1.0f), al));
     float pw0, pw1, al0, al1, tT0, tT1;
     upk(pw, pw0, pw1); upk(al, al0, al1); upk(tT, tT0, tT1);
-    v0 = !done0 && pw0 <= 0.0f && al0 >= kAlphaSkip;
-    v1 = !done1 && pw1 <= 0.0f && al1 >= kAlphaSkip;
+    v0 = active && !done0 && pw0 <= 0.0f && al0 >= kAlphaSkip;
+    v1 = active && !done1 && pw1 <= 0.0f && al1 >= kAlphaSkip;
     if (v0 && tT0 < kTStop) { done0 = true; v0 = false; }
     if (v1 && tT1 < kTStop) { done1 = true; v1 = false; }
     const f2 w = sel2(v0, v1, mul2(al, T), bc(0.f));

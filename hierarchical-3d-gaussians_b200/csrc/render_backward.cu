@@ -54,9 +54,29 @@ __device__ __forceinline__ float transpose_reduce10(const float (&v)[10], int la
     return d;
 }
 
+// Group walk: the same reduction over the 8 lanes of a group (xor 4, 2, 1): 5 + 3 + 2 = 10 shuffles leave the 10 totals
+// on 6 of the 8 lanes -- lanes with bit0 = 0 hold two (r0, r1), lanes with bit0 = 1 and bit1 = 0 hold one (r0).
+// group_slots(lane & 7) gives the accum columns of (r0, r1), -1 = none.
+__device__ __forceinline__ void group_slots(int k, int& s0, int& s1) {
+    const int b2 = (k >> 2) & 1, b1 = (k >> 1) & 1, b0 = k & 1, base = 5 * b2;
+    if (!b0) { s0 = base + (b1 ? 3 : 0); s1 = base + (b1 ? 4 : 1); }
+    else { s0 = b1 ? -1 : base + 2; s1 = -1; }
+}
+__device__ __forceinline__ void transpose_reduce10_g8(const float (&v)[10], int lane, float& r0, float& r1) {
+    const bool b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+    float a[5];
+    upk(xchg_add2(b2 ? v[5] : v[0], b2 ? v[0] : v[5], b2 ? v[6] : v[1], b2 ? v[1] : v[6], 4), a[0], a[1]);
+    upk(xchg_add2(b2 ? v[7] : v[2], b2 ? v[2] : v[7], b2 ? v[8] : v[3], b2 ? v[3] : v[8], 4), a[2], a[3]);
+    a[4] = xchg_add(b2 ? v[9] : v[4], b2 ? v[4] : v[9], 4);
+    float b[3];
+    upk(xchg_add2(b1 ? a[3] : a[0], b1 ? a[0] : a[3], b1 ? a[4] : a[1], b1 ? a[1] : a[4], 2), b[0], b[1]);
+    b[2] = xchg_add(b1 ? 0.f : a[2], b1 ? a[2] : 0.f, 2);
+    upk(xchg_add2(b0 ? b[2] : b[0], b0 ? b[0] : b[2], b0 ? 0.f : b[1], b0 ? b[1] : 0.f, 1), r0, r1);
+}
+
 constexpr int kBwdThreads = 128;      // two vertically adjacent pixels per thread (see render_forward.cu)
 
-template <bool HIER, bool DEPTH>
+template <bool HIER, bool DEPTH, bool GROUPS>
 __global__ void __launch_bounds__(kBwdThreads)
 render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, const uint2* __restrict__ ranges,
                        const Record* __restrict__ sorted, const uint32_t* __restrict__ point_list,
@@ -107,7 +127,11 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
         for (int it = 0; it < kBwdStages && it < nb; it++) issue(it);
 
     int px, py0;
-    quad_pixel(tile_x, tile_y, warp, lane, px, py0);
+    if (GROUPS) group_pixel(tile_x, tile_y, warp, lane, px, py0);
+    else quad_pixel(tile_x, tile_y, warp, lane, px, py0);
+    int gs0, gs1;
+    group_slots(lane & 7, gs0, gs1);
+    const int grp = lane >> 3;
     const int py1 = py0 + 1;
     const bool in0 = px < W && py0 < H, in1 = px < W && py1 < H;
     const float fpx = (float)px;
@@ -123,7 +147,7 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
     const f2 g0 = pk(ga0, gb0), g1 = pk(ga1, gb1), g2 = pk(ga2, gb2), gd = pk(gad, gbd);
     const f2 neg_bgd = pk(-(bg[0] * ga0 + bg[1] * ga1 + bg[2] * ga2), -(bg[0] * gb0 + bg[1] * gb1 + bg[2] * gb2));
     const int wlast = (int)__reduce_max_sync(0xffffffffu, (unsigned)max(last0, last1));   // nothing in this quadrant beyond it
-    const uint32_t qbit = 1u << (kQuadShift + warp);
+    const int qsel = kBlockShift + 4 * warp;                // this warp's four block bits in the entries' reach mask
 
     for (int it = 0; it < nb; it++) {
         const int st = it % kBwdStages, b = nb - 1 - it;
@@ -134,11 +158,18 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
         // this warp's quadrant at all (see render_forward.cu)
         for (int j0 = (cnt - 1) & ~31; j0 >= 0; j0 -= 32) {
             const int jl = j0 + lane;
-            const bool hit = jl < cnt && (b * kBwdBatch + jl) < wlast && (__float_as_uint(rec[jl].b.w) & qbit) != 0u;
-            uint32_t m = __ballot_sync(0xffffffffu, hit);
-            while (m) {
-                const int top = 31 - __clz(m);
-                m &= ~(1u << top);
+            const uint32_t nib = (jl < cnt && (b * kBwdBatch + jl) < wlast) ? (__float_as_uint(rec[jl].b.w) >> qsel) & 0xFu : 0u;
+            uint32_t m;
+            if (GROUPS) {
+                // one survivor list per 8-lane group (see render_forward.cu)
+                const uint32_t m0 = __ballot_sync(0xffffffffu, nib & 1u), m1 = __ballot_sync(0xffffffffu, nib & 2u);
+                const uint32_t m2 = __ballot_sync(0xffffffffu, nib & 4u), m3 = __ballot_sync(0xffffffffu, nib & 8u);
+                m = grp == 0 ? m0 : grp == 1 ? m1 : grp == 2 ? m2 : m3;
+            } else m = __ballot_sync(0xffffffffu, nib != 0u);
+            while (GROUPS ? __any_sync(0xffffffffu, m != 0u) : (m != 0u)) {
+                const bool has = !GROUPS || m != 0u;
+                const int top = has ? 31 - __clz(m) : 0;
+                m &= ~((has ? 1u : 0u) << top);
                 const int j = j0 + top;
                 const int e = b * kBwdBatch + j;              // 0-based list position; contributor number e+1
                 const float4 a = rec[j].a;
@@ -154,11 +185,11 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
                 upk(pw, pw0, pw1); upk(al, al0, al1);
                 // the hierarchy weight only lowers alpha (1 - (1-a)^(1/k) <= a), so an entry that no pixel of
                 // the warp takes at its base alpha is skipped before that arithmetic
-                bool v0 = e < last0 && pw0 <= 0.0f && al0 >= kAlphaSkip;
-                bool v1 = e < last1 && pw1 <= 0.0f && al1 >= kAlphaSkip;
+                bool v0 = has && e < last0 && pw0 <= 0.0f && al0 >= kAlphaSkip;
+                bool v1 = has && e < last1 && pw1 <= 0.0f && al1 >= kAlphaSkip;
                 if (!__any_sync(0xffffffffu, v0 || v1)) continue;            // warp-uniform
                 if (HIER) {
-                    pair_hier_alpha<HIER, true>(al, bb.z, kb, al, dadb);
+                    pair_hier_alpha<HIER, true>(al, bb.z, kb & kSortedKidsMask, al, dadb);
                     upk(al, al0, al1);
                     v0 = v0 && al0 >= kAlphaSkip;
                     v1 = v1 && al1 >= kAlphaSkip;
@@ -170,9 +201,19 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
                 if (DEPTH) cg = fma2(bc(c.w), gd, cg);
                 float v[10];
                 pair_grad<HIER, DEPTH>(a, bb, dx, d, G, al, dadb, cg, Tf, neg_bgd, g0, g1, g2, gd, ps, v);
-                const float total = transpose_reduce10(v, lane);
-                if (slot >= 0 && (DEPTH || slot < 9))
-                    atomicAdd(accum + (size_t)gid * kAccum + slot, total);
+                if (GROUPS) {
+                    // every group reduces its own entry over its 8 lanes; groups without a taker stay silent
+                    const bool taker = ((__ballot_sync(0xffffffffu, v0 || v1) >> (8 * grp)) & 0xFFu) != 0u;
+                    float r0, r1;
+                    transpose_reduce10_g8(v, lane, r0, r1);
+                    float* row = accum + (size_t)gid * kAccum;
+                    if (taker && gs0 >= 0 && (DEPTH || gs0 < 9)) atomicAdd(row + gs0, r0);
+                    if (taker && gs1 >= 0 && (DEPTH || gs1 < 9)) atomicAdd(row + gs1, r1);
+                } else {
+                    const float total = transpose_reduce10(v, lane);
+                    if (slot >= 0 && (DEPTH || slot < 9))
+                        atomicAdd(accum + (size_t)gid * kAccum + slot, total);
+                }
             }
         }
         __syncthreads();                      // every thread is done with stage st (records and ids)
@@ -197,12 +238,15 @@ int launch_render_backward(const h3dgs_raster_args& a, const uint32_t* ranges, c
     const bool depth = a.do_depth != 0 && dL_dinvdepth != nullptr;
     const dim3 grid(gx * rows), block(kBwdThreads);
     ProfScope prof(H3DGS_STAGE_RENDER_BWD, s);
-#define LAUNCH(HI, DE)                                                                                          \
-    render_backward_kernel<HI, DE><<<grid, block, 0, s>>>(W, H, gx, sc, si, (const uint2*)ranges, sorted_records, \
-                                                          point_list, a.bg, final_T, n_contrib, tile_max_contrib, \
-                                                          dL_dcolor, dL_dinvdepth, accum)
-    if (hier) { if (depth) LAUNCH(true, true); else LAUNCH(true, false); }
-    else      { if (depth) LAUNCH(false, true); else LAUNCH(false, false); }
+    const bool groups = use_group_walk();
+#define LAUNCH(HI, DE, GR)                                                                                          \
+    render_backward_kernel<HI, DE, GR><<<grid, block, 0, s>>>(W, H, gx, sc, si, (const uint2*)ranges, sorted_records, \
+                                                              point_list, a.bg, final_T, n_contrib, tile_max_contrib, \
+                                                              dL_dcolor, dL_dinvdepth, accum)
+#define LAUNCH2(HI, DE) do { if (groups) LAUNCH(HI, DE, true); else LAUNCH(HI, DE, false); } while (0)
+    if (hier) { if (depth) LAUNCH2(true, true); else LAUNCH2(true, false); }
+    else      { if (depth) LAUNCH2(false, true); else LAUNCH2(false, false); }
+#undef LAUNCH2
 #undef LAUNCH
     H3_LAUNCHED("render_backward", a.debug, s);
     return H3DGS_OK;

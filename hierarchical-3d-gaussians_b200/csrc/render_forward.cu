@@ -23,7 +23,7 @@ constexpr int kFwdStages = 2;
 // instructions (FFMA2 / FMUL2 / FADD2): the kernel is issue-bound, one instruction serves both pixels.
 constexpr int kFwdThreads = 128;
 
-template <bool HIER, bool DEPTH>
+template <bool HIER, bool DEPTH, bool GROUPS>
 __global__ void __launch_bounds__(kFwdThreads)
 render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, const uint2* __restrict__ ranges,
                       const Record* __restrict__ sorted, const float* __restrict__ bg, float* __restrict__ out_color,
@@ -60,7 +60,8 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
     issued = min(kFwdStages, nb);
 
     int px, py0;
-    quad_pixel(tile_x, tile_y, warp, lane, px, py0);
+    if (GROUPS) group_pixel(tile_x, tile_y, warp, lane, px, py0);
+    else quad_pixel(tile_x, tile_y, warp, lane, px, py0);
     const int py1 = py0 + 1;
     const bool in0 = px < W && py0 < H, in1 = px < W && py1 < H;
     const float fpx = (float)px;
@@ -70,7 +71,8 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
     f2 T = bc(1.0f);
     float Ca0 = 0.f, Ca1 = 0.f, Ca2 = 0.f, Cb0 = 0.f, Cb1 = 0.f, Cb2 = 0.f, inv0 = 0.f, inv1 = 0.f;
     uint32_t last0 = 0, last1 = 0;
-    const uint32_t qbit = 1u << (kQuadShift + warp);        // this warp's quadrant in the entries' reach mask
+    const int qsel = kBlockShift + 4 * warp;                // this warp's four block bits in the entries' reach mask
+    const int grp = lane >> 3;
 
     int waited = 0;
     for (int b = 0; b < nb; b++) {
@@ -90,10 +92,18 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
             for (int j0 = 0; j0 < cnt; j0 += 32) {
                 if (__all_sync(0xffffffffu, done0 && done1)) break;
                 const int jl = j0 + lane;
-                const bool hit = jl < cnt && (__float_as_uint(rec[jl].b.w) & qbit) != 0u;
-                uint32_t m = __ballot_sync(0xffffffffu, hit);
-                while (m) {
-                    const int j = j0 + __ffs(m) - 1;
+                const uint32_t nib = jl < cnt ? (__float_as_uint(rec[jl].b.w) >> qsel) & 0xFu : 0u;
+                uint32_t m;
+                if (GROUPS) {
+                    // one survivor list per 8-lane group: the entries that reach ITS 4x4 block
+                    const uint32_t m0 = __ballot_sync(0xffffffffu, nib & 1u), m1 = __ballot_sync(0xffffffffu, nib & 2u);
+                    const uint32_t m2 = __ballot_sync(0xffffffffu, nib & 4u), m3 = __ballot_sync(0xffffffffu, nib & 8u);
+                    m = grp == 0 ? m0 : grp == 1 ? m1 : grp == 2 ? m2 : m3;
+                } else m = __ballot_sync(0xffffffffu, nib != 0u);
+                // GROUPS: the four groups advance in lockstep, each through its own list, until the longest is done
+                while (GROUPS ? __any_sync(0xffffffffu, m != 0u) : (m != 0u)) {
+                    const bool has = !GROUPS || m != 0u;
+                    const int j = j0 + (has ? __ffs(m) - 1 : 0);
                     m &= m - 1;
                     const float4 a = rec[j].a;
                     const float4 bb = rec[j].b;
@@ -102,9 +112,9 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
                     f2 d, G, al, unused;
                     const f2 pw = pair_power(a, bb, a.x - fpx, nfpy, d);
                     pair_gauss(pw, bb.y, G, al);
-                    pair_hier_alpha<HIER, false>(al, bb.z, kb, al, unused);
+                    pair_hier_alpha<HIER, false>(al, bb.z, kb & kSortedKidsMask, al, unused);
                     bool v0, v1;
-                    const f2 w = pair_blend(pw, al, T, done0, done1, v0, v1);
+                    const f2 w = pair_blend(pw, al, T, done0, done1, v0, v1, has);
                     upk(fma2(bc(c.x), w, pk(Ca0, Cb0)), Ca0, Cb0);
                     upk(fma2(bc(c.y), w, pk(Ca1, Cb1)), Ca1, Cb1);
                     upk(fma2(bc(c.z), w, pk(Ca2, Cb2)), Ca2, Cb2);
@@ -171,12 +181,15 @@ int launch_render_forward(const h3dgs_raster_args& a, const uint32_t* ranges, co
     const bool depth = a.do_depth != 0;
     const dim3 grid(gx * rows), block(kFwdThreads);
     ProfScope prof(H3DGS_STAGE_RENDER_FWD, s);
-#define LAUNCH(HI, DE)                                                                                         \
-    render_forward_kernel<HI, DE><<<grid, block, 0, s>>>(W, H, gx, sc, si, (const uint2*)ranges, sorted_records, \
-                                                         a.bg, out_color, out_invdepth, final_T, n_contrib,      \
-                                                         tile_max_contrib)
-    if (hier) { if (depth) LAUNCH(true, true); else LAUNCH(true, false); }
-    else      { if (depth) LAUNCH(false, true); else LAUNCH(false, false); }
+    const bool groups = use_group_walk();
+#define LAUNCH(HI, DE, GR)                                                                                         \
+    render_forward_kernel<HI, DE, GR><<<grid, block, 0, s>>>(W, H, gx, sc, si, (const uint2*)ranges, sorted_records, \
+                                                             a.bg, out_color, out_invdepth, final_T, n_contrib,      \
+                                                             tile_max_contrib)
+#define LAUNCH2(HI, DE) do { if (groups) LAUNCH(HI, DE, true); else LAUNCH(HI, DE, false); } while (0)
+    if (hier) { if (depth) LAUNCH2(true, true); else LAUNCH2(true, false); }
+    else      { if (depth) LAUNCH2(false, true); else LAUNCH2(false, false); }
+#undef LAUNCH2
 #undef LAUNCH
     H3_LAUNCHED("render_forward", a.debug, s);
     return H3DGS_OK;

@@ -22,7 +22,7 @@ static void ref_alpha(const Entry& e, double px, double py, bool hier, double& p
     double a = fmin(0.99, e.b.y * G);
     alpha = a; dadb = 1.0;
     union { float f; uint32_t u; } kb; kb.f = e.b.w;
-    const uint32_t k = kb.u & 0xFFFFFu;
+    const uint32_t k = kb.u & 0xFFFu;
     const double t = e.b.z;
     if (hier && k > 1 && t < 1.0) {
         alpha = t * a + (1 - t) * (1 - pow(1 - a, 1.0 / k));
@@ -107,7 +107,7 @@ static int run(int trial, bool verbose) {
         f2 d, G, al, unused;
         const f2 pw = pair_power(e.a, e.b, e.a.x - fpx, nfpy, d);
         pair_gauss(pw, e.b.y, G, al);
-        pair_hier_alpha<HIER, false>(al, e.b.z, kb.u, al, unused);
+        pair_hier_alpha<HIER, false>(al, e.b.z, kb.u & kSortedKidsMask, al, unused);
         bool v0, v1;
         const f2 w = pair_blend(pw, al, T, done0, done1, v0, v1);
         const float cc[4] = {e.c.x, e.c.y, e.c.z, e.c.w};
@@ -141,7 +141,7 @@ static int run(int trial, bool verbose) {
         f2 d, G, al, dadb;
         const f2 pw = pair_power(en.a, en.b, dx, nfpy, d);
         pair_gauss(pw, en.b.y, G, al);
-        pair_hier_alpha<HIER, true>(al, en.b.z, kb.u, al, dadb);
+        pair_hier_alpha<HIER, true>(al, en.b.z, kb.u & kSortedKidsMask, al, dadb);
         const bool v0 = e < last0 && lo(pw) <= 0.0f && lo(al) >= kAlphaSkip;
         const bool v1 = e < last1 && hi(pw) <= 0.0f && hi(al) >= kAlphaSkip;
         float v[10] = {0};

@@ -39,10 +39,18 @@ def grad_close(a, b, name, tol=1e-5, max_rows=12):
 
 
 @pytest.fixture(scope="module")
-def emu(tmp_path_factory):
+def emu_lib(tmp_path_factory):
     from build_emu import build
     from emu_api import Emu
     return Emu(build(str(tmp_path_factory.mktemp("h3dgs_emu"))))
+
+
+@pytest.fixture(params=["quadrants", "groups"])
+def emu(emu_lib, request, monkeypatch):
+    """both variants of the blend kernels: one survivor list per warp (8x8 quadrant), or one per 8-lane group
+    (4x4 block; H3DGS_GROUPWALK=1)"""
+    monkeypatch.setenv("H3DGS_GROUPWALK", "1" if request.param == "groups" else "0")
+    return emu_lib
 
 
 def _check(emu, cam, sc, bg, ts=None, kids=None, do_depth=False, sh_degree=3, colors=None, cov=None, tol=1e-5):
