@@ -29,15 +29,18 @@ import numpy as np  # noqa: E402
 
 METRIC = "train-step images/sec (fwd+bwd) @1080p, 3M Gaussians, SH-3"
 UNIT = "images/s"
-W, H = 1920, 1080
+W, H = 1920, 1080                # overridden by the 4K workload (main)
+RESOLUTION = {"hier20m4k": (3840, 2160)}
 TAU = 6.0
 N_VIEWS = 8
 
 
 # ----------------------------------------------------------------------------- workload
-def build_workload(name, cache_dir="/tmp/h3dgs_cache"):
-    """Synthetic scene + cameras (numpy).  hier3m: 1.5M leaves + 1,499,999 interior nodes (config #3);
-    flat1m: 1M flat Gaussians (config #2)."""
+def build_workload(name, cache_dir="/tmp/h3dgs_cache", device=None):
+    """Synthetic scene + cameras.  hier3m: 1.5M leaves + 1,499,999 interior nodes (config #3); flat1m: 1M flat
+    Gaussians (config #2), both numpy, cached under /tmp.  hier20m4k: 10M leaves + 9,999,999 interior nodes at
+    3840x2160 (config #5), generated with torch ops directly on `device` (h3dgs.synth_torch; seconds on a GPU
+    where the numpy builder needs minutes) -- tensors, not cached."""
     from h3dgs import synth
     os.makedirs(cache_dir, exist_ok=True)
     path = os.path.join(cache_dir, f"{name}_v3.npz")
@@ -45,6 +48,11 @@ def build_workload(name, cache_dir="/tmp/h3dgs_cache"):
     rs = np.random.default_rng(2)
     for i in range(1, N_VIEWS):
         cams.append(synth.yaw_camera(W, H, float(rs.uniform(-15, 15)), rs.uniform(-0.5, 0.5, 3)))
+    if name == "hier20m4k":
+        from h3dgs import synth_torch
+        leaves = synth_torch.cloud(10_000_000, cams[0].tanfovx, cams[0].tanfovy, sh_degree=3, zmin=2.0, zmax=60.0, seed=0,
+                                   device=device or "cpu")
+        return synth_torch.build_hierarchy(leaves), cams
     if os.path.exists(path):
         z = np.load(path)
         return {k: z[k] for k in z.files}, cams
@@ -172,6 +180,7 @@ def cpu_step_fn(arrays, cams, frac):
 
 
 def run_cpu_arm(arrays, cams, steps, warmup, frac, budget_s=25.0):
+    arrays = {k: (v.detach().cpu().numpy() if hasattr(v, "detach") else v) for k, v in arrays.items()}
     from oracle import oracle
     oracle.set_threads(os.cpu_count() or 1)          # torchrun exports OMP_NUM_THREADS=1
     step = cpu_step_fn(arrays, cams, frac)
@@ -243,7 +252,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="hier3m", choices=["hier3m", "flat1m", "tiny"])
+    ap.add_argument("--workload", default="hier3m", choices=["hier3m", "flat1m", "tiny", "hier20m4k"])
     ap.add_argument("--cpu-frac", type=int, default=16, help="CPU arm renders every k-th cut Gaussian")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", action="store_true",
@@ -258,10 +267,14 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     hier = args.workload != "flat1m"
+    global W, H
+    W, H = RESOLUTION.get(args.workload, (W, H))
     config = {"workload": {"hier3m": "config #3: N_all=3M (1.5M leaves + 1,499,999 interior nodes), 1920x1080, SH-3, "
                                      "LOD cut tau=6px, fwd+bwd, 8 synthetic views",
                            "flat1m": "config #2: 1M flat Gaussians, 1920x1080, SH-3, fwd+bwd",
-                           "tiny": "smoke-size hierarchy"}[args.workload],
+                           "tiny": "smoke-size hierarchy",
+                           "hier20m4k": "config #5: N_all=20M (10M leaves + 9,999,999 interior nodes), 3840x2160, SH-3, "
+                                        "LOD cut tau=6px, fwd+bwd, 8 synthetic views"}[args.workload],
               "l2": "inputs larger than L2 (parameter arrays 0.7 GB, per-step state > 1 GB); no explicit flush",
               "parallelism": f"screen-tile-sharded x{world}" if world > 1 else "single GPU"}
 
@@ -293,11 +306,11 @@ def main():
     dev = f"cuda:{local_rank}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
-    if rank == 0:
-        arrays, cams = build_workload(args.workload)
+    if rank == 0 or args.workload == "hier20m4k":        # the 4K workload is generated on every rank's own GPU
+        arrays, cams = build_workload(args.workload, device=dev)
     if world > 1:
         dist.barrier()
-    if rank != 0:
+    if rank != 0 and args.workload != "hier20m4k":
         arrays, cams = build_workload(args.workload)
 
     from h3dgs import _lib, pipeline, synth
@@ -324,7 +337,7 @@ def main():
         mk = lambda **kw: GraphedStep(scene, W, H, c0.tanfovx, c0.tanfovy, bg, thr[0], world=world, rank=rank, **kw)
         # capacities: one eager sync-free pass over the views with generous sizes, then +15 % head room
         # (rows and entries) and the next power of two (longest tile list)
-        probe = mk(bin_capacity=1 << 23, sort_capacity=8192, capture=False)
+        probe = mk(bin_capacity=(1 << 23) if W <= 1920 else (1 << 27), sort_capacity=8192, capture=False)
         need = {"rows": 0, "D": 0, "longest_list": 0}
         for v in range(N_VIEWS):
             probe.step(dcams[v], gts_dev[v])
