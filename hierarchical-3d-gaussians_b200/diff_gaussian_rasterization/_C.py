@@ -20,6 +20,11 @@ def last_num_rendered():
     return _last_num_rendered
 
 
+def _on_device(t):
+    """the library takes device pointers (the CPU suite patches this to drive an emulation build)"""
+    return t.is_cuda
+
+
 def _ptr(t):
     return None if (t is None or t.numel() == 0) else t.data_ptr()
 
@@ -27,7 +32,7 @@ def _ptr(t):
 def _f32c(t, name):
     if t is None or t.numel() == 0:
         return None
-    if not t.is_cuda:
+    if not _on_device(t):
         raise RuntimeError(f"{name} must be a CUDA tensor")
     if t.dtype != torch.float32:
         t = t.float()
@@ -37,7 +42,7 @@ def _f32c(t, name):
 def _i32c(t, name):
     if t is None or t.numel() == 0:
         return None
-    if not t.is_cuda:
+    if not _on_device(t):
         t = t.cuda()
     if t.dtype != torch.int32:
         t = t.int()
@@ -89,7 +94,7 @@ def _prep_inputs(means3D, sh, colors_precomp, opacities, scales, rotations, cov3
     bg = _f32c(bg, "bg"); viewmatrix = _f32c(viewmatrix, "viewmatrix"); projmatrix = _f32c(projmatrix, "projmatrix")
     campos = _f32c(campos, "campos")
     ts = _f32c(interpolation_weights, "interpolation_weights") if (interpolation_weights is not None and interpolation_weights.numel()) else None
-    if ts is not None and not ts.is_cuda:
+    if ts is not None and not _on_device(ts):
         ts = ts.cuda()
     kids = _i32c(num_node_kids, "num_node_kids") if ts is not None else None
     if ts is not None and (ts.numel() < P or kids is None or kids.numel() < P):

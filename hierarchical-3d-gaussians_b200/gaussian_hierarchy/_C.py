@@ -10,8 +10,13 @@ from .hier_io import load_hierarchy, write_hierarchy  # noqa: F401
 _scratch = {}
 
 
+def _on_device(t):
+    """the library takes device pointers (the CPU suite patches this to drive an emulation build)"""
+    return t.is_cuda
+
+
 def _i32(t, name):
-    if not t.is_cuda or t.dtype != torch.int32 or not t.is_contiguous():
+    if not _on_device(t) or t.dtype != torch.int32 or not t.is_contiguous():
         raise RuntimeError(f"{name} must be a contiguous int32 CUDA tensor")
     return t
 
@@ -21,11 +26,11 @@ def expand_to_size(nodes, boxes, size, viewpoint, viewdir, render_indices, paren
     viewdir: CPU float tensor [3] (unused by the size metric, kept for signature parity)."""
     L = _lib.lib()
     nodes = _i32(nodes, "nodes")
-    if not boxes.is_cuda or boxes.dtype != torch.float32:
+    if not _on_device(boxes) or boxes.dtype != torch.float32:
         raise RuntimeError("boxes must be a float32 CUDA tensor")
     boxes = boxes.contiguous()
     N = nodes.shape[0]
-    vp = viewpoint if viewpoint.is_cuda else viewpoint.cuda()
+    vp = viewpoint if _on_device(viewpoint) else viewpoint.cuda()
     vp = vp.float().contiguous()
     vd = viewdir.detach().cpu().float().flatten().tolist() if viewdir is not None and viewdir.numel() >= 3 else [0.0, 0.0, 0.0]
     need = L.h3dgs_expand_scratch_bytes(N)
@@ -55,7 +60,7 @@ def get_interpolation_weights(node_indices, size, nodes, boxes, viewpoint, viewd
     boxes = boxes.contiguous()
     vp = viewpoint.detach().cpu().float().flatten().tolist()
     vd = viewdir.detach().cpu().float().flatten().tolist() if viewdir is not None and viewdir.numel() >= 3 else [0.0, 0.0, 0.0]
-    if not interpolation_weights.is_cuda or interpolation_weights.dtype != torch.float32:
+    if not _on_device(interpolation_weights) or interpolation_weights.dtype != torch.float32:
         raise RuntimeError("interpolation_weights must be a float32 CUDA tensor")
     with torch.cuda.device(nodes.device):
         _lib.check(L.h3dgs_get_interpolation_weights(n, node_indices.data_ptr(), float(size), nodes.data_ptr(),
