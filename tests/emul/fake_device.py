@@ -58,3 +58,40 @@ def cpu_as_device(so_path):
         for p in patches:
             st.enter_context(p)
         yield emu
+
+
+def _is_cuda_dev(d):
+    return (isinstance(d, str) and d.startswith("cuda")) or (isinstance(d, torch.device) and d.type == "cuda")
+
+
+@contextlib.contextmanager
+def cuda_names_mean_cpu():
+    """device="cuda" / .cuda() / .to("cuda") in test code land on the CPU: lets the GPU test files themselves run
+    against the emulation build (H3DGS_EMULATE=1, tests/conftest.py)."""
+    names = ["tensor", "zeros", "ones", "empty", "full", "rand", "randn", "arange", "as_tensor", "zeros_like", "ones_like",
+             "empty_like", "full_like", "rand_like", "randn_like", "linspace", "eye", "randint", "randperm"]
+    saved = {n: getattr(torch, n) for n in names}
+    saved_to, saved_cuda = torch.Tensor.to, torch.Tensor.cuda
+
+    def wrap(fn):
+        def f(*a, **k):
+            if _is_cuda_dev(k.get("device")):
+                k["device"] = "cpu"
+            return fn(*a, **k)
+        return f
+
+    def to(self, *a, **k):
+        a = tuple("cpu" if _is_cuda_dev(x) else x for x in a)
+        if _is_cuda_dev(k.get("device")):
+            k["device"] = "cpu"
+        return saved_to(self, *a, **k)
+    try:
+        for n in names:
+            setattr(torch, n, wrap(saved[n]))
+        torch.Tensor.to = to
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        yield
+    finally:
+        for n in names:
+            setattr(torch, n, saved[n])
+        torch.Tensor.to, torch.Tensor.cuda = saved_to, saved_cuda
