@@ -404,12 +404,19 @@ def main():
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        pending = None
         for i in range(nsteps):
             loss, radii, n = step(i, resident)
             if not resident:
-                loss_host = loss.item()          # D2H read of the step's result
+                # D2H read of every step's result, one step behind: the host reads loss i-1 while the device
+                # works on step i (what a training loop's logging does), so the read never drains the queue
+                if pending is not None:
+                    loss_host = pending.item()
+                pending = loss
             if collect is not None:
                 collect.append(n)            # ints only: holding tensors here would defeat the caching allocator
+        if pending is not None:
+            loss_host = pending.item()       # the last step's result, still inside the timed region
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
