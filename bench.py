@@ -398,25 +398,39 @@ def main():
             loss, radii, n = sharder.l1_step(scene, cam, bg, gt, thr[v] if hier else None, gt_ready=ready)
         return loss, radii, n
 
+    read_stream = torch.cuda.Stream(device=dev)
+    loss_pinned = torch.zeros(2, dtype=torch.float64).pin_memory()
+
     def timed(nsteps, resident, collect=None):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        pending = None
+        # e2e: the D2H read of every step's result happens one step behind, on a side stream into pinned memory --
+        # the host looks at loss i-1 while the device works on step i (what a training loop's logging does), so the
+        # read never drains the launch queue; all of it, including the last read, is inside the timed region
+        main_s, prev_done = torch.cuda.current_stream(), None
         for i in range(nsteps):
+            if prev_done is not None and gs is not None:
+                main_s.wait_event(prev_done)         # graph mode: the static result buffer is not overwritten before it was read
             loss, radii, n = step(i, resident)
             if not resident:
-                # D2H read of every step's result, one step behind: the host reads loss i-1 while the device
-                # works on step i (what a training loop's logging does), so the read never drains the queue
-                if pending is not None:
-                    loss_host = pending.item()
-                pending = loss
+                ev = torch.cuda.Event(); ev.record(main_s)
+                with torch.cuda.stream(read_stream):
+                    read_stream.wait_event(ev)
+                    loss.record_stream(read_stream)
+                    loss_pinned[i % 2].copy_(loss.detach(), non_blocking=True)
+                    done = torch.cuda.Event(); done.record(read_stream)
+                if prev_done is not None:
+                    prev_done.synchronize()
+                    loss_host = float(loss_pinned[(i - 1) % 2])
+                prev_done = done
             if collect is not None:
                 collect.append(n)            # ints only: holding tensors here would defeat the caching allocator
-        if pending is not None:
-            loss_host = pending.item()       # the last step's result, still inside the timed region
+        if prev_done is not None:
+            prev_done.synchronize()
+            loss_host = float(loss_pinned[(nsteps - 1) % 2])
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
