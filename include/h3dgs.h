@@ -26,7 +26,12 @@
  * (num_rendered sizing of the binning buffer; the int returned by expand_to_size) -- capacity mode
  * (h3dgs_raster_args.bin_capacity) and h3dgs_lod_cut have none.
  * Every entry point returns 0 on success, a negative H3DGS_E* code on error and
- * leaves a message retrievable with h3dgs_last_error().
+ * leaves a message retrievable with h3dgs_last_error() (thread-local).
+ *
+ * Threading: the reference drives this path from a single Python thread on the default stream
+ *  and so does the shim.  The library keeps one side stream and one pinned read-back
+ * slot PER DEVICE, so calls that target the same device must not overlap in time (different devices --
+ * one process or thread per GPU, as in the tile-sharded mode -- are independent).
  */
 #ifndef H3DGS_H
 #define H3DGS_H
