@@ -37,6 +37,17 @@ H3_PM_FN float rcp_approx(float x) { return 1.0f / x; }
 #else
 #define H3_PM_FN __device__ __forceinline__
 namespace h3dgs {
+#ifdef H3_PAIR_SCALAR
+// A/B switch (build with H3DGS_PAIR_SCALAR=1): the same functions on two scalar registers, i.e. FFMA / FMUL / FADD
+// instead of the packed instructions -- isolates what FFMA2 / FMUL2 / FADD2 themselves buy on a given GPU.
+struct f2 { float lo, hi; };
+H3_PM_FN f2 pk(float lo, float hi) { return f2{lo, hi}; }
+H3_PM_FN void upk(f2 v, float& lo, float& hi) { lo = v.lo; hi = v.hi; }
+H3_PM_FN f2 fma2(f2 a, f2 b, f2 c) { return f2{__fmaf_rn(a.lo, b.lo, c.lo), __fmaf_rn(a.hi, b.hi, c.hi)}; }
+H3_PM_FN f2 mul2(f2 a, f2 b) { return f2{__fmul_rn(a.lo, b.lo), __fmul_rn(a.hi, b.hi)}; }
+H3_PM_FN f2 add2(f2 a, f2 b) { return f2{__fadd_rn(a.lo, b.lo), __fadd_rn(a.hi, b.hi)}; }
+H3_PM_FN f2 sub2(f2 a, f2 b) { return f2{__fsub_rn(a.lo, b.lo), __fsub_rn(a.hi, b.hi)}; }
+#else
 typedef unsigned long long f2;
 H3_PM_FN f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 H3_PM_FN void upk(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
@@ -44,6 +55,7 @@ H3_PM_FN f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : 
 H3_PM_FN f2 mul2(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 H3_PM_FN f2 add2(f2 a, f2 b) { f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 H3_PM_FN f2 sub2(f2 a, f2 b) { f2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+#endif
 // 2^x as MUFU.EX2 (ftz: results below 2^-126 flush to 0, far below the 1/255 alpha cut)
 H3_PM_FN float fast_exp2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 // log2(x) for normal x: MUFU.LG2 without the denormal pre-scaling of __log2f
