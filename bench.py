@@ -29,15 +29,18 @@ import numpy as np  # noqa: E402
 
 METRIC = "train-step images/sec (fwd+bwd) @1080p, 3M Gaussians, SH-3"
 UNIT = "images/s"
-W, H = 1920, 1080
+W, H = 1920, 1080                # overridden by the 4K workload (main)
+RESOLUTION = {"hier20m4k": (3840, 2160)}
 TAU = 6.0
 N_VIEWS = 8
 
 
 # ----------------------------------------------------------------------------- workload
-def build_workload(name, cache_dir="/tmp/h3dgs_cache"):
-    """Synthetic scene + cameras (numpy).  hier3m: 1.5M leaves + 1,499,999 interior nodes (config #3);
-    flat1m: 1M flat Gaussians (config #2)."""
+def build_workload(name, cache_dir="/tmp/h3dgs_cache", device=None):
+    """Synthetic scene + cameras.  hier3m: 1.5M leaves + 1,499,999 interior nodes (config #3); flat1m: 1M flat
+    Gaussians (config #2), both numpy, cached under /tmp.  hier20m4k: 10M leaves + 9,999,999 interior nodes at
+    3840x2160 (config #5), generated with torch ops directly on `device` (h3dgs.synth_torch; seconds on a GPU
+    where the numpy builder needs minutes) -- tensors, not cached."""
     from h3dgs import synth
     os.makedirs(cache_dir, exist_ok=True)
     path = os.path.join(cache_dir, f"{name}_v3.npz")
@@ -45,6 +48,11 @@ def build_workload(name, cache_dir="/tmp/h3dgs_cache"):
     rs = np.random.default_rng(2)
     for i in range(1, N_VIEWS):
         cams.append(synth.yaw_camera(W, H, float(rs.uniform(-15, 15)), rs.uniform(-0.5, 0.5, 3)))
+    if name == "hier20m4k":
+        from h3dgs import synth_torch
+        leaves = synth_torch.cloud(10_000_000, cams[0].tanfovx, cams[0].tanfovy, sh_degree=3, zmin=2.0, zmax=60.0, seed=0,
+                                   device=device or "cpu")
+        return synth_torch.build_hierarchy(leaves), cams
     if os.path.exists(path):
         z = np.load(path)
         return {k: z[k] for k in z.files}, cams
@@ -172,6 +180,7 @@ def cpu_step_fn(arrays, cams, frac):
 
 
 def run_cpu_arm(arrays, cams, steps, warmup, frac, budget_s=25.0):
+    arrays = {k: (v.detach().cpu().numpy() if hasattr(v, "detach") else v) for k, v in arrays.items()}
     from oracle import oracle
     oracle.set_threads(os.cpu_count() or 1)          # torchrun exports OMP_NUM_THREADS=1
     step = cpu_step_fn(arrays, cams, frac)
@@ -243,9 +252,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="hier3m", choices=["hier3m", "flat1m", "tiny"])
+    ap.add_argument("--workload", default="hier3m", choices=["hier3m", "flat1m", "tiny", "hier20m4k"])
     ap.add_argument("--cpu-frac", type=int, default=16, help="CPU arm renders every k-th cut Gaussian")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="hierarchy workloads: the sync-free step replayed from CUDA graphs (h3dgs.graphstep) instead of "
+                         "the call-by-call public API; same kernels, no host round trips inside the step")
     ap.add_argument("--classic", action="store_true",
                     help="also time the classic-formulation blend kernels (baseline/classic) on the same binned state")
     args = ap.parse_args()
@@ -255,10 +267,14 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     hier = args.workload != "flat1m"
+    global W, H
+    W, H = RESOLUTION.get(args.workload, (W, H))
     config = {"workload": {"hier3m": "config #3: N_all=3M (1.5M leaves + 1,499,999 interior nodes), 1920x1080, SH-3, "
                                      "LOD cut tau=6px, fwd+bwd, 8 synthetic views",
                            "flat1m": "config #2: 1M flat Gaussians, 1920x1080, SH-3, fwd+bwd",
-                           "tiny": "smoke-size hierarchy"}[args.workload],
+                           "tiny": "smoke-size hierarchy",
+                           "hier20m4k": "config #5: N_all=20M (10M leaves + 9,999,999 interior nodes), 3840x2160, SH-3, "
+                                        "LOD cut tau=6px, fwd+bwd, 8 synthetic views"}[args.workload],
               "l2": "inputs larger than L2 (parameter arrays 0.7 GB, per-step state > 1 GB); no explicit flush",
               "parallelism": f"screen-tile-sharded x{world}" if world > 1 else "single GPU"}
 
@@ -290,11 +306,11 @@ def main():
     dev = f"cuda:{local_rank}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
-    if rank == 0:
-        arrays, cams = build_workload(args.workload)
+    if rank == 0 or args.workload == "hier20m4k":        # the 4K workload is generated on every rank's own GPU
+        arrays, cams = build_workload(args.workload, device=dev)
     if world > 1:
         dist.barrier()
-    if rank != 0:
+    if rank != 0 and args.workload != "hier20m4k":
         arrays, cams = build_workload(args.workload)
 
     from h3dgs import _lib, pipeline, synth
@@ -312,7 +328,52 @@ def main():
     host_cams = [(torch.tensor(c.world_view_transform).pin_memory(), torch.tensor(c.full_proj_transform).pin_memory(),
                   torch.tensor(c.camera_center).pin_memory()) for c in cams]
 
+    gs = None
+    if args.graph:
+        if not hier:
+            raise SystemExit("--graph drives the hierarchy step (LOD cut + fused gather/lerp)")
+        from h3dgs.graphstep import GraphedStep
+        c0 = cams[0]
+        mk = lambda **kw: GraphedStep(scene, W, H, c0.tanfovx, c0.tanfovy, bg, thr[0], world=world, rank=rank, **kw)
+        # capacities: one eager sync-free pass over the views with generous sizes, then +15 % head room
+        # (rows and entries) and the next power of two (longest tile list)
+        probe = mk(bin_capacity=(1 << 23) if W <= 1920 else (1 << 27), sort_capacity=8192, capture=False)
+        need = {"rows": 0, "D": 0, "longest_list": 0}
+        for v in range(N_VIEWS):
+            probe.step(dcams[v], gts_dev[v])
+            st = probe.status()
+            if st["overflow"]:
+                raise SystemExit(f"--graph: view {v} does not fit the probe capacities: {st}")
+            need = {k: max(need[k], st[k]) for k in need}
+        del probe
+        torch.cuda.empty_cache()
+        rows_cap = min(int(need["rows"] * 1.15) + 1, scene.means3D.shape[0])
+        if world > 1:       # the row blocks of the reduce-scatter must agree on every rank
+            t = torch.tensor([rows_cap], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); rows_cap = int(t.item())
+        sort_cap = 32
+        while sort_cap < min(int(need["longest_list"] * 1.25), 8192):
+            sort_cap *= 2
+        gs = mk(row_capacity=rows_cap, bin_capacity=int(need["D"] * 1.15) + 1, sort_capacity=sort_cap, capture=False)
+        gs.set_camera(dcams[0]); gs.gt.copy_(gts_dev[0])
+        gs.capture()
+        config["graph"] = {"row_capacity": rows_cap, "bin_capacity": gs.bin_capacity, "sort_capacity": sort_cap,
+                           "library_launches_per_step": int(gs.launches_per_step)}
+
+    def step_graph(i, resident=True):
+        v = i % N_VIEWS
+        ready = gs.upload_target(gts_dev[v] if resident else gts_host[v], copy_stream)
+        if resident:
+            gs.set_camera(dcams[v])
+        else:
+            gs.view.copy_(host_cams[v][0].reshape(16), non_blocking=True)
+            gs.proj.copy_(host_cams[v][1].reshape(16), non_blocking=True)
+            gs.campos.copy_(host_cams[v][2], non_blocking=True)
+        gs.step(gt_ready=ready)
+        return gs.status_dev[0], gs.radii, -1
+
     def step(i, resident=True):
+        if gs is not None:
+            return step_graph(i, resident)
         v = i % N_VIEWS
         ready = None
         if resident:
@@ -337,18 +398,39 @@ def main():
             loss, radii, n = sharder.l1_step(scene, cam, bg, gt, thr[v] if hier else None, gt_ready=ready)
         return loss, radii, n
 
+    read_stream = torch.cuda.Stream(device=dev)
+    loss_pinned = torch.zeros(2, dtype=torch.float64).pin_memory()
+
     def timed(nsteps, resident, collect=None):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        # e2e: the D2H read of every step's result happens one step behind, on a side stream into pinned memory --
+        # the host looks at loss i-1 while the device works on step i (what a training loop's logging does), so the
+        # read never drains the launch queue; all of it, including the last read, is inside the timed region
+        main_s, prev_done = torch.cuda.current_stream(), None
         for i in range(nsteps):
+            if prev_done is not None and gs is not None:
+                main_s.wait_event(prev_done)         # graph mode: the static result buffer is not overwritten before it was read
             loss, radii, n = step(i, resident)
             if not resident:
-                loss_host = loss.item()          # D2H read of the step's result
+                ev = torch.cuda.Event(); ev.record(main_s)
+                with torch.cuda.stream(read_stream):
+                    read_stream.wait_event(ev)
+                    loss.record_stream(read_stream)
+                    loss_pinned[i % 2].copy_(loss.detach(), non_blocking=True)
+                    done = torch.cuda.Event(); done.record(read_stream)
+                if prev_done is not None:
+                    prev_done.synchronize()
+                    loss_host = float(loss_pinned[(i - 1) % 2])
+                prev_done = done
             if collect is not None:
                 collect.append(n)            # ints only: holding tensors here would defeat the caching allocator
+        if prev_done is not None:
+            prev_done.synchronize()
+            loss_host = float(loss_pinned[(nsteps - 1) % 2])
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -384,11 +466,28 @@ def main():
 
     # bookkeeping for the roofline (untimed pass over the views): P (cut), V, D
     from diff_gaussian_rasterization import _C as rc
-    Pm = float(np.mean(stats))
     Vs, Ds = [], []
-    for i in range(N_VIEWS):
-        loss, radii, n = step(i)
-        Vs.append(int((radii > 0).sum().item())); Ds.append(rc.last_num_rendered())
+    if gs is None:
+        Pm = float(np.mean(stats))
+        for i in range(N_VIEWS):
+            loss, radii, n = step(i)
+            Vs.append(int((radii > 0).sum().item())); Ds.append(rc.last_num_rendered())
+    else:
+        # graph replays bypass the library's stage events and launch counter: the same sync-free step,
+        # run eagerly once per view, gives the per-stage device times; every view must have fitted
+        launches = gs.launches_per_step * args.steps
+        graphs, gs.graph_a, gs.graph_b = (gs.graph_a, gs.graph_b), None, None
+        _lib.profile_reset(); _lib.profile_enable(True)
+        Ps = []
+        for i in range(N_VIEWS):
+            step(i)
+            st = gs.status()
+            if st["overflow"]:
+                raise SystemExit(f"--graph: view {i} overflowed the capacities {config['graph']}: {st}; timed result invalid")
+            Ps.append(st["rows"]); Ds.append(st["D"]); Vs.append(int((gs.radii > 0).sum().item()))
+        prof = _lib.profile_read(); _lib.profile_enable(False)
+        gs.graph_a, gs.graph_b = graphs
+        Pm = float(np.mean(Ps))
     Vm, Dm = float(np.mean(Vs)), float(np.mean(Ds))
     stage_ms = {k: (v[0] / max(v[1], 1)) for k, v in prof.items() if v[1] > 0}
 
@@ -400,7 +499,8 @@ def main():
                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
                "clocks": clocks, "gpu_launches": int(launches),
                "e2e": {"value": 1000.0 / (ms_e2e / args.steps), "unit": UNIT,
-                       "h2d_bytes_per_step": 3 * H * W * 4 + 16 * 4 * 2 + 3 * 4, "d2h_bytes_per_step": 4},
+                       "h2d_bytes_per_step": 3 * H * W * 4 + 16 * 4 * 2 + 3 * 4,
+                       "d2h_bytes_per_step": 8 if gs is not None else 4},
                "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
                "counts": {"P_cut": Pm, "V": Vm, "D_rank0": Dm, "N_all": int(scene.means3D.shape[0])}}
         # roofline of the dominant kernel

@@ -38,7 +38,8 @@ def build(verbose=False, force=False):
         obj = os.path.join(objdir, name.replace(".cu", ".o"))
         if not force and not _needs_build(src, obj, deps):
             return obj, ""
-        cmd = [NVCC] + ARCH + COMMON + (["-fmad=false"] if name in NO_FMAD else []) + ["-c", src, "-o", obj]
+        cmd = [NVCC] + ARCH + COMMON + (["-fmad=false"] if name in NO_FMAD else []) + \
+            (["-DH3_PAIR_SCALAR"] if os.environ.get("H3DGS_PAIR_SCALAR") == "1" else []) + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {name}:\n{r.stdout}\n{r.stderr}")

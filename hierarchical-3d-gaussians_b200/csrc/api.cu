@@ -3,6 +3,7 @@
 // carving, and the stage sequence.  No torch types; device pointers only.
 #include <stdarg.h>
 #include <string.h>
+#include <algorithm>
 #include <mutex>
 #include <vector>
 #include "common.cuh"
@@ -32,15 +33,20 @@ static cudaEvent_t prof_event() {
     if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;
 }
+// stage events are timing events: they cannot be recorded into a stream that is being captured
+static bool capturing(cudaStream_t s) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    return cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone;
+}
 void prof_begin(int stage, cudaStream_t s) {
-    if (!g_prof_on) return;
+    if (!g_prof_on || capturing(s)) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
     cudaEvent_t e = prof_event();
     cudaEventRecord(e, s);
     g_prof_open[stage] = e;
 }
 void prof_end(int stage, cudaStream_t s) {
-    if (!g_prof_on) return;
+    if (!g_prof_on || capturing(s)) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
     cudaEvent_t e = prof_event();
     cudaEventRecord(e, s);
@@ -111,6 +117,11 @@ static int check_args(const h3dgs_raster_args* a) {
     if (a->shard_count > 1 && (a->shard_index < 0 || a->shard_index >= a->shard_count)) {
         set_error("bad tile shard %d/%d", a->shard_index, a->shard_count); return H3DGS_EINVAL;
     }
+    if (a->bin_capacity < 0 || a->sort_capacity < 0 || a->sort_capacity > kTileSortCap) {
+        set_error("bad capacities: bin %lld, sort %d (max %d)", (long long)a->bin_capacity, a->sort_capacity, kTileSortCap);
+        return H3DGS_EINVAL;
+    }
+    if (a->bin_capacity > 0 && a->debug) { set_error("capacity mode has no host synchronisation: debug must be off"); return H3DGS_EINVAL; }
     if (!a->means3D && a->P > 0) { set_error("means3D is NULL"); return H3DGS_EINVAL; }
     if (!a->bg || !a->viewmatrix || !a->projmatrix || !a->campos) { set_error("bg/viewmatrix/projmatrix/campos must be device pointers"); return H3DGS_EINVAL; }
     return H3DGS_OK;
@@ -184,22 +195,31 @@ extern "C" int h3dgs_rasterize_forward(const h3dgs_raster_args* a, h3dgs_alloc_f
         if (rc) return rc;
         H3_CUDA(cudaEventRecord(ss->fork, s));
         H3_CUDA(cudaStreamWaitEvent(ss->s, ss->fork, 0));
-        rc = launch_preprocess_color(*a, out_radii, records, ss->s);
+        rc = launch_preprocess_color(*a, out_radii, tiles, records, ss->s);
         if (rc) return rc;
         H3_CUDA(cudaEventRecord(ss->join, ss->s));
     } else {
-        rc = launch_preprocess_color(*a, out_radii, records, s);
+        rc = launch_preprocess_color(*a, out_radii, tiles, records, s);
         if (rc) return rc;
     }
-    rc = launch_tile_scan(*a, tile_count, ranges, info, s);
+    const bool capacity_mode = a->bin_capacity > 0;
+    const uint32_t cap_list = (uint32_t)(a->sort_capacity > 0 ? a->sort_capacity : kTileSortCap);
+    rc = launch_tile_scan(*a, tile_count, ranges, info, capacity_mode ? (uint32_t)std::min<int64_t>(a->bin_capacity, 0xFFFFFFFFll) : 0u,
+                          cap_list, s);
     if (rc) return rc;
-    // The reference API sizes the binning buffer from num_rendered: one D2H + sync.
-    void* pin = nullptr;
-    rc = pinned_scratch(&pin);
-    if (rc) return rc;
-    H3_CUDA(cudaMemcpyAsync(pin, info, sizeof(ScanInfo), cudaMemcpyDeviceToHost, s));
-    H3_CUDA(cudaStreamSynchronize(s));
-    const ScanInfo hinfo = *static_cast<const ScanInfo*>(pin);
+    ScanInfo hinfo;
+    if (capacity_mode) {
+        // sizes fixed by the caller; a frame that does not fit raises ScanInfo::overflow on the device
+        hinfo.D = (uint32_t)std::min<int64_t>(a->bin_capacity, 0xFFFFFFFFll); hinfo.max_count = cap_list; hinfo.overflow = 0;
+    } else {
+        // The reference API sizes the binning buffer from num_rendered: one D2H + sync.
+        void* pin = nullptr;
+        rc = pinned_scratch(&pin);
+        if (rc) return rc;
+        H3_CUDA(cudaMemcpyAsync(pin, info, sizeof(ScanInfo), cudaMemcpyDeviceToHost, s));
+        H3_CUDA(cudaStreamSynchronize(s));
+        hinfo = *static_cast<const ScanInfo*>(pin);
+    }
     const int64_t D = (int64_t)hinfo.D;
     if (num_rendered) *num_rendered = D;
     const BinLayout bl = bin_layout(D);
@@ -207,7 +227,7 @@ extern "C" int h3dgs_rasterize_forward(const h3dgs_raster_args* a, h3dgs_alloc_f
     if (!bin) { set_error("alloc callback returned NULL"); return H3DGS_ENOMEM; }
     if (hinfo.max_count <= (uint32_t)kTileSortCap) {
         if (side_color) H3_CUDA(cudaStreamWaitEvent(s, ss->join, 0));  // colours are needed by the record gather
-        rc = launch_tile_binning(*a, out_radii, depths, records, D, hinfo.max_count, bin, bl, ranges, tile_count, s);
+        rc = launch_tile_binning(*a, out_radii, depths, records, D, hinfo.max_count, bin, bl, ranges, info, tile_count, s);
         if (rc) return rc;
     } else {
         // a tile list too long for the shared-memory sort: global stable radix sort (CUB), same order
@@ -323,6 +343,7 @@ extern "C" int h3dgs_state_layout(int32_t P, int32_t W, int32_t H, int64_t D, co
         out->ranges = (const uint32_t*)(img + il.ranges);
         out->final_T = (const float*)(img + il.final_T);
         out->n_contrib = (const uint32_t*)(img + il.n_contrib);
+        out->scan_info = (const uint32_t*)(img + il.scan_info);
     }
     return H3DGS_OK;
 }

@@ -77,46 +77,58 @@ identify_tile_ranges_kernel(int64_t D, const uint64_t* __restrict__ keys, uint32
     if (i == D - 1) ranges[2 * tile + 1] = (uint32_t)D;
 }
 
-// Which of the four 8x8-pixel quadrants of tile (tile_x, tile_y) can entry (a, b) reach at all?
-__device__ __forceinline__ uint32_t quadrant_mask(const float4& a, const float4& b, int tile_x, int tile_y)
+// Which of the sixteen 4x4-pixel blocks of tile (tile_x, tile_y) can entry (a, b) reach at all?
+// Bit 4 q + g: quadrant q = (qx, qy) of the tile (the warp of the blend CTAs), block g = (bx, by) inside it
+// (an 8-lane group of that warp); the quadrant is reached iff any of its four bits is set.
+// alpha >= 1/255  <=>  q(d) = A dx^2 + 2 B dx dy + C dy^2 <= 2 ln(255 o): the exact minimum of the convex q over a
+// block's rectangle of pixel centres (0 if the mean is inside, else attained on an edge) is compared with
+// that bound (conservative margin for fp32 rounding).  Only the blocks inside the ellipse's bounding box are tested.
+__device__ __forceinline__ uint32_t block_mask16(const float4& a, const float4& b, int tile_x, int tile_y)
 {
-    uint32_t mask = 0xFu;
-    const float A = a.z, B = a.w, C = b.x;             // conic: q(d) = A dx^2 + 2 B dx dy + C dy^2 = -2 power
+    const float A = a.z, B = a.w, C = b.x;
     const float det = A * C - B * B;
     const float o255 = b.y * 255.0f;
-    if (!(o255 > 1.0f)) mask = 0u;                     // can never reach alpha >= 1/255
-    else if (det > 0.0f && A > 0.0f && C > 0.0f) {
-        // alpha >= 1/255  <=>  q(d) <= 2 ln(255 o): compare the exact minimum of q over each quadrant's
-        // rectangle of pixel centres with that bound (conservative margin for fp32 rounding)
-        const float bound = 2.0f * logf(o255) * 1.002f + 1e-3f;
-        const float rx = a.x - (float)(tile_x * kTile), ry = a.y - (float)(tile_y * kTile);
-        if (bound == bound && rx == rx && ry == ry) {
-            mask = 0u;
+    if (!(o255 > 1.0f)) return 0u;                     // can never reach alpha >= 1/255
+    const float bound = 2.0f * logf(o255) * 1.002f + 1e-3f;
+    const float rx = a.x - (float)(tile_x * kTile), ry = a.y - (float)(tile_y * kTile);
+    if (!(det > 0.0f && A > 0.0f && C > 0.0f) || !(bound == bound && rx == rx && ry == ry)) return 0xFFFFu;
+    // bounding box of {q <= bound}: |dx| <= sqrt(bound C / det), |dy| <= sqrt(bound A / det)
+    const float ex = sqrtf(bound * C / det) * 1.001f + 1e-3f, ey = sqrtf(bound * A / det) * 1.001f + 1e-3f;
+    if (!(ex == ex && ey == ey) || ex > 1e6f || ey > 1e6f) return 0xFFFFu;
+    // block i covers pixel centres 4 i .. 4 i + 3 in tile coordinates
+    const int bx0 = max(0, (int)ceilf((rx - ex - 3.0f) * 0.25f)), bx1 = min(3, (int)floorf((rx + ex) * 0.25f));
+    const int by0 = max(0, (int)ceilf((ry - ey - 3.0f) * 0.25f)), by1 = min(3, (int)floorf((ry + ey) * 0.25f));
+    uint32_t mask = 0u;
+    for (int by = by0; by <= by1; by++)
+        for (int bx = bx0; bx <= bx1; bx++) {
+            // rectangle of pixel centres relative to the mean: dx in [x0, x1], dy in [y0, y1]
+            const float x0 = (float)(4 * bx) - rx, x1 = x0 + 3.0f;
+            const float y0 = (float)(4 * by) - ry, y1 = y0 + 3.0f;
+            float qmin;
+            if (x0 <= 0.f && x1 >= 0.f && y0 <= 0.f && y1 >= 0.f) qmin = 0.f;          // the mean is inside
+            else {
+                qmin = 3.0e38f;
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                // rectangle of pixel centres relative to the mean: dx in [x0, x1], dy in [y0, y1]
-                const float x0 = (float)(8 * (q & 1)) - rx, x1 = x0 + 7.0f;
-                const float y0 = (float)(8 * (q >> 1)) - ry, y1 = y0 + 7.0f;
-                float qmin;
-                if (x0 <= 0.f && x1 >= 0.f && y0 <= 0.f && y1 >= 0.f) qmin = 0.f;      // the mean is inside
-                else {
-                    qmin = 3.0e38f;
-                    // vertical edges dx = xe: minimise over dy (dy* = -B xe / C, clamped)
-#pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        const float xe = e ? x1 : x0;
-                        const float dy = fminf(y1, fmaxf(y0, -B * xe / C));
-                        qmin = fminf(qmin, A * xe * xe + 2.0f * B * xe * dy + C * dy * dy);
-                        const float ye = e ? y1 : y0;
-                        const float dx = fminf(x1, fmaxf(x0, -B * ye / A));
-                        qmin = fminf(qmin, A * dx * dx + 2.0f * B * dx * ye + C * ye * ye);
-                    }
+                for (int e = 0; e < 2; e++) {
+                    const float xe = e ? x1 : x0;                                       // vertical edges: minimise over dy
+                    const float dy = fminf(y1, fmaxf(y0, -B * xe / C));
+                    qmin = fminf(qmin, A * xe * xe + 2.0f * B * xe * dy + C * dy * dy);
+                    const float ye = e ? y1 : y0;                                       // horizontal edges: minimise over dx
+                    const float dx = fminf(x1, fmaxf(x0, -B * ye / A));
+                    qmin = fminf(qmin, A * dx * dx + 2.0f * B * dx * ye + C * ye * ye);
                 }
-                if (!(qmin > bound)) mask |= 1u << q;
+            }
+            if (!(qmin > bound)) {
+                const int q = (bx >> 1) | ((by >> 1) << 1), g = (bx & 1) | ((by & 1) << 1);
+                mask |= 1u << (4 * q + g);
             }
         }
-    }
     return mask;
+}
+// kbits of the per-tile SORTED record copy: bits 0..11 num_node_kids (saturated), bits 16..31 the block mask.
+// (The unsorted record keeps K1's layout: kids in bits 0..19, SH clamp flags in 20..22.)
+__device__ __forceinline__ uint32_t sorted_kbits(uint32_t kbits, uint32_t mask16) {
+    return min(kbits & kKidsMask, kSortedKidsMask) | (mask16 << kBlockShift);
 }
 
 // sorted_records[j] = records[point_list[j]] : 48-B gathers out of an L2-resident array.
@@ -137,8 +149,7 @@ gather_records_kernel(int64_t D, const uint32_t* __restrict__ point_list, const 
     const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
     const uint32_t tile = (uint32_t)(keys[j] >> 32);
     const int tile_y = (int)(tile / (uint32_t)gx), tile_x = (int)(tile - (uint32_t)tile_y * (uint32_t)gx);
-    const uint32_t mask = quadrant_mask(a, b, tile_x, tile_y);
-    const uint32_t kb = (__float_as_uint(b.w) & 0x00FFFFFFu) | (mask << kQuadShift);
+    const uint32_t kb = sorted_kbits(__float_as_uint(b.w), block_mask16(a, b, tile_x, tile_y));
     float4* dst = reinterpret_cast<float4*>(sorted + j);
     dst[0] = a;
     dst[1] = make_float4(b.x, b.y, b.z, __uint_as_float(kb));
@@ -156,7 +167,8 @@ gather_records_kernel(int64_t D, const uint32_t* __restrict__ point_list, const 
 // global radix sort plus the separate gather.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
-tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges, ScanInfo* __restrict__ info)
+tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges, ScanInfo* __restrict__ info,
+                 uint32_t cap_entries, uint32_t cap_list)
 {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry, s_max;
@@ -189,18 +201,24 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restri
     local_max = __reduce_max_sync(0xffffffffu, local_max);
     if (lane == 0) atomicMax(&s_max, local_max);
     __syncthreads();
-    if (tid == 0) { info->D = s_carry; info->max_count = s_max; }
+    // capacity mode (cap_entries > 0): a frame that does not fit is turned into an empty one
+    const bool overflow = cap_entries != 0u && (s_carry > cap_entries || s_max > cap_list);
+    if (tid == 0) { info->D = s_carry; info->max_count = s_max; info->overflow = overflow ? 1u : 0u; }
+    if (overflow)
+        for (int t = tid; t < T; t += 1024) ranges[t] = make_uint2(0u, 0u);
 }
 
 __global__ void __launch_bounds__(256)
 emit_to_tiles_kernel(int P, int W, int H, int shard_count, int shard_index, const int* __restrict__ radii,
                      const float* __restrict__ depths, const Record* __restrict__ records,
-                     const uint2* __restrict__ ranges, uint32_t* __restrict__ tile_count, uint2* __restrict__ pairs)
+                     const uint2* __restrict__ ranges, const ScanInfo* __restrict__ info,
+                     uint32_t* __restrict__ tile_count, uint2* __restrict__ pairs)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     const int rad = radii[i];
     if (rad <= 0) return;
+    if (info->overflow) return;                  // capacity mode: the segments would not fit `pairs`
     const float4 a = records[i].a;
     const float ix = a.x, iy = a.y;
     const int gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
@@ -275,7 +293,7 @@ tile_sort_gather_kernel(int gx, int rows, int shard_count, int shard_index, cons
         point_list[pos] = g;
         const float4* src = reinterpret_cast<const float4*>(records + g);
         const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
-        const uint32_t kb = (__float_as_uint(b.w) & 0x00FFFFFFu) | (quadrant_mask(a, b, tile_x, tile_y) << kQuadShift);
+        const uint32_t kb = sorted_kbits(__float_as_uint(b.w), block_mask16(a, b, tile_x, tile_y));
         float4* dst = reinterpret_cast<float4*>(sorted + pos);
         dst[0] = a;
         dst[1] = make_float4(b.x, b.y, b.z, __uint_as_float(kb));
@@ -318,18 +336,18 @@ int launch_binning(const h3dgs_raster_args& a, const int32_t* radii, const float
 }
 
 int launch_tile_scan(const h3dgs_raster_args& a, const uint32_t* tile_count, uint32_t* ranges, ScanInfo* info,
-                     cudaStream_t s)
+                     uint32_t cap_entries, uint32_t cap_list, cudaStream_t s)
 {
     const int gx = (a.image_width + kTile - 1) / kTile, gy = (a.image_height + kTile - 1) / kTile;
     ProfScope prof(H3DGS_STAGE_SCAN, s);
-    tile_scan_kernel<<<1, 1024, 0, s>>>(gx * gy, tile_count, (uint2*)ranges, info);
+    tile_scan_kernel<<<1, 1024, 0, s>>>(gx * gy, tile_count, (uint2*)ranges, info, cap_entries, cap_list);
     H3_LAUNCHED("tile_scan", a.debug, s);
     return H3DGS_OK;
 }
 
 int launch_tile_binning(const h3dgs_raster_args& a, const int32_t* radii, const float* depths, const Record* records,
                         int64_t D, uint32_t max_count, uint8_t* bin, const BinLayout& bl, const uint32_t* ranges,
-                        uint32_t* tile_count, cudaStream_t s)
+                        const ScanInfo* info, uint32_t* tile_count, cudaStream_t s)
 {
     if (D == 0 || a.P == 0) return H3DGS_OK;
     const int W = a.image_width, H = a.image_height;
@@ -339,7 +357,7 @@ int launch_tile_binning(const h3dgs_raster_args& a, const int32_t* radii, const 
     uint2* pairs = (uint2*)(bin + bl.keys_unsorted);
     { ProfScope prof(H3DGS_STAGE_DUPLICATE, s);
     emit_to_tiles_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a.P, W, H, sc, si, radii, depths, records, (const uint2*)ranges,
-                                                           tile_count, pairs);
+                                                           info, tile_count, pairs);
     H3_LAUNCHED("emit_to_tiles", a.debug, s); }
     int m = 32;
     while (m < (int)max_count) m <<= 1;

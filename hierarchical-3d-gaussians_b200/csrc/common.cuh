@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "../../include/h3dgs.h"
 
 namespace h3dgs {
@@ -20,14 +21,18 @@ constexpr float kAlphaSkip = 1.0f / 255.0f;
 constexpr float kTStop = 0.0001f;
 constexpr float kWEps = 0.0000001f;
 constexpr uint32_t kKidsMask = 0xFFFFFu;
-constexpr int kClampShift = 20, kQuadShift = 24;
+constexpr int kClampShift = 20;
+// per-tile sorted record copy: kids saturate at 12 bits, the upper half holds the reach mask of the tile's
+// sixteen 4x4-pixel blocks (binning.cu::block_mask16)
+constexpr uint32_t kSortedKidsMask = 0xFFFu;
+constexpr int kBlockShift = 16;
 
 // Per-Gaussian projected record: 3 x float4 = 48 B, 16-B aligned, so a batch of
 // records is one contiguous cp.async.bulk (TMA) transfer.
 //   a = {x, y, conic.x, conic.y}
-//   b = {conic.z, opacity, t, kbits}     kbits: bits 0..19 num_node_kids, 20..22 SH clamp flags; in the
-//                                        per-tile SORTED copy also bits 24..27 = mask of the tile's four 8x8-pixel
-//                                        quadrants this entry can reach (quadrant culling, binning.cu)
+//   b = {conic.z, opacity, t, kbits}     kbits: bits 0..19 num_node_kids, 20..22 SH clamp flags; the per-tile
+//                                        SORTED copy instead holds kids in bits 0..11 and, in bits 16..31, the mask
+//                                        of the tile's sixteen 4x4-pixel blocks this entry can reach (binning.cu)
 //   c = {r, g, b, invdepth}
 struct __align__(16) Record { float4 a, b, c; };
 static_assert(sizeof(Record) == 48, "record must be 48 bytes");
@@ -46,8 +51,10 @@ struct BinLayout {
 struct ImgLayout {
     size_t final_T, n_contrib, ranges, tile_max_contrib, tile_count, scan_info, total;
 };
-// written by tile_scan_kernel, read back by the host (the one num_rendered round trip)
-struct ScanInfo { uint32_t D, max_count; };
+// written by tile_scan_kernel; read back by the host in exact mode (the one num_rendered round trip).
+// overflow: capacity mode only -- the frame does not fit (bin_capacity, sort_capacity); all ranges are
+// emptied and key emission is skipped, so every later stage is a no-op for this frame.
+struct ScanInfo { uint32_t D, max_count, overflow; };
 // largest per-tile list the shared-memory sort handles; bigger lists fall back to the global CUB sort
 constexpr int kTileSortCap = 8192;
 
@@ -98,11 +105,12 @@ extern int64_t g_launches;
 int launch_preprocess(const h3dgs_raster_args& a, int32_t* radii, float* depths, uint32_t* tiles_touched,
                       Record* records, uint32_t* tile_count, cudaStream_t s);
 int launch_tile_scan(const h3dgs_raster_args& a, const uint32_t* tile_count, uint32_t* ranges, ScanInfo* info,
-                     cudaStream_t s);
+                     uint32_t cap_entries, uint32_t cap_list, cudaStream_t s);
 int launch_tile_binning(const h3dgs_raster_args& a, const int32_t* radii, const float* depths, const Record* records,
                         int64_t D, uint32_t max_count, uint8_t* bin, const BinLayout& bl, const uint32_t* ranges,
-                        uint32_t* tile_count, cudaStream_t s);
-int launch_preprocess_color(const h3dgs_raster_args& a, const int32_t* radii, Record* records, cudaStream_t s);
+                        const ScanInfo* info, uint32_t* tile_count, cudaStream_t s);
+int launch_preprocess_color(const h3dgs_raster_args& a, const int32_t* radii, const uint32_t* tiles_touched,
+                            Record* records, cudaStream_t s);
 int launch_sh_backward(const h3dgs_raster_args& a, const int32_t* radii, const Record* records, const float* accum,
                        float* dL_dmeans3D, float* dL_dsh, cudaStream_t s);
 int launch_scan(const uint32_t* in, uint32_t* out, int n, void* temp, size_t temp_bytes, cudaStream_t s, bool debug);
@@ -123,30 +131,7 @@ int launch_preprocess_backward(const h3dgs_raster_args& a, const int32_t* radii,
                                float* dL_dcolors, float* dL_dopacities, float* dL_dscales, float* dL_drots,
                                float* dL_dcov3D, cudaStream_t s);
 
-// Hierarchy transition weight on the per-pixel blending weight (UNPINNED semantics,
-// DESIGN.md "hierarchy alpha"): a' = t a + (1-t)(1 - (1-a)^(1/k)); identity for k<=1 or t>=1.
-// One definition for forward and backward so both take identical skip decisions.
 #ifdef __CUDACC__
-// exp(x) for x <= 0 as one FMUL + MUFU.EX2 (ftz: results below 2^-126 flush to 0, far
-// below the 1/255 alpha cut).  Shared by forward and backward so both see the same alpha.
-__device__ __forceinline__ float fast_exp(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
-    return y;
-}
-
-// 1/x for x in [0.01, 2^20]: MUFU.RCP + one Newton step (no range/denormal handling needed
-// here; ~1 ulp), 3 instructions instead of the ~10 of the IEEE-rounded __frcp_rn
-__device__ __forceinline__ float fast_rcp(float x) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r * (2.0f - x * r);
-}
-__device__ __forceinline__ float fast_exp2(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 // Pixel layout of the blend kernels: CTA = 128 threads = 4 warps; warp q owns the 8x8 quadrant
 // (q & 1, q >> 1) of the 16x16 tile; lane l owns column (l & 7) and the two rows 2*(l >> 3), +1.
 __device__ __forceinline__ void quad_pixel(int tile_x, int tile_y, int warp, int lane, int& px, int& py0) {
@@ -154,34 +139,25 @@ __device__ __forceinline__ void quad_pixel(int tile_x, int tile_y, int warp, int
     py0 = tile_y * kTile + 8 * (warp >> 1) + 2 * (lane >> 3);
 }
 
-template <bool HIER>
-__device__ __forceinline__ void hier_alpha_grad(float a, float t, uint32_t kbits, float& alpha, float& dadb) {
-    alpha = a; dadb = 1.0f;
-    if (!HIER) return;
-    const uint32_t k = kbits & kKidsMask;
-    if (k <= 1u || t >= 1.0f) return;
-    // 1 - (1-a)^(1/k) = -expm1(log1p(-a)/k).  Near the 1/255 skip threshold a is small and the
-    // direct form cancels catastrophically (abs error ~2e-7 on a value ~4e-3 moves the skip
-    // decision for 100x more pixels than in flat mode), so small a uses the two series
-    // (relative error < 1e-7); larger a goes through MUFU.LG2 / MUFU.EX2.
-    const float ik = fast_rcp((float)k);
-    const float l2 = __log2f(1.0f - a);
-    const float L = -a * (1.0f + a * (0.5f + a * (0.33333334f + a * (0.25f + a * 0.2f))));
-    const float y = L * ik;
-    const float omr_series = -y * (1.0f + y * (0.5f + y * (0.16666667f + y * 0.041666668f)));
-    const float omr = a < 0.0625f ? omr_series : 1.0f - fast_exp2(l2 * ik);
-    alpha = t * a + (1.0f - t) * omr;
-    dadb = t + (1.0f - t) * ik * fast_exp2(l2 * (ik - 1.0f));
+// Group walk (render_*_kernel<..., GROUPS = true>): the same quadrant per warp, but lanes 8 g .. 8 g + 7 own the
+// 4x4-pixel block g = (g & 1, g >> 1) of it -- lane k of the group: column (k & 3), rows 2 (k >> 2), +1 -- and each
+// 8-lane group walks only the entries whose block bit is set (common.cuh kBlockShift, binning.cu::block_mask16).
+__device__ __forceinline__ void group_pixel(int tile_x, int tile_y, int warp, int lane, int& px, int& py0) {
+    const int g = lane >> 3, k = lane & 7;
+    px = tile_x * kTile + 8 * (warp & 1) + 4 * (g & 1) + (k & 3);
+    py0 = tile_y * kTile + 8 * (warp >> 1) + 4 * (g >> 1) + 2 * (k >> 2);
 }
-template <bool HIER>
-__device__ __forceinline__ float hier_alpha(float a, float t, uint32_t kbits) {
-    float alpha, dadb;
-    hier_alpha_grad<HIER>(a, t, kbits, alpha, dadb);
-    return alpha;
-}
+// H3DGS_GROUPWALK=1 selects the group-walk variants of the blend kernels (experimental: measured 27 % fewer
+// loop iterations under emulation on a scaled config #3, at 2.3x the gradient atomics; not yet timed on a GPU)
+inline bool use_group_walk() { const char* e = getenv("H3DGS_GROUPWALK"); return e && e[0] == '1'; }
+
 #endif
 
 // accum row layout (floats): 0,1 dmean2D.xy | 2,3,4 dconic | 5 dopacity | 6,7,8 dcolor | 9 dinvdepth
 constexpr int kAccum = 10;
 
 }  // namespace h3dgs
+
+#ifdef __CUDACC__
+#include "pair_math.cuh"      // packed FP32x2 arithmetic of the blend kernels
+#endif

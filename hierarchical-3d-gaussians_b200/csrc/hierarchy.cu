@@ -28,10 +28,11 @@ __device__ __forceinline__ float node_size(const float4* __restrict__ boxes, int
 
 __global__ void __launch_bounds__(256)
 mark_nodes_kernel(int N, const int* __restrict__ nodes, const float4* __restrict__ boxes, float target,
-                  const float* __restrict__ viewpoint, int* __restrict__ counts)
+                  const float* __restrict__ target_dev, const float* __restrict__ viewpoint, int* __restrict__ counts)
 {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N) return;
+    if (target_dev) target = *target_dev;
     const float vx = viewpoint[0], vy = viewpoint[1], vz = viewpoint[2];
     const int* nd = nodes + 7 * (size_t)n;
     const int depth = nd[0], parent = nd[1], cl = nd[3], cm = nd[4];
@@ -65,6 +66,21 @@ put_render_indices_kernel(int N, const int* __restrict__ nodes, const int* __res
     }
 }
 
+// transition weight of node `id` under `parent` (oracle_interpolation_weights)
+__device__ __forceinline__ float transition_weight(const float4* __restrict__ boxes, int id, int parent, float target,
+                                                   float vx, float vy, float vz)
+{
+    if (parent == -1) return 1.0f;
+    const float psize = node_size(boxes, parent, vx, vy, vz);
+    if (psize > 2.0f * target) return 1.0f;
+    const float size = node_size(boxes, id, vx, vy, vz);
+    const float start = fmaxf(0.5f * psize, size);
+    const float diff = psize - start;
+    if (diff <= 0) return 1.0f;
+    const float tdiff = fmaxf(0.0f, target - start);
+    return fmaxf(1.0f - (tdiff / diff), 0.0f);
+}
+
 __global__ void __launch_bounds__(256)
 interpolation_weights_kernel(int n, const int* __restrict__ node_indices, float target, const int* __restrict__ nodes,
                              const float4* __restrict__ boxes, float vx, float vy, float vz, float* __restrict__ ts,
@@ -74,21 +90,37 @@ interpolation_weights_kernel(int n, const int* __restrict__ node_indices, float 
     if (i >= n) return;
     const int id = node_indices[i];
     const int parent = nodes[7 * (size_t)id + 1];
-    float t;
-    if (parent == -1) t = 1.0f;
-    else {
-        const float psize = node_size(boxes, parent, vx, vy, vz);
-        if (psize > 2.0f * target) t = 1.0f;
-        else {
-            const float size = node_size(boxes, id, vx, vy, vz);
-            const float start = fmaxf(0.5f * psize, size);
-            const float diff = psize - start;
-            if (diff <= 0) t = 1.0f;
-            else { const float tdiff = fmaxf(0.0f, target - start); t = fmaxf(1.0f - (tdiff / diff), 0.0f); }
-        }
-    }
-    ts[i] = t;
+    ts[i] = transition_weight(boxes, id, parent, target, vx, vy, vz);
     kids[i] = parent == -1 ? 1 : nodes[7 * (size_t)parent + 6];
+}
+
+// Device-side cut (h3dgs_lod_cut): put_render_indices + interpolation_weights in one kernel -- the
+// emitting thread already holds the node and its parent -- plus the count for the consumer.
+__global__ void __launch_bounds__(256)
+put_cut_kernel(int N, const int* __restrict__ nodes, const float4* __restrict__ boxes, float target,
+               const float* __restrict__ target_dev, const float* __restrict__ viewpoint, const int* __restrict__ counts, const int* __restrict__ offsets,
+               int* __restrict__ render_indices, int* __restrict__ parent_indices, int* __restrict__ nodes_of_render,
+               float* __restrict__ ts, int* __restrict__ kids, int* __restrict__ total)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    if (target_dev) target = *target_dev;
+    if (n == N - 1) *total = offsets[N - 1];
+    const int count = counts[n];
+    if (count == 0) return;
+    const int off = offsets[n] - count;          // inclusive scan
+    const int* nd = nodes + 7 * (size_t)n;
+    const int parent = nd[1], start = nd[2];
+    const int pg = parent != -1 ? nodes[7 * (size_t)parent + 2] : -1;
+    const float t = transition_weight(boxes, n, parent, target, viewpoint[0], viewpoint[1], viewpoint[2]);
+    const int k = parent == -1 ? 1 : nodes[7 * (size_t)parent + 6];
+    for (int j = 0; j < count; j++) {
+        render_indices[off + j] = start + j;
+        parent_indices[off + j] = pg;
+        nodes_of_render[off + j] = n;
+        ts[off + j] = t;
+        kids[off + j] = k;
+    }
 }
 
 static size_t expand_scan_bytes(int N) {
@@ -120,7 +152,7 @@ extern "C" int h3dgs_expand_to_size(int32_t N, const int32_t* nodes, const float
     size_t temp_bytes = expand_scan_bytes(N);
     const int blocks = (N + 255) / 256;
     { ProfScope prof(H3DGS_STAGE_LOD_CUT, s);
-    mark_nodes_kernel<<<blocks, 256, 0, s>>>(N, nodes, (const float4*)boxes, target_size, viewpoint, counts);
+    mark_nodes_kernel<<<blocks, 256, 0, s>>>(N, nodes, (const float4*)boxes, target_size, nullptr, viewpoint, counts);
     H3_LAUNCHED("mark_nodes", 0, s);
     H3_CUDA(cub::DeviceScan::InclusiveSum(temp, temp_bytes, counts, offsets, N, s));
     H3_LAUNCHED("expand_scan", 0, s);
@@ -132,6 +164,34 @@ extern "C" int h3dgs_expand_to_size(int32_t N, const int32_t* nodes, const float
     H3_CUDA(cudaMemcpyAsync(pin, offsets + (N - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
     H3_CUDA(cudaStreamSynchronize(s));
     return *static_cast<const int*>(pin);
+}
+
+extern "C" int h3dgs_lod_cut(int32_t N, const int32_t* nodes, const float* boxes, float target_size,
+                             const float* target_size_dev, const float* viewpoint, int32_t* render_indices, int32_t* parent_indices,
+                             int32_t* nodes_for_render_indices, float* ts, int32_t* num_kids, int32_t* count,
+                             void* scratch, void* stream)
+{
+    if (N <= 0) { set_error("lod_cut: empty hierarchy"); return H3DGS_EINVAL; }
+    if (!nodes || !boxes || !viewpoint || !render_indices || !parent_indices || !nodes_for_render_indices || !ts ||
+        !num_kids || !count || !scratch) { set_error("lod_cut: NULL argument"); return H3DGS_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    uint8_t* base = (uint8_t*)scratch;
+    int* counts = (int*)base;
+    int* offsets = (int*)(base + align_up((size_t)N * 4));
+    void* temp = base + 2 * align_up((size_t)N * 4);
+    size_t temp_bytes = expand_scan_bytes(N);
+    const int blocks = (N + 255) / 256;
+    ProfScope prof(H3DGS_STAGE_LOD_CUT, s);
+    // rows after the cut: index -1 = "skip" for the rasterizer (the head is overwritten below)
+    H3_CUDA(cudaMemsetAsync(render_indices, 0xFF, (size_t)N * sizeof(int32_t), s));
+    mark_nodes_kernel<<<blocks, 256, 0, s>>>(N, nodes, (const float4*)boxes, target_size, target_size_dev, viewpoint, counts);
+    H3_LAUNCHED("mark_nodes", 0, s);
+    H3_CUDA(cub::DeviceScan::InclusiveSum(temp, temp_bytes, counts, offsets, N, s));
+    H3_LAUNCHED("expand_scan", 0, s);
+    put_cut_kernel<<<blocks, 256, 0, s>>>(N, nodes, (const float4*)boxes, target_size, target_size_dev, viewpoint, counts, offsets,
+                                          render_indices, parent_indices, nodes_for_render_indices, ts, num_kids, count);
+    H3_LAUNCHED("put_cut", 0, s);
+    return H3DGS_OK;
 }
 
 extern "C" int h3dgs_get_interpolation_weights(int32_t n, const int32_t* node_indices, float target_size,

@@ -1,16 +1,16 @@
 // preprocess_backward.cu -- K8 + K9 fused: per-Gaussian chain rule from the 2D-space
 // accumulators (dmean2D, dconic, dopacity, dcolor, dinvdepth) back to the inputs
 // (replaces BACKWARD::computeCov2DCUDA + BACKWARD::preprocessCUDA).  Semantics per
-// oracle/oracle.c::oracle_preprocess_backward.  The covariance chain (K8, K9c) is evaluated in
-// fp64: the published formulas contain cancellations (denom - a*c = -b^2; the rotation
-// gradient of a near-isotropic Gaussian) that cost fp32 one to two digits, and a few hundred
-// DFMA per Gaussian are free in an HBM-bound stream.  One thread per Gaussian; a pure HBM
+// oracle/oracle.c::oracle_preprocess_backward.  The covariance chain (K8, K9c) lives in
+// cov_grad.cuh: fp32 except the 2x2 screen covariance and the gradient of its inverse (~50 fp64
+// operations), which is where the published formulas cancel.  One thread per Gaussian; a pure HBM
 // stream: reads 40 B accum + 44 B params + 192 B SH, writes 248 B of gradients.
 // Every output row is written (zeros for culled Gaussians) so the caller never
 // pays a separate memset pass over the gradient tensors.  Two launches -- the fp64 covariance
 // chain (preprocess_backward_kernel) and the SH part (sh_backward_kernel) -- because fused they
 // needed 189 registers (11 % warp occupancy, latency-bound at a third of the DRAM roofline).
 #include "common.cuh"
+#include "cov_grad.cuh"
 
 namespace h3dgs {
 
@@ -78,11 +78,10 @@ preprocess_backward_kernel(int row0, int P, int deg, int M, const float* __restr
     const float mz = LERP(means3D[3 * c + 2], means3D[3 * p + 2]);
     float qsign = 1.0f;
 
-    // cov3D (recomputed: cheaper than a 24-B round trip through HBM)
-    double cov6[6];
-    double R[3][3], Mm[3][3], sc[3];
-    double qr = 1., qx = 0., qy = 0., qz = 0.;
-    if (cov3D_precomp) {
+    // cov3D (recomputed in fp32 exactly as the forward does: cheaper than a 24-B round trip through HBM)
+    float cov6[6], R[3][3], Mm[3][3], sc[3], qv[4] = {1.f, 0.f, 0.f, 0.f};
+    const bool have_sr = cov3D_precomp == nullptr;
+    if (!have_sr) {
 #pragma unroll
         for (int k = 0; k < 6; k++) cov6[k] = cov3D_precomp[6 * c + k];
     } else {
@@ -94,88 +93,18 @@ preprocess_backward_kernel(int row0, int P, int deg, int M, const float* __restr
             qq.x = LERP(qq.x, qsign * qp.x); qq.y = LERP(qq.y, qsign * qp.y);
             qq.z = LERP(qq.z, qsign * qp.z); qq.w = LERP(qq.w, qsign * qp.w);
         }
-        qr = qq.x; qx = qq.y; qy = qq.z; qz = qq.w;
-        R[0][0] = 1. - 2. * (qy * qy + qz * qz); R[0][1] = 2. * (qx * qy - qr * qz); R[0][2] = 2. * (qx * qz + qr * qy);
-        R[1][0] = 2. * (qx * qy + qr * qz); R[1][1] = 1. - 2. * (qx * qx + qz * qz); R[1][2] = 2. * (qy * qz - qr * qx);
-        R[2][0] = 2. * (qx * qz - qr * qy); R[2][1] = 2. * (qy * qz + qr * qx); R[2][2] = 1. - 2. * (qx * qx + qy * qy);
+        qv[0] = qq.x; qv[1] = qq.y; qv[2] = qq.z; qv[3] = qq.w;
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            sc[k] = (double)scale_mod * (double)LERP(scales[3 * c + k], scales[3 * p + k]);
-#pragma unroll
-            for (int j = 0; j < 3; j++) Mm[k][j] = sc[k] * R[j][k];
-        }
-        int o = 0;
-#pragma unroll
-        for (int a = 0; a < 3; a++)
-#pragma unroll
-            for (int b = a; b < 3; b++) cov6[o++] = Mm[0][a] * Mm[0][b] + Mm[1][a] * Mm[1][b] + Mm[2][a] * Mm[2][b];
+        for (int k = 0; k < 3; k++) sc[k] = scale_mod * LERP(scales[3 * c + k], scales[3 * p + k]);
+        cov3d_from_scale_quat(sc, qv, R, Mm, cov6);
     }
 
-    double dmean[3] = {0., 0., 0.};
-    double g6[6];
-    // ---- K8: conic -> cov2D -> cov3D, and mean through the Jacobian ----
-    {
-        double tx = (double)v[0] * mx + (double)v[4] * my + (double)v[8] * mz + (double)v[12];
-        double ty = (double)v[1] * mx + (double)v[5] * my + (double)v[9] * mz + (double)v[13];
-        const double tz = (double)v[2] * mx + (double)v[6] * my + (double)v[10] * mz + (double)v[14];
-        const double limx = kFovClamp * tanx, limy = kFovClamp * tany;
-        const double txtz = tx / tz, tytz = ty / tz;
-        tx = fmin(limx, fmax(-limx, txtz)) * tz;
-        ty = fmin(limy, fmax(-limy, tytz)) * tz;
-        const double x_grad_mul = (txtz < -limx || txtz > limx) ? 0. : 1.;
-        const double y_grad_mul = (tytz < -limy || tytz > limy) ? 0. : 1.;
-        const double J00 = fx / tz, J02 = -(fx * tx) / (tz * tz);
-        const double J11 = fy / tz, J12 = -(fy * ty) / (tz * tz);
-        double A[2][3];
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            A[0][c] = J00 * (double)v[4 * c + 0] + J02 * (double)v[4 * c + 2];
-            A[1][c] = J11 * (double)v[4 * c + 1] + J12 * (double)v[4 * c + 2];
-        }
-        const double V[3][3] = {{cov6[0], cov6[1], cov6[2]}, {cov6[1], cov6[3], cov6[4]}, {cov6[2], cov6[4], cov6[5]}};
-        double AV[2][3];
-#pragma unroll
-        for (int r = 0; r < 2; r++)
-#pragma unroll
-            for (int c = 0; c < 3; c++) AV[r][c] = A[r][0] * V[0][c] + A[r][1] * V[1][c] + A[r][2] * V[2][c];
-        const double a = (AV[0][0] * A[0][0] + AV[0][1] * A[0][1] + AV[0][2] * A[0][2]) + kDilation;
-        const double b = AV[0][0] * A[1][0] + AV[0][1] * A[1][1] + AV[0][2] * A[1][2];
-        const double c_ = (AV[1][0] * A[1][0] + AV[1][1] * A[1][1] + AV[1][2] * A[1][2]) + kDilation;
-        const double denom = a * c_ - b * b;
-        double dL_da = 0., dL_db = 0., dL_dc = 0.;
-        const double denom2inv = 1.0 / ((denom * denom) + 0.0000001);
-#pragma unroll
-        for (int k = 0; k < 6; k++) g6[k] = 0.;
-        if (denom2inv != 0.) {
-            dL_da = denom2inv * (-c_ * c_ * dcx + 2 * b * c_ * dcy + (denom - a * c_) * dcz);
-            dL_dc = denom2inv * (-a * a * dcz + 2 * a * b * dcy + (denom - a * c_) * dcx);
-            dL_db = denom2inv * 2 * (b * c_ * dcx - (denom + 2 * b * b) * dcy + a * b * dcz);
-            g6[0] = A[0][0] * A[0][0] * dL_da + A[0][0] * A[1][0] * dL_db + A[1][0] * A[1][0] * dL_dc;
-            g6[3] = A[0][1] * A[0][1] * dL_da + A[0][1] * A[1][1] * dL_db + A[1][1] * A[1][1] * dL_dc;
-            g6[5] = A[0][2] * A[0][2] * dL_da + A[0][2] * A[1][2] * dL_db + A[1][2] * A[1][2] * dL_dc;
-            g6[1] = 2 * A[0][0] * A[0][1] * dL_da + (A[0][0] * A[1][1] + A[0][1] * A[1][0]) * dL_db + 2 * A[1][0] * A[1][1] * dL_dc;
-            g6[2] = 2 * A[0][0] * A[0][2] * dL_da + (A[0][0] * A[1][2] + A[0][2] * A[1][0]) * dL_db + 2 * A[1][0] * A[1][2] * dL_dc;
-            g6[4] = 2 * A[0][2] * A[0][1] * dL_da + (A[0][1] * A[1][2] + A[0][2] * A[1][1]) * dL_db + 2 * A[1][1] * A[1][2] * dL_dc;
-        }
-        double dA[2][3];
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            dA[0][c] = 2 * AV[0][c] * dL_da + AV[1][c] * dL_db;
-            dA[1][c] = 2 * AV[1][c] * dL_dc + AV[0][c] * dL_db;
-        }
-        const double dJ00 = dA[0][0] * (double)v[0] + dA[0][1] * (double)v[4] + dA[0][2] * (double)v[8];
-        const double dJ02 = dA[0][0] * (double)v[2] + dA[0][1] * (double)v[6] + dA[0][2] * (double)v[10];
-        const double dJ11 = dA[1][0] * (double)v[1] + dA[1][1] * (double)v[5] + dA[1][2] * (double)v[9];
-        const double dJ12 = dA[1][0] * (double)v[2] + dA[1][1] * (double)v[6] + dA[1][2] * (double)v[10];
-        const double itz = 1. / tz, tz2 = itz * itz, tz3 = tz2 * itz;
-        const double dL_dtx = x_grad_mul * -fx * tz2 * dJ02;
-        const double dL_dty = y_grad_mul * -fy * tz2 * dJ12;
-        double dL_dtz = -fx * tz2 * dJ00 - fy * tz2 * dJ11 + (2 * fx * tx) * tz3 * dJ02 + (2 * fy * ty) * tz3 * dJ12;
-        if (use_depth) dL_dtz -= g_iv / (tz * tz);
-        dmean[0] += (double)v[0] * dL_dtx + (double)v[1] * dL_dty + (double)v[2] * dL_dtz;
-        dmean[1] += (double)v[4] * dL_dtx + (double)v[5] * dL_dty + (double)v[6] * dL_dtz;
-        dmean[2] += (double)v[8] * dL_dtx + (double)v[9] * dL_dty + (double)v[10] * dL_dtz;
-    }
+    // ---- K8 + K9c: conic -> cov2D -> cov3D -> scale / rotation, and the mean through the Jacobian
+    // (cov_grad.cuh: fp32 with the 2x2 screen covariance and the gradient of its inverse in fp64) ----
+    CovGradOut cg;
+    cov_chain_backward(v, mx, my, mz, fx, fy, tanx, tany, kFovClamp, kDilation, cov6, dcx, dcy, dcz, g_iv, use_depth != 0,
+                       have_sr, sc, qv, R, Mm, scale_mod, cg);
+    float dmean[3] = {cg.dmean[0], cg.dmean[1], cg.dmean[2]};
     // ---- K9a: screen-space mean -> 3D mean ----
     {
         const float* q = s_proj;
@@ -203,34 +132,18 @@ preprocess_backward_kernel(int row0, int P, int deg, int M, const float* __restr
 
     // ---- K9b (SH -> coefficients and view direction) lives in sh_backward_kernel ----
     if (colors_precomp && dL_dcolors) { dL_dcolors[3 * c] = g_r; dL_dcolors[3 * c + 1] = g_g; dL_dcolors[3 * c + 2] = g_b; }
-    EMIT(dL_dmeans3D, 3, 0, (float)dmean[0]); EMIT(dL_dmeans3D, 3, 1, (float)dmean[1]); EMIT(dL_dmeans3D, 3, 2, (float)dmean[2]);
+    EMIT(dL_dmeans3D, 3, 0, dmean[0]); EMIT(dL_dmeans3D, 3, 1, dmean[1]); EMIT(dL_dmeans3D, 3, 2, dmean[2]);
 
-    // ---- K9c: cov3D -> scale, rotation ----
-    if (cov3D_precomp) {
+    // ---- K9c outputs ----
+    if (!have_sr) {
         if (dL_dcov3D) {
 #pragma unroll
-            for (int k = 0; k < 6; k++) dL_dcov3D[6 * c + k] = (float)g6[k];
+            for (int k = 0; k < 6; k++) dL_dcov3D[6 * c + k] = cg.g6[k];
         }
     } else {
-        const double dS[3][3] = {{g6[0], 0.5 * g6[1], 0.5 * g6[2]}, {0.5 * g6[1], g6[3], 0.5 * g6[4]}, {0.5 * g6[2], 0.5 * g6[4], g6[5]}};
-        double dM[3][3];
 #pragma unroll
-        for (int k = 0; k < 3; k++)
-#pragma unroll
-            for (int j = 0; j < 3; j++) dM[k][j] = 2.0 * (Mm[k][0] * dS[0][j] + Mm[k][1] * dS[1][j] + Mm[k][2] * dS[2][j]);
-#pragma unroll
-        for (int k = 0; k < 3; k++)
-            EMIT(dL_dscales, 3, k, (float)((double)scale_mod * (R[0][k] * dM[k][0] + R[1][k] * dM[k][1] + R[2][k] * dM[k][2])));
-        double dR[3][3];
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-#pragma unroll
-            for (int k = 0; k < 3; k++) dR[j][k] = sc[k] * dM[k][j];
-        float4 dq;
-        dq.x = (float)(2 * qz * (dR[1][0] - dR[0][1]) + 2 * qy * (dR[0][2] - dR[2][0]) + 2 * qx * (dR[2][1] - dR[1][2]));
-        dq.y = (float)(2 * qy * (dR[0][1] + dR[1][0]) + 2 * qz * (dR[0][2] + dR[2][0]) + 2 * qr * (dR[2][1] - dR[1][2]) - 4 * qx * (dR[1][1] + dR[2][2]));
-        dq.z = (float)(2 * qx * (dR[0][1] + dR[1][0]) + 2 * qr * (dR[0][2] - dR[2][0]) + 2 * qz * (dR[1][2] + dR[2][1]) - 4 * qy * (dR[0][0] + dR[2][2]));
-        dq.w = (float)(2 * qr * (dR[1][0] - dR[0][1]) + 2 * qx * (dR[0][2] + dR[2][0]) + 2 * qy * (dR[1][2] + dR[2][1]) - 4 * qz * (dR[0][0] + dR[1][1]));
+        for (int k = 0; k < 3; k++) EMIT(dL_dscales, 3, k, cg.dscale[k]);
+        const float4 dq = make_float4(cg.dq[0], cg.dq[1], cg.dq[2], cg.dq[3]);
         if (!ridx) *reinterpret_cast<float4*>(dL_drots + 4 * i) = dq;
         else {
             atomicAdd(reinterpret_cast<float4*>(dL_drots) + c, make_float4(t * dq.x, t * dq.y, t * dq.z, t * dq.w));
@@ -238,10 +151,6 @@ preprocess_backward_kernel(int row0, int P, int deg, int M, const float* __restr
                 const float us = u * qsign;
                 atomicAdd(reinterpret_cast<float4*>(dL_drots) + p, make_float4(us * dq.x, us * dq.y, us * dq.z, us * dq.w));
             }
-        }
-        if (dL_dcov3D) {
-#pragma unroll
-            for (int k = 0; k < 6; k++) dL_dcov3D[6 * c + k] = (float)g6[k];
         }
     }
 #undef EMIT

@@ -2,7 +2,8 @@
 // Semantics per oracle/oracle.c::oracle_render_backward.
 //
 // One CTA (128 threads, two pixels each) per tile, records streamed back-to-front with the same TMA
-// double buffer as the forward; per-entry partials of a warp's 64 pixels are reduced with a
+// double buffer as the forward; the arithmetic of a thread's two pixels runs on packed FP32x2
+// instructions (one FFMA2 / FMUL2 / FADD2 serves both: the kernel is issue-bound); per-entry partials of a warp's 64 pixels are reduced with a
 // transpose-reduce (12 shuffles for 10 values) and 10 lanes issue ONE red.global.add for the warp --
 // 64x fewer atomics than the classic one-atomic-per-pixel formulation.
 #include "common.cuh"
@@ -30,79 +31,52 @@ __device__ __forceinline__ int reduce_slot(int lane) {
 __device__ __forceinline__ float xchg_add(float keep, float send, int mask) {
     return keep + __shfl_xor_sync(0xffffffffu, send, mask);
 }
+// two exchanges whose additions share one packed FADD2
+__device__ __forceinline__ f2 xchg_add2(float keep0, float send0, float keep1, float send1, int mask) {
+    return add2(pk(keep0, keep1), pk(__shfl_xor_sync(0xffffffffu, send0, mask), __shfl_xor_sync(0xffffffffu, send1, mask)));
+}
 __device__ __forceinline__ float transpose_reduce10(const float (&v)[10], int lane) {
     const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
     float a[5];
-#pragma unroll
-    for (int k = 0; k < 5; k++) a[k] = xchg_add(b4 ? v[k + 5] : v[k], b4 ? v[k] : v[k + 5], 16);
+    upk(xchg_add2(b4 ? v[5] : v[0], b4 ? v[0] : v[5], b4 ? v[6] : v[1], b4 ? v[1] : v[6], 16), a[0], a[1]);
+    upk(xchg_add2(b4 ? v[7] : v[2], b4 ? v[2] : v[7], b4 ? v[8] : v[3], b4 ? v[3] : v[8], 16), a[2], a[3]);
+    a[4] = xchg_add(b4 ? v[9] : v[4], b4 ? v[4] : v[9], 16);
     // 5 -> (3 | 2)
     float b[3];
-    b[0] = xchg_add(b3 ? a[3] : a[0], b3 ? a[0] : a[3], 8);
-    b[1] = xchg_add(b3 ? a[4] : a[1], b3 ? a[1] : a[4], 8);
+    upk(xchg_add2(b3 ? a[3] : a[0], b3 ? a[0] : a[3], b3 ? a[4] : a[1], b3 ? a[1] : a[4], 8), b[0], b[1]);
     b[2] = xchg_add(b3 ? 0.f : a[2], b3 ? a[2] : 0.f, 8);
     // 3 -> (2 | 1)
     float c[2];
-    c[0] = xchg_add(b2 ? b[2] : b[0], b2 ? b[0] : b[2], 4);
-    c[1] = xchg_add(b2 ? 0.f : b[1], b2 ? b[1] : 0.f, 4);
+    upk(xchg_add2(b2 ? b[2] : b[0], b2 ? b[0] : b[2], b2 ? 0.f : b[1], b2 ? b[1] : 0.f, 4), c[0], c[1]);
     // 2 -> (1 | 1)
     float d = xchg_add(b1 ? c[1] : c[0], b1 ? c[0] : c[1], 2);
     d += __shfl_xor_sync(0xffffffffu, d, 1);
     return d;
 }
 
+// Group walk: the same reduction over the 8 lanes of a group (xor 4, 2, 1): 5 + 3 + 2 = 10 shuffles leave the 10 totals
+// on 6 of the 8 lanes -- lanes with bit0 = 0 hold two (r0, r1), lanes with bit0 = 1 and bit1 = 0 hold one (r0).
+// group_slots(lane & 7) gives the accum columns of (r0, r1), -1 = none.
+__device__ __forceinline__ void group_slots(int k, int& s0, int& s1) {
+    const int b2 = (k >> 2) & 1, b1 = (k >> 1) & 1, b0 = k & 1, base = 5 * b2;
+    if (!b0) { s0 = base + (b1 ? 3 : 0); s1 = base + (b1 ? 4 : 1); }
+    else { s0 = b1 ? -1 : base + 2; s1 = -1; }
+}
+__device__ __forceinline__ void transpose_reduce10_g8(const float (&v)[10], int lane, float& r0, float& r1) {
+    const bool b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+    float a[5];
+    upk(xchg_add2(b2 ? v[5] : v[0], b2 ? v[0] : v[5], b2 ? v[6] : v[1], b2 ? v[1] : v[6], 4), a[0], a[1]);
+    upk(xchg_add2(b2 ? v[7] : v[2], b2 ? v[2] : v[7], b2 ? v[8] : v[3], b2 ? v[3] : v[8], 4), a[2], a[3]);
+    a[4] = xchg_add(b2 ? v[9] : v[4], b2 ? v[4] : v[9], 4);
+    float b[3];
+    upk(xchg_add2(b1 ? a[3] : a[0], b1 ? a[0] : a[3], b1 ? a[4] : a[1], b1 ? a[1] : a[4], 2), b[0], b[1]);
+    b[2] = xchg_add(b1 ? 0.f : a[2], b1 ? a[2] : 0.f, 2);
+    upk(xchg_add2(b0 ? b[2] : b[0], b0 ? b[0] : b[2], b0 ? 0.f : b[1], b0 ? b[1] : 0.f, 1), r0, r1);
+}
+
 constexpr int kBwdThreads = 128;      // two vertically adjacent pixels per thread (see render_forward.cu)
 
-// per-pixel replay state
-struct PixState {
-    float T, acc_s, last_cg, last_alpha;   // transmittance, (accum_rec . g), (last colour . g), last alpha
-};
-
-// alpha of one pixel for entry (a, bb), with exactly the forward's decisions
-template <bool HIER>
-__device__ __forceinline__ bool pixel_alpha(const float4& a, const float4& bb, uint32_t kb, float dx, float dy, bool in_list,
-                                            float& G, float& alpha, float& dadb)
-{
-    G = 0.f; alpha = 0.f; dadb = 1.f;
-    bool valid = false;
-    const float power = -0.5f * (a.z * dx * dx + bb.x * dy * dy) - a.w * dx * dy;
-    if (in_list && power <= 0.0f) {
-        G = fast_exp(power);
-        const float abase = fminf(kAlphaCap, bb.y * G);
-        hier_alpha_grad<HIER>(abase, bb.z, kb, alpha, dadb);
-        valid = alpha >= kAlphaSkip;
-    }
-    if (!valid) { G = 0.f; alpha = 0.f; }
-    return valid;
-}
-
-// One pixel's contribution of entry (a, bb, c) to the 10 per-Gaussian sums; branch-free so that an
-// invalid pixel (G = alpha = 0) adds exact zeros.
-template <bool DEPTH>
-__device__ __forceinline__ void pixel_grad(const float4& a, const float4& bb, float dx, float dy, bool valid, float G,
-                                           float alpha, float dadb, float cg, float T_final, float bg_dot, float g0,
-                                           float g1, float g2, float gd, PixState& st, float (&v)[10])
-{
-    const float rcp = fast_rcp(1.f - alpha);                   // one reciprocal serves T and the bg term
-    const float Tn = st.T * rcp;
-    const float as_n = st.last_alpha * st.last_cg + (1.f - st.last_alpha) * st.acc_s;
-    const float w = valid ? alpha * Tn : 0.f;                 // dchannel_dcolor
-    const float dL_dalpha = (cg - as_n) * Tn - (T_final * rcp) * bg_dot;
-    const float dL_dab = valid ? dL_dalpha * dadb : 0.f;
-    if (valid) { st.T = Tn; st.acc_s = as_n; st.last_cg = cg; st.last_alpha = alpha; }
-    const float dL_dG = bb.y * dL_dab;
-    const float gdx = G * dx, gdy = G * dy;
-    // constant factors (0.5 W, 0.5 H, -0.5) are applied once per Gaussian in preprocess_backward
-    v[0] += dL_dG * (-gdx * a.z - gdy * a.w);
-    v[1] += dL_dG * (-gdy * bb.x - gdx * a.w);
-    v[2] += gdx * dx * dL_dG;
-    v[3] += gdx * dy * dL_dG;
-    v[4] += gdy * dy * dL_dG;
-    v[5] += G * dL_dab;
-    v[6] += w * g0; v[7] += w * g1; v[8] += w * g2;
-    if (DEPTH) v[9] += w * gd;
-}
-
-template <bool HIER, bool DEPTH>
+template <bool HIER, bool DEPTH, bool GROUPS>
 __global__ void __launch_bounds__(kBwdThreads)
 render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, const uint2* __restrict__ ranges,
                        const Record* __restrict__ sorted, const uint32_t* __restrict__ point_list,
@@ -153,20 +127,27 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
         for (int it = 0; it < kBwdStages && it < nb; it++) issue(it);
 
     int px, py0;
-    quad_pixel(tile_x, tile_y, warp, lane, px, py0);
+    if (GROUPS) group_pixel(tile_x, tile_y, warp, lane, px, py0);
+    else quad_pixel(tile_x, tile_y, warp, lane, px, py0);
+    int gs0, gs1;
+    group_slots(lane & 7, gs0, gs1);
+    const int grp = lane >> 3;
     const int py1 = py0 + 1;
     const bool in0 = px < W && py0 < H, in1 = px < W && py1 < H;
-    const float fpx = (float)px, fpy0 = (float)py0, fpy1 = (float)py1;
+    const float fpx = (float)px;
+    const f2 nfpy = pk(-(float)py0, -(float)py1);
     const size_t pix0 = (size_t)py0 * W + px, pix1 = (size_t)py1 * W + px, plane = (size_t)H * W;
     const float Tf0 = in0 ? final_T[pix0] : 0.f, Tf1 = in1 ? final_T[pix1] : 0.f;
-    PixState st0 = {Tf0, 0.f, 0.f, 0.f}, st1 = {Tf1, 0.f, 0.f, 0.f};
+    const f2 Tf = pk(Tf0, Tf1);
+    PairState ps = {Tf, bc(0.f)};
     const int last0 = in0 ? (int)n_contrib[pix0] : 0, last1 = in1 ? (int)n_contrib[pix1] : 0;
     float ga0 = 0.f, ga1 = 0.f, ga2 = 0.f, gad = 0.f, gb0 = 0.f, gb1 = 0.f, gb2 = 0.f, gbd = 0.f;
     if (in0) { ga0 = dL_dcolor[pix0]; ga1 = dL_dcolor[plane + pix0]; ga2 = dL_dcolor[2 * plane + pix0]; if (DEPTH) gad = dL_dinvdepth[pix0]; }
     if (in1) { gb0 = dL_dcolor[pix1]; gb1 = dL_dcolor[plane + pix1]; gb2 = dL_dcolor[2 * plane + pix1]; if (DEPTH) gbd = dL_dinvdepth[pix1]; }
-    const float bgd0 = bg[0] * ga0 + bg[1] * ga1 + bg[2] * ga2, bgd1 = bg[0] * gb0 + bg[1] * gb1 + bg[2] * gb2;
+    const f2 g0 = pk(ga0, gb0), g1 = pk(ga1, gb1), g2 = pk(ga2, gb2), gd = pk(gad, gbd);
+    const f2 neg_bgd = pk(-(bg[0] * ga0 + bg[1] * ga1 + bg[2] * ga2), -(bg[0] * gb0 + bg[1] * gb1 + bg[2] * gb2));
     const int wlast = (int)__reduce_max_sync(0xffffffffu, (unsigned)max(last0, last1));   // nothing in this quadrant beyond it
-    const uint32_t qbit = 1u << (kQuadShift + warp);
+    const int qsel = kBlockShift + 4 * warp;                // this warp's four block bits in the entries' reach mask
 
     for (int it = 0; it < nb; it++) {
         const int st = it % kBwdStages, b = nb - 1 - it;
@@ -177,32 +158,62 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
         // this warp's quadrant at all (see render_forward.cu)
         for (int j0 = (cnt - 1) & ~31; j0 >= 0; j0 -= 32) {
             const int jl = j0 + lane;
-            const bool hit = jl < cnt && (b * kBwdBatch + jl) < wlast && (__float_as_uint(rec[jl].b.w) & qbit) != 0u;
-            uint32_t m = __ballot_sync(0xffffffffu, hit);
-            while (m) {
-                const int top = 31 - __clz(m);
-                m &= ~(1u << top);
+            const uint32_t nib = (jl < cnt && (b * kBwdBatch + jl) < wlast) ? (__float_as_uint(rec[jl].b.w) >> qsel) & 0xFu : 0u;
+            uint32_t m;
+            if (GROUPS) {
+                // one survivor list per 8-lane group (see render_forward.cu)
+                const uint32_t m0 = __ballot_sync(0xffffffffu, nib & 1u), m1 = __ballot_sync(0xffffffffu, nib & 2u);
+                const uint32_t m2 = __ballot_sync(0xffffffffu, nib & 4u), m3 = __ballot_sync(0xffffffffu, nib & 8u);
+                m = grp == 0 ? m0 : grp == 1 ? m1 : grp == 2 ? m2 : m3;
+            } else m = __ballot_sync(0xffffffffu, nib != 0u);
+            while (GROUPS ? __any_sync(0xffffffffu, m != 0u) : (m != 0u)) {
+                const bool has = !GROUPS || m != 0u;
+                const int top = has ? 31 - __clz(m) : 0;
+                m &= ~((has ? 1u : 0u) << top);
                 const int j = j0 + top;
                 const int e = b * kBwdBatch + j;              // 0-based list position; contributor number e+1
                 const float4 a = rec[j].a;
                 const float4 bb = rec[j].b;
+                const uint32_t gid = s_id[st][j];             // loaded with the record: same uniform address arithmetic
                 const uint32_t kb = __float_as_uint(bb.w);
-                const float dx = a.x - fpx, dy0 = a.y - fpy0, dy1 = a.y - fpy1;
-                float G0, al0, dd0, G1, al1, dd1;
-                const bool v0 = pixel_alpha<HIER>(a, bb, kb, dx, dy0, e < last0, G0, al0, dd0);
-                const bool v1 = pixel_alpha<HIER>(a, bb, kb, dx, dy1, e < last1, G1, al1, dd1);
+                const float dx = a.x - fpx;
+                // alpha of the two pixels with exactly the forward's arithmetic and decisions
+                f2 d, G, al, dadb = bc(1.0f);                // dadb is only read with HIER
+                const f2 pw = pair_power(a, bb, dx, nfpy, d);
+                pair_gauss(pw, bb.y, G, al);
+                float pw0, pw1, al0, al1;
+                upk(pw, pw0, pw1); upk(al, al0, al1);
+                // the hierarchy weight only lowers alpha (1 - (1-a)^(1/k) <= a), so an entry that no pixel of
+                // the warp takes at its base alpha is skipped before that arithmetic
+                bool v0 = has && e < last0 && pw0 <= 0.0f && al0 >= kAlphaSkip;
+                bool v1 = has && e < last1 && pw1 <= 0.0f && al1 >= kAlphaSkip;
                 if (!__any_sync(0xffffffffu, v0 || v1)) continue;            // warp-uniform
+                if (HIER) {
+                    pair_hier_alpha<HIER, true>(al, bb.z, kb & kSortedKidsMask, al, dadb);
+                    upk(al, al0, al1);
+                    v0 = v0 && al0 >= kAlphaSkip;
+                    v1 = v1 && al1 >= kAlphaSkip;
+                }
+                G = sel2(v0, v1, G, bc(0.f));
+                al = sel2(v0, v1, al, bc(0.f));
                 const float4 c = rec[j].c;
-                float cg0 = c.x * ga0 + c.y * ga1 + c.z * ga2, cg1 = c.x * gb0 + c.y * gb1 + c.z * gb2;
-                if (DEPTH) { cg0 += c.w * gad; cg1 += c.w * gbd; }
+                f2 cg = fma2(bc(c.z), g2, fma2(bc(c.y), g1, mul2(bc(c.x), g0)));
+                if (DEPTH) cg = fma2(bc(c.w), gd, cg);
                 float v[10];
-#pragma unroll
-                for (int k = 0; k < 10; k++) v[k] = 0.f;
-                pixel_grad<DEPTH>(a, bb, dx, dy0, v0, G0, al0, dd0, cg0, Tf0, bgd0, ga0, ga1, ga2, gad, st0, v);
-                pixel_grad<DEPTH>(a, bb, dx, dy1, v1, G1, al1, dd1, cg1, Tf1, bgd1, gb0, gb1, gb2, gbd, st1, v);
-                const float total = transpose_reduce10(v, lane);
-                if (slot >= 0 && (DEPTH || slot < 9))
-                    atomicAdd(accum + (size_t)s_id[st][j] * kAccum + slot, total);
+                pair_grad<HIER, DEPTH>(a, bb, dx, d, G, al, dadb, cg, Tf, neg_bgd, g0, g1, g2, gd, ps, v);
+                if (GROUPS) {
+                    // every group reduces its own entry over its 8 lanes; groups without a taker stay silent
+                    const bool taker = ((__ballot_sync(0xffffffffu, v0 || v1) >> (8 * grp)) & 0xFFu) != 0u;
+                    float r0, r1;
+                    transpose_reduce10_g8(v, lane, r0, r1);
+                    float* row = accum + (size_t)gid * kAccum;
+                    if (taker && gs0 >= 0 && (DEPTH || gs0 < 9)) atomicAdd(row + gs0, r0);
+                    if (taker && gs1 >= 0 && (DEPTH || gs1 < 9)) atomicAdd(row + gs1, r1);
+                } else {
+                    const float total = transpose_reduce10(v, lane);
+                    if (slot >= 0 && (DEPTH || slot < 9))
+                        atomicAdd(accum + (size_t)gid * kAccum + slot, total);
+                }
             }
         }
         __syncthreads();                      // every thread is done with stage st (records and ids)
@@ -227,12 +238,15 @@ int launch_render_backward(const h3dgs_raster_args& a, const uint32_t* ranges, c
     const bool depth = a.do_depth != 0 && dL_dinvdepth != nullptr;
     const dim3 grid(gx * rows), block(kBwdThreads);
     ProfScope prof(H3DGS_STAGE_RENDER_BWD, s);
-#define LAUNCH(HI, DE)                                                                                          \
-    render_backward_kernel<HI, DE><<<grid, block, 0, s>>>(W, H, gx, sc, si, (const uint2*)ranges, sorted_records, \
-                                                          point_list, a.bg, final_T, n_contrib, tile_max_contrib, \
-                                                          dL_dcolor, dL_dinvdepth, accum)
-    if (hier) { if (depth) LAUNCH(true, true); else LAUNCH(true, false); }
-    else      { if (depth) LAUNCH(false, true); else LAUNCH(false, false); }
+    const bool groups = use_group_walk();
+#define LAUNCH(HI, DE, GR)                                                                                          \
+    render_backward_kernel<HI, DE, GR><<<grid, block, 0, s>>>(W, H, gx, sc, si, (const uint2*)ranges, sorted_records, \
+                                                              point_list, a.bg, final_T, n_contrib, tile_max_contrib, \
+                                                              dL_dcolor, dL_dinvdepth, accum)
+#define LAUNCH2(HI, DE) do { if (groups) LAUNCH(HI, DE, true); else LAUNCH(HI, DE, false); } while (0)
+    if (hier) { if (depth) LAUNCH2(true, true); else LAUNCH2(true, false); }
+    else      { if (depth) LAUNCH2(false, true); else LAUNCH2(false, false); }
+#undef LAUNCH2
 #undef LAUNCH
     H3_LAUNCHED("render_backward", a.debug, s);
     return H3DGS_OK;

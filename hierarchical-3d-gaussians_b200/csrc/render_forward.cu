@@ -19,10 +19,11 @@ constexpr int kFwdStages = 2;
 // Two vertically adjacent pixels per thread: CTA = 128 threads = 4 warps, warp q owns one 8x8-pixel
 // quadrant of the tile (common.cuh::quad_pixel).
 // The entry's record, its dx terms, the survivor loop and (in backward) the warp reduction are
-// shared by the two pixels.
+// shared by the two pixels, and the per-pixel arithmetic of the pair runs on packed FP32x2
+// instructions (FFMA2 / FMUL2 / FADD2): the kernel is issue-bound, one instruction serves both pixels.
 constexpr int kFwdThreads = 128;
 
-template <bool HIER, bool DEPTH>
+template <bool HIER, bool DEPTH, bool GROUPS>
 __global__ void __launch_bounds__(kFwdThreads)
 render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, const uint2* __restrict__ ranges,
                       const Record* __restrict__ sorted, const float* __restrict__ bg, float* __restrict__ out_color,
@@ -59,15 +60,19 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
     issued = min(kFwdStages, nb);
 
     int px, py0;
-    quad_pixel(tile_x, tile_y, warp, lane, px, py0);
+    if (GROUPS) group_pixel(tile_x, tile_y, warp, lane, px, py0);
+    else quad_pixel(tile_x, tile_y, warp, lane, px, py0);
     const int py1 = py0 + 1;
     const bool in0 = px < W && py0 < H, in1 = px < W && py1 < H;
-    const float fpx = (float)px, fpy0 = (float)py0, fpy1 = (float)py1;
+    const float fpx = (float)px;
+    const f2 nfpy = pk(-(float)py0, -(float)py1);
     bool done0 = !in0, done1 = !in1;
-    float T0 = 1.0f, T1 = 1.0f;
+    // packed per-pixel state {pixel 0, pixel 1} (common.cuh "packed FP32 pairs")
+    f2 T = bc(1.0f);
     float Ca0 = 0.f, Ca1 = 0.f, Ca2 = 0.f, Cb0 = 0.f, Cb1 = 0.f, Cb2 = 0.f, inv0 = 0.f, inv1 = 0.f;
     uint32_t last0 = 0, last1 = 0;
-    const uint32_t qbit = 1u << (kQuadShift + warp);        // this warp's quadrant in the entries' reach mask
+    const int qsel = kBlockShift + 4 * warp;                // this warp's four block bits in the entries' reach mask
+    const int grp = lane >> 3;
 
     int waited = 0;
     for (int b = 0; b < nb; b++) {
@@ -77,53 +82,45 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
         const int cnt = min(kFwdBatch, n - b * kFwdBatch);
         // Per group of 32 entries each lane tests ONE entry against this warp's quadrant and a ballot
         // compacts the survivors, so culled entries cost nothing per pixel.  The survivor loop is
-        // warp-uniform (same mask in every lane) and its body is straight-line + short reconvergent
-        // `if`s: a per-thread `continue`/`break` here leaves the warp split into fragments that each
-        // re-walk the list (measured: 18x the instructions).  A warp leaves the batch only when all of
-        // its 64 pixels are done.
+        // warp-uniform (same mask in every lane) and its body is straight-line: a per-thread
+        // `continue`/`break` here leaves the warp split into fragments that each re-walk the list
+        // (measured: 18x the instructions).  A pixel that does not take an entry adds w = 0.
+        // A warp leaves the batch only when all of its 64 pixels are done.
         {
             const Record* rec = &s_rec[st][0];
             const uint32_t base = (uint32_t)(b * kFwdBatch);
             for (int j0 = 0; j0 < cnt; j0 += 32) {
                 if (__all_sync(0xffffffffu, done0 && done1)) break;
                 const int jl = j0 + lane;
-                const bool hit = jl < cnt && (__float_as_uint(rec[jl].b.w) & qbit) != 0u;
-                uint32_t m = __ballot_sync(0xffffffffu, hit);
-                while (m) {
-                    const int j = j0 + __ffs(m) - 1;
+                const uint32_t nib = jl < cnt ? (__float_as_uint(rec[jl].b.w) >> qsel) & 0xFu : 0u;
+                uint32_t m;
+                if (GROUPS) {
+                    // one survivor list per 8-lane group: the entries that reach ITS 4x4 block
+                    const uint32_t m0 = __ballot_sync(0xffffffffu, nib & 1u), m1 = __ballot_sync(0xffffffffu, nib & 2u);
+                    const uint32_t m2 = __ballot_sync(0xffffffffu, nib & 4u), m3 = __ballot_sync(0xffffffffu, nib & 8u);
+                    m = grp == 0 ? m0 : grp == 1 ? m1 : grp == 2 ? m2 : m3;
+                } else m = __ballot_sync(0xffffffffu, nib != 0u);
+                // GROUPS: the four groups advance in lockstep, each through its own list, until the longest is done
+                while (GROUPS ? __any_sync(0xffffffffu, m != 0u) : (m != 0u)) {
+                    const bool has = !GROUPS || m != 0u;
+                    const int j = j0 + (has ? __ffs(m) - 1 : 0);
                     m &= m - 1;
                     const float4 a = rec[j].a;
                     const float4 bb = rec[j].b;
+                    const float4 c = rec[j].c;
                     const uint32_t kb = __float_as_uint(bb.w);
-                    const float dx = a.x - fpx, dy0 = a.y - fpy0, dy1 = a.y - fpy1;
-                    const float qx = a.z * dx * dx, qxy = a.w * dx;
-                    const float pw0 = -0.5f * (qx + bb.x * dy0 * dy0) - qxy * dy0;
-                    const float pw1 = -0.5f * (qx + bb.x * dy1 * dy1) - qxy * dy1;
-                    float al0 = fminf(kAlphaCap, bb.y * fast_exp(pw0));
-                    float al1 = fminf(kAlphaCap, bb.y * fast_exp(pw1));
-                    al0 = hier_alpha<HIER>(al0, bb.z, kb);
-                    al1 = hier_alpha<HIER>(al1, bb.z, kb);
-                    const float tT0 = T0 * (1.0f - al0), tT1 = T1 * (1.0f - al1);
-                    bool v0 = !done0 && pw0 <= 0.0f && al0 >= kAlphaSkip;
-                    bool v1 = !done1 && pw1 <= 0.0f && al1 >= kAlphaSkip;
-                    if (v0 && tT0 < kTStop) { done0 = true; v0 = false; }
-                    if (v1 && tT1 < kTStop) { done1 = true; v1 = false; }
-                    if (v0 || v1) {
-                        const float4 c = rec[j].c;
-                        const uint32_t idx = base + (uint32_t)j + 1u;
-                        if (v0) {
-                            const float w = al0 * T0;
-                            Ca0 += c.x * w; Ca1 += c.y * w; Ca2 += c.z * w;
-                            if (DEPTH) inv0 += c.w * w;
-                            T0 = tT0; last0 = idx;
-                        }
-                        if (v1) {
-                            const float w = al1 * T1;
-                            Cb0 += c.x * w; Cb1 += c.y * w; Cb2 += c.z * w;
-                            if (DEPTH) inv1 += c.w * w;
-                            T1 = tT1; last1 = idx;
-                        }
-                    }
+                    f2 d, G, al, unused;
+                    const f2 pw = pair_power(a, bb, a.x - fpx, nfpy, d);
+                    pair_gauss(pw, bb.y, G, al);
+                    pair_hier_alpha<HIER, false>(al, bb.z, kb & kSortedKidsMask, al, unused);
+                    bool v0, v1;
+                    const f2 w = pair_blend(pw, al, T, done0, done1, v0, v1, has);
+                    upk(fma2(bc(c.x), w, pk(Ca0, Cb0)), Ca0, Cb0);
+                    upk(fma2(bc(c.y), w, pk(Ca1, Cb1)), Ca1, Cb1);
+                    upk(fma2(bc(c.z), w, pk(Ca2, Cb2)), Ca2, Cb2);
+                    if (DEPTH) upk(fma2(bc(c.w), w, pk(inv0, inv1)), inv0, inv1);
+                    const uint32_t idx = base + (uint32_t)j + 1u;
+                    last0 = v0 ? idx : last0; last1 = v1 ? idx : last1;
                 }
             }
         }
@@ -163,8 +160,8 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
             if (DEPTH) out_invdepth[pix] = invd;
         }
     };
-    store(in0, py0, T0, Ca0, Ca1, Ca2, inv0, last0);
-    store(in1, py1, T1, Cb0, Cb1, Cb2, inv1, last1);
+    store(in0, py0, lo(T), Ca0, Ca1, Ca2, inv0, last0);
+    store(in1, py1, hi(T), Cb0, Cb1, Cb2, inv1, last1);
     const uint32_t wmax = __reduce_max_sync(0xffffffffu, max(last0, last1));
     if (lane == 0) atomicMax(&s_max, wmax);
     __syncthreads();
@@ -184,12 +181,15 @@ int launch_render_forward(const h3dgs_raster_args& a, const uint32_t* ranges, co
     const bool depth = a.do_depth != 0;
     const dim3 grid(gx * rows), block(kFwdThreads);
     ProfScope prof(H3DGS_STAGE_RENDER_FWD, s);
-#define LAUNCH(HI, DE)                                                                                         \
-    render_forward_kernel<HI, DE><<<grid, block, 0, s>>>(W, H, gx, sc, si, (const uint2*)ranges, sorted_records, \
-                                                         a.bg, out_color, out_invdepth, final_T, n_contrib,      \
-                                                         tile_max_contrib)
-    if (hier) { if (depth) LAUNCH(true, true); else LAUNCH(true, false); }
-    else      { if (depth) LAUNCH(false, true); else LAUNCH(false, false); }
+    const bool groups = use_group_walk();
+#define LAUNCH(HI, DE, GR)                                                                                         \
+    render_forward_kernel<HI, DE, GR><<<grid, block, 0, s>>>(W, H, gx, sc, si, (const uint2*)ranges, sorted_records, \
+                                                             a.bg, out_color, out_invdepth, final_T, n_contrib,      \
+                                                             tile_max_contrib)
+#define LAUNCH2(HI, DE) do { if (groups) LAUNCH(HI, DE, true); else LAUNCH(HI, DE, false); } while (0)
+    if (hier) { if (depth) LAUNCH2(true, true); else LAUNCH2(true, false); }
+    else      { if (depth) LAUNCH2(false, true); else LAUNCH2(false, false); }
+#undef LAUNCH2
 #undef LAUNCH
     H3_LAUNCHED("render_forward", a.debug, s);
     return H3DGS_OK;

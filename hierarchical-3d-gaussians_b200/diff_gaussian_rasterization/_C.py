@@ -21,7 +21,7 @@ def last_num_rendered():
 
 
 def _on_device(t):
-    """the library takes device pointers (the CPU suite patches this to drive an emulation build of the kernels)"""
+    """the library takes device pointers (the CPU suite patches this to drive an emulation build)"""
     return t.is_cuda
 
 
@@ -105,8 +105,10 @@ def _prep_inputs(means3D, sh, colors_precomp, opacities, scales, rotations, cov3
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp,
                         viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height, image_width, sh, degree, campos,
                         prefiltered, debug, render_indices=None, parent_indices=None, interpolation_weights=None,
-                        num_node_kids=None, do_depth=False, shard=(1, 0)):
-    """-> (num_rendered, color[3,H,W], radii[P] i32, geomBuffer, binningBuffer, imgBuffer, invdepth[1,H,W])"""
+                        num_node_kids=None, do_depth=False, shard=(1, 0), grad_rows=(0, 0)):
+    """-> (num_rendered, color[3,H,W], radii[P] i32, geomBuffer, binningBuffer, imgBuffer, invdepth[1,H,W])
+    grad_rows: sharded frames only -- the rendered rows whose gradients this rank will finish (lets the
+    forward skip the SH colour of Gaussians no other stage of this rank reads)."""
     L = _lib.lib()
     (P, means3D, sh, colors, opacity, scales, rotations, cov3D_precomp, background, viewmatrix, projmatrix, campos,
      ts, kids, ridx, pidx) = _prep_inputs(means3D, sh, colors, opacity, scales, rotations, cov3D_precomp, background,
@@ -116,7 +118,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     H, W = int(image_height), int(image_width)
     a = _make_args(P, means3D, sh, colors, opacity, scales, rotations, cov3D_precomp, background, viewmatrix, projmatrix,
                    campos, tan_fovx, tan_fovy, H, W, degree, scale_modifier, prefiltered, debug, ts, kids, do_depth, shard,
-                   ridx, pidx, 0 if ridx is None else means3D.shape[0])
+                   ridx, pidx, 0 if ridx is None else means3D.shape[0], grad_rows)
     if shard[0] > 1:      # packed shard layout [owned tile rows][3][16][W]
         gy = (H + 15) // 16
         rows = (gy + shard[0] - 1 - shard[1]) // shard[0]

@@ -11,7 +11,7 @@ _scratch = {}
 
 
 def _on_device(t):
-    """the library takes device pointers (the CPU suite patches this to drive an emulation build of the kernels)"""
+    """the library takes device pointers (the CPU suite patches this to drive an emulation build)"""
     return t.is_cuda
 
 

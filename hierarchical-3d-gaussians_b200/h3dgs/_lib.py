@@ -14,6 +14,7 @@ ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int, C.c_size_t)
 EXPORTS = [
     "h3dgs_rasterize_forward", "h3dgs_rasterize_backward", "h3dgs_backward_scratch_bytes", "h3dgs_mark_visible",
     "h3dgs_state_layout", "h3dgs_expand_to_size", "h3dgs_expand_scratch_bytes", "h3dgs_get_interpolation_weights",
+    "h3dgs_lod_cut",
     "h3dgs_last_error", "h3dgs_version", "h3dgs_launch_count",
     "h3dgs_profile_enable", "h3dgs_profile_reset", "h3dgs_profile_read", "h3dgs_stage_name",
     "h3dgs_l1_ssim_forward", "h3dgs_l1_ssim_backward", "h3dgs_sparse_adam",
@@ -34,27 +35,22 @@ class RasterArgs(C.Structure):
         ("render_indices", C.c_void_p), ("parent_indices", C.c_void_p), ("num_source", C.c_int32),
         ("shard_count", C.c_int32), ("shard_index", C.c_int32),
         ("grad_row_begin", C.c_int32), ("grad_row_end", C.c_int32),
+        ("bin_capacity", C.c_int64), ("sort_capacity", C.c_int32),
     ]
 
 
 class StateView(C.Structure):
     """struct h3dgs_state_view"""
     _fields_ = [(n, C.c_void_p) for n in ("depths", "tiles_touched", "point_offsets", "records", "keys_sorted",
-                                          "point_list", "ranges", "final_T", "n_contrib")]
+                                          "point_list", "ranges", "final_T", "n_contrib", "scan_info")]
 
 
 _lib = None
 
 
-def lib():
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python hierarchical-3d-gaussians_b200/build.py` "
-            "(nvcc, sm_100a). There is no CPU fallback for this path.")
-    l = C.CDLL(LIB_PATH)
+def bind(l):
+    """ctypes prototypes of include/h3dgs.h on a loaded library (libh3dgs.so; the test suite also binds its
+    CPU emulation build of the same sources)."""
     l.h3dgs_last_error.restype = C.c_char_p
     l.h3dgs_launch_count.restype = C.c_int64
     l.h3dgs_backward_scratch_bytes.restype = C.c_size_t
@@ -78,15 +74,30 @@ def lib():
     l.h3dgs_get_interpolation_weights.restype = C.c_int
     l.h3dgs_get_interpolation_weights.argtypes = [C.c_int32, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p] + \
         [C.c_float] * 6 + [C.c_void_p, C.c_void_p, C.c_void_p]
-    l.h3dgs_l1_ssim_forward.restype = C.c_int
-    l.h3dgs_l1_ssim_forward.argtypes = [C.c_int32] * 3 + [C.c_void_p] * 5
-    l.h3dgs_l1_ssim_backward.restype = C.c_int
-    l.h3dgs_l1_ssim_backward.argtypes = [C.c_int32] * 3 + [C.c_void_p] * 6
-    l.h3dgs_sparse_adam.restype = C.c_int
-    l.h3dgs_sparse_adam.argtypes = [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                    C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_void_p]
+    l.h3dgs_lod_cut.restype = C.c_int
+    l.h3dgs_lod_cut.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_float] + [C.c_void_p] * 10
+    if hasattr(l, "h3dgs_l1_ssim_forward"):      # loss / optimizer kernels (absent from the emulation build)
+        l.h3dgs_l1_ssim_forward.restype = C.c_int
+        l.h3dgs_l1_ssim_forward.argtypes = [C.c_int32] * 3 + [C.c_void_p] * 5
+        l.h3dgs_l1_ssim_backward.restype = C.c_int
+        l.h3dgs_l1_ssim_backward.argtypes = [C.c_int32] * 3 + [C.c_void_p] * 6
+        l.h3dgs_sparse_adam.restype = C.c_int
+        l.h3dgs_sparse_adam.argtypes = [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_void_p]
     l.h3dgs_profile_read.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     l.h3dgs_stage_name.restype = C.c_char_p
+    return l
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python hierarchical-3d-gaussians_b200/build.py` "
+            "(nvcc, sm_100a). There is no CPU fallback for this path.")
+    l = bind(C.CDLL(LIB_PATH))
     _lib = l
     return l
 

@@ -101,7 +101,8 @@ class _ShardedRasterize(torch.autograd.Function):
         n, packed, radii, gb, bb, ib, _ = _C.rasterize_gaussians(
             rs.bg, means3D, None, opacities, scales, rotations, rs.scale_modifier, None, rs.viewmatrix, rs.projmatrix,
             rs.tanfovx, rs.tanfovy, H, W, shs, rs.sh_degree, rs.campos, rs.prefiltered, rs.debug, rs.render_indices,
-            rs.parent_indices, rs.interpolation_weights, rs.num_node_kids, False, shard=(world, rank))
+            rs.parent_indices, rs.interpolation_weights, rs.num_node_kids, False, shard=(world, rank),
+            grad_rows=row_block(rs.render_indices.numel() if rs.render_indices.numel() else means3D.shape[0], world, rank))
         image = gather_image(packed, H, W, world, group)
         ctx.rs, ctx.n, ctx.shard, ctx.group = rs, n, (world, rank), group
         ctx.save_for_backward(means3D, shs, opacities, scales, rotations, radii, gb, bb, ib)

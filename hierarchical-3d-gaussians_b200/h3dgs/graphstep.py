@@ -1,0 +1,253 @@
+"""Sync-free training-style step (hierarchy scenes), replayed from two CUDA graphs.
+
+The step of h3dgs.pipeline.l1_step has two host round trips that the reference API forces --
+the Python int returned by expand_to_size (train_post.py:91-99) and num_rendered, which sizes
+the binning buffer -- plus ~20 kernel launches issued from Python.  On one GPU they hide behind
+3 ms of kernels; with the frame sharded over 8 GPUs the kernels take 0.8 ms and the host becomes
+the critical path.  Here nothing returns to the host inside the step:
+
+  * h3dgs_lod_cut leaves the cut size on the device and marks the rows after the cut with index -1;
+    the rasterizer is handed P = row_capacity rows and skips the marked ones;
+  * capacity mode (h3dgs_raster_args.bin_capacity / sort_capacity) sizes the binning state from a
+    capacity learned on the first frames instead of from num_rendered;
+  * a frame that does not fit (cut > row_capacity, D > bin_capacity, a tile list > sort_capacity)
+    raises a device flag, renders the background only and contributes zero gradients; status()
+    reports it and the caller re-runs that frame through the exact path (pipeline.l1_step).
+
+With every size static the step is captured once: graph A = LOD cut + forward (+ the all-gather of
+the image slabs when sharded), graph B = L1 loss + its gradient + backward (+ the reduce-scatter of
+the [P,10] sums).  The split lets the 25 MB target upload of the end-to-end loop overlap graph A.
+
+The arithmetic is the one of the exact path: same kernels, same order, so images and gradients are
+bit-identical to pipeline.l1_step(fused=True) whenever the frame fits.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from . import dist as hdist
+
+
+def _ptr(t):
+    return None if (t is None or t.numel() == 0) else t.data_ptr()
+
+
+class GraphedStep:
+    """scene: pipeline.Scene with a hierarchy.  The camera-independent sizes (W, H, tanfov) are fixed per
+    instance (launch constants inside the graphs); camera, target and LOD threshold are device-resident
+    inputs that change between replays (set_camera, upload_target / step(gt=), set_threshold)."""
+
+    def __init__(self, scene, W, H, tanfovx, tanfovy, bg, threshold, sh_degree=3, row_capacity=None,
+                 bin_capacity=1 << 22, sort_capacity=4096, world=1, rank=0, group=None, capture=True):
+        if not scene.hier:
+            raise ValueError("GraphedStep drives the hierarchy path (LOD cut + fused gather/lerp)")
+        self.L = _lib.lib()
+        self.scene, self.W, self.H = scene, int(W), int(H)
+        self.threshold, self.sh_degree = float(threshold), int(sh_degree)
+        self.world, self.rank, self.group = int(world), int(rank), group
+        dev = scene.means3D.device
+        self.dev = dev
+        N = scene.means3D.shape[0]                     # rows of the parameter arrays (hierarchy + skybox)
+        self.N = N
+        self.N_nodes = scene.nodes.shape[0]
+        self.S = scene.skybox_points
+        self.P = int(row_capacity) if row_capacity else N
+        if not (0 < self.P <= N):
+            raise ValueError(f"row_capacity must be in (0, {N}]")
+        self.bin_capacity, self.sort_capacity = int(bin_capacity), int(sort_capacity)
+        f = lambda *s: torch.zeros(s, dtype=torch.float32, device=dev)
+        # static inputs
+        self.view, self.proj, self.campos = f(16), f(16), f(3)
+        self.bg = bg.to(dev).float().contiguous()
+        self.gt = f(3, H, W)
+        self.threshold_dev = torch.full((1,), self.threshold, dtype=torch.float32, device=dev)   # read by the cut kernels
+        # static outputs
+        self.count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.radii = torch.zeros(self.P, dtype=torch.int32, device=dev)
+        if world > 1:
+            rows = hdist.owned_rows(H, world, rank)
+            self.rpr = hdist.rows_per_rank(H, world)
+            self.slab = f(self.rpr, 3, 16, W)           # own packed slab (padded to the common slab height)
+            self.slabs = f(world * self.rpr, 3, 16, W)
+            self.rows = rows
+        else:
+            self.image = f(3, H, W)
+        self.dcolor = f(3, H, W)
+        self.status_dev = torch.zeros(6, dtype=torch.float64, device=dev)
+        M = scene.shs.shape[1]
+        self.grads = dict(means3D=f(N, 3), shs=f(N, M, 3), opacities=f(N, 1), scales=f(N, 3), rotations=f(N, 4))
+        self.d_means2D = f(self.P, 3)
+        chunk = (self.P + world - 1) // world
+        self.accum = torch.zeros(max(world * chunk, 1) * 10, dtype=torch.float32, device=dev)
+        self.lod_scratch = torch.empty(int(self.L.h3dgs_expand_scratch_bytes(self.N_nodes)), dtype=torch.uint8, device=dev)
+        self.sky_arange = torch.arange(self.S, dtype=torch.int64, device=dev)
+        self._bufs = [None, None, None]
+        self._alloc_cb = _lib.ALLOC_FN(self._alloc)     # keep the callback object alive
+        self.args = self._make_args(tanfovx, tanfovy)
+        self._scan_info = None
+        self.graph_a = self.graph_b = None
+        self.launches_per_step = 0
+        self._done = torch.cuda.Event()                 # recorded after part B: self.gt may be overwritten
+        self._done.record(torch.cuda.current_stream(dev))
+        if capture:
+            self.capture()
+
+    # ---- C-ABI plumbing -------------------------------------------------------------------
+    def _alloc(self, _user, which, nbytes):
+        t = self._bufs[which]
+        if t is None or t.numel() < nbytes:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("state buffer grew during capture: run one eager step first")
+            t = torch.empty((max(int(nbytes), 1),), dtype=torch.uint8, device=self.dev)
+            self._bufs[which] = t
+        return t.data_ptr()
+
+    def _make_args(self, tanfovx, tanfovy):
+        sc = self.scene
+        a = _lib.RasterArgs()
+        a.P, a.sh_degree, a.sh_coeffs = self.P, self.sh_degree, int(sc.shs.shape[1])
+        a.image_width, a.image_height = self.W, self.H
+        a.tanfovx, a.tanfovy, a.scale_modifier = float(tanfovx), float(tanfovy), 1.0
+        a.prefiltered, a.debug, a.do_depth = 0, 0, 0
+        a.bg, a.viewmatrix, a.projmatrix, a.campos = _ptr(self.bg), _ptr(self.view), _ptr(self.proj), _ptr(self.campos)
+        a.means3D, a.shs, a.colors_precomp, a.opacities = _ptr(sc.means3D), _ptr(sc.shs), None, _ptr(sc.opacities)
+        a.scales, a.rotations, a.cov3D_precomp = _ptr(sc.scales), _ptr(sc.rotations), None
+        a.interpolation_weights, a.num_node_kids = _ptr(sc.interpolation_weights), _ptr(sc.num_siblings)
+        a.render_indices, a.parent_indices, a.num_source = _ptr(sc.render_indices), _ptr(sc.parent_indices), self.N
+        a.shard_count, a.shard_index = self.world, self.rank
+        a.grad_row_begin, a.grad_row_end = hdist.row_block(self.P, self.world, self.rank) if self.world > 1 else (0, 0)
+        a.bin_capacity, a.sort_capacity = self.bin_capacity, self.sort_capacity
+        return a
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    # ---- the two halves of the step (eager or under capture) ------------------------------
+    def _part_a(self):
+        """LOD cut -> forward (-> image all-gather)."""
+        sc, L = self.scene, self.L
+        if self.N > self.N_nodes:
+            sc.render_indices[self.N_nodes:].fill_(-1)  # the library marks [n, N_nodes); these are the skybox slots beyond
+        _lib.check(L.h3dgs_lod_cut(self.N_nodes, sc.nodes.data_ptr(), sc.boxes.data_ptr(), self.threshold,
+                                   self.threshold_dev.data_ptr(), self.campos.data_ptr(), sc.render_indices.data_ptr(), sc.parent_indices.data_ptr(),
+                                   sc.nodes_for_render.data_ptr(), sc.interpolation_weights.data_ptr(),
+                                   sc.num_siblings.data_ptr(), self.count.data_ptr(), self.lod_scratch.data_ptr(),
+                                   self._stream()))
+        if self.S:
+            # skybox rows follow the cut as their own parents with t = 1, kids = 1 (render_post :220-234);
+            # a cut so large that they would not fit is reported as a row overflow by status()
+            idx = (self.count.long() + self.sky_arange).clamp_(max=self.N - 1)
+            sc.render_indices.index_copy_(0, idx, sc.skybox_inds)
+            sc.parent_indices.index_copy_(0, idx, sc.skybox_inds)
+            sc.interpolation_weights.index_fill_(0, idx, 1.0)
+            sc.num_siblings.index_fill_(0, idx, 1)
+        out = self.slab if self.world > 1 else self.image
+        n = C.c_int64(0)
+        _lib.check(L.h3dgs_rasterize_forward(C.byref(self.args), self._alloc_cb, None, out.data_ptr(),
+                                             self.radii.data_ptr(), None, C.byref(n), self._stream()))
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.slabs, self.slab, group=self.group)
+            self.image = hdist.unpack(self.slabs.view(self.world, self.rpr, 3, 16, self.W), self.H, self.W, self.world)
+
+    def _part_b(self):
+        """L1 loss, its gradient, backward (-> reduce-scatter of the [P,10] sums between the phases)."""
+        L = self.L
+        diff = self.image - self.gt
+        torch.sign(diff, out=self.dcolor)
+        self.dcolor.mul_(1.0 / diff.numel())
+        loss = diff.abs().mean()
+        g = self.grads
+        outs = (g["means3D"].data_ptr(), self.d_means2D.data_ptr(), g["shs"].data_ptr(), None, g["opacities"].data_ptr(),
+                g["scales"].data_ptr(), g["rotations"].data_ptr(), None)
+        state = (self.radii.data_ptr(), self._bufs[0].data_ptr(), self._bufs[1].data_ptr(), self._bufs[2].data_ptr(),
+                 self.bin_capacity, self.dcolor.data_ptr(), None)
+        if self.world == 1:
+            _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 3, self._stream()))
+        else:
+            # rows [P, world*chunk) of accum are zero since construction and never written: the blocks reduce cleanly
+            _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 1, self._stream()))
+            hdist.reduce_accum(self.accum.view(torch.uint8), self.P, self.world, self.rank, self.group)
+            # phase 2 rewrites exactly the own row block of d_means2D; the other rows stay zero since construction
+            _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 2, self._stream()))
+        info = self.scan_info().double()
+        rows_needed = (self.count + self.S).double()
+        self.status_dev[:5].copy_(torch.cat([loss.double().reshape(1), rows_needed, info]))
+        self.status_dev[5:].copy_((rows_needed > self.P).double())
+
+    def scan_info(self):
+        """int32 view [D, longest tile list, overflow] inside the image state."""
+        if self._scan_info is None:
+            v = _lib.StateView()
+            b = self._bufs
+            _lib.check(self.L.h3dgs_state_layout(self.P, self.W, self.H, self.bin_capacity, b[0].data_ptr(),
+                                                 b[1].data_ptr(), b[2].data_ptr(), C.byref(v)))
+            off = v.scan_info - b[2].data_ptr()
+            self._scan_info = b[2][off:off + 12].view(torch.int32)
+        return self._scan_info
+
+    # ---- driving --------------------------------------------------------------------------
+    def set_camera(self, cam):
+        """cam: pipeline.DeviceCamera (device tensors) -- three small device copies."""
+        self.view.copy_(cam.viewmatrix.reshape(16), non_blocking=True)
+        self.proj.copy_(cam.projmatrix.reshape(16), non_blocking=True)
+        self.campos.copy_(cam.campos.reshape(3), non_blocking=True)
+
+    def set_threshold(self, threshold):
+        """A new LOD threshold for the next step (train_post.py:66-74 draws one per step)."""
+        self.threshold = float(threshold)
+        self.threshold_dev.fill_(self.threshold)
+
+    def upload_target(self, src, stream):
+        """Copy this step's target (device tensor or pinned host tensor) into the static buffer on
+        `stream`, after the previous step has finished reading it; returns the event to hand to step()
+        as gt_ready.  The copy then overlaps the LOD cut and the forward pass (graph A)."""
+        with torch.cuda.stream(stream):
+            stream.wait_event(self._done)
+            self.gt.copy_(src, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(stream)
+        return ready
+
+    def capture(self):
+        """One eager step (sizes the state buffers, creates the library's side stream), then capture."""
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            self._part_a(); self._part_b()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        l0 = _lib.launch_count()
+        self.graph_a, self.graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_a):
+            self._part_a()
+        with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):
+            self._part_b()
+        self.launches_per_step = _lib.launch_count() - l0      # library kernels inside one replay of A + B
+
+    def step(self, cam=None, gt=None, gt_ready=None):
+        """cam/gt: optional new inputs (copied into the static buffers).  gt_ready: event after which
+        self.gt holds this step's target when the caller uploads it on another stream."""
+        if cam is not None:
+            self.set_camera(cam)
+        if gt is not None:
+            self.gt.copy_(gt, non_blocking=True)
+        if self.graph_a is None:
+            self._part_a()
+            if gt_ready is not None:
+                torch.cuda.current_stream(self.dev).wait_event(gt_ready)
+            self._part_b()
+        else:
+            self.graph_a.replay()
+            if gt_ready is not None:
+                torch.cuda.current_stream(self.dev).wait_event(gt_ready)
+            self.graph_b.replay()
+        self._done.record(torch.cuda.current_stream(self.dev))
+        return self.status_dev
+
+    def status(self):
+        """One 48-byte read-back: loss, rows needed, D, longest tile list, overflow flags."""
+        s = self.status_dev.cpu()
+        return dict(loss=float(s[0]), rows=int(s[1]), D=int(s[2]), longest_list=int(s[3]),
+                    overflow=bool(s[4] != 0 or s[5] != 0))

@@ -22,7 +22,7 @@ class Scene:
     caller-preallocated LOD scratch of train_post.py:59-63."""
 
     def __init__(self, arrays, device="cuda", requires_grad=True):
-        t = lambda a: torch.tensor(a, device=device)
+        t = lambda a: a.to(device) if torch.is_tensor(a) else torch.tensor(a, device=device)
         self.device = device
         self.means3D = t(arrays["means3D"]).requires_grad_(requires_grad)
         self.scales = t(arrays["scales"]).requires_grad_(requires_grad)

@@ -7,6 +7,7 @@
  *   diff_gaussian_rasterization._C.mark_visible                 -> h3dgs_mark_visible
  *   gaussian_hierarchy._C.expand_to_size                        -> h3dgs_expand_to_size
  *   gaussian_hierarchy._C.get_interpolation_weights             -> h3dgs_get_interpolation_weights
+ *   (both of the above, device-side, for a graph-captured step)  -> h3dgs_lod_cut
  *
  * The reference binds those through two pip packages whose source is absent from
  * /root/reference (empty submodules, .gitmodules:5-13); the interface is pinned by
@@ -22,7 +23,8 @@
  * this boundary; the Python shim (hierarchical-3d-gaussians_b200/diff_gaussian_rasterization)
  * passes tensor.data_ptr() values through ctypes.  All work is enqueued on `stream`;
  * the only host synchronisations are the ones the reference API itself forces
- * (num_rendered sizing of the binning buffer; the int returned by expand_to_size).
+ * (num_rendered sizing of the binning buffer; the int returned by expand_to_size) -- capacity mode
+ * (h3dgs_raster_args.bin_capacity) and h3dgs_lod_cut have none.
  * Every entry point returns 0 on success, a negative H3DGS_E* code on error and
  * leaves a message retrievable with h3dgs_last_error() (thread-local).
  *
@@ -97,8 +99,21 @@ typedef struct h3dgs_raster_args {
     int32_t shard_count, shard_index;
     /* Backward phase 2 (per-Gaussian chain rule) only for rendered rows [grad_row_begin, grad_row_end);
      * (0, 0) = all rows.  The multi-GPU mode reduce-scatters the [P][10] sums and lets every rank finish
-     * only its own row block, so the final gradients come out sharded by rendered row. */
+     * only its own row block, so the final gradients come out sharded by rendered row.  When the row block
+     * is also given to the FORWARD of a sharded frame, the SH colour is evaluated only for the Gaussians this
+     * rank needs: those touching its tile rows and those in its row block. */
     int32_t grad_row_begin, grad_row_end;
+    /* Capacity mode -- no host synchronisation, so the call can be captured in a CUDA graph.  With
+     * bin_capacity > 0 the binning state is sized for bin_capacity (tile, Gaussian) entries instead of
+     * num_rendered, the per-tile sort is launched for lists of at most sort_capacity entries (0 = 8192,
+     * the shared-memory limit) and nothing is read back: *num_rendered = bin_capacity, which is also the
+     * value to hand to backward.  A frame that needs more (D > bin_capacity, or a tile list longer than
+     * sort_capacity) sets word 2 of h3dgs_state_view.scan_info; its image is the background only and its
+     * backward adds nothing -- the caller re-runs it in exact mode (bin_capacity = 0).
+     * In both modes a rendered row whose render_indices entry is negative is skipped (radius 0): that is
+     * the tail h3dgs_lod_cut leaves after the cut when P is the capacity of the index arrays. */
+    int64_t bin_capacity;
+    int32_t sort_capacity;
 } h3dgs_raster_args;   /* NOTE: keep hierarchical-3d-gaussians_b200/h3dgs/_lib.py::RasterArgs in sync */
 
 /* Forward: K1 preprocess -> scan -> duplicateWithKeys -> radix sort -> tile ranges
@@ -144,6 +159,7 @@ typedef struct h3dgs_state_view {
     const uint32_t* ranges;           /* [tiles][2]                                             */
     const float* final_T;             /* [H*W]                                                  */
     const uint32_t* n_contrib;        /* [H*W]                                                  */
+    const uint32_t* scan_info;        /* [3] D, longest tile list, capacity overflow (0/1)      */
 } h3dgs_state_view;
 int h3dgs_state_layout(int32_t P, int32_t W, int32_t H, int64_t num_rendered,
                        const void* geom_state, const void* binning_state, const void* image_state,
@@ -166,6 +182,18 @@ int h3dgs_get_interpolation_weights(int32_t n, const int32_t* node_indices, floa
                                     float viewpoint_x, float viewpoint_y, float viewpoint_z,
                                     float viewdir_x, float viewdir_y, float viewdir_z,
                                     float* ts, int32_t* num_kids, void* stream);
+
+/* Device-side LOD cut for the sync-free step: expand_to_size and get_interpolation_weights in one
+ * pass with the same arithmetic, nothing returned to the host.  Outputs as the two calls above
+ * (render_indices, parent_indices, nodes_for_render_indices, ts, num_kids: first n entries); in addition
+ * render_indices[n .. N) = -1 (rows the rasterizer skips when handed P = N) and *count [device] = n.
+ * target_size_dev, when not NULL, is a device float that overrides target_size: train_post.py:66-74 draws a
+ * new threshold every step, and a value read on the device can change between replays of a captured graph.
+ * scratch as for h3dgs_expand_to_size. */
+int h3dgs_lod_cut(int32_t N, const int32_t* nodes, const float* boxes, float target_size, const float* target_size_dev,
+                  const float* viewpoint,
+                  int32_t* render_indices, int32_t* parent_indices, int32_t* nodes_for_render_indices,
+                  float* ts, int32_t* num_kids, int32_t* count, void* scratch, void* stream);
 
 /* ---- fused L1 + SSIM loss (replaces utils/loss_utils.py:17-63 as used in
  * train_post.py:134-140: loss = (1-l) * L1 + l * (1 - SSIM), 11x11 Gaussian window, sigma 1.5) ----

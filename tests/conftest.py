@@ -22,9 +22,9 @@ def golden_dir():
 
 @pytest.fixture(scope="session", autouse=True)
 def _emulate_gpu_tests(tmp_path_factory):
-    """H3DGS_EMULATE=1 (CPU only): run the `-m gpu` test files against the emulation build of the kernels
-    (tests/emul/) -- device="cuda" in test code lands on the CPU.  NCCL tests and the loss / optimizer kernels cannot
-    run this way; the big frames are slow.  Without the variable this fixture does nothing."""
+    """H3DGS_EMULATE=1 (development aid, CPU only): run the `-m gpu` test files against the emulation build of the
+    kernels (tests/emul/) -- device="cuda" in test code lands on the CPU.  Graph capture and NCCL tests cannot run
+    this way; the big frames are slow.  Without the variable this fixture does nothing."""
     if os.environ.get("H3DGS_EMULATE") != "1":
         yield
         return

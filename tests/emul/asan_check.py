@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY.  A memcheck for the kernels without a GPU: build the emulation library with
 AddressSanitizer (heap and globals -- `__shared__` arrays are globals in the emulator; stack instrumentation is off
 because the fibers switch stacks by hand), preload libasan so that numpy's buffers get red zones too, and run a set
-of scenes through the blend kernels, the tile shards, the fused cut gather and the LOD-cut ops.  Usage:   python tests/emul/asan_check.py          (re-executes itself under LD_PRELOAD)
+of scenes through both blend variants, the sharded schedule, the fused cut gather and the device-side LOD cut /
+capacity mode.  Usage:   python tests/emul/asan_check.py          (re-executes itself under LD_PRELOAD)
 A deliberately short output buffer is reported as heap-buffer-overflow (checked by --negative-control)."""
 import os
 import subprocess
@@ -53,7 +54,8 @@ def run_cases(so, negative):
         return
     import test_emu_kernels_cpu as T
     n = 0
-    for _ in (0,):
+    for gw in ("0", "1"):
+        os.environ["H3DGS_GROUPWALK"] = gw
         for (P, W, H, kw, depth) in [(3000, 256, 192, dict(mode="hier", seed=42), True), (1500, 160, 96, dict(seed=7), False),
                                      (300, 15, 33, dict(seed=3, scale_k=2e-2), False),
                                      (6000, 96, 64, dict(seed=11, scale_k=3e-2, zmax=6.0), False),
@@ -61,8 +63,9 @@ def run_cases(so, negative):
             cam, sc, ts, kids, bg = make_scene(P, W, H, **kw)
             T._check(emu, cam, sc, bg, ts, kids, do_depth=depth, tol=5e-5)
             n += 1
-        for name in ("test_tile_shards_equal_the_whole_frame", "test_fused_cut_gather_and_scatter", "test_lod_cut_ops_bit_exact"):
-            getattr(T, name)(emu)
+        for t in (T.test_tile_shards_equal_the_whole_frame, T.test_sharded_frame_with_row_blocks,
+                  T.test_fused_cut_gather_and_scatter, T.test_device_lod_cut_and_skipped_rows):
+            t(emu)
             n += 1
     print(f"asan check complete: {n} cases, no report")
 

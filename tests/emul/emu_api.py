@@ -33,34 +33,9 @@ def ptr(a):
     return None if a is None else a.ctypes.data
 
 
-def _bind(l):
-    """prototypes of the entry points used here (include/h3dgs.h)"""
-    l.h3dgs_last_error.restype = C.c_char_p
-    l.h3dgs_backward_scratch_bytes.restype = C.c_size_t
-    l.h3dgs_backward_scratch_bytes.argtypes = [C.c_int32]
-    l.h3dgs_expand_scratch_bytes.restype = C.c_size_t
-    l.h3dgs_expand_scratch_bytes.argtypes = [C.c_int32]
-    l.h3dgs_rasterize_forward.restype = C.c_int
-    l.h3dgs_rasterize_forward.argtypes = [C.POINTER(_lib.RasterArgs), _lib.ALLOC_FN, C.c_void_p, C.c_void_p, C.c_void_p,
-                                          C.c_void_p, C.POINTER(C.c_int64), C.c_void_p]
-    l.h3dgs_rasterize_backward.restype = C.c_int
-    l.h3dgs_rasterize_backward.argtypes = [C.POINTER(_lib.RasterArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                           C.c_int64, C.c_void_p, C.c_void_p] + [C.c_void_p] * 8 + [C.c_void_p, C.c_int, C.c_void_p]
-    l.h3dgs_state_layout.restype = C.c_int
-    l.h3dgs_state_layout.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
-                                     C.POINTER(_lib.StateView)]
-    l.h3dgs_expand_to_size.restype = C.c_int
-    l.h3dgs_expand_to_size.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_float, C.c_float,
-                                       C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    l.h3dgs_get_interpolation_weights.restype = C.c_int
-    l.h3dgs_get_interpolation_weights.argtypes = [C.c_int32, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p] + \
-        [C.c_float] * 6 + [C.c_void_p, C.c_void_p, C.c_void_p]
-    return l
-
-
 class Emu:
     def __init__(self, so_path):
-        self.L = _bind(C.CDLL(so_path))
+        self.L = _lib.bind(C.CDLL(so_path))
 
     def check(self, rc):
         if rc < 0:
@@ -68,7 +43,7 @@ class Emu:
         return rc
 
     def args(self, cam, bg, sc, sh_degree=3, ts=None, kids=None, do_depth=False, ridx=None, pidx=None, shard=(1, 0),
-             colors=None, cov=None, bin_capacity=0, sort_capacity=0, P=None):
+             colors=None, cov=None, bin_capacity=0, sort_capacity=0, P=None, grad_rows=(0, 0)):
         a = _lib.RasterArgs()
         keep = dict(bg=f32(bg), view=f32(cam.world_view_transform), proj=f32(cam.full_proj_transform), campos=f32(cam.camera_center),
                     means=f32(sc["means3D"]), opac=f32(sc["opacities"]),
@@ -89,9 +64,8 @@ class Emu:
         a.interpolation_weights, a.num_node_kids = ptr(keep["ts"]), ptr(keep["kids"])
         a.render_indices, a.parent_indices, a.num_source = ptr(keep["ridx"]), ptr(keep["pidx"]), (n_src if ridx is not None else 0)
         a.shard_count, a.shard_index = shard
-        a.grad_row_begin = a.grad_row_end = 0
-        if hasattr(a, "bin_capacity"):
-            a.bin_capacity, a.sort_capacity = int(bin_capacity), int(sort_capacity)
+        a.grad_row_begin, a.grad_row_end = int(grad_rows[0]), int(grad_rows[1])
+        a.bin_capacity, a.sort_capacity = int(bin_capacity), int(sort_capacity)
         return a, keep
 
     def forward(self, a, keep):
@@ -128,7 +102,9 @@ class Emu:
             out["keys_sorted"] = view(b[1], v.keys_sorted, np.uint64, D)
         return out
 
-    def backward(self, a, fwd, dL_dcolor, dL_dinvdepth=None, phases=3):
+    def backward(self, a, fwd, dL_dcolor, dL_dinvdepth=None, phases=3, scratch=None):
+        """phases / scratch as in h3dgs_rasterize_backward: 1 fills `scratch` with the [P][10] sums (returned as
+        g["scratch"]), 2 consumes it"""
         P = a.P
         N = a.num_source if a.render_indices else P
         M = a.sh_coeffs
@@ -139,7 +115,8 @@ class Emu:
                  scales=aligned(N * 12, np.float32, (N, 3)) if a.scales else None,
                  rotations=aligned(N * 16, np.float32, (N, 4)) if a.rotations else None,
                  cov3Ds_precomp=aligned(N * 24, np.float32, (N, 6)) if a.cov3D_precomp else None)
-        scratch = aligned(self.L.h3dgs_backward_scratch_bytes(P))
+        if scratch is None:
+            scratch = aligned(self.L.h3dgs_backward_scratch_bytes(P))
         gcol = f32(dL_dcolor)
         gdep = f32(dL_dinvdepth) if (a.do_depth and dL_dinvdepth is not None) else None
         b = fwd["bufs"]
@@ -147,4 +124,5 @@ class Emu:
                                                    ptr(gcol), ptr(gdep), ptr(g["means3D"]), ptr(g["means2D"]), ptr(g["sh"]),
                                                    ptr(g["colors_precomp"]), ptr(g["opacities"]), ptr(g["scales"]),
                                                    ptr(g["rotations"]), ptr(g["cov3Ds_precomp"]), ptr(scratch), int(phases), None))
+        g["scratch"] = scratch
         return g

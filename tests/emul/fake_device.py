@@ -1,8 +1,8 @@
 """TEST INFRASTRUCTURE ONLY.  Lets the CPU suite run the product's Python layer -- the drop-in packages,
-h3dgs.pipeline, h3dgs.dist -- unchanged on CPU tensors, with libh3dgs_emu.so (the kernels
+h3dgs.pipeline, h3dgs.dist, h3dgs.graphstep -- unchanged on CPU tensors, with libh3dgs_emu.so (the kernels
 compiled against the SIMT emulator) standing in for libh3dgs.so: ctypes loads the emulation build, the
 "is this a device tensor" checks of the shims answer yes, and the handful of torch.cuda stream / event calls
-become no-ops.  NCCL is out of reach (collectives run on gloo)."""
+become no-ops.  CUDA graphs and NCCL are out of reach (GraphedStep runs with capture=False, collectives on gloo)."""
 import contextlib
 import ctypes as C
 from unittest import mock
@@ -41,13 +41,7 @@ def cpu_as_device(so_path):
     from h3dgs import _lib
     import diff_gaussian_rasterization._C as rc
     import gaussian_hierarchy._C as gc
-    import emu_api
-    emu = emu_api._bind(C.CDLL(so_path))
-    emu.h3dgs_launch_count.restype = C.c_int64
-    emu.h3dgs_mark_visible.restype = C.c_int
-    emu.h3dgs_mark_visible.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    emu.h3dgs_profile_read.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
-    emu.h3dgs_stage_name.restype = C.c_char_p
+    emu = _lib.bind(C.CDLL(so_path))
     patches = [
         mock.patch.object(_lib, "_lib", emu),
         mock.patch.object(rc, "_on_device", lambda t: True),

@@ -39,10 +39,18 @@ def grad_close(a, b, name, tol=1e-5, max_rows=12):
 
 
 @pytest.fixture(scope="module")
-def emu(tmp_path_factory):
+def emu_lib(tmp_path_factory):
     from build_emu import build
     from emu_api import Emu
     return Emu(build(str(tmp_path_factory.mktemp("h3dgs_emu"))))
+
+
+@pytest.fixture(params=["quadrants", "groups"])
+def emu(emu_lib, request, monkeypatch):
+    """both variants of the blend kernels: one survivor list per warp (8x8 quadrant), or one per 8-lane group
+    (4x4 block; H3DGS_GROUPWALK=1)"""
+    monkeypatch.setenv("H3DGS_GROUPWALK", "1" if request.param == "groups" else "0")
+    return emu_lib
 
 
 def _check(emu, cam, sc, bg, ts=None, kids=None, do_depth=False, sh_degree=3, colors=None, cov=None, tol=1e-5):
@@ -128,6 +136,35 @@ def test_tile_shards_equal_the_whole_frame(emu):
         grad_close(acc[k], b[k], k)
 
 
+def test_sharded_frame_with_row_blocks(emu):
+    """the multi-GPU schedule on one CPU: every shard renders its tile rows (the forward knows its gradient
+    row block and skips foreign SH colours), phase 1 fills each shard's [P][10] sums, their total is what the
+    reduce-scatter delivers, phase 2 finishes each shard's own row block."""
+    cam, sc, ts, kids, bg = make_scene(2500, 160, 112, mode="hier", seed=8)
+    f, b, gcol, gdep = oracle_run(cam, sc, bg, ts, kids)
+    P, G = 2500, 3
+    chunk = (P + G - 1) // G
+    rows = [(min(r * chunk, P), min((r + 1) * chunk, P)) for r in range(G)]
+    shards = []
+    for r in range(G):
+        a, keep = emu.args(cam, bg, sc, ts=ts, kids=kids, shard=(G, r), grad_rows=rows[r])
+        fw = emu.forward(a, keep)
+        g1 = emu.backward(a, fw, gcol, phases=1)
+        shards.append((a, keep, fw, g1["scratch"].view(np.float32)[: P * 10].copy()))
+    total = sum(s[3].astype(np.float64) for s in shards).astype(np.float32)
+    out = {k: np.zeros_like(b[k]) for k in ("means3D", "sh", "opacities", "scales", "rotations", "means2D")}
+    for r, (a, keep, fw, _) in enumerate(shards):
+        from emu_api import aligned
+        scratch = aligned(emu.L.h3dgs_backward_scratch_bytes(P))
+        scratch.view(np.float32)[: P * 10] = total
+        g2 = emu.backward(a, fw, gcol, phases=2, scratch=scratch)
+        lo, hi = rows[r]
+        for k in out:
+            out[k][lo:hi] = g2[k][lo:hi]
+    for k in out:
+        grad_close(out[k], b[k], k)
+
+
 def test_fused_cut_gather_and_scatter(emu):
     from oracle import oracle
     cam = synth.make_camera(160, 112)
@@ -154,8 +191,10 @@ def test_fused_cut_gather_and_scatter(emu):
         grad_close(g[k], b[k], k)
 
 
-def test_lod_cut_ops_bit_exact(emu):
-    """expand_to_size / get_interpolation_weights kernels vs the oracle: indices, weights and kids bit-exact"""
+def test_device_lod_cut_and_skipped_rows(emu):
+    """h3dgs_lod_cut = expand_to_size + get_interpolation_weights; rows after the cut are marked -1 and
+    the rasterizer handed P = capacity skips them (the sync-free step)."""
+    import ctypes as C
     from emu_api import aligned, f32, i32, ptr
     from oracle import oracle
     cam = synth.make_camera(160, 112)
@@ -164,22 +203,48 @@ def test_lod_cut_ops_bit_exact(emu):
     leaves["scales"] = (8e-3 * np.sqrt(2 * z) * np.ones((1, 3))).astype(np.float32)
     h = synth.build_hierarchy(leaves)
     N = h["nodes"].shape[0]
+    thr = synth.tau_threshold(6.0, cam)
+    n, ri, pi, ni = oracle.expand_to_size(h["nodes"], h["boxes"], thr, cam.camera_center)
+    ts, kids = oracle.get_interpolation_weights(ni, thr, h["nodes"], h["boxes"], cam.camera_center)
     L = emu.L
-    nodes, boxes, vp = i32(h["nodes"]), f32(h["boxes"]), f32(cam.camera_center)
+    nodes, boxes, vp, thr_dev = i32(h["nodes"]), f32(h["boxes"]), f32(cam.camera_center), f32([thr])
+    r2, p2, n2, k2 = (aligned(N * 4, np.int32, (N,)) for _ in range(4))
+    t2 = aligned(N * 4, np.float32, (N,))
+    count = aligned(4, np.int32, (1,))
     scratch = aligned(L.h3dgs_expand_scratch_bytes(N))
-    for tau in (0.0, 6.0, 40.0):
-        thr = synth.tau_threshold(tau, cam)
-        n, ri, pi, ni = oracle.expand_to_size(h["nodes"], h["boxes"], thr, cam.camera_center)
-        ts, kids = oracle.get_interpolation_weights(ni, thr, h["nodes"], h["boxes"], cam.camera_center)
-        r3, p3, n3, k3 = (aligned(N * 4, np.int32, (N,)) for _ in range(4))
-        t3 = aligned(N * 4, np.float32, (N,))
-        got = L.h3dgs_expand_to_size(N, ptr(nodes), ptr(boxes), thr, ptr(vp), 0.0, 0.0, 0.0, ptr(r3), ptr(p3), ptr(n3), ptr(scratch), None)
-        assert got == n and n > 0
-        assert np.array_equal(r3[:n], ri) and np.array_equal(p3[:n], pi) and np.array_equal(n3[:n], ni)
-        c = cam.camera_center
-        emu.check(L.h3dgs_get_interpolation_weights(n, ptr(n3), thr, ptr(nodes), ptr(boxes), float(c[0]), float(c[1]), float(c[2]),
-                                                    0.0, 0.0, 0.0, ptr(t3), ptr(k3), None))
-        assert np.array_equal(t3[:n].view(np.uint32), ts.view(np.uint32)) and np.array_equal(k3[:n], kids)
+    emu.check(L.h3dgs_lod_cut(N, ptr(nodes), ptr(boxes), -1.0, ptr(thr_dev), ptr(vp), ptr(r2), ptr(p2), ptr(n2), ptr(t2),
+                              ptr(k2), ptr(count), ptr(scratch), None))
+    assert int(count[0]) == n
+    assert np.array_equal(r2[:n], ri) and np.array_equal(p2[:n], pi) and np.array_equal(n2[:n], ni)
+    assert np.array_equal(t2[:n].view(np.uint32), ts.view(np.uint32)) and np.array_equal(k2[:n], kids)
+    assert (r2[n:] == -1).all()
+    # the two-call API on the same library gives the same
+    r3, p3, n3 = (aligned(N * 4, np.int32, (N,)) for _ in range(3))
+    got = L.h3dgs_expand_to_size(N, ptr(nodes), ptr(boxes), thr, ptr(vp), 0.0, 0.0, 0.0, ptr(r3), ptr(p3), ptr(n3), ptr(scratch), None)
+    assert got == n and np.array_equal(r3[:n], ri)
+    # capacity-sized rasterization over the marked index array == exact rasterization of the cut
+    bg = np.array([0.1, 0.2, 0.3], np.float32)
+    a0, keep0 = emu.args(cam, bg, h, ts=ts, kids=kids, ridx=ri, pidx=pi)
+    exact = emu.forward(a0, keep0)
+    a1, keep1 = emu.args(cam, bg, h, ts=t2, kids=k2, ridx=r2, pidx=p2, P=N, bin_capacity=exact["D"] + 10, sort_capacity=4096)
+    cap = emu.forward(a1, keep1)
+    st = emu.state(a1, cap)
+    assert list(st["scan_info"]) == [exact["D"], st["scan_info"][1], 0]
+    assert np.array_equal(cap["color"], exact["color"])
+    assert np.array_equal(cap["radii"][:n], exact["radii"]) and (cap["radii"][n:] == 0).all()
+    gcol = synth.l1_grad(exact["color"])
+    g0, g1 = emu.backward(a0, exact, gcol), emu.backward(a1, cap, gcol)
+    for k in ("means3D", "sh", "opacities", "scales", "rotations"):
+        assert rel_err(g1[k], g0[k]) < 1e-6, k
+    # a frame that does not fit: flagged, background only, zero gradients
+    for kw in (dict(bin_capacity=exact["D"] // 2, sort_capacity=4096), dict(bin_capacity=exact["D"] + 10, sort_capacity=32)):
+        a2, keep2 = emu.args(cam, bg, h, ts=t2, kids=k2, ridx=r2, pidx=p2, P=N, **kw)
+        ov = emu.forward(a2, keep2)
+        s2 = emu.state(a2, ov)
+        assert s2["scan_info"][2] == 1 and s2["scan_info"][0] == exact["D"]
+        assert np.array_equal(ov["color"], np.broadcast_to(bg.reshape(3, 1, 1), ov["color"].shape))
+        g2 = emu.backward(a2, ov, gcol)
+        assert all(float(np.abs(v).sum()) == 0.0 for k, v in g2.items() if v is not None and k != "means2D")
 
 
 def test_equal_depths_and_long_lists_fall_back_to_the_global_sort(emu):
@@ -187,3 +252,30 @@ def test_equal_depths_and_long_lists_fall_back_to_the_global_sort(emu):
     sc["means3D"][:, 2] = np.round(sc["means3D"][:, 2] * 4) / 4       # many equal depths: order must follow the index
     f, fw, st, g = _check(emu, cam, sc, bg, tol=5e-5)
     assert (st["ranges"][:, 1] - st["ranges"][:, 0]).max() > 8192    # longer than the shared-memory sort handles
+
+
+def test_random_scenes_functional(emu):
+    """a small fuzz over sizes, modes, depth, opacities above one and needle-shaped Gaussians.  The bar here is
+    functional (no lost or doubled contributions, no crash, no deadlock): on ill-conditioned scenes the fp32
+    oracle itself is 3e-5 away from a double-precision blend, so the 1e-5 parity bar does not apply."""
+    rng = np.random.default_rng(20)
+    for it in range(10):
+        P = int(rng.choice([1, 7, 64, 500, 2000]))
+        W, H = int(rng.integers(1, 160)), int(rng.integers(1, 120))
+        mode = str(rng.choice(["flat", "hier"]))
+        cam, sc, ts, kids, bg = make_scene(P, W, H, mode=mode, seed=int(rng.integers(0, 10**6)),
+                                           scale_k=float(10 ** rng.uniform(-3, -1.2)), zmax=float(rng.uniform(4, 40)))
+        if rng.uniform() < 0.3:
+            sc["opacities"] = (sc["opacities"] * rng.uniform(0.5, 3.0)).astype(np.float32)
+        if rng.uniform() < 0.3:
+            sc["scales"] = (sc["scales"] * np.array([1.0, 8.0, 0.2], np.float32)).astype(np.float32)
+        f, b, gcol, gdep = oracle_run(cam, sc, bg, ts, kids, do_depth=True)
+        a, keep = emu.args(cam, bg, sc, ts=ts, kids=kids, do_depth=True)
+        fw = emu.forward(a, keep)
+        assert fw["D"] == f["num_rendered"] and np.array_equal(fw["radii"], f["radii"])
+        scale = max(np.abs(f["color"]).max(), 1.0)
+        d = np.abs(fw["color"] - f["color"])
+        assert (d > 1e-4 * scale).sum() <= 6 and d.max() < 1.5 / 255 * scale, (it, float(d.max()))
+        g = emu.backward(a, fw, gcol, gdep)
+        for k in ("means3D", "sh", "opacities", "scales", "rotations"):
+            grad_close(g[k], b[k], k, tol=2e-4)

@@ -55,6 +55,69 @@ def _worker(rank, world, port, out):
     dist.barrier(); dist.destroy_process_group()
 
 
+def _graph_worker(rank, world, port, out):
+    """the same comparison for the sync-free step replayed from CUDA graphs (collectives captured)"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "hierarchical-3d-gaussians_b200")); sys.path.insert(0, os.path.join(root, "tests"))
+    import torch
+    import torch.distributed as dist
+    from h3dgs import synth, pipeline
+    from h3dgs.graphstep import GraphedStep
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = f"cuda:{rank}"
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    cam = synth.make_camera(640, 360)
+    leaves = synth.cloud_v1(20000, cam, zmin=2.0, zmax=40.0, seed=3, scale_k=1.0)
+    z = leaves["means3D"][:, 2:3]
+    leaves["scales"] = (5e-3 * np.sqrt(2.0 * z) * np.ones((1, 3))).astype(np.float32)
+    h = synth.build_hierarchy(leaves)
+    thr = synth.tau_threshold(6.0, cam)
+    scene = pipeline.Scene(h, device=dev)
+    rs = np.random.default_rng(2)
+    cams = [cam] + [synth.yaw_camera(cam.W, cam.H, float(rs.uniform(-15, 15)), rs.uniform(-0.5, 0.5, 3)) for _ in range(2)]
+    dcams = [pipeline.DeviceCamera(c, device=dev) for c in cams]
+    bg = torch.tensor([0.1, 0.2, 0.3], device=dev)
+    gen = torch.Generator().manual_seed(1)
+    gts = [torch.rand((3, cam.H, cam.W), generator=gen).to(dev) for _ in cams]
+    gs = GraphedStep(scene, cam.W, cam.H, cam.tanfovx, cam.tanfovy, bg, thr, bin_capacity=1 << 20, sort_capacity=4096,
+                     world=world, rank=rank, capture=False)
+    gs.set_camera(dcams[0]); gs.gt.copy_(gts[0])
+    gs.capture()
+    ok, errs = True, []
+    for v in (0, 1, 2, 0):
+        loss1, radii1, n1 = pipeline.l1_step(scene, dcams[v], bg, gts[v], thr)
+        g1 = {k: getattr(scene, k).grad.clone() for k in ("means3D", "shs", "opacities", "scales", "rotations")}
+        with torch.no_grad():
+            img1 = pipeline.render_hier_fused(scene, dcams[v], bg, thr)[0]
+        gs.step(dcams[v], gts[v])
+        st = gs.status()
+        ok = ok and not st["overflow"] and st["rows"] == n1 and abs(st["loss"] - loss1.item()) < 1e-7
+        ok = ok and torch.equal(gs.image, img1) and torch.equal(gs.radii[:n1], radii1)
+        for k, ref in g1.items():
+            t_ = gs.grads[k].clone()
+            dist.all_reduce(t_, op=dist.ReduceOp.SUM)          # sharded by rendered row: the sum is the full gradient
+            errs.append(float((ref - t_).abs().max() / ref.abs().max().clamp_min(1e-30)))
+    ok = ok and max(errs) < 1e-5
+    res = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(res, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        torch.save((bool(res.item() == 1.0), errs), out)
+    dist.barrier(); dist.destroy_process_group()
+
+
+def test_graphed_sharded_step_equals_single_gpu(tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = min(torch.cuda.device_count(), 4)
+    out = str(tmp_path / "r.pt")
+    mp.spawn(_graph_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    ok, errs = torch.load(out)
+    assert ok, errs
+
+
 def test_tile_sharded_step_equals_single_gpu(tmp_path):
     import torch
     import torch.multiprocessing as mp
