@@ -69,7 +69,7 @@ def cuda_names_mean_cpu():
     """device="cuda" / .cuda() / .to("cuda") in test code land on the CPU: lets the GPU test files themselves run
     against the emulation build (H3DGS_EMULATE=1, tests/conftest.py)."""
     names = ["tensor", "zeros", "ones", "empty", "full", "rand", "randn", "arange", "as_tensor", "zeros_like", "ones_like",
-             "empty_like", "full_like", "rand_like", "randn_like", "linspace", "eye", "randint", "randperm"]
+             "empty_like", "full_like", "rand_like", "randn_like", "linspace", "eye", "randint", "randperm", "range"]
     saved = {n: getattr(torch, n) for n in names}
     saved_to, saved_cuda = torch.Tensor.to, torch.Tensor.cuda
 

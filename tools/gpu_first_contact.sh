@@ -23,3 +23,4 @@ for f in sorted(glob.glob("gpurun_out/fc_bench_*.json")):
 PY
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/fc_launches.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/fc_ncu_bench.log 2>&1
+bash tools/ncu_capture.sh fc > gpurun_out/fc_ncu_capture.log 2>&1
