@@ -6,6 +6,7 @@
 // preprocess.cu (the rect is re-derived from the stored pixel centre and radius).
 #include <cub/cub.cuh>
 #include "common.cuh"
+#include "reach_mask.cuh"
 
 namespace h3dgs {
 
@@ -77,54 +78,6 @@ identify_tile_ranges_kernel(int64_t D, const uint64_t* __restrict__ keys, uint32
     if (i == D - 1) ranges[2 * tile + 1] = (uint32_t)D;
 }
 
-// Which of the sixteen 4x4-pixel blocks of tile (tile_x, tile_y) can entry (a, b) reach at all?
-// Bit 4 q + g: quadrant q = (qx, qy) of the tile (the warp of the blend CTAs), block g = (bx, by) inside it
-// (an 8-lane group of that warp); the quadrant is reached iff any of its four bits is set.
-// alpha >= 1/255  <=>  q(d) = A dx^2 + 2 B dx dy + C dy^2 <= 2 ln(255 o): the exact minimum of the convex q over a
-// block's rectangle of pixel centres (0 if the mean is inside, else attained on an edge) is compared with
-// that bound (conservative margin for fp32 rounding).  Only the blocks inside the ellipse's bounding box are tested.
-__device__ __forceinline__ uint32_t block_mask16(const float4& a, const float4& b, int tile_x, int tile_y)
-{
-    const float A = a.z, B = a.w, C = b.x;
-    const float det = A * C - B * B;
-    const float o255 = b.y * 255.0f;
-    if (!(o255 > 1.0f)) return 0u;                     // can never reach alpha >= 1/255
-    const float bound = 2.0f * logf(o255) * 1.002f + 1e-3f;
-    const float rx = a.x - (float)(tile_x * kTile), ry = a.y - (float)(tile_y * kTile);
-    if (!(det > 0.0f && A > 0.0f && C > 0.0f) || !(bound == bound && rx == rx && ry == ry)) return 0xFFFFu;
-    // bounding box of {q <= bound}: |dx| <= sqrt(bound C / det), |dy| <= sqrt(bound A / det)
-    const float ex = sqrtf(bound * C / det) * 1.001f + 1e-3f, ey = sqrtf(bound * A / det) * 1.001f + 1e-3f;
-    if (!(ex == ex && ey == ey) || ex > 1e6f || ey > 1e6f) return 0xFFFFu;
-    // block i covers pixel centres 4 i .. 4 i + 3 in tile coordinates
-    const int bx0 = max(0, (int)ceilf((rx - ex - 3.0f) * 0.25f)), bx1 = min(3, (int)floorf((rx + ex) * 0.25f));
-    const int by0 = max(0, (int)ceilf((ry - ey - 3.0f) * 0.25f)), by1 = min(3, (int)floorf((ry + ey) * 0.25f));
-    uint32_t mask = 0u;
-    for (int by = by0; by <= by1; by++)
-        for (int bx = bx0; bx <= bx1; bx++) {
-            // rectangle of pixel centres relative to the mean: dx in [x0, x1], dy in [y0, y1]
-            const float x0 = (float)(4 * bx) - rx, x1 = x0 + 3.0f;
-            const float y0 = (float)(4 * by) - ry, y1 = y0 + 3.0f;
-            float qmin;
-            if (x0 <= 0.f && x1 >= 0.f && y0 <= 0.f && y1 >= 0.f) qmin = 0.f;          // the mean is inside
-            else {
-                qmin = 3.0e38f;
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    const float xe = e ? x1 : x0;                                       // vertical edges: minimise over dy
-                    const float dy = fminf(y1, fmaxf(y0, -B * xe / C));
-                    qmin = fminf(qmin, A * xe * xe + 2.0f * B * xe * dy + C * dy * dy);
-                    const float ye = e ? y1 : y0;                                       // horizontal edges: minimise over dx
-                    const float dx = fminf(x1, fmaxf(x0, -B * ye / A));
-                    qmin = fminf(qmin, A * dx * dx + 2.0f * B * dx * ye + C * ye * ye);
-                }
-            }
-            if (!(qmin > bound)) {
-                const int q = (bx >> 1) | ((by >> 1) << 1), g = (bx & 1) | ((by & 1) << 1);
-                mask |= 1u << (4 * q + g);
-            }
-        }
-    return mask;
-}
 // kbits of the per-tile SORTED record copy: bits 0..11 num_node_kids (saturated), bits 16..31 the block mask.
 // (The unsorted record keeps K1's layout: kids in bits 0..19, SH clamp flags in 20..22.)
 __device__ __forceinline__ uint32_t sorted_kbits(uint32_t kbits, uint32_t mask16) {

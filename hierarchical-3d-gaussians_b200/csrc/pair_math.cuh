@@ -34,6 +34,7 @@ H3_PM_FN f2 sub2(f2 a, f2 b) { return f2{a.lo - b.lo, a.hi - b.hi}; }
 H3_PM_FN float fast_exp2(float x) { return exp2f(x); }
 H3_PM_FN float fast_log2(float x) { return log2f(x); }
 H3_PM_FN float rcp_approx(float x) { return 1.0f / x; }
+H3_PM_FN float rsq_approx(float x) { return 1.0f / sqrtf(x); }
 #else
 #define H3_PM_FN __device__ __forceinline__
 namespace h3dgs {
@@ -61,6 +62,7 @@ H3_PM_FN float fast_exp2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : 
 // log2(x) for normal x: MUFU.LG2 without the denormal pre-scaling of __log2f
 H3_PM_FN float fast_log2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 H3_PM_FN float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+H3_PM_FN float rsq_approx(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 #endif
 
 H3_PM_FN f2 bc(float x) { return pk(x, x); }
@@ -107,10 +109,28 @@ H3_PM_FN void pair_hier_alpha(f2 a, float t, uint32_t k /* num_node_kids */, f2&
     alpha = a; dadb = bc(1.0f);
     if (!HIER) return;
     if (k <= 1u || t >= 1.0f) return;
-    const float ik = fast_rcp((float)k), u = 1.0f - t;
+    const float u = 1.0f - t;
     float a0, a1; upk(a, a0, a1);
-    float o0, o1; upk(sub2(bc(1.0f), a), o0, o1);
-    const f2 l2 = pk(fast_log2(o0), fast_log2(o1));            // 1 - a is in [0.01, 1]
+    float o0, o1; upk(sub2(bc(1.0f), a), o0, o1);             // 1 - a is in [0.01, 1]
+    if (k == 2u) {
+        // Two siblings -- every interior node of a binary hierarchy (the reference's BVH builder, our synthetic trees):
+        // 1 - sqrt(1-a) in closed form.  Small a (the ones that sit at the 1/255 threshold) use the series
+        // a/2 + a^2/8 + a^3/16 + 5a^4/128 + 7a^5/256 (relative error < 5e-8 below 1/16), larger a the direct
+        // difference; one MUFU.RSQ per pixel serves the value (sqrt = x rsqrt x) and the derivative
+        // da'/da = t + (1-t) / (2 sqrt(1-a)).
+        const f2 r = pk(rsq_approx(o0), rsq_approx(o1));
+        const f2 s = mul2(pk(o0, o1), r);
+        f2 S = fma2(a, bc(0.02734375f), bc(0.0390625f));
+        S = fma2(a, S, bc(0.0625f));
+        S = fma2(a, S, bc(0.125f));
+        S = fma2(a, S, bc(0.5f));
+        const f2 omr = sel2(a0 < 0.0625f, a1 < 0.0625f, mul2(a, S), sub2(bc(1.0f), s));
+        alpha = fma2(bc(u), omr, mul2(bc(t), a));
+        if (GRAD) dadb = fma2(bc(0.5f * u), r, bc(t));
+        return;
+    }
+    const float ik = fast_rcp((float)k);
+    const f2 l2 = pk(fast_log2(o0), fast_log2(o1));
     // -log1p(-a) = a (1 + a/2 + a^2/3 + a^3/4 + a^4/5);  yn = -log1p(-a)/k >= 0
     f2 L = fma2(a, bc(0.2f), bc(0.25f));
     L = fma2(a, L, bc(0.33333334f));

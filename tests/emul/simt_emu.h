@@ -86,6 +86,7 @@ static inline float __fmul_rn(float a, float b) { volatile float r = a * b; retu
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 #define __log2f(x) log2f(x)        /* glibc declares functions of these names */
 #define __expf(x) expf(x)
+#define __logf(x) logf(x)
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
