@@ -187,6 +187,16 @@ class GraphedStep:
             self._scan_info = b[2][off:off + 12].view(torch.int32)
         return self._scan_info
 
+    def n_contrib_view(self):
+        """int32 view [H*W] of the per-pixel last-contributor index inside the image state (bench bookkeeping:
+        its sum is the number of list positions the classic per-pixel formulation walks)."""
+        v = _lib.StateView()
+        b = self._bufs
+        _lib.check(self.L.h3dgs_state_layout(self.P, self.W, self.H, self.bin_capacity, b[0].data_ptr(),
+                                             b[1].data_ptr(), b[2].data_ptr(), C.byref(v)))
+        off = v.n_contrib - b[2].data_ptr()
+        return b[2][off:off + 4 * self.W * self.H].view(torch.int32)
+
     # ---- driving --------------------------------------------------------------------------
     def set_camera(self, cam):
         """cam: pipeline.DeviceCamera (device tensors) -- three small device copies."""
