@@ -1,0 +1,73 @@
+// l1_loss.cu -- L1 loss and its gradient in one pass (the loss of the step bench.py and h3dgs.graphstep time:
+// train_post.py:134-142 with lambda_dssim = 0; the SSIM term lives in loss.cu).
+#include <algorithm>
+#include "common.cuh"
+
+namespace h3dgs {
+
+__device__ __forceinline__ float warp_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 16); v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);  v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+// L1 loss and its gradient in ONE pass (the step of bench.py / h3dgs.graphstep: loss = mean |img - gt|,
+// dL/dimg = sign(img - gt) * scale), optionally only over the 16-pixel tile rows one rank of a tile-sharded frame
+// owns (y_tile % shard_count == shard_index): L1 is per pixel, so a rank needs no pixel it did not render.
+// float4 streams; sum |d| goes to a device double with one atomic per CTA.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+l1_grad_kernel(int C, int H, int W, int shard_count, int shard_index, const float* __restrict__ img,
+               const float* __restrict__ gt, float scale, float* __restrict__ dL_dimg, double* __restrict__ loss_sum)
+{
+    __shared__ float s_red[8];
+    const int W4 = W / VEC;                                  // VEC = 4 needs W % 4 == 0 (launcher)
+    const size_t total4 = (size_t)C * H * W4;
+    float acc = 0.f;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total4; i += (size_t)gridDim.x * 256) {
+        const int y = (int)((i / W4) % H);
+        if (shard_count > 1 && ((y >> 4) % shard_count) != shard_index) continue;
+        if (VEC == 1) {
+            const float d = img[i] - gt[i];
+            acc += fabsf(d);
+            dL_dimg[i] = d > 0.f ? scale : (d < 0.f ? -scale : 0.f);
+            continue;
+        }
+        const float4 a = reinterpret_cast<const float4*>(img)[i], b = reinterpret_cast<const float4*>(gt)[i];
+        const float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z, d3 = a.w - b.w;
+        acc += (fabsf(d0) + fabsf(d1)) + (fabsf(d2) + fabsf(d3));
+        float4 g;
+        g.x = d0 > 0.f ? scale : (d0 < 0.f ? -scale : 0.f); g.y = d1 > 0.f ? scale : (d1 < 0.f ? -scale : 0.f);
+        g.z = d2 > 0.f ? scale : (d2 < 0.f ? -scale : 0.f); g.w = d3 > 0.f ? scale : (d3 < 0.f ? -scale : 0.f);
+        reinterpret_cast<float4*>(dL_dimg)[i] = g;
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const float t = warp_sum(threadIdx.x < 8 ? s_red[threadIdx.x] : 0.f);
+        if (threadIdx.x == 0 && t != 0.f) atomicAdd(loss_sum, (double)t);
+    }
+}
+
+}  // namespace h3dgs
+
+using namespace h3dgs;
+
+extern "C" int h3dgs_l1_loss_grad(int32_t C, int32_t H, int32_t W, const float* img, const float* gt, float scale,
+                                  int32_t shard_count, int32_t shard_index, float* dL_dimg, double* loss_sum, void* stream)
+{
+    if (C <= 0 || H <= 0 || W <= 0 || !img || !gt || !dL_dimg || !loss_sum) { set_error("l1_loss_grad: bad arguments"); return H3DGS_EINVAL; }
+    if (shard_count > 1 && (shard_index < 0 || shard_index >= shard_count)) { set_error("l1_loss_grad: bad shard"); return H3DGS_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    H3_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(double), s));
+    const bool vec = (W & 3) == 0;
+    const size_t total = (size_t)C * H * (vec ? (W >> 2) : W);
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    const int sc = shard_count > 1 ? shard_count : 1, si = shard_count > 1 ? shard_index : 0;
+    if (vec) l1_grad_kernel<4><<<blocks, 256, 0, s>>>(C, H, W, sc, si, img, gt, scale, dL_dimg, loss_sum);
+    else l1_grad_kernel<1><<<blocks, 256, 0, s>>>(C, H, W, sc, si, img, gt, scale, dL_dimg, loss_sum);
+    H3_LAUNCHED("l1_loss_grad", 0, s);
+    return H3DGS_OK;
+}

@@ -17,7 +17,7 @@ EXPORTS = [
     "h3dgs_lod_cut",
     "h3dgs_last_error", "h3dgs_version", "h3dgs_launch_count",
     "h3dgs_profile_enable", "h3dgs_profile_reset", "h3dgs_profile_read", "h3dgs_stage_name",
-    "h3dgs_l1_ssim_forward", "h3dgs_l1_ssim_backward", "h3dgs_sparse_adam",
+    "h3dgs_l1_ssim_forward", "h3dgs_l1_ssim_backward", "h3dgs_l1_loss_grad", "h3dgs_sparse_adam",
 ]
 
 
@@ -74,6 +74,9 @@ def bind(l):
     l.h3dgs_get_interpolation_weights.restype = C.c_int
     l.h3dgs_get_interpolation_weights.argtypes = [C.c_int32, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p] + \
         [C.c_float] * 6 + [C.c_void_p, C.c_void_p, C.c_void_p]
+    l.h3dgs_l1_loss_grad.restype = C.c_int
+    l.h3dgs_l1_loss_grad.argtypes = [C.c_int32] * 3 + [C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]
     l.h3dgs_lod_cut.restype = C.c_int
     l.h3dgs_lod_cut.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_float] + [C.c_void_p] * 10
     if hasattr(l, "h3dgs_l1_ssim_forward"):      # loss / optimizer kernels (absent from the emulation build)

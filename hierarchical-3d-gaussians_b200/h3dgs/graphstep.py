@@ -75,6 +75,7 @@ class GraphedStep:
         else:
             self.image = f(3, H, W)
         self.dcolor = f(3, H, W)
+        self.loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
         self.status_dev = torch.zeros(6, dtype=torch.float64, device=dev)
         M = scene.shs.shape[1]
         self.grads = dict(means3D=f(N, 3), shs=f(N, M, 3), opacities=f(N, 1), scales=f(N, 3), rotations=f(N, 4))
@@ -154,10 +155,12 @@ class GraphedStep:
     def _part_b(self):
         """L1 loss, its gradient, backward (-> reduce-scatter of the [P,10] sums between the phases)."""
         L = self.L
-        diff = self.image - self.gt
-        torch.sign(diff, out=self.dcolor)
-        self.dcolor.mul_(1.0 / diff.numel())
-        loss = diff.abs().mean()
+        # loss = mean |image - gt| and dL/dimage in one pass (csrc/l1_loss.cu); every rank evaluates the full image,
+        # so the loss value needs no further exchange
+        numel = self.image.numel()
+        _lib.check(L.h3dgs_l1_loss_grad(3, self.H, self.W, self.image.data_ptr(), self.gt.data_ptr(), 1.0 / numel, 1, 0,
+                                        self.dcolor.data_ptr(), self.loss_sum.data_ptr(), self._stream()))
+        loss = self.loss_sum / numel
         g = self.grads
         outs = (g["means3D"].data_ptr(), self.d_means2D.data_ptr(), g["shs"].data_ptr(), None, g["opacities"].data_ptr(),
                 g["scales"].data_ptr(), g["rotations"].data_ptr(), None)
@@ -173,7 +176,7 @@ class GraphedStep:
             _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 2, self._stream()))
         info = self.scan_info().double()
         rows_needed = (self.count + self.S).double()
-        self.status_dev[:5].copy_(torch.cat([loss.double().reshape(1), rows_needed, info]))
+        self.status_dev[:5].copy_(torch.cat([loss.reshape(1), rows_needed, info]))
         self.status_dev[5:].copy_((rows_needed > self.P).double())
 
     def scan_info(self):

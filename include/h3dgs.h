@@ -45,6 +45,8 @@ extern "C" {
 
 #define H3DGS_VERSION 1
 #define H3DGS_TILE 16            /* 16x16-pixel tiles                                         */
+#define H3DGS_MAX_PEERS 8        /* ranks of the tile-sharded mode that can share peer memory  */
+#define H3DGS_IPC_HANDLE_BYTES 64
 
 #define H3DGS_OK 0
 #define H3DGS_EINVAL (-1)        /* bad argument combination (shs xor colors, scales xor cov) */
@@ -114,6 +116,21 @@ typedef struct h3dgs_raster_args {
      * the tail h3dgs_lod_cut leaves after the cut when P is the capacity of the index arrays. */
     int64_t bin_capacity;
     int32_t sort_capacity;
+    /* Peer mode of a tile-sharded frame (peer_count == shard_count > 1; one process per GPU on one NVLink / NVSwitch
+     * box; memory from h3dgs_peer_alloc / h3dgs_peer_open): the collectives are fused into the blend kernels.
+     *  forward : every finished pixel of this rank's tile rows is stored into peer_image[r] ([3,H,W], one per rank,
+     *            peer_image[shard_index] = the local one) for all r -- the all-gather of rendered tiles, tile by tile;
+     *            out_color is not written.
+     *  backward: phase 1 adds each (tile, Gaussian) row of the [P][10] sums into peer_accum[owner(row)] (each a full
+     *            [P][10] array on its rank; owner(row) = (row >> grad_cyclic_log2) % peer_count, i.e. blocks of
+     *            2^grad_cyclic_log2 rendered rows dealt round-robin) -- the reduce-scatter is the red.global.add itself.
+     *            `scratch` must be peer_accum[shard_index]; it is NOT zeroed by the call (the owner zeroes it between
+     *            its phase 2 and the next barrier).  Phase 2 finishes exactly the rows this rank owns.
+     * The caller separates the phases with h3dgs_peer_barrier.  peer_count <= 1: off (grad_row_begin/end apply). */
+    int32_t peer_count;
+    int32_t grad_cyclic_log2;
+    void* peer_image[H3DGS_MAX_PEERS];
+    void* peer_accum[H3DGS_MAX_PEERS];
 } h3dgs_raster_args;   /* NOTE: keep hierarchical-3d-gaussians_b200/h3dgs/_lib.py::RasterArgs in sync */
 
 /* Forward: K1 preprocess -> scan -> duplicateWithKeys -> radix sort -> tile ranges
@@ -195,6 +212,23 @@ int h3dgs_lod_cut(int32_t N, const int32_t* nodes, const float* boxes, float tar
                   int32_t* render_indices, int32_t* parent_indices, int32_t* nodes_for_render_indices,
                   float* ts, int32_t* num_kids, int32_t* count, void* scratch, void* stream);
 
+/* ---- peer memory for the tile-sharded multi-GPU mode (csrc/peer.cu) ----
+ * h3dgs_peer_alloc: zero-filled device allocation that can be exported to the other ranks' processes (CUDA IPC);
+ * h3dgs_peer_export / h3dgs_peer_open: 64-byte handle out / mapped pointer in (the host side exchanges the handles,
+ * e.g. with torch.distributed.all_gather_object).  h3dgs_peer_barrier: device-side barrier among `world` ranks, an
+ * ordinary kernel on `stream` (no host synchronisation; capturable): flags = this rank's block of
+ * h3dgs_peer_flag_bytes() zero-initialised peer memory, peer_flags[r] [host array of `world` device pointers] the
+ * block of rank r (peer_flags[rank] == flags).  Everything enqueued on `stream` before the barrier -- including
+ * stores and reductions into peer memory -- is visible to every rank's work after it. */
+size_t h3dgs_peer_flag_bytes(void);
+int h3dgs_peer_alloc(size_t bytes, void** ptr);
+int h3dgs_peer_free(void* ptr);
+int h3dgs_peer_export(const void* ptr, void* handle /* [H3DGS_IPC_HANDLE_BYTES] */);
+int h3dgs_peer_open(const void* handle, void** ptr);
+int h3dgs_peer_close(void* ptr);
+int h3dgs_peer_barrier(int32_t world, int32_t rank, uint32_t* flags, uint32_t* const* peer_flags, void* stream);
+int h3dgs_peer_barrier_status(const uint32_t* flags, void* stream);   /* 1 = a barrier timed out (a peer never arrived) */
+
 /* ---- fused L1 + SSIM loss (replaces utils/loss_utils.py:17-63 as used in
  * train_post.py:134-140: loss = (1-l) * L1 + l * (1 - SSIM), 11x11 Gaussian window, sigma 1.5) ----
  * forward: sums[0] = sum |img-gt|, sums[1] = sum of the SSIM map (device doubles, zeroed here);
@@ -205,6 +239,18 @@ int h3dgs_l1_ssim_forward(int32_t C, int32_t H, int32_t W, const float* img, con
                           float* maps, void* stream);
 int h3dgs_l1_ssim_backward(int32_t C, int32_t H, int32_t W, const float* img, const float* gt, const float* maps,
                            const float* coeffs, float* dL_dimg, void* stream);
+
+/* L1 loss and its gradient in one pass (the loss of bench.py's step; train_post.py:134-142 with lambda_dssim = 0):
+ * *loss_sum [device double, zeroed here] = sum |img - gt|, dL_dimg = sign(img - gt) * scale (scale = 1 / numel for the
+ * mean).  With shard_count > 1 only the 16-pixel tile rows y_tile % shard_count == shard_index are visited (loss_sum is
+ * then this rank's partial sum and the other rows of dL_dimg are left untouched). */
+int h3dgs_l1_loss_grad(int32_t C, int32_t H, int32_t W, const float* img, const float* gt, float scale,
+                       int32_t shard_count, int32_t shard_index, float* dL_dimg, double* loss_sum, void* stream);
+/* the same, adding this rank's partial sum into loss_sums[0..peer_count) [host array of device pointers, one double
+ * per rank in peer memory; NOT zeroed here] so that every rank ends up with the loss of the whole frame */
+int h3dgs_l1_loss_grad_peer(int32_t C, int32_t H, int32_t W, const float* img, const float* gt, float scale,
+                            int32_t shard_count, int32_t shard_index, float* dL_dimg, int32_t peer_count,
+                            double* const* loss_sums, void* stream);
 
 /* ---- sparse Adam (replaces scene/OurAdam.py:249-337 as driven by train_single.py:170-178) ----
  * In-place Adam update of the rows listed in relevant[num_relevant] (int64 row indices) of one parameter

@@ -279,3 +279,23 @@ def test_random_scenes_functional(emu):
         g = emu.backward(a, fw, gcol, gdep)
         for k in ("means3D", "sh", "opacities", "scales", "rotations"):
             grad_close(g[k], b[k], k, tol=2e-4)
+
+
+@pytest.mark.parametrize("W,shard", [(64, (1, 0)), (50, (1, 0)), (64, (3, 1))])
+def test_fused_l1_loss_and_gradient(emu, W, shard):
+    """csrc/l1_loss.cu under emulation: loss sum and sign gradient vs numpy, float4 and scalar streams, tile-row shard."""
+    import ctypes as C
+    H = 40
+    g = np.random.default_rng(0)
+    img = g.uniform(0, 1, (3, H, W)).astype(np.float32); gt = g.uniform(0, 1, (3, H, W)).astype(np.float32)
+    gt[0, 3, 5] = img[0, 3, 5]                                  # sign(0) = 0
+    out = np.full((3, H, W), 7.0, np.float32); s = np.zeros(1, np.float64)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = emu.L.h3dgs_l1_loss_grad(3, H, W, p(img), p(gt), C.c_float(0.25), shard[0], shard[1], p(out), p(s), None)
+    assert rc == 0
+    rows = np.arange(H)
+    own = ((rows // 16) % shard[0]) == shard[1]
+    d = (img - gt)[:, own]
+    assert abs(s[0] - np.abs(d.astype(np.float64)).sum()) < 1e-3
+    assert np.array_equal(out[:, own], np.sign(d) * np.float32(0.25))
+    assert np.all(out[:, ~own] == 7.0)
