@@ -121,6 +121,16 @@ static int check_args(const h3dgs_raster_args* a) {
         set_error("bad capacities: bin %lld, sort %d (max %d)", (long long)a->bin_capacity, a->sort_capacity, kTileSortCap);
         return H3DGS_EINVAL;
     }
+    if (a->peer_count > 1) {
+        const int n = a->peer_count;
+        if (n != a->shard_count || n > H3DGS_MAX_PEERS || (n & (n - 1)) || a->grad_cyclic_log2 < 5 || a->grad_cyclic_log2 > 24 || a->do_depth) {
+            set_error("peer mode needs peer_count == shard_count in {2,4,8}, 5 <= grad_cyclic_log2 <= 24, do_depth off (got %d/%d, log2 %d)",
+                      n, a->shard_count, a->grad_cyclic_log2);
+            return H3DGS_EINVAL;
+        }
+        for (int r = 0; r < n; r++)
+            if (!a->peer_image[r] || !a->peer_accum[r]) { set_error("peer mode: peer_image / peer_accum [%d] is NULL", r); return H3DGS_EINVAL; }
+    }
     if (a->bin_capacity > 0 && a->debug) { set_error("capacity mode has no host synchronisation: debug must be off"); return H3DGS_EINVAL; }
     if (!a->means3D && a->P > 0) { set_error("means3D is NULL"); return H3DGS_EINVAL; }
     if (!a->bg || !a->viewmatrix || !a->projmatrix || !a->campos) { set_error("bg/viewmatrix/projmatrix/campos must be device pointers"); return H3DGS_EINVAL; }
@@ -163,7 +173,7 @@ extern "C" int h3dgs_rasterize_forward(const h3dgs_raster_args* a, h3dgs_alloc_f
 {
     int rc = check_args(a);
     if (rc) return rc;
-    if (!alloc || !out_color || (!out_radii && a->P > 0) || (a->do_depth && !out_invdepth)) {
+    if (!alloc || (!out_color && a->peer_count <= 1) || (!out_radii && a->P > 0) || (a->do_depth && !out_invdepth)) {
         set_error("missing output buffer or alloc callback"); return H3DGS_EINVAL;
     }
     cudaStream_t s = (cudaStream_t)stream;
@@ -287,7 +297,11 @@ extern "C" int h3dgs_rasterize_backward(const h3dgs_raster_args* a, const int32_
         H3_CUDA(cudaEventRecord(ss->join, ss->s));
         zero_joined = false;
     }
-    if (phases & 1) H3_CUDA(cudaMemsetAsync(accum, 0, (size_t)a->P * kAccum * sizeof(float), s));
+    if (a->peer_count > 1 && scratch != a->peer_accum[a->shard_index]) {
+        set_error("peer mode: scratch must be peer_accum[shard_index]"); return H3DGS_EINVAL;
+    }
+    // peer mode: the other ranks add into this accumulator too -- its owner zeroes it between steps (see h3dgs.h)
+    if ((phases & 1) && a->peer_count <= 1) H3_CUDA(cudaMemsetAsync(accum, 0, (size_t)a->P * kAccum * sizeof(float), s));
     if (D > 0 && (phases & 1)) {
         rc = launch_render_backward(b, (const uint32_t*)(img + il.ranges), (const Record*)(bin + bl.sorted_records),
                                     (const uint32_t*)(bin + bl.vals_sorted), (const float*)(img + il.final_T),

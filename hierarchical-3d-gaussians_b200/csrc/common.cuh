@@ -121,7 +121,7 @@ int launch_binning(const h3dgs_raster_args& a, const int32_t* radii, const float
                    cudaStream_t s);
 int launch_render_forward(const h3dgs_raster_args& a, const uint32_t* ranges, const Record* sorted_records,
                           float* out_color, float* out_invdepth, float* final_T, uint32_t* n_contrib,
-                          uint32_t* tile_max_contrib, cudaStream_t s);
+                          uint32_t* tile_max_contrib, cudaStream_t s);   // peer mode: pixels go to a.peer_image[*]
 int launch_render_backward(const h3dgs_raster_args& a, const uint32_t* ranges, const Record* sorted_records,
                            const uint32_t* point_list, const float* final_T, const uint32_t* n_contrib,
                            const uint32_t* tile_max_contrib, const float* dL_dcolor, const float* dL_dinvdepth,
@@ -151,6 +151,32 @@ __device__ __forceinline__ void group_pixel(int tile_x, int tile_y, int warp, in
 // 27 % fewer loop iterations at 2.3x the gradient reductions); H3DGS_GROUPWALK=0 selects the one-list-per-warp variants.
 inline bool use_group_walk() { const char* e = getenv("H3DGS_GROUPWALK"); return !(e && e[0] == '0'); }
 
+#endif
+
+// peer mode (h3dgs_raster_args.peer_count > 1): device pointers into the memory of every rank, by value in the kernel parameters
+struct PeerPtrs { void* p[H3DGS_MAX_PEERS]; int n; };
+inline PeerPtrs peer_ptrs(void* const* src, int n) {
+    PeerPtrs r; r.n = n > 1 ? n : 0;
+    for (int k = 0; k < H3DGS_MAX_PEERS; k++) r.p[k] = (k < r.n) ? src[k] : nullptr;
+    return r;
+}
+// block-cyclic ownership of rendered rows in peer mode: blocks of 2^shift rows dealt round-robin to the ranks
+struct RowCycle { int shift, world, rank; };
+inline RowCycle row_cycle(const h3dgs_raster_args& a) {
+    RowCycle c; c.world = a.peer_count > 1 ? a.peer_count : 0; c.rank = a.shard_index; c.shift = a.grad_cyclic_log2;
+    return c;
+}
+// number of rows (padded to whole blocks) rank `c.rank` owns out of P
+inline int cyclic_local_rows(const RowCycle& c, int P) {
+    const int blocks = (P + (1 << c.shift) - 1) >> c.shift;
+    return ((blocks + c.world - 1 - c.rank) / c.world) << c.shift;
+}
+#ifdef __CUDACC__
+// local (dense) index -> rendered row of the owning rank
+__device__ __forceinline__ int cyclic_row(const RowCycle& c, int local) {
+    return ((((local >> c.shift) * c.world + c.rank)) << c.shift) + (local & ((1 << c.shift) - 1));
+}
+__device__ __forceinline__ bool cyclic_owned(const RowCycle& c, int row) { return ((row >> c.shift) % c.world) == c.rank; }
 #endif
 
 // accum row layout (floats): 0,1 dmean2D.xy | 2,3,4 dconic | 5 dopacity | 6,7,8 dcolor | 9 dinvdepth

@@ -19,7 +19,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 template <int VEC>
 __global__ void __launch_bounds__(256)
 l1_grad_kernel(int C, int H, int W, int shard_count, int shard_index, const float* __restrict__ img,
-               const float* __restrict__ gt, float scale, float* __restrict__ dL_dimg, double* __restrict__ loss_sum)
+               const float* __restrict__ gt, float scale, float* __restrict__ dL_dimg, double* __restrict__ loss_sum,
+               const PeerPtrs peers)
 {
     __shared__ float s_red[8];
     const int W4 = W / VEC;                                  // VEC = 4 needs W % 4 == 0 (launcher)
@@ -47,13 +48,29 @@ l1_grad_kernel(int C, int H, int W, int shard_count, int shard_index, const floa
     __syncthreads();
     if (threadIdx.x < 32) {
         const float t = warp_sum(threadIdx.x < 8 ? s_red[threadIdx.x] : 0.f);
-        if (threadIdx.x == 0 && t != 0.f) atomicAdd(loss_sum, (double)t);
+        if (threadIdx.x == 0 && t != 0.f) {
+            if (peers.n > 1) { for (int r = 0; r < peers.n; r++) atomicAdd_system(static_cast<double*>(peers.p[r]), (double)t); }
+            else atomicAdd(loss_sum, (double)t);
+        }
     }
 }
 
 }  // namespace h3dgs
 
 using namespace h3dgs;
+
+static int l1_launch(int32_t C, int32_t H, int32_t W, const float* img, const float* gt, float scale, int32_t shard_count,
+                     int32_t shard_index, float* dL_dimg, double* loss_sum, const PeerPtrs& peers, cudaStream_t s)
+{
+    const bool vec = (W & 3) == 0;
+    const size_t total = (size_t)C * H * (vec ? (W >> 2) : W);
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    const int sc = shard_count > 1 ? shard_count : 1, si = shard_count > 1 ? shard_index : 0;
+    if (vec) l1_grad_kernel<4><<<blocks, 256, 0, s>>>(C, H, W, sc, si, img, gt, scale, dL_dimg, loss_sum, peers);
+    else l1_grad_kernel<1><<<blocks, 256, 0, s>>>(C, H, W, sc, si, img, gt, scale, dL_dimg, loss_sum, peers);
+    H3_LAUNCHED("l1_loss_grad", 0, s);
+    return H3DGS_OK;
+}
 
 extern "C" int h3dgs_l1_loss_grad(int32_t C, int32_t H, int32_t W, const float* img, const float* gt, float scale,
                                   int32_t shard_count, int32_t shard_index, float* dL_dimg, double* loss_sum, void* stream)
@@ -62,12 +79,19 @@ extern "C" int h3dgs_l1_loss_grad(int32_t C, int32_t H, int32_t W, const float* 
     if (shard_count > 1 && (shard_index < 0 || shard_index >= shard_count)) { set_error("l1_loss_grad: bad shard"); return H3DGS_EINVAL; }
     cudaStream_t s = (cudaStream_t)stream;
     H3_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(double), s));
-    const bool vec = (W & 3) == 0;
-    const size_t total = (size_t)C * H * (vec ? (W >> 2) : W);
-    const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-    const int sc = shard_count > 1 ? shard_count : 1, si = shard_count > 1 ? shard_index : 0;
-    if (vec) l1_grad_kernel<4><<<blocks, 256, 0, s>>>(C, H, W, sc, si, img, gt, scale, dL_dimg, loss_sum);
-    else l1_grad_kernel<1><<<blocks, 256, 0, s>>>(C, H, W, sc, si, img, gt, scale, dL_dimg, loss_sum);
-    H3_LAUNCHED("l1_loss_grad", 0, s);
-    return H3DGS_OK;
+    PeerPtrs none; none.n = 0;
+    for (int k = 0; k < H3DGS_MAX_PEERS; k++) none.p[k] = nullptr;
+    return l1_launch(C, H, W, img, gt, scale, shard_count, shard_index, dL_dimg, loss_sum, none, s);
+}
+
+extern "C" int h3dgs_l1_loss_grad_peer(int32_t C, int32_t H, int32_t W, const float* img, const float* gt, float scale,
+                                       int32_t shard_count, int32_t shard_index, float* dL_dimg, int32_t peer_count,
+                                       double* const* loss_sums, void* stream)
+{
+    if (C <= 0 || H <= 0 || W <= 0 || !img || !gt || !dL_dimg || !loss_sums || peer_count < 2 || peer_count > H3DGS_MAX_PEERS) {
+        set_error("l1_loss_grad_peer: bad arguments"); return H3DGS_EINVAL;
+    }
+    if (shard_count > 1 && (shard_index < 0 || shard_index >= shard_count)) { set_error("l1_loss_grad_peer: bad shard"); return H3DGS_EINVAL; }
+    return l1_launch(C, H, W, img, gt, scale, shard_count, shard_index, dL_dimg, nullptr,
+                     peer_ptrs(reinterpret_cast<void* const*>(loss_sums), peer_count), (cudaStream_t)stream);
 }

@@ -198,14 +198,15 @@ __global__ void __launch_bounds__(256)
 preprocess_color_kernel(int P, int deg, int M, const float* __restrict__ means3D, const float* __restrict__ shs,
                         const float* __restrict__ ts, const int* __restrict__ ridx, const int* __restrict__ pidx,
                         const float* __restrict__ campos, const int* __restrict__ radii,
-                        const uint32_t* __restrict__ own_tiles, int row_begin, int row_end, Record* __restrict__ records)
+                        const uint32_t* __restrict__ own_tiles, int row_begin, int row_end, const RowCycle cyc,
+                        Record* __restrict__ records)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     if (radii[i] <= 0) return;
     // tile-sharded frame: the colour (and its clamp flags) of a Gaussian is read by the ranks whose tile rows
     // it touches (forward gather) and by the rank that owns its gradient row (SH backward); nobody else needs it
-    if (own_tiles && own_tiles[i] == 0u && (i < row_begin || i >= row_end)) return;
+    if (own_tiles && own_tiles[i] == 0u && (cyc.world > 1 ? !cyclic_owned(cyc, i) : (i < row_begin || i >= row_end))) return;
     int c = i, p = i;
     float t = 1.0f, u = 0.0f;
     if (ridx) {
@@ -301,12 +302,13 @@ int launch_preprocess_color(const h3dgs_raster_args& a, const int32_t* radii, co
     if (a.P == 0 || a.colors_precomp) return H3DGS_OK;
     const int threads = 256, blocks = (a.P + threads - 1) / threads;
     // only when the caller told the forward which gradient rows this rank will finish (otherwise every visible row may be needed)
-    const bool skip_foreign = a.shard_count > 1 && a.grad_row_end > a.grad_row_begin;
+    const RowCycle cyc = row_cycle(a);
+    const bool skip_foreign = a.shard_count > 1 && (a.grad_row_end > a.grad_row_begin || cyc.world > 1);
     ProfScope prof(H3DGS_STAGE_PREPROCESS_COLOR, s);
     preprocess_color_kernel<<<blocks, threads, 0, s>>>(a.P, a.sh_degree, a.sh_coeffs, a.means3D, a.shs,
                                                        a.interpolation_weights, a.render_indices, a.parent_indices,
                                                        a.campos, radii, skip_foreign ? tiles_touched : nullptr,
-                                                       a.grad_row_begin, a.grad_row_end, records);
+                                                       a.grad_row_begin, a.grad_row_end, cyc, records);
     H3_LAUNCHED("preprocess_color", a.debug, s);
     return H3DGS_OK;
 }

@@ -27,7 +27,7 @@ __device__ __forceinline__ void store_zero(float* p, int n) {
 }
 
 __global__ void __launch_bounds__(128)
-preprocess_backward_kernel(int row0, int P, int deg, int M, const float* __restrict__ means3D, const float* __restrict__ scales,
+preprocess_backward_kernel(int row0, int P, const RowCycle cyc, int deg, int M, const float* __restrict__ means3D, const float* __restrict__ scales,
                            float scale_mod, const float* __restrict__ rots, const float* __restrict__ shs,
                            const float* __restrict__ cov3D_precomp, const float* __restrict__ colors_precomp,
                            const float* __restrict__ ts, const int* __restrict__ ridx, const int* __restrict__ pidx,
@@ -42,7 +42,8 @@ preprocess_backward_kernel(int row0, int P, int deg, int M, const float* __restr
     __shared__ float s_view[16], s_proj[16];
     if (threadIdx.x < 16) { s_view[threadIdx.x] = view[threadIdx.x]; s_proj[threadIdx.x] = proj[threadIdx.x]; }
     __syncthreads();
-    const int i = row0 + blockIdx.x * blockDim.x + threadIdx.x;      // rows [row0, P)
+    const int local = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = cyc.world > 1 ? cyclic_row(cyc, local) : row0 + local;      // rows [row0, P), or the blocks this rank owns
     if (i >= P) return;
 
     if (radii[i] <= 0) {
@@ -160,12 +161,13 @@ preprocess_backward_kernel(int row0, int P, int deg, int M, const float* __restr
 // K9b: dL/dcolour -> dL/dSH (basis x dL/dRGB, no intermediate array) and, through the view
 // direction, an ADDITIVE term of dL/dmean (runs after preprocess_backward_kernel on the stream).
 __global__ void __launch_bounds__(128)
-sh_backward_kernel(int row0, int P, int deg, int M, const float* __restrict__ means3D, const float* __restrict__ shs,
+sh_backward_kernel(int row0, int P, const RowCycle cyc, int deg, int M, const float* __restrict__ means3D, const float* __restrict__ shs,
                    const float* __restrict__ ts, const int* __restrict__ ridx, const int* __restrict__ pidx,
                    const float* __restrict__ campos, const int* __restrict__ radii, const Record* __restrict__ records,
                    const float* __restrict__ accum, float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dsh)
 {
-    const int i = row0 + blockIdx.x * blockDim.x + threadIdx.x;      // rows [row0, P)
+    const int local = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = cyc.world > 1 ? cyclic_row(cyc, local) : row0 + local;      // rows [row0, P), or the blocks this rank owns
     if (i >= P) return;
     const int SH3 = M * 3;
     if (radii[i] <= 0) {
@@ -306,12 +308,14 @@ int launch_preprocess_backward(const h3dgs_raster_args& a, const int32_t* radii,
 {
     if (a.P == 0) return H3DGS_OK;
     const float fx = a.image_width / (2.0f * a.tanfovx), fy = a.image_height / (2.0f * a.tanfovy);
-    const int r0 = a.grad_row_end > a.grad_row_begin ? a.grad_row_begin : 0;
-    const int r1 = a.grad_row_end > a.grad_row_begin ? min(a.grad_row_end, a.P) : a.P;
-    if (r1 <= r0) return H3DGS_OK;
+    const RowCycle cyc = row_cycle(a);
+    const int r0 = (cyc.world > 1 || a.grad_row_end <= a.grad_row_begin) ? 0 : a.grad_row_begin;
+    const int r1 = (cyc.world > 1 || a.grad_row_end <= a.grad_row_begin) ? a.P : min(a.grad_row_end, a.P);
+    const int rows = cyc.world > 1 ? cyclic_local_rows(cyc, a.P) : r1 - r0;
+    if (rows <= 0) return H3DGS_OK;
     ProfScope prof(H3DGS_STAGE_PREPROCESS_BWD, s);
-    preprocess_backward_kernel<<<(r1 - r0 + 127) / 128, 128, 0, s>>>(
-        r0, r1, a.sh_degree, a.sh_coeffs, a.means3D, a.scales, a.scale_modifier, a.rotations, a.shs, a.cov3D_precomp,
+    preprocess_backward_kernel<<<(rows + 127) / 128, 128, 0, s>>>(
+        r0, r1, cyc, a.sh_degree, a.sh_coeffs, a.means3D, a.scales, a.scale_modifier, a.rotations, a.shs, a.cov3D_precomp,
         a.colors_precomp, a.interpolation_weights, a.render_indices, a.parent_indices, a.viewmatrix, a.projmatrix, a.campos, a.image_width, a.image_height, a.tanfovx, a.tanfovy,
         fx, fy, a.do_depth, radii, records, accum, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacities,
         dL_dscales, dL_drots, dL_dcov3D);
@@ -323,11 +327,13 @@ int launch_sh_backward(const h3dgs_raster_args& a, const int32_t* radii, const R
                        float* dL_dmeans3D, float* dL_dsh, cudaStream_t s)
 {
     if (a.P == 0 || a.colors_precomp) return H3DGS_OK;
-    const int r0 = a.grad_row_end > a.grad_row_begin ? a.grad_row_begin : 0;
-    const int r1 = a.grad_row_end > a.grad_row_begin ? min(a.grad_row_end, a.P) : a.P;
-    if (r1 <= r0) return H3DGS_OK;
+    const RowCycle cyc = row_cycle(a);
+    const int r0 = (cyc.world > 1 || a.grad_row_end <= a.grad_row_begin) ? 0 : a.grad_row_begin;
+    const int r1 = (cyc.world > 1 || a.grad_row_end <= a.grad_row_begin) ? a.P : min(a.grad_row_end, a.P);
+    const int rows = cyc.world > 1 ? cyclic_local_rows(cyc, a.P) : r1 - r0;
+    if (rows <= 0) return H3DGS_OK;
     ProfScope prof(H3DGS_STAGE_SH_BACKWARD, s);
-    sh_backward_kernel<<<(r1 - r0 + 127) / 128, 128, 0, s>>>(r0, r1, a.sh_degree, a.sh_coeffs, a.means3D, a.shs,
+    sh_backward_kernel<<<(rows + 127) / 128, 128, 0, s>>>(r0, r1, cyc, a.sh_degree, a.sh_coeffs, a.means3D, a.shs,
                                                          a.interpolation_weights, a.render_indices, a.parent_indices,
                                                          a.campos, radii, records, accum, dL_dmeans3D, dL_dsh);
     H3_LAUNCHED("sh_backward", a.debug, s);

@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(kFwdThreads)
 render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, const uint2* __restrict__ ranges,
                       const Record* __restrict__ sorted, const float* __restrict__ bg, float* __restrict__ out_color,
                       float* __restrict__ out_invdepth, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
-                      uint32_t* __restrict__ tile_max_contrib)
+                      uint32_t* __restrict__ tile_max_contrib, const PeerPtrs peers)
 {
     __shared__ __align__(128) Record s_rec[kFwdStages][kFwdBatch];
     __shared__ __align__(8) uint64_t s_full[kFwdStages];
@@ -146,7 +146,17 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
         const size_t pix = (size_t)py * W + px;
         final_T[pix] = T;
         n_contrib[pix] = last;
-        if (shard_count > 1) {
+        if (peers.n > 1) {
+            // peer mode: the finished pixel goes straight into the [3,H,W] image of EVERY rank (plain stores; remote ones
+            // travel over NVLink while other tiles are still blending) -- the all-gather of rendered tiles, fused
+            const size_t plane = (size_t)H * W;
+            const float v0 = c0 + T * bg0, v1 = c1 + T * bg1, v2 = c2 + T * bg2;
+            for (int r = 0; r < peers.n; r++) {
+                float* o = static_cast<float*>(peers.p[r]);
+                o[pix] = v0; o[plane + pix] = v1; o[2 * plane + pix] = v2;
+            }
+            if (DEPTH) out_invdepth[(((size_t)(blockIdx.x / gx)) * kTile + (size_t)(py & (kTile - 1))) * W + px] = invd;
+        } else if (shard_count > 1) {
             // packed shard layout [local tile row][channel][16][W]: one contiguous slab per
             // rank, so the image exchange is a single all-gather (h3dgs/dist.py)
             const size_t local_row = blockIdx.x / gx;
@@ -182,10 +192,11 @@ int launch_render_forward(const h3dgs_raster_args& a, const uint32_t* ranges, co
     const dim3 grid(gx * rows), block(kFwdThreads);
     ProfScope prof(H3DGS_STAGE_RENDER_FWD, s);
     const bool groups = use_group_walk();
+    const PeerPtrs peers = peer_ptrs(a.peer_image, a.peer_count);
 #define LAUNCH(HI, DE, GR)                                                                                         \
     render_forward_kernel<HI, DE, GR><<<grid, block, 0, s>>>(W, H, gx, sc, si, (const uint2*)ranges, sorted_records, \
                                                              a.bg, out_color, out_invdepth, final_T, n_contrib,      \
-                                                             tile_max_contrib)
+                                                             tile_max_contrib, peers)
 #define LAUNCH2(HI, DE) do { if (groups) LAUNCH(HI, DE, true); else LAUNCH(HI, DE, false); } while (0)
     if (hier) { if (depth) LAUNCH2(true, true); else LAUNCH2(true, false); }
     else      { if (depth) LAUNCH2(false, true); else LAUNCH2(false, false); }

@@ -17,8 +17,12 @@ EXPORTS = [
     "h3dgs_lod_cut",
     "h3dgs_last_error", "h3dgs_version", "h3dgs_launch_count",
     "h3dgs_profile_enable", "h3dgs_profile_reset", "h3dgs_profile_read", "h3dgs_stage_name",
-    "h3dgs_l1_ssim_forward", "h3dgs_l1_ssim_backward", "h3dgs_l1_loss_grad", "h3dgs_sparse_adam",
+    "h3dgs_l1_ssim_forward", "h3dgs_l1_ssim_backward", "h3dgs_l1_loss_grad", "h3dgs_l1_loss_grad_peer", "h3dgs_sparse_adam",
+    "h3dgs_peer_flag_bytes", "h3dgs_peer_alloc", "h3dgs_peer_free", "h3dgs_peer_export", "h3dgs_peer_open", "h3dgs_peer_close",
+    "h3dgs_peer_barrier", "h3dgs_peer_barrier_status",
 ]
+MAX_PEERS = 8
+IPC_HANDLE_BYTES = 64
 
 
 class RasterArgs(C.Structure):
@@ -36,6 +40,8 @@ class RasterArgs(C.Structure):
         ("shard_count", C.c_int32), ("shard_index", C.c_int32),
         ("grad_row_begin", C.c_int32), ("grad_row_end", C.c_int32),
         ("bin_capacity", C.c_int64), ("sort_capacity", C.c_int32),
+        ("peer_count", C.c_int32), ("grad_cyclic_log2", C.c_int32),
+        ("peer_image", C.c_void_p * 8), ("peer_accum", C.c_void_p * 8),
     ]
 
 
@@ -77,6 +83,25 @@ def bind(l):
     l.h3dgs_l1_loss_grad.restype = C.c_int
     l.h3dgs_l1_loss_grad.argtypes = [C.c_int32] * 3 + [C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
+    l.h3dgs_l1_loss_grad_peer.restype = C.c_int
+    l.h3dgs_l1_loss_grad_peer.argtypes = [C.c_int32] * 3 + [C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32,
+                                          C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.c_void_p]
+    if hasattr(l, "h3dgs_peer_alloc"):           # peer memory (CUDA IPC, device-side barrier): absent from the emulation build
+        l.h3dgs_peer_flag_bytes.restype = C.c_size_t
+        l.h3dgs_peer_alloc.restype = C.c_int
+        l.h3dgs_peer_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+        l.h3dgs_peer_free.restype = C.c_int
+        l.h3dgs_peer_free.argtypes = [C.c_void_p]
+        l.h3dgs_peer_export.restype = C.c_int
+        l.h3dgs_peer_export.argtypes = [C.c_void_p, C.c_void_p]
+        l.h3dgs_peer_open.restype = C.c_int
+        l.h3dgs_peer_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        l.h3dgs_peer_close.restype = C.c_int
+        l.h3dgs_peer_close.argtypes = [C.c_void_p]
+        l.h3dgs_peer_barrier.restype = C.c_int
+        l.h3dgs_peer_barrier.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
+        l.h3dgs_peer_barrier_status.restype = C.c_int
+        l.h3dgs_peer_barrier_status.argtypes = [C.c_void_p, C.c_void_p]
     l.h3dgs_lod_cut.restype = C.c_int
     l.h3dgs_lod_cut.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_float] + [C.c_void_p] * 10
     if hasattr(l, "h3dgs_l1_ssim_forward"):      # loss / optimizer kernels (absent from the emulation build)

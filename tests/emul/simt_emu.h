@@ -124,6 +124,8 @@ static inline double atomicAdd(double* p, double v) { double o = *p; *p = o + v;
 static inline int atomicAdd(int* p, int v) { int o = *p; *p = o + v; return o; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 static inline float4 atomicAdd(float4* p, float4 v) { float4 o = *p; p->x += v.x; p->y += v.y; p->z += v.z; p->w += v.w; return o; }
+static inline float atomicAdd_system(float* p, float v) { return atomicAdd(p, v); }
+static inline double atomicAdd_system(double* p, double v) { return atomicAdd(p, v); }
 static inline unsigned atomicSub(unsigned* p, unsigned v) { unsigned o = *p; *p = o - v; return o; }
 static inline unsigned atomicMax(unsigned* p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
 static inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }

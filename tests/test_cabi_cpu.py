@@ -34,7 +34,7 @@ def test_ctypes_struct_mirrors_header():
         if not decl:
             continue
         for part in decl.split(","):
-            m = re.search(r"(\w+)\s*$", part.strip())
+            m = re.search(r"(\w+)\s*(?:\[\w+\])?\s*$", part.strip())
             if m:
                 names.append(m.group(1))
     assert names == [f[0] for f in _lib.RasterArgs._fields_]

@@ -299,3 +299,61 @@ def test_fused_l1_loss_and_gradient(emu, W, shard):
     assert abs(s[0] - np.abs(d.astype(np.float64)).sum()) < 1e-3
     assert np.array_equal(out[:, own], np.sign(d) * np.float32(0.25))
     assert np.all(out[:, ~own] == 7.0)
+
+
+@pytest.mark.parametrize("G", [2, 4])
+def test_peer_mode_fused_collectives_schedule(emu, G):
+    """Peer mode (h3dgs_raster_args.peer_count) on one CPU: G "ranks" run one after the other with numpy arrays standing in
+    for peer memory.  Forward: every rank stores the pixels of ITS tile rows into the image of EVERY rank -> all G images
+    equal the unsharded one bit for bit.  Backward phase 1: each rank adds its (tile, Gaussian) sums straight into the
+    accumulator of the rank that owns the row (block-cyclic, 2^5 rows) -> the owners' accumulators hold the complete sums of
+    their rows and nothing else; phase 2 finishes exactly the owned rows.  Fused gather/scatter (render_indices) on top."""
+    from oracle import oracle
+    from emu_api import aligned, ptr
+    cam = synth.make_camera(160, 112)
+    leaves = synth.cloud_v1(1500, cam, zmin=2.0, zmax=30.0, seed=2, scale_k=1.0)
+    z = leaves["means3D"][:, 2:3]
+    leaves["scales"] = (8e-3 * np.sqrt(2 * z) * np.ones((1, 3))).astype(np.float32)
+    h = synth.build_hierarchy(leaves)
+    thr = synth.tau_threshold(6.0, cam)
+    n, ri, pi, ni = oracle.expand_to_size(h["nodes"], h["boxes"], thr, cam.camera_center)
+    ts, kids = oracle.get_interpolation_weights(ni, thr, h["nodes"], h["boxes"], cam.camera_center)
+    bg = np.array([0.3, 0.2, 0.1], np.float32)
+    f = oracle.rasterize_forward(h["means3D"], h["shs"], None, h["opacities"], h["scales"], h["rotations"], None,
+                                 cam.world_view_transform, cam.full_proj_transform, cam.camera_center, bg, cam.W, cam.H,
+                                 cam.tanfovx, cam.tanfovy, ts=ts, kids=kids, render_indices=ri, parent_indices=pi)
+    gcol = synth.l1_grad(f["color"])
+    b = oracle.rasterize_backward(f, gcol)
+    a0, keep0 = emu.args(cam, bg, h, ts=ts, kids=kids, ridx=ri, pidx=pi)
+    whole = emu.forward(a0, keep0)
+    P, SHIFT = n, 5
+    images = [aligned(3 * cam.H * cam.W * 4, np.float32, (3, cam.H, cam.W)) for _ in range(G)]
+    accums = [aligned(emu.L.h3dgs_backward_scratch_bytes(P)) for _ in range(G)]
+    ranks = []
+    for r in range(G):
+        a, keep = emu.args(cam, bg, h, ts=ts, kids=kids, ridx=ri, pidx=pi, shard=(G, r))
+        a.peer_count, a.grad_cyclic_log2 = G, SHIFT
+        for k in range(G):
+            a.peer_image[k], a.peer_accum[k] = ptr(images[k]), ptr(accums[k])
+        ranks.append((a, keep, emu.forward(a, keep)))
+    for img in images:
+        assert np.array_equal(img, whole["color"])
+    for a, keep, fw in ranks:                                    # phase 1 everywhere ("barrier"), then phase 2
+        emu.backward(a, fw, gcol, phases=1, scratch=accums[a.shard_index])
+    rows = np.arange(P)
+    owner = (rows >> SHIFT) % G
+    for r in range(G):
+        acc = accums[r].view(np.float32)[: P * 10].reshape(P, 10)
+        assert not acc[owner != r].any() and acc[owner == r].any()
+    total = {k: np.zeros(b[k].shape, np.float64) for k in ("means3D", "sh", "opacities", "scales", "rotations")}
+    m2d = np.zeros((P, 3), np.float32)
+    for a, keep, fw in ranks:
+        g2 = emu.backward(a, fw, gcol, phases=2, scratch=accums[a.shard_index])
+        for k in total:
+            total[k] += g2[k]
+        own = owner == a.shard_index
+        assert not g2["means2D"][~own].any()
+        m2d[own] = g2["means2D"][own]
+    for k in total:
+        grad_close(total[k].astype(np.float32), b[k], k)
+    grad_close(m2d, b["means2D"], "means2D")
