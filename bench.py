@@ -385,6 +385,9 @@ def main():
     ap.add_argument("--graph", action="store_true", help="same as --mode graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the value_api / value_dropin / N-rank check passes")
+    ap.add_argument("--no-peer", action="store_true",
+                    help="N > 1, graph mode: NCCL all-gather + reduce-scatter instead of the collectives fused into the blend "
+                         "kernels over peer memory (the default on 2, 4 or 8 GPUs)")
     ap.add_argument("--classic", action="store_true",
                     help="also time the classic-formulation blend kernels (baseline/classic) on the same binned state")
     args = ap.parse_args()
@@ -446,7 +449,11 @@ def main():
     if mode == "graph":
         from h3dgs.graphstep import GraphedStep
         c0 = cams[0]
-        mk = lambda **kw: GraphedStep(scene, W, H, c0.tanfovx, c0.tanfovy, bg, thr[0], world=world, rank=rank, **kw)
+        use_peer = world in (2, 4, 8) and not args.no_peer
+        config["collectives"] = ("fused into the blend kernels over NVLink peer memory (stores into every rank's image, red.add into "
+                                 "the owner's accumulator) + 3 device-side barrier kernels per step" if use_peer else
+                                 ("NCCL all-gather (image slabs) + reduce-scatter ([P,10] sums)" if world > 1 else "none"))
+        mk = lambda **kw: GraphedStep(scene, W, H, c0.tanfovx, c0.tanfovy, bg, thr[0], world=world, rank=rank, peer=use_peer, **kw)
         # capacities: one eager sync-free pass over the views with generous sizes, then +15 % head room
         # (rows and entries) and the next power of two (longest tile list)
         probe = mk(bin_capacity=(1 << 23) if W <= 1920 else (1 << 27), sort_capacity=8192, capture=False)
@@ -458,6 +465,8 @@ def main():
             if st["overflow"]:
                 raise SystemExit(f"--mode graph: view {v} does not fit the probe capacities: {st}")
             need = {k: max(need[k], st[k]) for k in need}
+        if probe.arena is not None:
+            probe.arena.close()
         del probe
         torch.cuda.empty_cache()
         rows_cap = min(int(need["rows"] * 1.15) + 1, scene.means3D.shape[0])
@@ -661,6 +670,18 @@ def main():
             e1.record(); torch.cuda.synchronize()
             t = torch.tensor([e0.elapsed_time(e1) / 20], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
             comm[name] = round(float(t.item()), 4)
+        if gs is not None and gs.peer:
+            for _ in range(5):
+                gs.arena.barrier()
+            dist.barrier(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(50):
+                gs.arena.barrier()
+            e1.record(); torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / 50], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            comm = {"peer_barrier_kernel": round(float(t.item()), 4), "barrier_timed_out": gs.arena.timed_out(),
+                    "nccl_for_comparison": comm}
         nrank = {"equals_single_gpu": bool(ok.item() == 1.0), "grad_rel_err_max": max(errs), "comm_ms": comm,
                  "comm_bytes": {"all_gather_image": int(slabs.numel() * 4), "reduce_scatter_accum": int(acc.numel())}}
 

@@ -14,6 +14,14 @@ the critical path.  Here nothing returns to the host inside the step:
     raises a device flag, renders the background only and contributes zero gradients; status()
     reports it and the caller re-runs that frame through the exact path (pipeline.l1_step).
 
+Sharded over G > 1 ranks the step has two forms.  peer=False: the image slabs travel in one NCCL all-gather, the
+[P,10] gradient sums in one NCCL reduce-scatter (h3dgs.dist).  peer=True (G in {2,4,8} on one NVLink box): the
+collectives are fused into the blend kernels through peer memory (h3dgs.peer, csrc/peer.cu) -- the forward stores every
+finished pixel into the image of every rank, the backward adds each (tile, Gaussian) row of sums into the accumulator of
+the rank that owns the Gaussian (block-cyclic row ownership), the L1 kernel evaluates only the rank's own tile rows and
+adds its partial loss into every rank's sum; what remains are three device-side barrier kernels per step (start: every
+rank's accumulator is zero and its image buffer free; middle of backward: all sums have landed; end: image complete).
+
 With every size static the step is captured once: graph A = LOD cut + forward (+ the all-gather of
 the image slabs when sharded), graph B = L1 loss + its gradient + backward (+ the reduce-scatter of
 the [P,10] sums).  The split lets the 25 MB target upload of the end-to-end loop overlap graph A.
@@ -40,13 +48,18 @@ class GraphedStep:
     inputs that change between replays (set_camera, upload_target / step(gt=), set_threshold)."""
 
     def __init__(self, scene, W, H, tanfovx, tanfovy, bg, threshold, sh_degree=3, row_capacity=None,
-                 bin_capacity=1 << 22, sort_capacity=4096, world=1, rank=0, group=None, capture=True):
+                 bin_capacity=1 << 22, sort_capacity=4096, world=1, rank=0, group=None, capture=True, peer=False,
+                 cyclic_log2=12):
         if not scene.hier:
             raise ValueError("GraphedStep drives the hierarchy path (LOD cut + fused gather/lerp)")
         self.L = _lib.lib()
         self.scene, self.W, self.H = scene, int(W), int(H)
         self.threshold, self.sh_degree = float(threshold), int(sh_degree)
         self.world, self.rank, self.group = int(world), int(rank), group
+        self.peer = bool(peer) and self.world > 1
+        if self.peer and (self.world & (self.world - 1) or self.world > _lib.MAX_PEERS):
+            raise ValueError("peer mode needs 2, 4 or 8 ranks")
+        self.cyclic_log2 = int(cyclic_log2)
         dev = scene.means3D.device
         self.dev = dev
         N = scene.means3D.shape[0]                     # rows of the parameter arrays (hierarchy + skybox)
@@ -66,7 +79,14 @@ class GraphedStep:
         # static outputs
         self.count = torch.zeros(1, dtype=torch.int32, device=dev)
         self.radii = torch.zeros(self.P, dtype=torch.int32, device=dev)
-        if world > 1:
+        self.arena = None
+        if self.peer:
+            from .peer import PeerArena
+            self.arena = PeerArena({"loss": 8, "image": 3 * H * W * 4, "accum": max(self.P, 1) * 10 * 4}, world, rank, dev, group)
+            self.image = self.arena.tensor("image", torch.float32, (3, H, W))
+            self.loss_sum = self.arena.tensor("loss", torch.float64, (1,))
+            self._loss_ptrs = (C.c_void_p * world)(*self.arena.ptrs("loss"))
+        elif world > 1:
             rows = hdist.owned_rows(H, world, rank)
             self.rpr = hdist.rows_per_rank(H, world)
             self.slab = f(self.rpr, 3, 16, W)           # own packed slab (padded to the common slab height)
@@ -75,13 +95,17 @@ class GraphedStep:
         else:
             self.image = f(3, H, W)
         self.dcolor = f(3, H, W)
-        self.loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+        if not self.peer:
+            self.loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
         self.status_dev = torch.zeros(6, dtype=torch.float64, device=dev)
         M = scene.shs.shape[1]
         self.grads = dict(means3D=f(N, 3), shs=f(N, M, 3), opacities=f(N, 1), scales=f(N, 3), rotations=f(N, 4))
         self.d_means2D = f(self.P, 3)
         chunk = (self.P + world - 1) // world
-        self.accum = torch.zeros(max(world * chunk, 1) * 10, dtype=torch.float32, device=dev)
+        if self.peer:
+            self.accum = self.arena.tensor("accum", torch.float32, (max(self.P, 1) * 10,))
+        else:
+            self.accum = torch.zeros(max(world * chunk, 1) * 10, dtype=torch.float32, device=dev)
         self.lod_scratch = torch.empty(int(self.L.h3dgs_expand_scratch_bytes(self.N_nodes)), dtype=torch.uint8, device=dev)
         self.sky_arange = torch.arange(self.S, dtype=torch.int64, device=dev)
         self._bufs = [None, None, None]
@@ -118,8 +142,12 @@ class GraphedStep:
         a.interpolation_weights, a.num_node_kids = _ptr(sc.interpolation_weights), _ptr(sc.num_siblings)
         a.render_indices, a.parent_indices, a.num_source = _ptr(sc.render_indices), _ptr(sc.parent_indices), self.N
         a.shard_count, a.shard_index = self.world, self.rank
-        a.grad_row_begin, a.grad_row_end = hdist.row_block(self.P, self.world, self.rank) if self.world > 1 else (0, 0)
+        a.grad_row_begin, a.grad_row_end = hdist.row_block(self.P, self.world, self.rank) if (self.world > 1 and not self.peer) else (0, 0)
         a.bin_capacity, a.sort_capacity = self.bin_capacity, self.sort_capacity
+        if self.peer:
+            a.peer_count, a.grad_cyclic_log2 = self.world, self.cyclic_log2
+            for r in range(self.world):
+                a.peer_image[r], a.peer_accum[r] = self.arena.ptr("image", r), self.arena.ptr("accum", r)
         return a
 
     def _stream(self):
@@ -129,6 +157,9 @@ class GraphedStep:
     def _part_a(self):
         """LOD cut -> forward (-> image all-gather)."""
         sc, L = self.scene, self.L
+        if self.peer:
+            # every rank has zeroed its accumulator / loss sum and is done with its image buffer (end of its previous step)
+            self.arena.barrier()
         if self.N > self.N_nodes:
             sc.render_indices[self.N_nodes:].fill_(-1)  # the library marks [n, N_nodes); these are the skybox slots beyond
         _lib.check(L.h3dgs_lod_cut(self.N_nodes, sc.nodes.data_ptr(), sc.boxes.data_ptr(), self.threshold,
@@ -144,11 +175,11 @@ class GraphedStep:
             sc.parent_indices.index_copy_(0, idx, sc.skybox_inds)
             sc.interpolation_weights.index_fill_(0, idx, 1.0)
             sc.num_siblings.index_fill_(0, idx, 1)
-        out = self.slab if self.world > 1 else self.image
+        out = None if self.peer else (self.slab if self.world > 1 else self.image)
         n = C.c_int64(0)
-        _lib.check(L.h3dgs_rasterize_forward(C.byref(self.args), self._alloc_cb, None, out.data_ptr(),
+        _lib.check(L.h3dgs_rasterize_forward(C.byref(self.args), self._alloc_cb, None, _ptr(out),
                                              self.radii.data_ptr(), None, C.byref(n), self._stream()))
-        if self.world > 1:
+        if self.world > 1 and not self.peer:
             dist.all_gather_into_tensor(self.slabs, self.slab, group=self.group)
             self.image = hdist.unpack(self.slabs.view(self.world, self.rpr, 3, 16, self.W), self.H, self.W, self.world)
 
@@ -158,9 +189,14 @@ class GraphedStep:
         # loss = mean |image - gt| and dL/dimage in one pass (csrc/l1_loss.cu); every rank evaluates the full image,
         # so the loss value needs no further exchange
         numel = self.image.numel()
-        _lib.check(L.h3dgs_l1_loss_grad(3, self.H, self.W, self.image.data_ptr(), self.gt.data_ptr(), 1.0 / numel, 1, 0,
-                                        self.dcolor.data_ptr(), self.loss_sum.data_ptr(), self._stream()))
-        loss = self.loss_sum / numel
+        if self.peer:
+            # own tile rows only (they were written locally); the partial sum goes into every rank's loss accumulator
+            _lib.check(L.h3dgs_l1_loss_grad_peer(3, self.H, self.W, self.image.data_ptr(), self.gt.data_ptr(), 1.0 / numel,
+                                                 self.world, self.rank, self.dcolor.data_ptr(), self.world, self._loss_ptrs,
+                                                 self._stream()))
+        else:
+            _lib.check(L.h3dgs_l1_loss_grad(3, self.H, self.W, self.image.data_ptr(), self.gt.data_ptr(), 1.0 / numel, 1, 0,
+                                            self.dcolor.data_ptr(), self.loss_sum.data_ptr(), self._stream()))
         g = self.grads
         outs = (g["means3D"].data_ptr(), self.d_means2D.data_ptr(), g["shs"].data_ptr(), None, g["opacities"].data_ptr(),
                 g["scales"].data_ptr(), g["rotations"].data_ptr(), None)
@@ -168,16 +204,25 @@ class GraphedStep:
                  self.bin_capacity, self.dcolor.data_ptr(), None)
         if self.world == 1:
             _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 3, self._stream()))
+        elif self.peer:
+            # phase 1 adds into the owners' accumulators over NVLink; the barrier is the whole "reduce-scatter"
+            _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 1, self._stream()))
+            self.arena.barrier()
+            _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 2, self._stream()))
         else:
             # rows [P, world*chunk) of accum are zero since construction and never written: the blocks reduce cleanly
             _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 1, self._stream()))
             hdist.reduce_accum(self.accum.view(torch.uint8), self.P, self.world, self.rank, self.group)
             # phase 2 rewrites exactly the own row block of d_means2D; the other rows stay zero since construction
             _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 2, self._stream()))
+        loss = self.loss_sum / numel               # peer mode: complete since the mid-backward barrier
         info = self.scan_info().double()
         rows_needed = (self.count + self.S).double()
         self.status_dev[:5].copy_(torch.cat([loss.reshape(1), rows_needed, info]))
         self.status_dev[5:].copy_((rows_needed > self.P).double())
+        if self.peer:
+            self.accum.zero_(); self.loss_sum.zero_()       # for the next step; ordered before anybody's next phase 1 by the barriers
+            self.arena.barrier()                              # every rank's pixels have landed: self.image is the whole frame
 
     def scan_info(self):
         """int32 view [D, longest tile list, overflow] inside the image state."""

@@ -55,8 +55,10 @@ def _worker(rank, world, port, out):
     dist.barrier(); dist.destroy_process_group()
 
 
-def _graph_worker(rank, world, port, out):
-    """the same comparison for the sync-free step replayed from CUDA graphs (collectives captured)"""
+def _graph_worker(rank, world, port, out, peer=False):
+    """the same comparison for the sync-free step replayed from CUDA graphs (collectives captured); peer=True: the
+    collectives fused into the blend kernels over peer memory (forward stores into every rank's image, backward adds
+    into the owner's accumulator, device-side barriers)"""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, os.path.join(root, "hierarchical-3d-gaussians_b200")); sys.path.insert(0, os.path.join(root, "tests"))
     import torch
@@ -81,7 +83,7 @@ def _graph_worker(rank, world, port, out):
     gen = torch.Generator().manual_seed(1)
     gts = [torch.rand((3, cam.H, cam.W), generator=gen).to(dev) for _ in cams]
     gs = GraphedStep(scene, cam.W, cam.H, cam.tanfovx, cam.tanfovy, bg, thr, bin_capacity=1 << 20, sort_capacity=4096,
-                     world=world, rank=rank, capture=False)
+                     world=world, rank=rank, capture=False, peer=peer, cyclic_log2=7)
     gs.set_camera(dcams[0]); gs.gt.copy_(gts[0])
     gs.capture()
     ok, errs = True, []
@@ -99,11 +101,28 @@ def _graph_worker(rank, world, port, out):
             dist.all_reduce(t_, op=dist.ReduceOp.SUM)          # sharded by rendered row: the sum is the full gradient
             errs.append(float((ref - t_).abs().max() / ref.abs().max().clamp_min(1e-30)))
     ok = ok and max(errs) < 1e-5
+    if peer:
+        ok = ok and not gs.arena.timed_out()
     res = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(res, op=dist.ReduceOp.MIN)
     if rank == 0:
         torch.save((bool(res.item() == 1.0), errs), out)
+    if peer:
+        gs.arena.close()
     dist.barrier(); dist.destroy_process_group()
+
+
+def test_graphed_peer_step_equals_single_gpu(tmp_path):
+    """peer mode: no NCCL inside the step"""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 4 if torch.cuda.device_count() >= 4 else 2
+    out = str(tmp_path / "r.pt")
+    mp.spawn(_graph_worker, args=(world, _free_port(), out, True), nprocs=world, join=True)
+    ok, errs = torch.load(out)
+    assert ok, errs
 
 
 def test_graphed_sharded_step_equals_single_gpu(tmp_path):
