@@ -5,9 +5,8 @@
 //
 // The cut is a flat map over all N nodes (a node is emitted when it is finer than the
 // target while its parent is not, or when it is too coarse but holds leaf Gaussians),
-// followed by an order-preserving compaction: mark -> inclusive scan -> scatter.
+// with an order-preserving compaction -- one kernel, one pass (lod_cut_fused_kernel).
 // HBM-bound: 28 B node + 32 B box (+ the parent's box, an L2 hit in BFS order) per node.
-#include <cub/cub.cuh>
 #include <float.h>
 #include "common.cuh"
 
@@ -24,46 +23,6 @@ __device__ __forceinline__ float node_size(const float4* __restrict__ boxes, int
     const float cz = fmaxf(mn.z, fminf(mx.z, vz)) - vz;
     const float dist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz)));
     return mn.w / dist;
-}
-
-__global__ void __launch_bounds__(256)
-mark_nodes_kernel(int N, const int* __restrict__ nodes, const float4* __restrict__ boxes, float target,
-                  const float* __restrict__ target_dev, const float* __restrict__ viewpoint, int* __restrict__ counts)
-{
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    if (target_dev) target = *target_dev;
-    const float vx = viewpoint[0], vy = viewpoint[1], vz = viewpoint[2];
-    const int* nd = nodes + 7 * (size_t)n;
-    const int depth = nd[0], parent = nd[1], cl = nd[3], cm = nd[4];
-    const float size = node_size(boxes, n, vx, vy, vz);
-    int count = 0;
-    if (size >= target) count = cl;
-    else if (parent != -1) {
-        const float psize = node_size(boxes, parent, vx, vy, vz);
-        if (psize >= target) { count = cl; if (depth != 0) count += cm; }
-    }
-    counts[n] = count;
-}
-
-__global__ void __launch_bounds__(256)
-put_render_indices_kernel(int N, const int* __restrict__ nodes, const int* __restrict__ counts,
-                          const int* __restrict__ offsets, int* __restrict__ render_indices,
-                          int* __restrict__ parent_indices, int* __restrict__ nodes_of_render)
-{
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    const int count = counts[n];
-    if (count == 0) return;
-    const int off = offsets[n] - count;          // inclusive scan
-    const int* nd = nodes + 7 * (size_t)n;
-    const int parent = nd[1], start = nd[2];
-    const int pg = parent != -1 ? nodes[7 * (size_t)parent + 2] : -1;
-    for (int k = 0; k < count; k++) {
-        render_indices[off + k] = start + k;
-        parent_indices[off + k] = pg;
-        nodes_of_render[off + k] = n;
-    }
 }
 
 // transition weight of node `id` under `parent` (oracle_interpolation_weights)
@@ -94,39 +53,122 @@ interpolation_weights_kernel(int n, const int* __restrict__ node_indices, float 
     kids[i] = parent == -1 ? 1 : nodes[7 * (size_t)parent + 6];
 }
 
-// Device-side cut (h3dgs_lod_cut): put_render_indices + interpolation_weights in one kernel -- the
-// emitting thread already holds the node and its parent -- plus the count for the consumer.
-__global__ void __launch_bounds__(256)
-put_cut_kernel(int N, const int* __restrict__ nodes, const float4* __restrict__ boxes, float target,
-               const float* __restrict__ target_dev, const float* __restrict__ viewpoint, const int* __restrict__ counts, const int* __restrict__ offsets,
-               int* __restrict__ render_indices, int* __restrict__ parent_indices, int* __restrict__ nodes_of_render,
-               float* __restrict__ ts, int* __restrict__ kids, int* __restrict__ total)
-{
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    if (target_dev) target = *target_dev;
-    if (n == N - 1) *total = offsets[N - 1];
-    const int count = counts[n];
-    if (count == 0) return;
-    const int off = offsets[n] - count;          // inclusive scan
-    const int* nd = nodes + 7 * (size_t)n;
-    const int parent = nd[1], start = nd[2];
-    const int pg = parent != -1 ? nodes[7 * (size_t)parent + 2] : -1;
-    const float t = transition_weight(boxes, n, parent, target, viewpoint[0], viewpoint[1], viewpoint[2]);
-    const int k = parent == -1 ? 1 : nodes[7 * (size_t)parent + 6];
-    for (int j = 0; j < count; j++) {
-        render_indices[off + j] = start + j;
-        parent_indices[off + j] = pg;
-        nodes_of_render[off + j] = n;
-        ts[off + j] = t;
-        kids[off + j] = k;
-    }
-}
+// ------------------------------------------------------------------------------------------------------------
+// Single-pass cut: mark + order-preserving compaction + emission (+ weights) in ONE kernel, every node and box read
+// once.  CTAs take tiles of kCutTile consecutive nodes in launch order (dynamic tile id); the position of a tile's
+// output is the sum of the counts of all earlier tiles, obtained with a decoupled look-back over a per-tile status
+// word (aggregate available -> inclusive prefix available), so no second pass over the counts is needed.
+// Algorithmic traffic: 28 B node + 32 B box per node (the parent's box and node are L2 hits in BFS order) in,
+// 20 B per emitted row out.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kCutThreads = 256, kCutItems = 4, kCutTile = kCutThreads * kCutItems;
+constexpr unsigned long long kTileAgg = 1ull << 62, kTilePrefix = 2ull << 62, kTileValue = (1ull << 62) - 1;
 
-static size_t expand_scan_bytes(int N) {
-    size_t b = 0;
-    cub::DeviceScan::InclusiveSum(nullptr, b, (const int*)nullptr, (int*)nullptr, N > 0 ? N : 1);
-    return b;
+__global__ void __launch_bounds__(kCutThreads)
+lod_cut_fused_kernel(int N, const int* __restrict__ nodes, const float4* __restrict__ boxes, float target,
+                     const float* __restrict__ target_dev, const float* __restrict__ viewpoint,
+                     unsigned long long* __restrict__ tile_state /* [tiles] zeroed */, unsigned int* __restrict__ tile_counter /* zeroed */,
+                     int* __restrict__ render_indices, int* __restrict__ parent_indices, int* __restrict__ nodes_of_render,
+                     float* __restrict__ ts, int* __restrict__ kids, int* __restrict__ total)
+{
+    __shared__ int s_warp[kCutThreads / 32];
+    __shared__ int s_tile, s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = (int)atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const int tile = s_tile;
+    if (target_dev) target = *target_dev;
+    const float vx = viewpoint[0], vy = viewpoint[1], vz = viewpoint[2];
+
+    int cnt[kCutItems], par[kCutItems], start[kCutItems], excl[kCutItems];
+    float tw[kCutItems];
+    int carry = 0;                                            // nodes before item k inside this tile
+#pragma unroll
+    for (int k = 0; k < kCutItems; k++) {
+        const int n = tile * kCutTile + k * kCutThreads + tid;
+        int count = 0; par[k] = -1; start[k] = 0; tw[k] = 1.0f;
+        if (n < N) {
+            const int* nd = nodes + 7 * (size_t)n;
+            const int depth = nd[0], parent = nd[1], cl = nd[3], cm = nd[4];
+            par[k] = parent; start[k] = nd[2];
+            const float size = node_size(boxes, n, vx, vy, vz);
+            float psize = 0.f;
+            if (size >= target) count = cl;
+            else if (parent != -1) {
+                psize = node_size(boxes, parent, vx, vy, vz);
+                if (psize >= target) { count = cl; if (depth != 0) count += cm; }
+            }
+            if (count > 0 && ts && parent != -1) {
+                // transition weight with the sizes at hand (same arithmetic as transition_weight)
+                if (size >= target) psize = node_size(boxes, parent, vx, vy, vz);
+                if (!(psize > 2.0f * target)) {
+                    const float st = fmaxf(0.5f * psize, size), diff = psize - st;
+                    if (diff > 0) tw[k] = fmaxf(1.0f - (fmaxf(0.0f, target - st) / diff), 0.0f);
+                }
+            }
+        }
+        cnt[k] = count;
+        // block-wide exclusive scan of `count` over the 256 nodes of item k
+        int incl = count;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int wbase = 0, all = 0;
+#pragma unroll
+        for (int w = 0; w < kCutThreads / 32; w++) { const int v = s_warp[w]; if (w < warp) wbase += v; all += v; }
+        excl[k] = carry + wbase + incl - count;
+        carry += all;
+        __syncthreads();
+    }
+    // ---- decoupled look-back: exclusive prefix of this tile over all earlier tiles ----
+    if (warp == 0) {
+        const unsigned long long agg = (unsigned long long)carry;
+        if (lane == 0) {
+            __threadfence();
+            *((volatile unsigned long long*)(tile_state + tile)) = (tile == 0 ? kTilePrefix : kTileAgg) | agg;
+        }
+        long long prefix = 0;
+        int idx = tile - 1;
+        while (idx >= 0) {
+            const int j = idx - lane;
+            unsigned long long st = kTilePrefix;              // lanes past the beginning: "prefix 0"
+            if (j >= 0) { do { st = *((volatile unsigned long long*)(tile_state + j)); } while ((st >> 62) == 0ull); }
+            const unsigned full = __ballot_sync(0xffffffffu, (st >> 62) == 2ull);
+            const int first = full ? __ffs(full) - 1 : 32;    // nearest predecessor whose inclusive prefix is known
+            long long v = (lane <= first) ? (long long)(st & kTileValue) : 0ll;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            prefix += v;
+            if (full) break;
+            idx -= 32;
+        }
+        if (lane == 0) {
+            if (tile != 0) {
+                __threadfence();
+                *((volatile unsigned long long*)(tile_state + tile)) = kTilePrefix | ((unsigned long long)prefix + agg);
+            }
+            s_base = (int)prefix;
+            if (tile == (N + kCutTile - 1) / kCutTile - 1) *total = (int)(prefix + (long long)agg);
+        }
+    }
+    __syncthreads();
+    const int base = s_base;
+#pragma unroll
+    for (int k = 0; k < kCutItems; k++) {
+        if (cnt[k] == 0) continue;
+        const int n = tile * kCutTile + k * kCutThreads + tid;
+        const int off = base + excl[k];
+        const int pg = par[k] != -1 ? nodes[7 * (size_t)par[k] + 2] : -1;
+        const int kk = (kids && par[k] != -1) ? nodes[7 * (size_t)par[k] + 6] : 1;
+        for (int j = 0; j < cnt[k]; j++) {
+            render_indices[off + j] = start[k] + j;
+            parent_indices[off + j] = pg;
+            nodes_of_render[off + j] = n;
+            if (ts) ts[off + j] = tw[k];
+            if (kids) kids[off + j] = kk;
+        }
+    }
 }
 
 }  // namespace h3dgs
@@ -134,8 +176,24 @@ static size_t expand_scan_bytes(int N) {
 using namespace h3dgs;
 
 extern "C" size_t h3dgs_expand_scratch_bytes(int32_t N) {
-    const size_t n = (size_t)(N > 0 ? N : 1);
-    return align_up(n * 4) * 2 + align_up(expand_scan_bytes(N)) + 256;
+    const size_t tiles = ((size_t)(N > 0 ? N : 1) + kCutTile - 1) / kCutTile;
+    return align_up(tiles * 8 + 8) + 256;          // tile status words + tile counter | the count of h3dgs_expand_to_size
+}
+
+// one launch of the single-pass cut; scratch holds the tile status words and the tile counter
+static int launch_cut(int N, const int32_t* nodes, const float* boxes, float target_size, const float* target_size_dev,
+                      const float* viewpoint, int32_t* render_indices, int32_t* parent_indices, int32_t* nodes_for_render_indices,
+                      float* ts, int32_t* num_kids, int32_t* total, void* scratch, cudaStream_t s)
+{
+    const int tiles = (N + kCutTile - 1) / kCutTile;
+    unsigned long long* state = (unsigned long long*)scratch;
+    unsigned int* counter = (unsigned int*)(state + tiles);
+    H3_CUDA(cudaMemsetAsync(scratch, 0, (size_t)tiles * 8 + 8, s));
+    lod_cut_fused_kernel<<<tiles, kCutThreads, 0, s>>>(N, nodes, (const float4*)boxes, target_size, target_size_dev, viewpoint, state,
+                                                       counter, render_indices, parent_indices, nodes_for_render_indices, ts,
+                                                       num_kids, total);
+    H3_LAUNCHED("lod_cut_fused", 0, s);
+    return H3DGS_OK;
 }
 
 extern "C" int h3dgs_expand_to_size(int32_t N, const int32_t* nodes, const float* boxes, float target_size,
@@ -145,23 +203,14 @@ extern "C" int h3dgs_expand_to_size(int32_t N, const int32_t* nodes, const float
 {
     if (N <= 0) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    uint8_t* base = (uint8_t*)scratch;
-    int* counts = (int*)base;
-    int* offsets = (int*)(base + align_up((size_t)N * 4));
-    void* temp = base + 2 * align_up((size_t)N * 4);
-    size_t temp_bytes = expand_scan_bytes(N);
-    const int blocks = (N + 255) / 256;
+    const int tiles = (N + kCutTile - 1) / kCutTile;
+    int32_t* total = (int32_t*)((uint8_t*)scratch + align_up((size_t)tiles * 8 + 8));
     { ProfScope prof(H3DGS_STAGE_LOD_CUT, s);
-    mark_nodes_kernel<<<blocks, 256, 0, s>>>(N, nodes, (const float4*)boxes, target_size, nullptr, viewpoint, counts);
-    H3_LAUNCHED("mark_nodes", 0, s);
-    H3_CUDA(cub::DeviceScan::InclusiveSum(temp, temp_bytes, counts, offsets, N, s));
-    H3_LAUNCHED("expand_scan", 0, s);
-    put_render_indices_kernel<<<blocks, 256, 0, s>>>(N, nodes, counts, offsets, render_indices, parent_indices,
-                                                     nodes_for_render_indices);
-    H3_LAUNCHED("put_render_indices", 0, s); }
+    if (int rc = launch_cut(N, nodes, boxes, target_size, nullptr, viewpoint, render_indices, parent_indices,
+                            nodes_for_render_indices, nullptr, nullptr, total, scratch, s)) return rc; }
     void* pin = nullptr;
     if (int rc = pinned_scratch(&pin)) return rc;
-    H3_CUDA(cudaMemcpyAsync(pin, offsets + (N - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
+    H3_CUDA(cudaMemcpyAsync(pin, total, sizeof(int), cudaMemcpyDeviceToHost, s));
     H3_CUDA(cudaStreamSynchronize(s));
     return *static_cast<const int*>(pin);
 }
@@ -175,23 +224,11 @@ extern "C" int h3dgs_lod_cut(int32_t N, const int32_t* nodes, const float* boxes
     if (!nodes || !boxes || !viewpoint || !render_indices || !parent_indices || !nodes_for_render_indices || !ts ||
         !num_kids || !count || !scratch) { set_error("lod_cut: NULL argument"); return H3DGS_EINVAL; }
     cudaStream_t s = (cudaStream_t)stream;
-    uint8_t* base = (uint8_t*)scratch;
-    int* counts = (int*)base;
-    int* offsets = (int*)(base + align_up((size_t)N * 4));
-    void* temp = base + 2 * align_up((size_t)N * 4);
-    size_t temp_bytes = expand_scan_bytes(N);
-    const int blocks = (N + 255) / 256;
     ProfScope prof(H3DGS_STAGE_LOD_CUT, s);
-    // rows after the cut: index -1 = "skip" for the rasterizer (the head is overwritten below)
+    // rows after the cut: index -1 = "skip" for the rasterizer (the head is overwritten by the cut)
     H3_CUDA(cudaMemsetAsync(render_indices, 0xFF, (size_t)N * sizeof(int32_t), s));
-    mark_nodes_kernel<<<blocks, 256, 0, s>>>(N, nodes, (const float4*)boxes, target_size, target_size_dev, viewpoint, counts);
-    H3_LAUNCHED("mark_nodes", 0, s);
-    H3_CUDA(cub::DeviceScan::InclusiveSum(temp, temp_bytes, counts, offsets, N, s));
-    H3_LAUNCHED("expand_scan", 0, s);
-    put_cut_kernel<<<blocks, 256, 0, s>>>(N, nodes, (const float4*)boxes, target_size, target_size_dev, viewpoint, counts, offsets,
-                                          render_indices, parent_indices, nodes_for_render_indices, ts, num_kids, count);
-    H3_LAUNCHED("put_cut", 0, s);
-    return H3DGS_OK;
+    return launch_cut(N, nodes, boxes, target_size, target_size_dev, viewpoint, render_indices, parent_indices,
+                      nodes_for_render_indices, ts, num_kids, count, scratch, s);
 }
 
 extern "C" int h3dgs_get_interpolation_weights(int32_t n, const int32_t* node_indices, float target_size,

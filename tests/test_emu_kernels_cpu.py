@@ -357,3 +357,33 @@ def test_peer_mode_fused_collectives_schedule(emu, G):
     for k in total:
         grad_close(total[k].astype(np.float32), b[k], k)
     grad_close(m2d, b["means2D"], "means2D")
+
+
+@pytest.mark.parametrize("tau", [0.0, 6.0, 60.0])
+def test_single_pass_cut_over_many_tiles(emu_lib, tau):
+    """lod_cut_fused_kernel with 80 tiles of 1024 nodes: the decoupled look-back walks more than one window of 32
+    predecessor tiles; indices, parents, nodes, weights (bit-exact) and kids against the oracle."""
+    from emu_api import aligned, f32, i32, ptr
+    from oracle import oracle
+    cam = synth.make_camera(320, 200)
+    leaves = synth.cloud_v1(41000, cam, zmin=2.0, zmax=40.0, seed=11, scale_k=1.0)
+    z = leaves["means3D"][:, 2:3]
+    leaves["scales"] = (4e-3 * np.sqrt(2 * z) * np.ones((1, 3))).astype(np.float32)
+    h = synth.build_hierarchy(leaves)
+    N = h["nodes"].shape[0]
+    assert N > 80 * 1024
+    thr = synth.tau_threshold(tau, cam)
+    n, ri, pi, ni = oracle.expand_to_size(h["nodes"], h["boxes"], thr, cam.camera_center)
+    ts, kids = oracle.get_interpolation_weights(ni, thr, h["nodes"], h["boxes"], cam.camera_center)
+    L = emu_lib.L
+    nodes, boxes, vp = i32(h["nodes"]), f32(h["boxes"]), f32(cam.camera_center)
+    r2, p2, n2, k2 = (aligned(N * 4, np.int32, (N,)) for _ in range(4))
+    t2 = aligned(N * 4, np.float32, (N,))
+    count = aligned(4, np.int32, (1,))
+    scratch = aligned(L.h3dgs_expand_scratch_bytes(N))
+    emu_lib.check(L.h3dgs_lod_cut(N, ptr(nodes), ptr(boxes), thr, None, ptr(vp), ptr(r2), ptr(p2), ptr(n2), ptr(t2), ptr(k2),
+                                  ptr(count), ptr(scratch), None))
+    assert int(count[0]) == n > 0
+    assert np.array_equal(r2[:n], ri) and np.array_equal(p2[:n], pi) and np.array_equal(n2[:n], ni)
+    assert np.array_equal(t2[:n].view(np.uint32), ts.view(np.uint32)) and np.array_equal(k2[:n], kids)
+    assert (r2[n:] == -1).all()
