@@ -12,6 +12,9 @@ namespace h3dgs {
 
 static thread_local char g_err[1024] = "";
 int64_t g_launches = 0;
+#ifdef H3_SIMT_EMU
+long long g_emu_stats[16] = {0};
+#endif
 
 void set_error(const char* fmt, ...) {
     va_list ap; va_start(ap, fmt);
@@ -361,3 +364,7 @@ extern "C" int h3dgs_state_layout(int32_t P, int32_t W, int32_t H, int64_t D, co
     }
     return H3DGS_OK;
 }
+
+#ifdef H3_SIMT_EMU
+extern "C" long long* h3dgs_emu_stats(void) { return h3dgs::g_emu_stats; }     // emulation build only (tests/emul)
+#endif

@@ -179,6 +179,16 @@ __device__ __forceinline__ int cyclic_row(const RowCycle& c, int local) {
 __device__ __forceinline__ bool cyclic_owned(const RowCycle& c, int row) { return ((row >> c.shift) % c.world) == c.rank; }
 #endif
 
+// Loop statistics of the blend kernels, HOST EMULATION BUILD ONLY (tests/emul; the emulator is single-threaded):
+// 0 bwd warp iterations | 1 bwd iterations left at the no-taker vote | 2 bwd pixel-entries taken | 3 bwd group-iterations
+// with an entry | 4 of those without any taker | 8 fwd warp iterations | 9 fwd pixel-entries taken | 10 fwd group-iterations
+#ifdef H3_SIMT_EMU
+extern long long g_emu_stats[16];
+#define H3_STAT(i, n) (h3dgs::g_emu_stats[i] += (n))
+#else
+#define H3_STAT(i, n) ((void)0)
+#endif
+
 // accum row layout (floats): 0,1 dmean2D.xy | 2,3,4 dconic | 5 dopacity | 6,7,8 dcolor | 9 dinvdepth
 constexpr int kAccum = 10;
 

@@ -49,7 +49,10 @@ l1_grad_kernel(int C, int H, int W, int shard_count, int shard_index, const floa
     if (threadIdx.x < 32) {
         const float t = warp_sum(threadIdx.x < 8 ? s_red[threadIdx.x] : 0.f);
         if (threadIdx.x == 0 && t != 0.f) {
-            if (peers.n > 1) { for (int r = 0; r < peers.n; r++) atomicAdd_system(static_cast<double*>(peers.p[r]), (double)t); }
+            if (peers.n > 1) {
+#pragma unroll
+                for (int r = 0; r < H3DGS_MAX_PEERS; r++) if (r < peers.n) atomicAdd_system(static_cast<double*>(peers.p[r]), (double)t);
+            }
             else atomicAdd(loss_sum, (double)t);
         }
     }

@@ -90,6 +90,8 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
     __shared__ __align__(128) Record s_rec[kBwdStages][kBwdBatch];
     __shared__ uint32_t s_id[kBwdStages][kBwdBatch];
     __shared__ __align__(8) uint64_t s_full[kBwdStages];
+    __shared__ uint8_t s_list[GROUPS ? kBwdThreads / 32 : 1][4][GROUPS ? kBwdBatch : 4];   // group walk: per warp, four lists of entry positions
+    __shared__ float* s_peer[PEER ? H3DGS_MAX_PEERS : 1];      // peer mode: the accumulators of the ranks, indexed by a row's owner
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int slot = reduce_slot(lane);
@@ -117,6 +119,10 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
     if (tid == 0) {
         for (int s = 0; s < kBwdStages; s++) mbar_init(&s_full[s], 1);
         fence_mbar_init();
+    }
+    if (PEER) {
+#pragma unroll
+        for (int r = 0; r < H3DGS_MAX_PEERS; r++) if (tid == r) s_peer[r] = static_cast<float*>(peers.p[r]);
     }
     __syncthreads();
     auto issue = [&](int it) {
@@ -150,71 +156,112 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
     const f2 neg_bgd = pk(-(bg[0] * ga0 + bg[1] * ga1 + bg[2] * ga2), -(bg[0] * gb0 + bg[1] * gb1 + bg[2] * gb2));
     const int wlast = (int)__reduce_max_sync(0xffffffffu, (unsigned)max(last0, last1));   // nothing in this quadrant beyond it
     const int qsel = kBlockShift + 4 * warp;                // this warp's four block bits in the entries' reach mask
+    // group walk: nothing of a group's 16 pixels lies beyond its own last contributor
+    int gl0, gl1, gl2, gl3;
+    {
+        int gm = max(last0, last1);
+        gm = max(gm, __shfl_xor_sync(0xffffffffu, gm, 4)); gm = max(gm, __shfl_xor_sync(0xffffffffu, gm, 2));
+        gm = max(gm, __shfl_xor_sync(0xffffffffu, gm, 1));
+        gl0 = __shfl_sync(0xffffffffu, gm, 0); gl1 = __shfl_sync(0xffffffffu, gm, 8);
+        gl2 = __shfl_sync(0xffffffffu, gm, 16); gl3 = __shfl_sync(0xffffffffu, gm, 24);
+    }
 
     for (int it = 0; it < nb; it++) {
         const int st = it % kBwdStages, b = nb - 1 - it;
         mbar_wait(&s_full[st], (uint32_t)((it / kBwdStages) & 1));
         const int cnt = min(kBwdBatch, n - b * kBwdBatch);
         const Record* rec = &s_rec[st][0];
-        // back to front; per group of 32 entries a ballot compacts the entries that can reach
-        // this warp's quadrant at all (see render_forward.cu)
-        for (int j0 = (cnt - 1) & ~31; j0 >= 0; j0 -= 32) {
-            const int jl = j0 + lane;
-            const uint32_t nib = (jl < cnt && (b * kBwdBatch + jl) < wlast) ? (__float_as_uint(rec[jl].b.w) >> qsel) & 0xFu : 0u;
-            uint32_t m;
+        // one entry at the thread's two pixels; has = false: this lane's group has no entry in this iteration
+        auto replay_entry = [&](int j, bool has) {
+            const int e = b * kBwdBatch + j;              // 0-based list position; contributor number e+1
+            const float4 a = rec[j].a;
+            const float4 bb = rec[j].b;
+            const uint32_t gid = s_id[st][j];             // loaded with the record: same uniform address arithmetic
+            const uint32_t kb = __float_as_uint(bb.w);
+            const float dx = a.x - fpx;
+            // alpha of the two pixels with exactly the forward's arithmetic and decisions
+            f2 d, G, al, dadb = bc(1.0f);                // dadb is only read with HIER
+            const f2 pw = pair_power(a, bb, dx, nfpy, d);
+            pair_gauss(pw, bb.y, G, al);
+            float pw0, pw1, al0, al1;
+            upk(pw, pw0, pw1); upk(al, al0, al1);
+            // the hierarchy weight only lowers alpha (1 - (1-a)^(1/k) <= a), so an entry that no pixel of
+            // the warp takes at its base alpha is skipped before that arithmetic
+            bool v0 = has && e < last0 && pw0 <= 0.0f && al0 >= kAlphaSkip;
+            bool v1 = has && e < last1 && pw1 <= 0.0f && al1 >= kAlphaSkip;
+            if (lane == 0) H3_STAT(0, 1);
+            if ((lane & 7) == 0 && has) H3_STAT(3, 1);
+            if (!__any_sync(0xffffffffu, v0 || v1)) { if (lane == 0) H3_STAT(1, 1); return; }            // warp-uniform
+            if (HIER) {
+                pair_hier_alpha<HIER, true>(al, bb.z, kb & kSortedKidsMask, al, dadb);
+                upk(al, al0, al1);
+                v0 = v0 && al0 >= kAlphaSkip;
+                v1 = v1 && al1 >= kAlphaSkip;
+            }
+            H3_STAT(2, (v0 ? 1 : 0) + (v1 ? 1 : 0));
+#ifdef H3_SIMT_EMU
+            { const uint32_t tk = __ballot_sync(0xffffffffu, v0 || v1);
+              if (GROUPS && (lane & 7) == 0 && has && ((tk >> (8 * grp)) & 0xFFu) == 0u) H3_STAT(4, 1); }
+#endif
+            G = sel2(v0, v1, G, bc(0.f));
+            al = sel2(v0, v1, al, bc(0.f));
+            const float4 c = rec[j].c;
+            f2 cg = fma2(bc(c.z), g2, fma2(bc(c.y), g1, mul2(bc(c.x), g0)));
+            if (DEPTH) cg = fma2(bc(c.w), gd, cg);
+            float v[10];
+            pair_grad<HIER, DEPTH>(a, bb, dx, d, G, al, dadb, cg, Tf, neg_bgd, g0, g1, g2, gd, ps, v);
             if (GROUPS) {
-                // one survivor list per 8-lane group (see render_forward.cu)
+                // every group reduces its own entry over its 8 lanes; groups without a taker stay silent
+                const bool taker = ((__ballot_sync(0xffffffffu, v0 || v1) >> (8 * grp)) & 0xFFu) != 0u;
+                float r0, r1;
+                transpose_reduce10_g8(v, lane, r0, r1);
+                float* row = (PEER ? s_peer[(gid >> peer_shift) & (uint32_t)(peers.n - 1)] : accum) + (size_t)gid * kAccum;
+                if (taker && gs0 >= 0 && (DEPTH || gs0 < 9)) { if (PEER) atomicAdd_system(row + gs0, r0); else atomicAdd(row + gs0, r0); }
+                if (taker && gs1 >= 0 && (DEPTH || gs1 < 9)) { if (PEER) atomicAdd_system(row + gs1, r1); else atomicAdd(row + gs1, r1); }
+            } else {
+                const float total = transpose_reduce10(v, lane);
+                float* row = (PEER ? s_peer[(gid >> peer_shift) & (uint32_t)(peers.n - 1)] : accum) + (size_t)gid * kAccum;
+                if (slot >= 0 && (DEPTH || slot < 9)) { if (PEER) atomicAdd_system(row + slot, total); else atomicAdd(row + slot, total); }
+            }
+        };
+        if (GROUPS) {
+            // Group walk (see render_forward.cu): per batch the warp compacts four lists of entry positions -- an entry is
+            // listed for a group when its block bit is set and it lies before the group's last contributor -- and the
+            // groups replay their lists back to front in lockstep.
+            uint8_t* lst = &s_list[warp][0][0];
+            const uint32_t lt = (1u << lane) - 1u;
+            int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+            for (int j0 = 0; j0 < cnt; j0 += 32) {
+                const int jl = j0 + lane, e = b * kBwdBatch + jl;
+                uint32_t nib = jl < cnt ? (__float_as_uint(rec[jl].b.w) >> qsel) & 0xFu : 0u;
+                nib &= (e < gl0 ? 1u : 0u) | (e < gl1 ? 2u : 0u) | (e < gl2 ? 4u : 0u) | (e < gl3 ? 8u : 0u);
                 const uint32_t m0 = __ballot_sync(0xffffffffu, nib & 1u), m1 = __ballot_sync(0xffffffffu, nib & 2u);
                 const uint32_t m2 = __ballot_sync(0xffffffffu, nib & 4u), m3 = __ballot_sync(0xffffffffu, nib & 8u);
-                m = grp == 0 ? m0 : grp == 1 ? m1 : grp == 2 ? m2 : m3;
-            } else m = __ballot_sync(0xffffffffu, nib != 0u);
-            while (GROUPS ? __any_sync(0xffffffffu, m != 0u) : (m != 0u)) {
-                const bool has = !GROUPS || m != 0u;
-                const int top = has ? 31 - __clz(m) : 0;
-                m &= ~((has ? 1u : 0u) << top);
-                const int j = j0 + top;
-                const int e = b * kBwdBatch + j;              // 0-based list position; contributor number e+1
-                const float4 a = rec[j].a;
-                const float4 bb = rec[j].b;
-                const uint32_t gid = s_id[st][j];             // loaded with the record: same uniform address arithmetic
-                const uint32_t kb = __float_as_uint(bb.w);
-                const float dx = a.x - fpx;
-                // alpha of the two pixels with exactly the forward's arithmetic and decisions
-                f2 d, G, al, dadb = bc(1.0f);                // dadb is only read with HIER
-                const f2 pw = pair_power(a, bb, dx, nfpy, d);
-                pair_gauss(pw, bb.y, G, al);
-                float pw0, pw1, al0, al1;
-                upk(pw, pw0, pw1); upk(al, al0, al1);
-                // the hierarchy weight only lowers alpha (1 - (1-a)^(1/k) <= a), so an entry that no pixel of
-                // the warp takes at its base alpha is skipped before that arithmetic
-                bool v0 = has && e < last0 && pw0 <= 0.0f && al0 >= kAlphaSkip;
-                bool v1 = has && e < last1 && pw1 <= 0.0f && al1 >= kAlphaSkip;
-                if (!__any_sync(0xffffffffu, v0 || v1)) continue;            // warp-uniform
-                if (HIER) {
-                    pair_hier_alpha<HIER, true>(al, bb.z, kb & kSortedKidsMask, al, dadb);
-                    upk(al, al0, al1);
-                    v0 = v0 && al0 >= kAlphaSkip;
-                    v1 = v1 && al1 >= kAlphaSkip;
-                }
-                G = sel2(v0, v1, G, bc(0.f));
-                al = sel2(v0, v1, al, bc(0.f));
-                const float4 c = rec[j].c;
-                f2 cg = fma2(bc(c.z), g2, fma2(bc(c.y), g1, mul2(bc(c.x), g0)));
-                if (DEPTH) cg = fma2(bc(c.w), gd, cg);
-                float v[10];
-                pair_grad<HIER, DEPTH>(a, bb, dx, d, G, al, dadb, cg, Tf, neg_bgd, g0, g1, g2, gd, ps, v);
-                if (GROUPS) {
-                    // every group reduces its own entry over its 8 lanes; groups without a taker stay silent
-                    const bool taker = ((__ballot_sync(0xffffffffu, v0 || v1) >> (8 * grp)) & 0xFFu) != 0u;
-                    float r0, r1;
-                    transpose_reduce10_g8(v, lane, r0, r1);
-                    float* row = (PEER ? static_cast<float*>(peers.p[(gid >> peer_shift) & (uint32_t)(peers.n - 1)]) : accum) + (size_t)gid * kAccum;
-                    if (taker && gs0 >= 0 && (DEPTH || gs0 < 9)) { if (PEER) atomicAdd_system(row + gs0, r0); else atomicAdd(row + gs0, r0); }
-                    if (taker && gs1 >= 0 && (DEPTH || gs1 < 9)) { if (PEER) atomicAdd_system(row + gs1, r1); else atomicAdd(row + gs1, r1); }
-                } else {
-                    const float total = transpose_reduce10(v, lane);
-                    float* row = (PEER ? static_cast<float*>(peers.p[(gid >> peer_shift) & (uint32_t)(peers.n - 1)]) : accum) + (size_t)gid * kAccum;
-                    if (slot >= 0 && (DEPTH || slot < 9)) { if (PEER) atomicAdd_system(row + slot, total); else atomicAdd(row + slot, total); }
+                if (nib & 1u) lst[c0 + __popc(m0 & lt)] = (uint8_t)jl;
+                if (nib & 2u) lst[kBwdBatch + c1 + __popc(m1 & lt)] = (uint8_t)jl;
+                if (nib & 4u) lst[2 * kBwdBatch + c2 + __popc(m2 & lt)] = (uint8_t)jl;
+                if (nib & 8u) lst[3 * kBwdBatch + c3 + __popc(m3 & lt)] = (uint8_t)jl;
+                c0 += __popc(m0); c1 += __popc(m1); c2 += __popc(m2); c3 += __popc(m3);
+            }
+            __syncwarp();
+            const int mylen = grp == 0 ? c0 : grp == 1 ? c1 : grp == 2 ? c2 : c3;
+            const int maxlen = max(max(c0, c1), max(c2, c3));
+            const uint8_t* my = lst + grp * kBwdBatch;
+            for (int i = maxlen - 1; i >= 0; i--) {
+                const bool has = i < mylen;
+                replay_entry(has ? (int)my[i] : 0, has);
+            }
+            __syncwarp();                     // the lists are rebuilt for the next batch
+        } else {
+            // back to front; per round of 32 entries a ballot compacts the entries that can reach this warp's quadrant at all
+            for (int j0 = (cnt - 1) & ~31; j0 >= 0; j0 -= 32) {
+                const int jl = j0 + lane;
+                const uint32_t nib = (jl < cnt && (b * kBwdBatch + jl) < wlast) ? (__float_as_uint(rec[jl].b.w) >> qsel) & 0xFu : 0u;
+                uint32_t m = __ballot_sync(0xffffffffu, nib != 0u);
+                while (m != 0u) {
+                    const int top = 31 - __clz(m);
+                    m &= ~(1u << top);
+                    replay_entry(j0 + top, true);
                 }
             }
         }

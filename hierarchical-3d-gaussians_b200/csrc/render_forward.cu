@@ -33,6 +33,7 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
     __shared__ __align__(128) Record s_rec[kFwdStages][kFwdBatch];
     __shared__ __align__(8) uint64_t s_full[kFwdStages];
     __shared__ uint32_t s_max;
+    __shared__ uint8_t s_list[GROUPS ? kFwdThreads / 32 : 1][4][GROUPS ? kFwdBatch : 4];   // group walk: per warp, four lists of entry positions
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile_x = blockIdx.x % gx;
@@ -80,47 +81,80 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
         mbar_wait(&s_full[st], (uint32_t)((b / kFwdStages) & 1));
         waited = b + 1;
         const int cnt = min(kFwdBatch, n - b * kFwdBatch);
-        // Per group of 32 entries each lane tests ONE entry against this warp's quadrant and a ballot
-        // compacts the survivors, so culled entries cost nothing per pixel.  The survivor loop is
-        // warp-uniform (same mask in every lane) and its body is straight-line: a per-thread
-        // `continue`/`break` here leaves the warp split into fragments that each re-walk the list
-        // (measured: 18x the instructions).  A pixel that does not take an entry adds w = 0.
-        // A warp leaves the batch only when all of its 64 pixels are done.
-        {
-            const Record* rec = &s_rec[st][0];
-            const uint32_t base = (uint32_t)(b * kFwdBatch);
+        const Record* rec = &s_rec[st][0];
+        const uint32_t base = (uint32_t)(b * kFwdBatch);
+        // one entry at the thread's two pixels (straight-line: a per-thread `continue`/`break` here leaves the warp split
+        // into fragments that each re-walk the list -- measured: 18x the instructions); has = false: this lane's group
+        // has no entry in this iteration, nothing is taken
+        auto blend_entry = [&](int j, bool has) {
+            const float4 a = rec[j].a;
+            const float4 bb = rec[j].b;
+            const float4 c = rec[j].c;
+            const uint32_t kb = __float_as_uint(bb.w);
+            f2 d, G, al, unused;
+            const f2 pw = pair_power(a, bb, a.x - fpx, nfpy, d);
+            pair_gauss(pw, bb.y, G, al);
+            pair_hier_alpha<HIER, false>(al, bb.z, kb & kSortedKidsMask, al, unused);
+            bool v0, v1;
+            const f2 w = pair_blend(pw, al, T, done0, done1, v0, v1, has);
+            upk(fma2(bc(c.x), w, pk(Ca0, Cb0)), Ca0, Cb0);
+            upk(fma2(bc(c.y), w, pk(Ca1, Cb1)), Ca1, Cb1);
+            upk(fma2(bc(c.z), w, pk(Ca2, Cb2)), Ca2, Cb2);
+            if (DEPTH) upk(fma2(bc(c.w), w, pk(inv0, inv1)), inv0, inv1);
+            if (lane == 0) H3_STAT(8, 1);
+            if ((lane & 7) == 0 && has) H3_STAT(10, 1);
+            H3_STAT(9, (v0 ? 1 : 0) + (v1 ? 1 : 0));
+            const uint32_t idx = base + (uint32_t)j + 1u;
+            last0 = v0 ? idx : last0; last1 = v1 ? idx : last1;
+        };
+        if (GROUPS) {
+            // Group walk.  Each 8-lane group owns a 4x4 block and blends only the entries whose block bit is set.  Per BATCH
+            // the warp compacts four lists of entry positions in shared memory (per round of 32 entries: one mask test per
+            // lane, four ballots, four predicated byte stores); the four groups then advance in lockstep, each through its
+            // own list, for max(len) iterations -- balancing the groups over 256 entries instead of 32.
+            uint8_t* lst = &s_list[warp][0][0];
+            const uint32_t dm = __ballot_sync(0xffffffffu, done0 && done1);
+            if (dm != 0xffffffffu) {
+                // groups whose 16 pixels are finished list nothing
+                const uint32_t live = ((dm & 0xFFu) != 0xFFu ? 1u : 0u) | (((dm >> 8) & 0xFFu) != 0xFFu ? 2u : 0u) |
+                                      (((dm >> 16) & 0xFFu) != 0xFFu ? 4u : 0u) | ((dm >> 24) != 0xFFu ? 8u : 0u);
+                const uint32_t lt = (1u << lane) - 1u;
+                int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+                for (int j0 = 0; j0 < cnt; j0 += 32) {
+                    const int jl = j0 + lane;
+                    const uint32_t nib = jl < cnt ? (__float_as_uint(rec[jl].b.w) >> qsel) & live : 0u;
+                    const uint32_t m0 = __ballot_sync(0xffffffffu, nib & 1u), m1 = __ballot_sync(0xffffffffu, nib & 2u);
+                    const uint32_t m2 = __ballot_sync(0xffffffffu, nib & 4u), m3 = __ballot_sync(0xffffffffu, nib & 8u);
+                    if (nib & 1u) lst[c0 + __popc(m0 & lt)] = (uint8_t)jl;
+                    if (nib & 2u) lst[kFwdBatch + c1 + __popc(m1 & lt)] = (uint8_t)jl;
+                    if (nib & 4u) lst[2 * kFwdBatch + c2 + __popc(m2 & lt)] = (uint8_t)jl;
+                    if (nib & 8u) lst[3 * kFwdBatch + c3 + __popc(m3 & lt)] = (uint8_t)jl;
+                    c0 += __popc(m0); c1 += __popc(m1); c2 += __popc(m2); c3 += __popc(m3);
+                }
+                __syncwarp();
+                const int mylen = grp == 0 ? c0 : grp == 1 ? c1 : grp == 2 ? c2 : c3;
+                const int maxlen = max(max(c0, c1), max(c2, c3));
+                const uint8_t* my = lst + grp * kFwdBatch;
+                for (int i = 0; i < maxlen; i++) {
+                    const bool has = i < mylen;
+                    blend_entry(has ? (int)my[i] : 0, has);
+                    if ((i & 15) == 15 && __all_sync(0xffffffffu, done0 && done1)) break;
+                }
+                __syncwarp();                 // the lists are rebuilt for the next batch
+            }
+        } else {
+            // One list per warp: per round of 32 entries each lane tests ONE entry against this warp's quadrant and a ballot
+            // compacts the survivors, so culled entries cost nothing per pixel.  The survivor loop is warp-uniform (same
+            // mask in every lane).  A warp leaves the batch only when all of its 64 pixels are done.
             for (int j0 = 0; j0 < cnt; j0 += 32) {
                 if (__all_sync(0xffffffffu, done0 && done1)) break;
                 const int jl = j0 + lane;
                 const uint32_t nib = jl < cnt ? (__float_as_uint(rec[jl].b.w) >> qsel) & 0xFu : 0u;
-                uint32_t m;
-                if (GROUPS) {
-                    // one survivor list per 8-lane group: the entries that reach ITS 4x4 block
-                    const uint32_t m0 = __ballot_sync(0xffffffffu, nib & 1u), m1 = __ballot_sync(0xffffffffu, nib & 2u);
-                    const uint32_t m2 = __ballot_sync(0xffffffffu, nib & 4u), m3 = __ballot_sync(0xffffffffu, nib & 8u);
-                    m = grp == 0 ? m0 : grp == 1 ? m1 : grp == 2 ? m2 : m3;
-                } else m = __ballot_sync(0xffffffffu, nib != 0u);
-                // GROUPS: the four groups advance in lockstep, each through its own list, until the longest is done
-                while (GROUPS ? __any_sync(0xffffffffu, m != 0u) : (m != 0u)) {
-                    const bool has = !GROUPS || m != 0u;
-                    const int j = j0 + (has ? __ffs(m) - 1 : 0);
+                uint32_t m = __ballot_sync(0xffffffffu, nib != 0u);
+                while (m != 0u) {
+                    const int j = j0 + __ffs(m) - 1;
                     m &= m - 1;
-                    const float4 a = rec[j].a;
-                    const float4 bb = rec[j].b;
-                    const float4 c = rec[j].c;
-                    const uint32_t kb = __float_as_uint(bb.w);
-                    f2 d, G, al, unused;
-                    const f2 pw = pair_power(a, bb, a.x - fpx, nfpy, d);
-                    pair_gauss(pw, bb.y, G, al);
-                    pair_hier_alpha<HIER, false>(al, bb.z, kb & kSortedKidsMask, al, unused);
-                    bool v0, v1;
-                    const f2 w = pair_blend(pw, al, T, done0, done1, v0, v1, has);
-                    upk(fma2(bc(c.x), w, pk(Ca0, Cb0)), Ca0, Cb0);
-                    upk(fma2(bc(c.y), w, pk(Ca1, Cb1)), Ca1, Cb1);
-                    upk(fma2(bc(c.z), w, pk(Ca2, Cb2)), Ca2, Cb2);
-                    if (DEPTH) upk(fma2(bc(c.w), w, pk(inv0, inv1)), inv0, inv1);
-                    const uint32_t idx = base + (uint32_t)j + 1u;
-                    last0 = v0 ? idx : last0; last1 = v1 ? idx : last1;
+                    blend_entry(j, true);
                 }
             }
         }
@@ -151,10 +185,12 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
             // travel over NVLink while other tiles are still blending) -- the all-gather of rendered tiles, fused
             const size_t plane = (size_t)H * W;
             const float v0 = c0 + T * bg0, v1 = c1 + T * bg1, v2 = c2 + T * bg2;
-            for (int r = 0; r < peers.n; r++) {
-                float* o = static_cast<float*>(peers.p[r]);
-                o[pix] = v0; o[plane + pix] = v1; o[2 * plane + pix] = v2;
-            }
+#pragma unroll
+            for (int r = 0; r < H3DGS_MAX_PEERS; r++)        // compile-time indices: the pointers stay in the parameter bank
+                if (r < peers.n) {
+                    float* o = static_cast<float*>(peers.p[r]);
+                    o[pix] = v0; o[plane + pix] = v1; o[2 * plane + pix] = v2;
+                }
             if (DEPTH) out_invdepth[(((size_t)(blockIdx.x / gx)) * kTile + (size_t)(py & (kTile - 1))) * W + px] = invd;
         } else if (shard_count > 1) {
             // packed shard layout [local tile row][channel][16][W]: one contiguous slab per
