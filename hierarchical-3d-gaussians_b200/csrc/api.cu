@@ -83,6 +83,18 @@ static int side_stream(SideStream** out) {
     return H3DGS_OK;
 }
 
+// Once work has been forked onto the side stream, EVERY exit path of the entry point -- error returns included -- must
+// make the caller's stream wait for it: the caller may free or reuse the buffers the side work still writes.
+struct SideJoin {
+    SideStream* ss = nullptr; cudaStream_t main = nullptr; bool armed = false;
+    void arm(SideStream* s_, cudaStream_t m) { ss = s_; main = m; armed = true; }
+    ~SideJoin() {
+        if (!armed) return;
+        // a fresh record on the side stream covers everything enqueued there so far (idempotent with the explicit joins)
+        if (cudaEventRecord(ss->join, ss->s) == cudaSuccess) cudaStreamWaitEvent(main, ss->join, 0);
+    }
+};
+
 static void* g_pinned[64] = {nullptr};
 int pinned_scratch(void** out) {
     int dev = 0;
@@ -191,7 +203,7 @@ extern "C" int h3dgs_rasterize_forward(const h3dgs_raster_args* a, h3dgs_alloc_f
     uint32_t* offsets = (uint32_t*)(geom + gl.offsets);
     Record* records = (Record*)(geom + gl.records);
 
-    // per-tile histogram (filled by K1) -> ranges; its memset also covers ScanInfo
+    // per-tile histogram (filled by K1) -> ranges (tile_scan writes ScanInfo itself)
     uint32_t* tile_count = (uint32_t*)(img + il.tile_count);
     ScanInfo* info = (ScanInfo*)(img + il.scan_info);
     uint32_t* ranges = (uint32_t*)(img + il.ranges);
@@ -202,12 +214,14 @@ extern "C" int h3dgs_rasterize_forward(const h3dgs_raster_args* a, h3dgs_alloc_f
     // SH -> RGB only feeds record.c (read again by the record gather): run it on the side stream,
     // overlapped with the tile scan, the num_rendered round trip and key emission
     SideStream* ss = nullptr;
+    SideJoin side_guard;
     const bool side_color = !a->colors_precomp && P > 0 && !a->debug;
     if (side_color) {
         rc = side_stream(&ss);
         if (rc) return rc;
         H3_CUDA(cudaEventRecord(ss->fork, s));
         H3_CUDA(cudaStreamWaitEvent(ss->s, ss->fork, 0));
+        side_guard.arm(ss, s);
         rc = launch_preprocess_color(*a, out_radii, tiles, records, ss->s);
         if (rc) return rc;
         H3_CUDA(cudaEventRecord(ss->join, ss->s));
@@ -285,6 +299,7 @@ extern "C" int h3dgs_rasterize_backward(const h3dgs_raster_args* a, const int32_
     if (!dL_dinvdepth && (phases & 1)) b.do_depth = 0;
     bool zero_joined = true;
     SideStream* ss = nullptr;
+    SideJoin side_guard;
     if ((phases & 2) && a->render_indices) {
         // scatter mode: gradients have num_source rows and must start from zero
         rc = side_stream(&ss);
@@ -292,6 +307,7 @@ extern "C" int h3dgs_rasterize_backward(const h3dgs_raster_args* a, const int32_
         const size_t N = (size_t)a->num_source;
         H3_CUDA(cudaEventRecord(ss->fork, s));              // outputs may still be in use by earlier work on s
         H3_CUDA(cudaStreamWaitEvent(ss->s, ss->fork, 0));
+        side_guard.arm(ss, s);
         H3_CUDA(cudaMemsetAsync(dL_dmeans3D, 0, N * 3 * sizeof(float), ss->s));
         H3_CUDA(cudaMemsetAsync(dL_dopacities, 0, N * sizeof(float), ss->s));
         H3_CUDA(cudaMemsetAsync(dL_dsh, 0, N * (size_t)a->sh_coeffs * 3 * sizeof(float), ss->s));
@@ -313,7 +329,8 @@ extern "C" int h3dgs_rasterize_backward(const h3dgs_raster_args* a, const int32_
         if (rc) return rc;
     }
     if (!(phases & 2)) return H3DGS_OK;
-    if (!zero_joined && !a->debug && !a->colors_precomp) {
+    static const bool k9_serial = [] { const char* e = getenv("H3DGS_K9_SERIAL"); return e && e[0] == '1'; }();
+    if (!zero_joined && !a->debug && !a->colors_precomp && !k9_serial) {
         // scatter mode: every output is an atomic reduction, so the SH kernel (side stream, right
         // after its zero-fill) and the covariance kernel (main stream) run concurrently
         H3_CUDA(cudaEventRecord(ss->fork, s));                           // accum is complete at this point of s

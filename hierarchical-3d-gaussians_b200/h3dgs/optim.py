@@ -3,6 +3,8 @@
 kernels / three scatters.  Same constructor defaults, `step(relevant)` signature and state keys
 (`step`, `exp_avg`, `exp_avg_sq`).  amsgrad / weight_decay / maximize / capturable are not supported
 (the reference's call sites never set them).  No CPU fallback."""
+import os
+
 import torch
 from torch.optim.optimizer import Optimizer
 
@@ -19,7 +21,10 @@ class Adam(Optimizer):
 
     @torch.no_grad()
     def step(self, relevant, closure=None):
-        """relevant: int64 CUDA tensor of row indices to update (scene/OurAdam.py:116)."""
+        """relevant: int64 CUDA tensor of row indices to update (scene/OurAdam.py:116).  The rows must be UNIQUE and in
+        range -- what the reference's call site produces (`(grad != 0).nonzero()`, train_single.py:170-174): the kernel
+        updates rows in place, so a duplicate index is a data race (the reference's gather / scatter would be
+        last-write-wins) and an index >= rows an out-of-bounds write.  H3DGS_DEBUG_CHECKS=1 verifies both (one sync)."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -27,6 +32,7 @@ class Adam(Optimizer):
         L = _lib.lib()
         relevant = relevant.to(torch.int64).contiguous()
         R = int(relevant.numel())
+        debug = os.environ.get("H3DGS_DEBUG_CHECKS") == "1"
         for group in self.param_groups:
             b1, b2 = group["betas"]
             for p in group["params"]:
@@ -34,6 +40,11 @@ class Adam(Optimizer):
                     continue
                 if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
                     raise RuntimeError("sparse Adam needs contiguous float32 CUDA parameters (no CPU fallback)")
+                if relevant.device != p.device:
+                    raise RuntimeError(f"relevant lives on {relevant.device}, the parameter on {p.device}")
+                if debug and R and (int(relevant.min()) < 0 or int(relevant.max()) >= p.shape[0] or
+                                    int(torch.unique(relevant).numel()) != R):
+                    raise RuntimeError("sparse Adam: relevant must hold unique row indices in [0, rows)")
                 st = self.state[p]
                 if len(st) == 0:
                     st["step"] = torch.tensor(0.0)
