@@ -449,7 +449,12 @@ def main():
     if mode == "graph":
         from h3dgs.graphstep import GraphedStep
         c0 = cams[0]
-        use_peer = world in (2, 4, 8) and not args.no_peer
+        use_peer, peer_note = world in (2, 4, 8) and not args.no_peer, ""
+        if use_peer:
+            from h3dgs import peer as hpeer
+            use_peer, peer_note = hpeer.probe(world, rank, dev)           # same answer on every rank
+            if not use_peer:
+                config["peer_probe"] = f"peer memory unavailable on this box ({peer_note}): NCCL form of the sharded step"
         config["collectives"] = ("fused into the blend kernels over NVLink peer memory (stores into every rank's image, red.add into "
                                  "the owner's accumulator) + 3 device-side barrier kernels per step" if use_peer else
                                  ("NCCL all-gather (image slabs) + reduce-scatter ([P,10] sums)" if world > 1 else "none"))

@@ -86,3 +86,62 @@ class PeerArena:
             self._local = None
             self.L.h3dgs_peer_free(C.c_void_p(self.bases[self.rank]))
             self.bases = None
+
+
+def probe(world, rank, device, group=None):
+    """Can the ranks of `group` map each other's memory (CUDA IPC + peer access) and run the device-side barrier?
+    Collective; every rank takes part in every exchange whatever happened locally, and all ranks return the same
+    answer: (True, "") or (False, reason).  bench.py falls back to the NCCL form of the sharded step on False."""
+    L = _lib.lib()
+    dev = torch.device(device)
+    err, base, opened = "", C.c_void_p(0), []
+    handle = bytes(_lib.IPC_HANDLE_BYTES)
+    nbytes = _align(L.h3dgs_peer_flag_bytes()) + 256
+    try:
+        with torch.cuda.device(dev):
+            _lib.check(L.h3dgs_peer_alloc(nbytes, C.byref(base)))
+            buf = (C.c_ubyte * _lib.IPC_HANDLE_BYTES)()
+            _lib.check(L.h3dgs_peer_export(base, buf))
+            handle = bytes(buf)
+    except Exception as e:          # noqa: BLE001
+        err = f"rank {rank}: alloc/export failed: {e}"
+    handles = [None] * world
+    dist.all_gather_object(handles, (handle, err), group=group)
+    err = err or next((h[1] for h in handles if h[1]), "")
+    ptrs = [0] * world
+    if not err:
+        try:
+            with torch.cuda.device(dev):
+                for r in range(world):
+                    if r == rank:
+                        ptrs[r] = int(base.value)
+                    else:
+                        p = C.c_void_p(0)
+                        _lib.check(L.h3dgs_peer_open((C.c_ubyte * _lib.IPC_HANDLE_BYTES).from_buffer_copy(handles[r][0]), C.byref(p)))
+                        ptrs[r] = int(p.value); opened.append(p)
+        except Exception as e:      # noqa: BLE001
+            err = f"rank {rank}: open failed: {e}"
+    errs = [None] * world
+    dist.all_gather_object(errs, err, group=group)
+    err = next((e for e in errs if e), "")
+    if not err:
+        try:
+            with torch.cuda.device(dev):
+                fp = (C.c_void_p * world)(*ptrs)
+                s = torch.cuda.current_stream(dev).cuda_stream
+                for _ in range(3):
+                    _lib.check(L.h3dgs_peer_barrier(world, rank, ptrs[rank], fp, s))
+                if L.h3dgs_peer_barrier_status(ptrs[rank], s):
+                    err = f"rank {rank}: device-side barrier timed out"
+        except Exception as e:      # noqa: BLE001
+            err = f"rank {rank}: barrier failed: {e}"
+    dist.all_gather_object(errs, err, group=group)
+    err = next((e for e in errs if e), "")
+    torch.cuda.synchronize(dev)
+    dist.barrier(group=group)
+    for p in opened:
+        L.h3dgs_peer_close(p)
+    dist.barrier(group=group)
+    if base.value:
+        L.h3dgs_peer_free(base)
+    return (not err), err
