@@ -398,6 +398,18 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     hier = args.workload != "flat1m"
     mode = args.mode or ("graph" if (args.graph or hier) else "api")
+    # N > 1 without an explicit --mode: only host forms that have passed their equivalence tests on multi-GPU hardware
+    # (recorded in profiles/multi_gpu_validated.json after a successful tools/gpu_multi.sh run) are used by default
+    validated = {}
+    if world > 1 and not args.mode and not args.graph:
+        try:
+            validated = json.load(open(os.path.join(ROOT, "profiles", "multi_gpu_validated.json")))
+        except Exception:
+            validated = {}
+        if not (validated.get("graph_peer") or validated.get("graph_nccl")):
+            mode = "api"
+        if not validated.get("graph_peer"):
+            args.no_peer = True
     if mode == "graph" and not hier:
         raise SystemExit("--mode graph drives the hierarchy step (LOD cut + fused gather/lerp)")
     global W, H
