@@ -9,9 +9,14 @@ $T python -m pytest tests -m gpu -q -p no:cacheprovider -rs > gpurun_out/${tag}_
 tail -30 gpurun_out/${tag}_tests.log
 $T python bench.py --steps 20 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 H3DGS_GROUPWALK=0 $T python bench.py --steps 20 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/${tag}_bench_gw0.json 2> gpurun_out/${tag}_bench_gw0.err
+H3DGS_K9_SERIAL=1 $T python bench.py --steps 20 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/${tag}_bench_k9serial.json 2> gpurun_out/${tag}_bench_k9serial.err
 $T python bench.py --workload flat1m --classic --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_flat1m.json 2> gpurun_out/${tag}_bench_flat1m.err
 $T python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err
 $T python bench.py --impl reference-cuda > gpurun_out/${tag}_bench_refcuda.json 2> gpurun_out/${tag}_bench_refcuda.err
+CONFIG4_VIEWS=12 CONFIG4_LEAVES=20000 $T python tools/config4_train_post.py > gpurun_out/${tag}_config4_small.json 2> gpurun_out/${tag}_config4_small.err
+tail -c 600 gpurun_out/${tag}_config4_small.json; tail -3 gpurun_out/${tag}_config4_small.err
+timeout 900 python tools/config4_train_post.py > gpurun_out/${tag}_config4.json 2> gpurun_out/${tag}_config4.err
+tail -c 800 gpurun_out/${tag}_config4.json; tail -3 gpurun_out/${tag}_config4.err
 python - <<PY
 import json, glob
 for f in sorted(glob.glob("gpurun_out/${tag}_bench*.json")):
