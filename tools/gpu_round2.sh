@@ -30,7 +30,7 @@ for f in sorted(glob.glob("gpurun_out/${tag}_bench*.json")):
 PY
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_launches.csv \
   python bench.py --mode api --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/${tag}_ncu_bench.log 2>&1
-for k in render_backward_kernel render_forward_kernel tile_sort_gather_kernel preprocess_kernel emit_to_tiles_kernel lod_cut_fused_kernel preprocess_color_kernel; do
+for k in render_backward_kernel render_forward_kernel tile_sort_gather_kernel preprocess_kernel emit_to_tiles_kernel lod_cut_fused_kernel preprocess_color_kernel preprocess_backward_kernel sh_backward_kernel; do
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:^$k -s 6 -c 1 -f -o gpurun_out/${tag}_$k \
     python bench.py --mode api --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/${tag}_$k.log 2>&1
   ncu -i gpurun_out/${tag}_$k.ncu-rep --page raw --csv > gpurun_out/${tag}_${k}_raw.csv 2>/dev/null
