@@ -156,7 +156,7 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restri
     __syncthreads();
     // capacity mode (cap_entries > 0): a frame that does not fit is turned into an empty one
     const bool overflow = cap_entries != 0u && (s_carry > cap_entries || s_max > cap_list);
-    if (tid == 0) { info->D = s_carry; info->max_count = s_max; info->overflow = overflow ? 1u : 0u; }
+    if (tid == 0) { info->D = s_carry; info->max_count = s_max; info->overflow = overflow ? 1u : 0u; }      // prefilter_bad: K1's
     if (overflow)
         for (int t = tid; t < T; t += 1024) ranges[t] = make_uint2(0u, 0u);
 }

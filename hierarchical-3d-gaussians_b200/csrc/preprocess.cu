@@ -47,7 +47,7 @@ preprocess_kernel(int P, const float* __restrict__ means3D, const float* __restr
                   const int* __restrict__ kids, const int* __restrict__ ridx, const int* __restrict__ pidx,
                   const float* __restrict__ view, const float* __restrict__ proj,
                   int W, int H, float tanx, float tany, float fx, float fy,
-                  int shard_count, int shard_index,
+                  int shard_count, int shard_index, int prefiltered, ScanInfo* __restrict__ info,
                   int* __restrict__ radii, float* __restrict__ depths, uint32_t* __restrict__ tiles_touched,
                   Record* __restrict__ records, uint32_t* __restrict__ tile_count)
 {
@@ -187,6 +187,7 @@ preprocess_kernel(int P, const float* __restrict__ means3D, const float* __restr
             }
         }
     }
+    else if (prefiltered) info->prefilter_bad = 1u;    // the caller promised that nothing is behind the near plane
 #undef LERP
     radii[i] = out_radius;
     tiles_touched[i] = out_tiles;
@@ -280,7 +281,7 @@ preprocess_color_kernel(int P, int deg, int M, const float* __restrict__ means3D
 }
 
 int launch_preprocess(const h3dgs_raster_args& a, int32_t* radii, float* depths, uint32_t* tiles_touched,
-                      Record* records, uint32_t* tile_count, cudaStream_t s)
+                      Record* records, uint32_t* tile_count, ScanInfo* info, cudaStream_t s)
 {
     if (a.P == 0) return H3DGS_OK;
     const float fx = a.image_width / (2.0f * a.tanfovx), fy = a.image_height / (2.0f * a.tanfovy);
@@ -291,7 +292,7 @@ int launch_preprocess(const h3dgs_raster_args& a, int32_t* radii, float* depths,
                                                  a.num_node_kids, a.render_indices, a.parent_indices, a.viewmatrix,
                                                  a.projmatrix, a.image_width, a.image_height, a.tanfovx, a.tanfovy, fx, fy,
                                                  a.shard_count > 0 ? a.shard_count : 1, a.shard_count > 0 ? a.shard_index : 0,
-                                                 radii, depths, tiles_touched, records, tile_count);
+                                                 a.prefiltered, info, radii, depths, tiles_touched, records, tile_count);
     H3_LAUNCHED("preprocess", a.debug, s);
     return H3DGS_OK;
 }
