@@ -119,6 +119,9 @@ gather_records_kernel(int64_t D, const uint32_t* __restrict__ point_list, const 
 // 8 D (emit) + 8 D (read) + 12 D (keys/list out) + 96 D (records) instead of ~7 x 24 D for the
 // global radix sort plus the separate gather.
 // ------------------------------------------------------------------------------------------
+// One CTA, kScanItems consecutive tiles per thread per pass (8160 tiles at 1080p = one pass of 1024 x 8): a thread
+// scans its items in registers, one block-wide scan of the thread sums follows.
+constexpr int kScanItems = 8;
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges, ScanInfo* __restrict__ info,
                  uint32_t cap_entries, uint32_t cap_list)
@@ -129,11 +132,16 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restri
     if (tid == 0) { s_carry = 0; s_max = 0; }
     __syncthreads();
     uint32_t local_max = 0;
-    for (int base = 0; base < T; base += 1024) {
-        const int t = base + tid;
-        const uint32_t cnt = t < T ? tile_count[t] : 0u;
-        local_max = max(local_max, cnt);
-        uint32_t incl = cnt;
+    for (int base = 0; base < T; base += 1024 * kScanItems) {
+        const int t0 = base + tid * kScanItems;
+        uint32_t cnt[kScanItems], sum = 0;
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++) {
+            cnt[k] = (t0 + k) < T ? tile_count[t0 + k] : 0u;
+            local_max = max(local_max, cnt[k]);
+            sum += cnt[k];
+        }
+        uint32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
         if (lane == 31) s_warp[warp] = incl;
@@ -145,10 +153,14 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restri
             s_warp[lane] = w;
         }
         __syncthreads();
-        const uint32_t start = s_carry + (warp ? s_warp[warp - 1] : 0u) + incl - cnt;
-        if (t < T) ranges[t] = cnt ? make_uint2(start, start + cnt) : make_uint2(0u, 0u);   // empty tiles: (0,0)
+        uint32_t start = s_carry + (warp ? s_warp[warp - 1] : 0u) + incl - sum;
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++) {
+            if ((t0 + k) < T) ranges[t0 + k] = cnt[k] ? make_uint2(start, start + cnt[k]) : make_uint2(0u, 0u);   // empty tiles: (0,0)
+            start += cnt[k];
+        }
         __syncthreads();
-        if (tid == 1023) s_carry = start + cnt;
+        if (tid == 1023) s_carry = start;
         __syncthreads();
     }
     local_max = __reduce_max_sync(0xffffffffu, local_max);

@@ -404,3 +404,15 @@ def test_prefiltered_flag_traps_on_a_culled_point(emu_lib):
         emu_lib.forward(a2, keep2)
     a2.prefiltered = 0
     assert emu_lib.forward(a2, keep2)["radii"][7] == 0
+
+
+def test_tile_scan_over_more_than_one_pass(emu_lib):
+    """9000 tiles: the single-CTA tile scan needs two passes of 1024 x 8 tiles; ranges and keys against the oracle."""
+    cam, sc, ts, kids, bg = make_scene(400, 1600, 1440, seed=13)
+    f, b, gcol, gdep = oracle_run(cam, sc, bg, backward=False)
+    a, keep = emu_lib.args(cam, bg, sc)
+    fw = emu_lib.forward(a, keep)
+    st = emu_lib.state(a, fw)
+    assert fw["D"] == f["num_rendered"] > 0
+    assert np.array_equal(st["ranges"], f["ranges"]) and np.array_equal(st["keys_sorted"], f["keys"])
+    assert np.array_equal(st["point_list"], f["point_list"])
