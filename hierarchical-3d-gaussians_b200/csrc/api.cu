@@ -208,8 +208,10 @@ extern "C" int h3dgs_rasterize_forward(const h3dgs_raster_args* a, h3dgs_alloc_f
     ScanInfo* info = (ScanInfo*)(img + il.scan_info);
     uint32_t* ranges = (uint32_t*)(img + il.ranges);
     const int gxy = ((a->image_width + kTile - 1) / kTile) * ((a->image_height + kTile - 1) / kTile);
-    H3_CUDA(cudaMemsetAsync(tile_count, 0, (size_t)gxy * sizeof(uint32_t), s));
-    rc = launch_preprocess(*a, out_radii, depths, tiles, records, tile_count, s);
+    // one memset covers the histogram and ScanInfo (adjacent regions of the image state)
+    H3_CUDA(cudaMemsetAsync(tile_count, 0, (size_t)((uint8_t*)info - (uint8_t*)tile_count) + sizeof(ScanInfo), s));
+    (void)gxy;
+    rc = launch_preprocess(*a, out_radii, depths, tiles, records, tile_count, info, s);
     if (rc) return rc;
     // SH -> RGB only feeds record.c (read again by the record gather): run it on the side stream,
     // overlapped with the tile scan, the num_rendered round trip and key emission
@@ -237,7 +239,7 @@ extern "C" int h3dgs_rasterize_forward(const h3dgs_raster_args* a, h3dgs_alloc_f
     ScanInfo hinfo;
     if (capacity_mode) {
         // sizes fixed by the caller; a frame that does not fit raises ScanInfo::overflow on the device
-        hinfo.D = (uint32_t)std::min<int64_t>(a->bin_capacity, 0xFFFFFFFFll); hinfo.max_count = cap_list; hinfo.overflow = 0;
+        hinfo.D = (uint32_t)std::min<int64_t>(a->bin_capacity, 0xFFFFFFFFll); hinfo.max_count = cap_list; hinfo.overflow = 0; hinfo.prefilter_bad = 0;
     } else {
         // The reference API sizes the binning buffer from num_rendered: one D2H + sync.
         void* pin = nullptr;
@@ -246,6 +248,9 @@ extern "C" int h3dgs_rasterize_forward(const h3dgs_raster_args* a, h3dgs_alloc_f
         H3_CUDA(cudaMemcpyAsync(pin, info, sizeof(ScanInfo), cudaMemcpyDeviceToHost, s));
         H3_CUDA(cudaStreamSynchronize(s));
         hinfo = *static_cast<const ScanInfo*>(pin);
+        if (hinfo.prefilter_bad) {       // the reference's kernel traps here ("Point is filtered although prefiltered is set")
+            set_error("Point is filtered although prefiltered is set. This shouldn't happen!"); return H3DGS_EINVAL;
+        }
     }
     const int64_t D = (int64_t)hinfo.D;
     if (num_rendered) *num_rendered = D;

@@ -119,6 +119,9 @@ gather_records_kernel(int64_t D, const uint32_t* __restrict__ point_list, const 
 // 8 D (emit) + 8 D (read) + 12 D (keys/list out) + 96 D (records) instead of ~7 x 24 D for the
 // global radix sort plus the separate gather.
 // ------------------------------------------------------------------------------------------
+// One CTA, kScanItems consecutive tiles per thread per pass (8160 tiles at 1080p = one pass of 1024 x 8): a thread
+// scans its items in registers, one block-wide scan of the thread sums follows.
+constexpr int kScanItems = 8;
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges, ScanInfo* __restrict__ info,
                  uint32_t cap_entries, uint32_t cap_list)
@@ -129,11 +132,16 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restri
     if (tid == 0) { s_carry = 0; s_max = 0; }
     __syncthreads();
     uint32_t local_max = 0;
-    for (int base = 0; base < T; base += 1024) {
-        const int t = base + tid;
-        const uint32_t cnt = t < T ? tile_count[t] : 0u;
-        local_max = max(local_max, cnt);
-        uint32_t incl = cnt;
+    for (int base = 0; base < T; base += 1024 * kScanItems) {
+        const int t0 = base + tid * kScanItems;
+        uint32_t cnt[kScanItems], sum = 0;
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++) {
+            cnt[k] = (t0 + k) < T ? tile_count[t0 + k] : 0u;
+            local_max = max(local_max, cnt[k]);
+            sum += cnt[k];
+        }
+        uint32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
         if (lane == 31) s_warp[warp] = incl;
@@ -145,10 +153,14 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restri
             s_warp[lane] = w;
         }
         __syncthreads();
-        const uint32_t start = s_carry + (warp ? s_warp[warp - 1] : 0u) + incl - cnt;
-        if (t < T) ranges[t] = cnt ? make_uint2(start, start + cnt) : make_uint2(0u, 0u);   // empty tiles: (0,0)
+        uint32_t start = s_carry + (warp ? s_warp[warp - 1] : 0u) + incl - sum;
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++) {
+            if ((t0 + k) < T) ranges[t0 + k] = cnt[k] ? make_uint2(start, start + cnt[k]) : make_uint2(0u, 0u);   // empty tiles: (0,0)
+            start += cnt[k];
+        }
         __syncthreads();
-        if (tid == 1023) s_carry = start + cnt;
+        if (tid == 1023) s_carry = start;
         __syncthreads();
     }
     local_max = __reduce_max_sync(0xffffffffu, local_max);
@@ -156,7 +168,7 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_count, uint2* __restri
     __syncthreads();
     // capacity mode (cap_entries > 0): a frame that does not fit is turned into an empty one
     const bool overflow = cap_entries != 0u && (s_carry > cap_entries || s_max > cap_list);
-    if (tid == 0) { info->D = s_carry; info->max_count = s_max; info->overflow = overflow ? 1u : 0u; }
+    if (tid == 0) { info->D = s_carry; info->max_count = s_max; info->overflow = overflow ? 1u : 0u; }      // prefilter_bad: K1's
     if (overflow)
         for (int t = tid; t < T; t += 1024) ranges[t] = make_uint2(0u, 0u);
 }
@@ -168,39 +180,43 @@ emit_to_tiles_kernel(int P, int W, int H, int shard_count, int shard_index, cons
                      uint32_t* __restrict__ tile_count, uint2* __restrict__ pairs)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    const int rad = radii[i];
-    if (rad <= 0) return;
-    if (info->overflow) return;                  // capacity mode: the segments would not fit `pairs`
-    const float4 a = records[i].a;
-    const float ix = a.x, iy = a.y;
+    const int lane = threadIdx.x & 31;
     const int gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
-    const int rminx = min(gx, max(0, (int)((ix - rad) / kTile)));
-    const int rminy = min(gy, max(0, (int)((iy - rad) / kTile)));
-    const int rmaxx = min(gx, max(0, (int)((ix + rad + kTile - 1) / kTile)));
-    const int rmaxy = min(gy, max(0, (int)((iy + rad + kTile - 1) / kTile)));
-    const uint32_t dbits = __float_as_uint(depths[i]);
-    // The slot claims return a value, so each costs a full L2 round trip: walk the rect as a flat index
-    // and keep four independent claims (then four range loads, then four stores) in flight per thread.
-    const int w = rmaxx - rminx, area = w * (rmaxy - rminy);
-    for (int t0 = 0; t0 < area; t0 += 4) {
-        int tl[4]; uint32_t sl[4], st[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            tl[k] = -1;
-            const int t = t0 + k;
-            if (t < area) {
-                const int y = rminy + t / w, x = rminx + t % w;
-                if (shard_count <= 1 || (y % shard_count) == shard_index) tl[k] = y * gx + x;
-            }
+    int rminx = 0, rminy = 0, w = 0, area = 0;
+    uint32_t dbits = 0;
+    // capacity mode: with the overflow flag up the segments would not fit `pairs`
+    if (i < P && radii[i] > 0 && !info->overflow) {
+        const int rad = radii[i];
+        const float4 a = records[i].a;
+        const float ix = a.x, iy = a.y;
+        rminx = min(gx, max(0, (int)((ix - rad) / kTile)));
+        rminy = min(gy, max(0, (int)((iy - rad) / kTile)));
+        const int rmaxx = min(gx, max(0, (int)((ix + rad + kTile - 1) / kTile)));
+        const int rmaxy = min(gy, max(0, (int)((iy + rad + kTile - 1) / kTile)));
+        w = rmaxx - rminx; area = w * (rmaxy - rminy);
+        dbits = __float_as_uint(depths[i]);
+    }
+    // Slot claims return a value, so each costs an L2 round trip.  Rows arrive in hierarchy (Morton) order: per step every
+    // lane proposes one tile of its rect, equal proposals are grouped with match.any, the lowest lane of a group claims
+    // popc(group) slots with ONE atomic (the histogram doubles as the cursor) and every member takes its own slot of the
+    // claim -- the order inside a tile's segment is arbitrary, the per-tile sort fixes it.
+    const int steps = (int)__reduce_max_sync(0xffffffffu, (unsigned)area);
+    for (int k = 0; k < steps; k++) {
+        uint32_t tile = 0x80000000u | (uint32_t)lane;                      // no proposal: a value nobody else has
+        if (k < area) {
+            const int y = rminy + k / w, x = rminx + k % w;
+            if (shard_count <= 1 || (y % shard_count) == shard_index) tile = (uint32_t)(y * gx + x);
         }
-#pragma unroll
-        for (int k = 0; k < 4; k++) if (tl[k] >= 0) sl[k] = atomicSub(tile_count + tl[k], 1u) - 1u;   // histogram doubles as cursor
-#pragma unroll
-        for (int k = 0; k < 4; k++) if (tl[k] >= 0) st[k] = ranges[tl[k]].x;
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (tl[k] >= 0) pairs[st[k] + sl[k]] = make_uint2((uint32_t)i, dbits);   // little-endian u64 = depth << 32 | idx
+        const bool has = !(tile & 0x80000000u);
+        const uint32_t grp = __match_any_sync(0xffffffffu, tile);
+        const int leader = __ffs(grp) - 1;
+        uint32_t base = 0;
+        if (has && leader == lane) base = atomicSub(tile_count + tile, (uint32_t)__popc(grp));      // returns the old count
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (has) {
+            const uint32_t slot = base - 1u - (uint32_t)__popc(grp & ((1u << lane) - 1u));
+            pairs[ranges[tile].x + slot] = make_uint2((uint32_t)i, dbits);   // little-endian u64 = depth << 32 | idx
+        }
     }
 }
 

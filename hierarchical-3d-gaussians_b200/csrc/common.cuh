@@ -54,7 +54,7 @@ struct ImgLayout {
 // written by tile_scan_kernel; read back by the host in exact mode (the one num_rendered round trip).
 // overflow: capacity mode only -- the frame does not fit (bin_capacity, sort_capacity); all ranges are
 // emptied and key emission is skipped, so every later stage is a no-op for this frame.
-struct ScanInfo { uint32_t D, max_count, overflow; };
+struct ScanInfo { uint32_t D, max_count, overflow, prefilter_bad; };   // prefilter_bad: K1 culled a point although prefiltered was set
 // largest per-tile list the shared-memory sort handles; bigger lists fall back to the global CUB sort
 constexpr int kTileSortCap = 8192;
 
@@ -103,7 +103,7 @@ extern int64_t g_launches;
 
 // ---- stage entry points (one per .cu file) ----
 int launch_preprocess(const h3dgs_raster_args& a, int32_t* radii, float* depths, uint32_t* tiles_touched,
-                      Record* records, uint32_t* tile_count, cudaStream_t s);
+                      Record* records, uint32_t* tile_count, ScanInfo* info, cudaStream_t s);
 int launch_tile_scan(const h3dgs_raster_args& a, const uint32_t* tile_count, uint32_t* ranges, ScanInfo* info,
                      uint32_t cap_entries, uint32_t cap_list, cudaStream_t s);
 int launch_tile_binning(const h3dgs_raster_args& a, const int32_t* radii, const float* depths, const Record* records,

@@ -47,7 +47,7 @@ preprocess_kernel(int P, const float* __restrict__ means3D, const float* __restr
                   const int* __restrict__ kids, const int* __restrict__ ridx, const int* __restrict__ pidx,
                   const float* __restrict__ view, const float* __restrict__ proj,
                   int W, int H, float tanx, float tany, float fx, float fy,
-                  int shard_count, int shard_index,
+                  int shard_count, int shard_index, int prefiltered, ScanInfo* __restrict__ info,
                   int* __restrict__ radii, float* __restrict__ depths, uint32_t* __restrict__ tiles_touched,
                   Record* __restrict__ records, uint32_t* __restrict__ tile_count)
 {
@@ -55,19 +55,19 @@ preprocess_kernel(int P, const float* __restrict__ means3D, const float* __restr
     if (threadIdx.x < 16) { s_view[threadIdx.x] = view[threadIdx.x]; s_proj[threadIdx.x] = proj[threadIdx.x]; }
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-
     int out_radius = 0; uint32_t out_tiles = 0;
+    int hx0 = 0, hx1 = 0, hy0 = 0, hy1 = 0;          // tile rect for the histogram (empty unless the row is rendered)
+    bool skip_row = i >= P;
     // in-kernel cut gather + parent lerp: x = t*x[c] + (1-t)*x[p], evaluated as two rounded
     // products and one rounded sum (bit-identical to the PyTorch expression of render_post)
     int c = i, p = i;
     float t = 1.0f, u = 0.0f;
-    if (ridx) {
+    if (ridx && !skip_row) {
         c = ridx[i];
-        if (c < 0) { radii[i] = 0; tiles_touched[i] = 0; return; }   // tail after a device-side LOD cut (h3dgs_lod_cut)
-        p = pidx[i]; if (p < 0) p = c;
-        t = ts[i]; u = 1.0f - t;
+        if (c < 0) { skip_row = true; c = 0; }                       // tail after a device-side LOD cut (h3dgs_lod_cut)
+        else { p = pidx[i]; if (p < 0) p = c; t = ts[i]; u = 1.0f - t; }
     }
+    if (skip_row) { c = 0; p = 0; t = 1.0f; u = 0.0f; }
     const bool lerp = ridx != nullptr && u != 0.0f;
 #define LERP(a, b) (lerp ? (t * (a) + u * (b)) : (a))
     const float px_ = LERP(means3D[3 * c], means3D[3 * p]);
@@ -77,7 +77,7 @@ preprocess_kernel(int P, const float* __restrict__ means3D, const float* __restr
     const float vx = m[0] * px_ + m[4] * py_ + m[8] * pz_ + m[12];
     const float vy = m[1] * px_ + m[5] * py_ + m[9] * pz_ + m[13];
     const float vz = m[2] * px_ + m[6] * py_ + m[10] * pz_ + m[14];
-    if (vz > kNearPlane) {
+    if (vz > kNearPlane && !skip_row) {
         const float* q = s_proj;
         const float hx = q[0] * px_ + q[4] * py_ + q[8] * pz_ + q[12];
         const float hy = q[1] * px_ + q[5] * py_ + q[9] * pz_ + q[13];
@@ -179,17 +179,32 @@ preprocess_kernel(int P, const float* __restrict__ means3D, const float* __restr
                 const int rows = (rmaxy + shard_count - 1 - shard_index) / shard_count
                                - (rminy + shard_count - 1 - shard_index) / shard_count;
                 out_tiles = (uint32_t)(rows * (rmaxx - rminx));
-                // per-tile histogram for the per-tile sort (binning.cu): replaces the scan over P
-                for (int y = rminy; y < rmaxy; y++) {
-                    if (shard_count > 1 && (y % shard_count) != shard_index) continue;
-                    for (int x = rminx; x < rmaxx; x++) atomicAdd(tile_count + (y * gx + x), 1u);
-                }
+                hx0 = rminx; hx1 = rmaxx; hy0 = rminy; hy1 = rmaxy;
             }
         }
     }
+    else if (prefiltered && !skip_row) info->prefilter_bad = 1u;    // the caller promised that nothing is behind the near plane
 #undef LERP
-    radii[i] = out_radius;
-    tiles_touched[i] = out_tiles;
+    if (i < P) { radii[i] = out_radius; tiles_touched[i] = out_tiles; }
+    // Per-tile histogram for the per-tile sort (binning.cu).  Rows arrive in hierarchy (Morton) order, so the lanes of a
+    // warp mostly hit the same few tiles: per step every lane proposes one tile of its rect, equal proposals are grouped
+    // with match.any and the lowest lane of a group adds the group's size -- one reduction per distinct tile instead of
+    // one per (Gaussian, tile).  All 32 lanes stay in the loop (full-mask collectives).
+    {
+        const int gx = (W + kTile - 1) / kTile;
+        const int w = hx1 - hx0, area = w * (hy1 - hy0);
+        const int steps = (int)__reduce_max_sync(0xffffffffu, (unsigned)area);
+        const int lane = threadIdx.x & 31;
+        for (int k = 0; k < steps; k++) {
+            uint32_t tile = 0x80000000u | (uint32_t)lane;                  // no proposal: a value nobody else has
+            if (k < area) {
+                const int y = hy0 + k / w, x = hx0 + k % w;
+                if (shard_count <= 1 || (y % shard_count) == shard_index) tile = (uint32_t)(y * gx + x);
+            }
+            const uint32_t grp = __match_any_sync(0xffffffffu, tile);
+            if (!(tile & 0x80000000u) && (__ffs(grp) - 1) == lane) atomicAdd(tile_count + tile, (uint32_t)__popc(grp));
+        }
+    }
 }
 
 // K1b: SH -> RGB for the visible Gaussians only (192 B/row, x2 on lerped rows): reads the same
@@ -280,7 +295,7 @@ preprocess_color_kernel(int P, int deg, int M, const float* __restrict__ means3D
 }
 
 int launch_preprocess(const h3dgs_raster_args& a, int32_t* radii, float* depths, uint32_t* tiles_touched,
-                      Record* records, uint32_t* tile_count, cudaStream_t s)
+                      Record* records, uint32_t* tile_count, ScanInfo* info, cudaStream_t s)
 {
     if (a.P == 0) return H3DGS_OK;
     const float fx = a.image_width / (2.0f * a.tanfovx), fy = a.image_height / (2.0f * a.tanfovy);
@@ -291,7 +306,7 @@ int launch_preprocess(const h3dgs_raster_args& a, int32_t* radii, float* depths,
                                                  a.num_node_kids, a.render_indices, a.parent_indices, a.viewmatrix,
                                                  a.projmatrix, a.image_width, a.image_height, a.tanfovx, a.tanfovy, fx, fy,
                                                  a.shard_count > 0 ? a.shard_count : 1, a.shard_count > 0 ? a.shard_index : 0,
-                                                 radii, depths, tiles_touched, records, tile_count);
+                                                 a.prefiltered, info, radii, depths, tiles_touched, records, tile_count);
     H3_LAUNCHED("preprocess", a.debug, s);
     return H3DGS_OK;
 }

@@ -68,7 +68,7 @@ typedef struct h3dgs_raster_args {
     int32_t image_width, image_height;
     /* per-call constants (GaussianRasterizationSettings) */
     float tanfovx, tanfovy, scale_modifier;
-    int32_t prefiltered, debug, do_depth;
+    int32_t prefiltered, debug, do_depth;   /* prefiltered: the caller's promise that no point is behind the near plane; a broken promise is an error (exact mode) / word 3 of scan_info (capacity mode), as the reference's kernel traps */
     const float* bg;            /* [3]                                                          */
     const float* viewmatrix;    /* [16] world->view, transposed storage (scene/cameras.py:95)   */
     const float* projmatrix;    /* [16] full projection, transposed storage (:97)               */
@@ -176,7 +176,7 @@ typedef struct h3dgs_state_view {
     const uint32_t* ranges;           /* [tiles][2]                                             */
     const float* final_T;             /* [H*W]                                                  */
     const uint32_t* n_contrib;        /* [H*W]                                                  */
-    const uint32_t* scan_info;        /* [3] D, longest tile list, capacity overflow (0/1)      */
+    const uint32_t* scan_info;        /* [4] D, longest tile list, capacity overflow (0/1), prefiltered violated (0/1) */
 } h3dgs_state_view;
 int h3dgs_state_layout(int32_t P, int32_t W, int32_t H, int64_t num_rendered,
                        const void* geom_state, const void* binning_state, const void* image_state,

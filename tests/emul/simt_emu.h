@@ -105,6 +105,11 @@ static inline unsigned __ballot_sync(unsigned, int pred) { return (unsigned)simt
 static inline int __any_sync(unsigned, int pred) { return (int)simt::warp_reduce(pred ? 1 : 0, 3); }
 static inline int __all_sync(unsigned, int pred) { return (int)simt::warp_reduce(pred ? 1 : 0, 2); }
 static inline unsigned __reduce_max_sync(unsigned, unsigned v) { return (unsigned)simt::warp_reduce(v, 1); }
+static inline unsigned __match_any_sync(unsigned, unsigned v) {          // 32 exchanges: slow, but exact
+    unsigned m = 0;
+    for (int src = 0; src < 32; src++) if ((unsigned)simt::warp_exchange((uint64_t)v, src) == v) m |= 1u << src;
+    return m;
+}
 template <class T> static inline T __shfl_sync(unsigned, T v, int src) {
     uint64_t raw = 0; memcpy(&raw, &v, sizeof(T));
     raw = simt::warp_exchange(raw, src & 31);

@@ -387,3 +387,32 @@ def test_single_pass_cut_over_many_tiles(emu_lib, tau):
     assert np.array_equal(r2[:n], ri) and np.array_equal(p2[:n], pi) and np.array_equal(n2[:n], ni)
     assert np.array_equal(t2[:n].view(np.uint32), ts.view(np.uint32)) and np.array_equal(k2[:n], kids)
     assert (r2[n:] == -1).all()
+
+
+def test_prefiltered_flag_traps_on_a_culled_point(emu_lib):
+    """prefiltered=True is the caller's promise that nothing lies behind the near plane; the reference's kernel traps
+    when the promise is broken -- here the forward returns an error instead of rendering."""
+    cam, sc, ts, kids, bg = make_scene(300, 64, 48, seed=5)
+    a, keep = emu_lib.args(cam, bg, sc)
+    a.prefiltered = 1
+    fw = emu_lib.forward(a, keep)                     # every point of this scene is in front of the camera
+    assert fw["D"] > 0
+    sc2 = dict(sc); sc2["means3D"] = sc["means3D"].copy(); sc2["means3D"][7, 2] = -1.0
+    a2, keep2 = emu_lib.args(cam, bg, sc2)
+    a2.prefiltered = 1
+    with pytest.raises(RuntimeError, match="filtered although prefiltered"):
+        emu_lib.forward(a2, keep2)
+    a2.prefiltered = 0
+    assert emu_lib.forward(a2, keep2)["radii"][7] == 0
+
+
+def test_tile_scan_over_more_than_one_pass(emu_lib):
+    """9000 tiles: the single-CTA tile scan needs two passes of 1024 x 8 tiles; ranges and keys against the oracle."""
+    cam, sc, ts, kids, bg = make_scene(400, 1600, 1440, seed=13)
+    f, b, gcol, gdep = oracle_run(cam, sc, bg, backward=False)
+    a, keep = emu_lib.args(cam, bg, sc)
+    fw = emu_lib.forward(a, keep)
+    st = emu_lib.state(a, fw)
+    assert fw["D"] == f["num_rendered"] > 0
+    assert np.array_equal(st["ranges"], f["ranges"]) and np.array_equal(st["keys_sorted"], f["keys"])
+    assert np.array_equal(st["point_list"], f["point_list"])
