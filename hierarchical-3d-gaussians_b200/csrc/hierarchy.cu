@@ -64,7 +64,7 @@ interpolation_weights_kernel(int n, const int* __restrict__ node_indices, float 
 constexpr int kCutThreads = 256, kCutItems = 4, kCutTile = kCutThreads * kCutItems;
 constexpr unsigned long long kTileAgg = 1ull << 62, kTilePrefix = 2ull << 62, kTileValue = (1ull << 62) - 1;
 
-__global__ void __launch_bounds__(kCutThreads)
+__global__ void __launch_bounds__(kCutThreads, 4)
 lod_cut_fused_kernel(int N, const int* __restrict__ nodes, const float4* __restrict__ boxes, float target,
                      const float* __restrict__ target_dev, const float* __restrict__ viewpoint,
                      unsigned long long* __restrict__ tile_state /* [tiles] zeroed */, unsigned int* __restrict__ tile_counter /* zeroed */,
@@ -80,31 +80,22 @@ lod_cut_fused_kernel(int N, const int* __restrict__ nodes, const float4* __restr
     if (target_dev) target = *target_dev;
     const float vx = viewpoint[0], vy = viewpoint[1], vz = viewpoint[2];
 
-    int cnt[kCutItems], par[kCutItems], start[kCutItems], excl[kCutItems];
-    float tw[kCutItems];
+    // Pass 1 keeps only (count, position inside the tile) per node -- the kernel is a latency-bound stream, registers are
+    // occupancy; what the emission needs is re-read below from lines this CTA has just pulled into L1 / L2.
+    int cnt[kCutItems], excl[kCutItems];
     int carry = 0;                                            // nodes before item k inside this tile
 #pragma unroll
     for (int k = 0; k < kCutItems; k++) {
         const int n = tile * kCutTile + k * kCutThreads + tid;
-        int count = 0; par[k] = -1; start[k] = 0; tw[k] = 1.0f;
+        int count = 0;
         if (n < N) {
             const int* nd = nodes + 7 * (size_t)n;
             const int depth = nd[0], parent = nd[1], cl = nd[3], cm = nd[4];
-            par[k] = parent; start[k] = nd[2];
             const float size = node_size(boxes, n, vx, vy, vz);
-            float psize = 0.f;
             if (size >= target) count = cl;
             else if (parent != -1) {
-                psize = node_size(boxes, parent, vx, vy, vz);
+                const float psize = node_size(boxes, parent, vx, vy, vz);
                 if (psize >= target) { count = cl; if (depth != 0) count += cm; }
-            }
-            if (count > 0 && ts && parent != -1) {
-                // transition weight with the sizes at hand (same arithmetic as transition_weight)
-                if (size >= target) psize = node_size(boxes, parent, vx, vy, vz);
-                if (!(psize > 2.0f * target)) {
-                    const float st = fmaxf(0.5f * psize, size), diff = psize - st;
-                    if (diff > 0) tw[k] = fmaxf(1.0f - (fmaxf(0.0f, target - st) / diff), 0.0f);
-                }
             }
         }
         cnt[k] = count;
@@ -154,18 +145,22 @@ lod_cut_fused_kernel(int N, const int* __restrict__ nodes, const float4* __restr
     }
     __syncthreads();
     const int base = s_base;
+    // ---- emission (about half of the nodes): re-read the node, weight from the two sizes ----
 #pragma unroll
     for (int k = 0; k < kCutItems; k++) {
         if (cnt[k] == 0) continue;
         const int n = tile * kCutTile + k * kCutThreads + tid;
         const int off = base + excl[k];
-        const int pg = par[k] != -1 ? nodes[7 * (size_t)par[k] + 2] : -1;
-        const int kk = (kids && par[k] != -1) ? nodes[7 * (size_t)par[k] + 6] : 1;
+        const int* nd = nodes + 7 * (size_t)n;
+        const int parent = nd[1], start = nd[2];
+        const int pg = parent != -1 ? nodes[7 * (size_t)parent + 2] : -1;
+        const int kk = (kids && parent != -1) ? nodes[7 * (size_t)parent + 6] : 1;
+        const float tw = ts ? transition_weight(boxes, n, parent, target, vx, vy, vz) : 1.0f;
         for (int j = 0; j < cnt[k]; j++) {
-            render_indices[off + j] = start[k] + j;
+            render_indices[off + j] = start + j;
             parent_indices[off + j] = pg;
             nodes_of_render[off + j] = n;
-            if (ts) ts[off + j] = tw[k];
+            if (ts) ts[off + j] = tw;
             if (kids) kids[off + j] = kk;
         }
     }

@@ -14,7 +14,17 @@ run() {  # name, extra args
     bench.py --gpus $N --steps 20 --warmup 5 "$@" > gpurun_out/${tag}_${name}.json 2> gpurun_out/${tag}_${name}.err
   tail -c 1500 gpurun_out/${tag}_${name}.json | head -c 1500; echo; tail -3 gpurun_out/${tag}_${name}.err
 }
+# one rank alone on this box: the single-GPU line of the same build (stage times of the kernels changed since the last call)
+timeout 600 python bench.py --steps 20 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/${tag}_bench_n1.json 2> gpurun_out/${tag}_bench_n1.err
+python - <<PY
+import json
+try:
+    d = json.loads(open("gpurun_out/${tag}_bench_n1.json").read().strip().splitlines()[-1])
+    print("N=1", round(d["value"], 1), "img/s", d["stage_ms"], "gap", d.get("host_gap_ms"))
+except Exception as e:
+    print("N=1 bench failed", e, open("gpurun_out/${tag}_bench_n1.err").read()[-800:])
+PY
 for w in $WL; do
-  run bench_${w}_peer --workload $w
-  if [ "$w" = "hier3m" ]; then run bench_${w}_nccl --workload $w --no-peer --no-extras; fi
+  run bench_${w}_peer --workload $w --mode graph
+  if [ "$w" = "hier3m" ]; then run bench_${w}_nccl --workload $w --mode graph --no-peer --no-extras; run bench_${w}_api --workload $w --mode api --no-extras; fi
 done
