@@ -220,10 +220,72 @@ emit_to_tiles_kernel(int P, int W, int H, int shard_count, int shard_index, cons
     }
 }
 
-// one CTA per tile: bitonic sort of (depth bits << 32 | idx) in shared memory, then gather.
-// 128 threads: a typical list (a few hundred entries, m = 512) gives each thread two comparators per
-// stage (ILP) and halves the warps that meet at each of the 45 barriers.
+// one CTA (128 threads) per tile: bitonic sort of (depth bits << 32 | idx), then gather.
+//
+// Lists of up to 128 x 8 entries are sorted IN REGISTERS: thread t holds the IPT consecutive elements
+// t*IPT .. t*IPT + IPT-1 of a network over M = 128*IPT keys, so of the log2(M)(log2(M)+1)/2 stages (45 for
+// M = 512) the strides below IPT are compare-exchanges between a thread's own registers, the strides below
+// 32*IPT are one 64-bit lane exchange per element (partner lane = lane ^ stride/IPT), and only the three stages
+// whose stride crosses warps go through shared memory (element r of thread t at [r][t]: conflict-free).  The
+// shared-memory network it replaces met at a block barrier after every stage and was issue-bound on LDS/STS
+// (ncu r02: 124 M warp-instructions, 15.7 M bank conflicts, 0.22 ms on config #3).  Longer lists (up to
+// kTileSortCap) keep the shared-memory network.
 constexpr int kSortThreads = 128;
+constexpr int kSortRegCap = kSortThreads * 8;
+
+template <int IPT>
+__device__ __forceinline__ void sort_tile_in_registers(uint64_t* s_key, int n, const uint64_t* __restrict__ src)
+{
+    constexpr int M = kSortThreads * IPT;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // coalesced load, then the thread's IPT consecutive elements
+    for (int k = tid; k < M; k += kSortThreads) s_key[k] = k < n ? src[k] : 0xFFFFFFFFFFFFFFFFull;
+    __syncthreads();
+    uint64_t key[IPT];
+#pragma unroll
+    for (int r = 0; r < IPT; r++) key[r] = s_key[tid * IPT + r];
+    __syncthreads();
+#pragma unroll
+    for (int size = 2; size <= M; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32 * IPT) {                                  // partner in another warp
+#pragma unroll
+                for (int r = 0; r < IPT; r++) s_key[r * kSortThreads + tid] = key[r];
+                __syncthreads();
+                const int ptid = tid ^ (stride / IPT);
+                const bool keep_min = ((tid & (stride / IPT)) == 0) == (((tid * IPT) & size) == 0);
+#pragma unroll
+                for (int r = 0; r < IPT; r++) {
+                    const uint64_t y = s_key[r * kSortThreads + ptid];
+                    if ((key[r] > y) == keep_min) key[r] = y;
+                }
+                __syncthreads();
+            } else if (stride >= IPT) {                                // partner in another lane of this warp
+                const int lmask = stride / IPT;
+                const bool keep_min = ((lane & lmask) == 0) == (((tid * IPT) & size) == 0);
+#pragma unroll
+                for (int r = 0; r < IPT; r++) {
+                    const uint64_t y = __shfl_xor_sync(0xffffffffu, key[r], lmask);
+                    if ((key[r] > y) == keep_min) key[r] = y;
+                }
+            } else {                                                   // both in this thread's registers
+#pragma unroll
+                for (int r = 0; r < IPT; r++) {
+                    if ((r & stride) == 0) {
+                        const bool up = (((tid * IPT + r) & size) == 0);
+                        const uint64_t x = key[r], y = key[r + stride];
+                        if ((x > y) == up) { key[r] = y; key[r + stride] = x; }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < IPT; r++) s_key[tid * IPT + r] = key[r];
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(kSortThreads)
 tile_sort_gather_kernel(int gx, int rows, int shard_count, int shard_index, const uint2* __restrict__ ranges,
                         const uint64_t* __restrict__ pairs, const Record* __restrict__ records,
@@ -238,20 +300,26 @@ tile_sort_gather_kernel(int gx, int rows, int shard_count, int shard_index, cons
     const uint2 range = ranges[tile];
     const int n = (int)(range.y - range.x);
     if (n == 0) return;
-    int m = 32;
-    while (m < n) m <<= 1;
-    for (int k = tid; k < m; k += kSortThreads) s_key[k] = k < n ? pairs[range.x + k] : 0xFFFFFFFFFFFFFFFFull;
-    __syncthreads();
-    for (int size = 2; size <= m; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int k = tid; k < (m >> 1); k += kSortThreads) {
-                const int lo = 2 * k - (k & (stride - 1));             // index of the lower partner
-                const int hi = lo + stride;
-                const bool up = (lo & size) == 0;
-                const uint64_t x = s_key[lo], y = s_key[hi];
-                if ((x > y) == up) { s_key[lo] = y; s_key[hi] = x; }
+    if (n <= kSortThreads) sort_tile_in_registers<1>(s_key, n, pairs + range.x);
+    else if (n <= kSortThreads * 2) sort_tile_in_registers<2>(s_key, n, pairs + range.x);
+    else if (n <= kSortThreads * 4) sort_tile_in_registers<4>(s_key, n, pairs + range.x);
+    else if (n <= kSortRegCap) sort_tile_in_registers<8>(s_key, n, pairs + range.x);
+    else {
+        int m = 32;
+        while (m < n) m <<= 1;
+        for (int k = tid; k < m; k += kSortThreads) s_key[k] = k < n ? pairs[range.x + k] : 0xFFFFFFFFFFFFFFFFull;
+        __syncthreads();
+        for (int size = 2; size <= m; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int k = tid; k < (m >> 1); k += kSortThreads) {
+                    const int lo = 2 * k - (k & (stride - 1));             // index of the lower partner
+                    const int hi = lo + stride;
+                    const bool up = (lo & size) == 0;
+                    const uint64_t x = s_key[lo], y = s_key[hi];
+                    if ((x > y) == up) { s_key[lo] = y; s_key[hi] = x; }
+                }
+                __syncthreads();
             }
-            __syncthreads();
         }
     }
     for (int k = tid; k < n; k += kSortThreads) {
@@ -328,7 +396,7 @@ int launch_tile_binning(const h3dgs_raster_args& a, const int32_t* radii, const 
     emit_to_tiles_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a.P, W, H, sc, si, radii, depths, records, (const uint2*)ranges,
                                                            info, tile_count, pairs);
     H3_LAUNCHED("emit_to_tiles", a.debug, s); }
-    int m = 32;
+    int m = kSortThreads;                                       // the register sort stages at least 128 keys
     while (m < (int)max_count) m <<= 1;
     const size_t smem = (size_t)m * sizeof(uint64_t);
     if (smem > 48 * 1024)     // per device, idempotent: only the rare long lists need the opt-in

@@ -254,6 +254,29 @@ def test_equal_depths_and_long_lists_fall_back_to_the_global_sort(emu):
     assert (st["ranges"][:, 1] - st["ranges"][:, 0]).max() > 8192    # longer than the shared-memory sort handles
 
 
+def test_register_sort_size_classes_with_equal_depths(emu_lib):
+    """tile lists of 33 .. ~700 entries: every size class of the in-register sort (1, 2, 4, 8 keys per thread), with
+    many equal depths, so the (depth bits, index) order -- the stable order of the reference's global sort -- is
+    checked through the lane exchanges, the in-thread stages and the cross-warp stages alike"""
+    n = 14000
+    cam, sc, ts, kids, bg = make_scene(n, 160, 128, seed=17, scale_k=1.5e-2, zmax=8.0)
+    x = sc["means3D"][:, 0] / sc["means3D"][:, 2]
+    ramp = (x - x.min()) / (x.max() - x.min())
+    keep = np.random.default_rng(1).uniform(size=n) < 0.03 + 0.97 * ramp ** 2       # dense right, sparse left
+    sc = {k: v[keep] for k, v in sc.items()}
+    sc["means3D"][:, 2] = np.round(sc["means3D"][:, 2] * 4) / 4
+    f = oracle_run(cam, sc, bg, backward=False)[0]
+    lens = f["ranges"].reshape(-1, 2)[:, 1] - f["ranges"].reshape(-1, 2)[:, 0]
+    assert all(((lens > lo) & (lens <= hi)).any() for lo, hi in [(0, 128), (128, 256), (256, 512), (512, 1024)])
+    a, keepalive = emu_lib.args(cam, bg, sc)
+    fw = emu_lib.forward(a, keepalive)
+    st = emu_lib.state(a, fw)
+    assert fw["D"] == f["num_rendered"]
+    assert np.array_equal(st["keys_sorted"], f["keys"])
+    assert np.array_equal(st["point_list"], f["point_list"])
+    image_close(fw["color"], f["color"])
+
+
 def test_random_scenes_functional(emu):
     """a small fuzz over sizes, modes, depth, opacities above one and needle-shaped Gaussians.  The bar here is
     functional (no lost or doubled contributions, no crash, no deadlock): on ill-conditioned scenes the fp32

@@ -6,6 +6,8 @@ WL=${@:-hier3m}
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 nvidia-smi topo -m > gpurun_out/${tag}_topo.txt 2>&1
+timeout 400 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fullsize_parity.py -q -p no:cacheprovider -rs > gpurun_out/${tag}_parity_tests.log 2>&1
+tail -4 gpurun_out/${tag}_parity_tests.log
 timeout 600 python -m pytest tests/test_gpu_dist.py -q -p no:cacheprovider -rs > gpurun_out/${tag}_dist_tests.log 2>&1
 tail -15 gpurun_out/${tag}_dist_tests.log
 run() {  # name, extra args
