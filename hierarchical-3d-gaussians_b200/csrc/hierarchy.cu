@@ -9,6 +9,7 @@
 // HBM-bound: 28 B node + 32 B box (+ the parent's box, an L2 hit in BFS order) per node.
 #include <float.h>
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace h3dgs {
 
@@ -58,60 +59,109 @@ interpolation_weights_kernel(int n, const int* __restrict__ node_indices, float 
 // once.  CTAs take tiles of kCutTile consecutive nodes in launch order (dynamic tile id); the position of a tile's
 // output is the sum of the counts of all earlier tiles, obtained with a decoupled look-back over a per-tile status
 // word (aggregate available -> inclusive prefix available), so no second pass over the counts is needed.
+//
+// The kernel is a latency-bound stream (7-int node rows and the dependent fetch of the parent's box), so the tile's
+// two contiguous slabs -- 28 KB of nodes, 32 KB of boxes -- are brought into shared memory by two bulk copies (TMA)
+// issued by one thread: no registers or LSU issue slots are spent on the stream, three CTAs per SM keep 180 KB in
+// flight, and the threads read their rows from shared memory (stride 7 words: conflict-free).  A thread owns four
+// CONSECUTIVE nodes (siblings share the parent's box), keeps their two sizes for the weight, fetches what the
+// emission needs from the parent's node while the scan and the look-back run, and one block scan serves the tile.
 // Algorithmic traffic: 28 B node + 32 B box per node (the parent's box and node are L2 hits in BFS order) in,
 // 20 B per emitted row out.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kCutThreads = 256, kCutItems = 4, kCutTile = kCutThreads * kCutItems;
 constexpr unsigned long long kTileAgg = 1ull << 62, kTilePrefix = 2ull << 62, kTileValue = (1ull << 62) - 1;
+constexpr size_t kCutSmem = (size_t)kCutTile * 7 * sizeof(int) + (size_t)kCutTile * 2 * sizeof(float4);
 
-__global__ void __launch_bounds__(kCutThreads, 4)
+__device__ __forceinline__ float box_size(const float4 mn, const float4 mx, float vx, float vy, float vz) {
+    const bool inside = vx >= mn.x && vx <= mx.x && vy >= mn.y && vy <= mx.y && vz >= mn.z && vz <= mx.z;
+    if (inside) return FLT_MAX;
+    const float cx = fmaxf(mn.x, fminf(mx.x, vx)) - vx;
+    const float cy = fmaxf(mn.y, fminf(mx.y, vy)) - vy;
+    const float cz = fmaxf(mn.z, fminf(mx.z, vz)) - vz;
+    const float dist = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz)));
+    return mn.w / dist;
+}
+
+__global__ void __launch_bounds__(kCutThreads, 3)
 lod_cut_fused_kernel(int N, const int* __restrict__ nodes, const float4* __restrict__ boxes, float target,
                      const float* __restrict__ target_dev, const float* __restrict__ viewpoint,
                      unsigned long long* __restrict__ tile_state /* [tiles] zeroed */, unsigned int* __restrict__ tile_counter /* zeroed */,
                      int* __restrict__ render_indices, int* __restrict__ parent_indices, int* __restrict__ nodes_of_render,
                      float* __restrict__ ts, int* __restrict__ kids, int* __restrict__ total)
 {
+    extern __shared__ float4 s_cut[];                         // boxes [kCutTile][2] | nodes [kCutTile][7]
+    __shared__ uint64_t s_bar[2];
     __shared__ int s_warp[kCutThreads / 32];
     __shared__ int s_tile, s_base;
+    float4* s_box = s_cut;
+    int* s_node = reinterpret_cast<int*>(s_cut + 2 * kCutTile);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = (int)atomicAdd(tile_counter, 1u);
+    const bool aligned = ((((uintptr_t)nodes) | ((uintptr_t)boxes)) & 15) == 0;
+    if (tid == 0) {
+        const int t = (int)atomicAdd(tile_counter, 1u);
+        s_tile = t;
+        const int cnt = min(kCutTile, N - t * kCutTile);
+        if (aligned && (cnt & 3) == 0) {                      // 28 * cnt bytes must be a multiple of 16
+            mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
+            fence_mbar_init();
+            mbar_arrive_expect_tx(&s_bar[0], (uint32_t)cnt * 32u);
+            tma_load_1d(s_box, boxes + 2 * (size_t)t * kCutTile, (uint32_t)cnt * 32u, &s_bar[0]);
+            mbar_arrive_expect_tx(&s_bar[1], (uint32_t)cnt * 28u);
+            tma_load_1d(s_node, nodes + 7 * (size_t)t * kCutTile, (uint32_t)cnt * 28u, &s_bar[1]);
+        }
+    }
     __syncthreads();
     const int tile = s_tile;
+    const int tile_nodes = min(kCutTile, N - tile * kCutTile);
     if (target_dev) target = *target_dev;
     const float vx = viewpoint[0], vy = viewpoint[1], vz = viewpoint[2];
-
-    // Pass 1 keeps only (count, position inside the tile) per node -- the kernel is a latency-bound stream, registers are
-    // occupancy; what the emission needs is re-read below from lines this CTA has just pulled into L1 / L2.
-    int cnt[kCutItems], excl[kCutItems];
-    int carry = 0;                                            // nodes before item k inside this tile
-#pragma unroll
-    for (int k = 0; k < kCutItems; k++) {
-        const int n = tile * kCutTile + k * kCutThreads + tid;
-        int count = 0;
-        if (n < N) {
-            const int* nd = nodes + 7 * (size_t)n;
-            const int depth = nd[0], parent = nd[1], cl = nd[3], cm = nd[4];
-            const float size = node_size(boxes, n, vx, vy, vz);
-            if (size >= target) count = cl;
-            else if (parent != -1) {
-                const float psize = node_size(boxes, parent, vx, vy, vz);
-                if (psize >= target) { count = cl; if (depth != 0) count += cm; }
-            }
-        }
-        cnt[k] = count;
-        // block-wide exclusive scan of `count` over the 256 nodes of item k
-        int incl = count;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        int wbase = 0, all = 0;
-#pragma unroll
-        for (int w = 0; w < kCutThreads / 32; w++) { const int v = s_warp[w]; if (w < warp) wbase += v; all += v; }
-        excl[k] = carry + wbase + incl - count;
-        carry += all;
+    if (aligned && (tile_nodes & 3) == 0) {
+        mbar_wait(&s_bar[0], 0u);
+        mbar_wait(&s_bar[1], 0u);
+    } else {                                                  // ragged last tile / unaligned views: plain loads
+        for (int k = tid; k < tile_nodes * 2; k += kCutThreads) s_box[k] = boxes[2 * (size_t)tile * kCutTile + k];
+        for (int k = tid; k < tile_nodes * 7; k += kCutThreads) s_node[k] = nodes[7 * (size_t)tile * kCutTile + k];
         __syncthreads();
     }
+
+    int cnt[kCutItems], pg[kCutItems], kk[kCutItems];
+    float size[kCutItems], psize[kCutItems];
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < kCutItems; k++) {
+        const int j = tid * kCutItems + k;
+        int count = 0;
+        size[k] = 0.f; psize[k] = 0.f; pg[k] = -1; kk[k] = 1;
+        if (j < tile_nodes) {
+            const int* nd = s_node + 7 * j;
+            const int depth = nd[0], parent = nd[1], cl = nd[3], cm = nd[4];
+            size[k] = box_size(s_box[2 * j], s_box[2 * j + 1], vx, vy, vz);
+            const bool coarse = size[k] >= target;
+            // the parent's box decides the nodes that are fine enough, and the weight of every emitted node
+            if (parent != -1 && (!coarse || cl > 0)) {
+                psize[k] = box_size(__ldg(boxes + 2 * (size_t)parent), __ldg(boxes + 2 * (size_t)parent + 1), vx, vy, vz);
+                if (coarse) count = cl;
+                else if (psize[k] >= target) { count = cl; if (depth != 0) count += cm; }
+                if (count > 0) {
+                    pg[k] = __ldg(nodes + 7 * (size_t)parent + 2);
+                    if (kids) kk[k] = __ldg(nodes + 7 * (size_t)parent + 6);
+                }
+            } else if (coarse) count = cl;                    // the root
+        }
+        cnt[k] = count;
+        sum += count;
+    }
+    // ---- one block-wide exclusive scan of the thread sums ----
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int wbase = 0, carry = 0;
+#pragma unroll
+    for (int w = 0; w < kCutThreads / 32; w++) { const int v = s_warp[w]; if (w < warp) wbase += v; carry += v; }
+    int off = wbase + incl - sum;                             // position of this thread's first row inside the tile
     // ---- decoupled look-back: exclusive prefix of this tile over all earlier tiles ----
     if (warp == 0) {
         const unsigned long long agg = (unsigned long long)carry;
@@ -144,25 +194,28 @@ lod_cut_fused_kernel(int N, const int* __restrict__ nodes, const float4* __restr
         }
     }
     __syncthreads();
-    const int base = s_base;
-    // ---- emission (about half of the nodes): re-read the node, weight from the two sizes ----
+    off += s_base;
+    // ---- emission (about half of the nodes) ----
 #pragma unroll
     for (int k = 0; k < kCutItems; k++) {
         if (cnt[k] == 0) continue;
-        const int n = tile * kCutTile + k * kCutThreads + tid;
-        const int off = base + excl[k];
-        const int* nd = nodes + 7 * (size_t)n;
-        const int parent = nd[1], start = nd[2];
-        const int pg = parent != -1 ? nodes[7 * (size_t)parent + 2] : -1;
-        const int kk = (kids && parent != -1) ? nodes[7 * (size_t)parent + 6] : 1;
-        const float tw = ts ? transition_weight(boxes, n, parent, target, vx, vy, vz) : 1.0f;
-        for (int j = 0; j < cnt[k]; j++) {
-            render_indices[off + j] = start + j;
-            parent_indices[off + j] = pg;
-            nodes_of_render[off + j] = n;
-            if (ts) ts[off + j] = tw;
-            if (kids) kids[off + j] = kk;
+        const int j = tid * kCutItems + k;
+        const int n = tile * kCutTile + j;
+        const int start = s_node[7 * j + 2];
+        float tw = 1.0f;                                      // oracle_interpolation_weights
+        if (ts && s_node[7 * j + 1] != -1 && !(psize[k] > 2.0f * target)) {
+            const float st = fmaxf(0.5f * psize[k], size[k]);
+            const float diff = psize[k] - st;
+            if (diff > 0) tw = fmaxf(1.0f - (fmaxf(0.0f, target - st) / diff), 0.0f);
         }
+        for (int q = 0; q < cnt[k]; q++) {
+            render_indices[off + q] = start + q;
+            parent_indices[off + q] = pg[k];
+            nodes_of_render[off + q] = n;
+            if (ts) ts[off + q] = tw;
+            if (kids) kids[off + q] = kk[k];
+        }
+        off += cnt[k];
     }
 }
 
@@ -184,7 +237,14 @@ static int launch_cut(int N, const int32_t* nodes, const float* boxes, float tar
     unsigned long long* state = (unsigned long long*)scratch;
     unsigned int* counter = (unsigned int*)(state + tiles);
     H3_CUDA(cudaMemsetAsync(scratch, 0, (size_t)tiles * 8 + 8, s));
-    lod_cut_fused_kernel<<<tiles, kCutThreads, 0, s>>>(N, nodes, (const float4*)boxes, target_size, target_size_dev, viewpoint, state,
+    static bool smem_opt_in[64] = {};                          // per device, once (and never inside a stream capture: the
+    int dev = 0;                                               // first cut of a GraphedStep is its eager probe pass)
+    H3_CUDA(cudaGetDevice(&dev));
+    if (!smem_opt_in[dev & 63]) {
+        H3_CUDA(cudaFuncSetAttribute(lod_cut_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCutSmem));
+        smem_opt_in[dev & 63] = true;
+    }
+    lod_cut_fused_kernel<<<tiles, kCutThreads, kCutSmem, s>>>(N, nodes, (const float4*)boxes, target_size, target_size_dev, viewpoint, state,
                                                        counter, render_indices, parent_indices, nodes_for_render_indices, ts,
                                                        num_kids, total);
     H3_LAUNCHED("lod_cut_fused", 0, s);

@@ -382,8 +382,8 @@ def test_peer_mode_fused_collectives_schedule(emu, G):
     grad_close(m2d, b["means2D"], "means2D")
 
 
-@pytest.mark.parametrize("tau", [0.0, 6.0, 60.0])
-def test_single_pass_cut_over_many_tiles(emu_lib, tau):
+@pytest.mark.parametrize("tau,misalign", [(0.0, False), (6.0, False), (60.0, False), (6.0, True)])
+def test_single_pass_cut_over_many_tiles(emu_lib, tau, misalign):
     """lod_cut_fused_kernel with 80 tiles of 1024 nodes: the decoupled look-back walks more than one window of 32
     predecessor tiles; indices, parents, nodes, weights (bit-exact) and kids against the oracle."""
     from emu_api import aligned, f32, i32, ptr
@@ -400,6 +400,13 @@ def test_single_pass_cut_over_many_tiles(emu_lib, tau):
     ts, kids = oracle.get_interpolation_weights(ni, thr, h["nodes"], h["boxes"], cam.camera_center)
     L = emu_lib.L
     nodes, boxes, vp = i32(h["nodes"]), f32(h["boxes"]), f32(cam.camera_center)
+    assert nodes.ctypes.data % 16 == 0 and boxes.ctypes.data % 16 == 0        # whole tiles arrive by bulk copy (TMA wrappers) ...
+    if misalign:                                                              # ... views that are not 16-B aligned by plain loads
+        buf = np.zeros(nodes.size + 4, np.int32)
+        off = 1 + (-(buf.ctypes.data // 4) % 4)
+        buf[off:off + nodes.size] = nodes.ravel()
+        nodes = buf[off:off + nodes.size].reshape(nodes.shape)
+        assert nodes.ctypes.data % 16 == 4
     r2, p2, n2, k2 = (aligned(N * 4, np.int32, (N,)) for _ in range(4))
     t2 = aligned(N * 4, np.float32, (N,))
     count = aligned(4, np.int32, (1,))
