@@ -398,18 +398,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     hier = args.workload != "flat1m"
     mode = args.mode or ("graph" if (args.graph or hier) else "api")
-    # N > 1 without an explicit --mode: only host forms that have passed their equivalence tests on multi-GPU hardware
-    # (recorded in profiles/multi_gpu_validated.json after a successful tools/gpu_multi.sh run) are used by default
-    validated = {}
-    if world > 1 and not args.mode and not args.graph:
-        try:
-            validated = json.load(open(os.path.join(ROOT, "profiles", "multi_gpu_validated.json")))
-        except Exception:
-            validated = {}
-        if not (validated.get("graph_peer") or validated.get("graph_nccl")):
-            mode = "api"
-        if not validated.get("graph_peer"):
-            args.no_peer = True
+    # N > 1 without an explicit --mode: the graphed step with the collectives fused over peer memory when the ranks can map
+    # each other's memory (validated on 2 GPUs incl. the N-rank equality check: profiles/r02_m2b_*); otherwise the call-by-call
+    # NCCL form (--mode graph --no-peer selects the graphed NCCL form explicitly)
+    auto_mode = world > 1 and not args.mode and not args.graph
     if mode == "graph" and not hier:
         raise SystemExit("--mode graph drives the hierarchy step (LOD cut + fused gather/lerp)")
     global W, H
@@ -466,9 +458,15 @@ def main():
             from h3dgs import peer as hpeer
             use_peer, peer_note = hpeer.probe(world, rank, dev)           # same answer on every rank
             if not use_peer:
-                config["peer_probe"] = f"peer memory unavailable on this box ({peer_note}): NCCL form of the sharded step"
-        config["collectives"] = ("fused into the blend kernels over NVLink peer memory (stores into every rank's image, red.add into "
-                                 "the owner's accumulator) + 3 device-side barrier kernels per step" if use_peer else
+                config["peer_probe"] = (f"peer memory unavailable on this box ({peer_note}): " +
+                                        ("call-by-call NCCL form of the sharded step" if auto_mode else "graphed NCCL form of the sharded step"))
+        if auto_mode and not use_peer:
+            mode = "api"
+            config["mode"] = "call by call through the drop-in packages, cut gather/lerp fused into K1/K9"
+    if mode == "graph":
+        config["collectives"] = ("fused into the kernels over NVLink peer memory (forward: stores into every rank's image; backward: the "
+                                 "owner's chain-rule kernels pull the partial [P,10] rows of the ranks that touch a Gaussian) + 2 device-side "
+                                 "barrier kernels per step" if use_peer else
                                  ("NCCL all-gather (image slabs) + reduce-scatter ([P,10] sums)" if world > 1 else "none"))
         mk = lambda **kw: GraphedStep(scene, W, H, c0.tanfovx, c0.tanfovy, bg, thr[0], world=world, rank=rank, peer=use_peer, **kw)
         # capacities: one eager sync-free pass over the views with generous sizes, then +15 % head room

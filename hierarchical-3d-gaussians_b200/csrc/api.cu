@@ -211,7 +211,7 @@ extern "C" int h3dgs_rasterize_forward(const h3dgs_raster_args* a, h3dgs_alloc_f
     // one memset covers the histogram and ScanInfo (adjacent regions of the image state)
     H3_CUDA(cudaMemsetAsync(tile_count, 0, (size_t)((uint8_t*)info - (uint8_t*)tile_count) + sizeof(ScanInfo), s));
     (void)gxy;
-    rc = launch_preprocess(*a, out_radii, depths, tiles, records, tile_count, info, s);
+    rc = launch_preprocess(*a, out_radii, depths, tiles, geom + gl.rank_mask, records, tile_count, info, s);
     if (rc) return rc;
     // SH -> RGB only feeds record.c (read again by the record gather): run it on the side stream,
     // overlapped with the tile scan, the num_rendered round trip and key emission
@@ -324,8 +324,9 @@ extern "C" int h3dgs_rasterize_backward(const h3dgs_raster_args* a, const int32_
     if (a->peer_count > 1 && scratch != a->peer_accum[a->shard_index]) {
         set_error("peer mode: scratch must be peer_accum[shard_index]"); return H3DGS_EINVAL;
     }
-    // peer mode: the other ranks add into this accumulator too -- its owner zeroes it between steps (see h3dgs.h)
-    if ((phases & 1) && a->peer_count <= 1) H3_CUDA(cudaMemsetAsync(accum, 0, (size_t)a->P * kAccum * sizeof(float), s));
+    // peer mode: phase 1 fills THIS rank's partial sums; the owners pull them in phase 2, after the caller's barrier --
+    // and the barrier at the start of the caller's next step orders their reads before this memset (see h3dgs.h)
+    if (phases & 1) H3_CUDA(cudaMemsetAsync(accum, 0, (size_t)a->P * kAccum * sizeof(float), s));
     if (D > 0 && (phases & 1)) {
         rc = launch_render_backward(b, (const uint32_t*)(img + il.ranges), (const Record*)(bin + bl.sorted_records),
                                     (const uint32_t*)(bin + bl.vals_sorted), (const float*)(img + il.final_T),
@@ -340,21 +341,21 @@ extern "C" int h3dgs_rasterize_backward(const h3dgs_raster_args* a, const int32_
         // after its zero-fill) and the covariance kernel (main stream) run concurrently
         H3_CUDA(cudaEventRecord(ss->fork, s));                           // accum is complete at this point of s
         H3_CUDA(cudaStreamWaitEvent(ss->s, ss->fork, 0));
-        rc = launch_sh_backward(b, radii, (const Record*)(geom + gl.records), accum, dL_dmeans3D, dL_dsh, ss->s);
+        rc = launch_sh_backward(b, radii, geom + gl.rank_mask, (const Record*)(geom + gl.records), accum, dL_dmeans3D, dL_dsh, ss->s);
         if (rc) return rc;
         H3_CUDA(cudaStreamWaitEvent(s, ss->join, 0));                    // zero-fill done before our own reductions
         H3_CUDA(cudaEventRecord(ss->join, ss->s));
-        rc = launch_preprocess_backward(b, radii, (const Record*)(geom + gl.records), accum, dL_dmeans3D, dL_dmeans2D,
+        rc = launch_preprocess_backward(b, radii, geom + gl.rank_mask, (const Record*)(geom + gl.records), accum, dL_dmeans3D, dL_dmeans2D,
                                         dL_dsh, dL_dcolors_precomp, dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D, s);
         if (rc) return rc;
         H3_CUDA(cudaStreamWaitEvent(s, ss->join, 0));
         return H3DGS_OK;
     }
     if (!zero_joined) H3_CUDA(cudaStreamWaitEvent(s, ss->join, 0));
-    rc = launch_preprocess_backward(b, radii, (const Record*)(geom + gl.records), accum, dL_dmeans3D, dL_dmeans2D,
+    rc = launch_preprocess_backward(b, radii, geom + gl.rank_mask, (const Record*)(geom + gl.records), accum, dL_dmeans3D, dL_dmeans2D,
                                     dL_dsh, dL_dcolors_precomp, dL_dopacities, dL_dscales, dL_drotations, dL_dcov3D, s);
     if (rc) return rc;
-    return launch_sh_backward(b, radii, (const Record*)(geom + gl.records), accum, dL_dmeans3D, dL_dsh, s);
+    return launch_sh_backward(b, radii, geom + gl.rank_mask, (const Record*)(geom + gl.records), accum, dL_dmeans3D, dL_dsh, s);
 }
 
 extern "C" int h3dgs_state_layout(int32_t P, int32_t W, int32_t H, int64_t D, const void* geom_state,

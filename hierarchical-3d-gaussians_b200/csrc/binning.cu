@@ -180,43 +180,39 @@ emit_to_tiles_kernel(int P, int W, int H, int shard_count, int shard_index, cons
                      uint32_t* __restrict__ tile_count, uint2* __restrict__ pairs)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
+    if (i >= P) return;
+    const int rad = radii[i];
+    if (rad <= 0) return;
+    if (info->overflow) return;                  // capacity mode: the segments would not fit `pairs`
+    const float4 a = records[i].a;
+    const float ix = a.x, iy = a.y;
     const int gx = (W + kTile - 1) / kTile, gy = (H + kTile - 1) / kTile;
-    int rminx = 0, rminy = 0, w = 0, area = 0;
-    uint32_t dbits = 0;
-    // capacity mode: with the overflow flag up the segments would not fit `pairs`
-    if (i < P && radii[i] > 0 && !info->overflow) {
-        const int rad = radii[i];
-        const float4 a = records[i].a;
-        const float ix = a.x, iy = a.y;
-        rminx = min(gx, max(0, (int)((ix - rad) / kTile)));
-        rminy = min(gy, max(0, (int)((iy - rad) / kTile)));
-        const int rmaxx = min(gx, max(0, (int)((ix + rad + kTile - 1) / kTile)));
-        const int rmaxy = min(gy, max(0, (int)((iy + rad + kTile - 1) / kTile)));
-        w = rmaxx - rminx; area = w * (rmaxy - rminy);
-        dbits = __float_as_uint(depths[i]);
-    }
-    // Slot claims return a value, so each costs an L2 round trip.  Rows arrive in hierarchy (Morton) order: per step every
-    // lane proposes one tile of its rect, equal proposals are grouped with match.any, the lowest lane of a group claims
-    // popc(group) slots with ONE atomic (the histogram doubles as the cursor) and every member takes its own slot of the
-    // claim -- the order inside a tile's segment is arbitrary, the per-tile sort fixes it.
-    const int steps = (int)__reduce_max_sync(0xffffffffu, (unsigned)area);
-    for (int k = 0; k < steps; k++) {
-        uint32_t tile = 0x80000000u | (uint32_t)lane;                      // no proposal: a value nobody else has
-        if (k < area) {
-            const int y = rminy + k / w, x = rminx + k % w;
-            if (shard_count <= 1 || (y % shard_count) == shard_index) tile = (uint32_t)(y * gx + x);
+    const int rminx = min(gx, max(0, (int)((ix - rad) / kTile)));
+    const int rminy = min(gy, max(0, (int)((iy - rad) / kTile)));
+    const int rmaxx = min(gx, max(0, (int)((ix + rad + kTile - 1) / kTile)));
+    const int rmaxy = min(gy, max(0, (int)((iy + rad + kTile - 1) / kTile)));
+    const uint32_t dbits = __float_as_uint(depths[i]);
+    // The slot claims return a value, so each costs a full L2 round trip: walk the rect as a flat index
+    // and keep four independent claims (then four range loads, then four stores) in flight per thread.
+    const int w = rmaxx - rminx, area = w * (rmaxy - rminy);
+    for (int t0 = 0; t0 < area; t0 += 4) {
+        int tl[4]; uint32_t sl[4], st[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            tl[k] = -1;
+            const int t = t0 + k;
+            if (t < area) {
+                const int y = rminy + t / w, x = rminx + t % w;
+                if (shard_count <= 1 || (y % shard_count) == shard_index) tl[k] = y * gx + x;
+            }
         }
-        const bool has = !(tile & 0x80000000u);
-        const uint32_t grp = __match_any_sync(0xffffffffu, tile);
-        const int leader = __ffs(grp) - 1;
-        uint32_t base = 0;
-        if (has && leader == lane) base = atomicSub(tile_count + tile, (uint32_t)__popc(grp));      // returns the old count
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (has) {
-            const uint32_t slot = base - 1u - (uint32_t)__popc(grp & ((1u << lane) - 1u));
-            pairs[ranges[tile].x + slot] = make_uint2((uint32_t)i, dbits);   // little-endian u64 = depth << 32 | idx
-        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (tl[k] >= 0) sl[k] = atomicSub(tile_count + tl[k], 1u) - 1u;   // histogram doubles as cursor
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (tl[k] >= 0) st[k] = ranges[tl[k]].x;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (tl[k] >= 0) pairs[st[k] + sl[k]] = make_uint2((uint32_t)i, dbits);   // little-endian u64 = depth << 32 | idx
     }
 }
 
@@ -415,6 +411,7 @@ GeomLayout geom_layout(int P) {
     l.depths = o; o = align_up(o + n * 4);
     l.tiles_touched = o; o = align_up(o + n * 4);
     l.offsets = o; o = align_up(o + n * 4);
+    l.rank_mask = o; o = align_up(o + n);
     l.records = o; o = align_up(o + n * sizeof(Record));
     l.scan_temp_bytes = scan_temp_bytes(P);
     l.scan_temp = o; o = align_up(o + l.scan_temp_bytes);

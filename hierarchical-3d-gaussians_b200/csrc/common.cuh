@@ -41,7 +41,7 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a = 256) { return (x
 
 // ---- state buffer layouts (byte offsets inside the three alloc'd buffers) ----
 struct GeomLayout {
-    size_t depths, tiles_touched, offsets, records, scan_temp, total;
+    size_t depths, tiles_touched, offsets, rank_mask, records, scan_temp, total;
     size_t scan_temp_bytes;
 };
 struct BinLayout {
@@ -103,7 +103,7 @@ extern int64_t g_launches;
 
 // ---- stage entry points (one per .cu file) ----
 int launch_preprocess(const h3dgs_raster_args& a, int32_t* radii, float* depths, uint32_t* tiles_touched,
-                      Record* records, uint32_t* tile_count, ScanInfo* info, cudaStream_t s);
+                      uint8_t* rank_mask, Record* records, uint32_t* tile_count, ScanInfo* info, cudaStream_t s);
 int launch_tile_scan(const h3dgs_raster_args& a, const uint32_t* tile_count, uint32_t* ranges, ScanInfo* info,
                      uint32_t cap_entries, uint32_t cap_list, cudaStream_t s);
 int launch_tile_binning(const h3dgs_raster_args& a, const int32_t* radii, const float* depths, const Record* records,
@@ -111,8 +111,8 @@ int launch_tile_binning(const h3dgs_raster_args& a, const int32_t* radii, const 
                         const ScanInfo* info, uint32_t* tile_count, cudaStream_t s);
 int launch_preprocess_color(const h3dgs_raster_args& a, const int32_t* radii, const uint32_t* tiles_touched,
                             Record* records, cudaStream_t s);
-int launch_sh_backward(const h3dgs_raster_args& a, const int32_t* radii, const Record* records, const float* accum,
-                       float* dL_dmeans3D, float* dL_dsh, cudaStream_t s);
+int launch_sh_backward(const h3dgs_raster_args& a, const int32_t* radii, const uint8_t* rank_mask, const Record* records,
+                       const float* accum, float* dL_dmeans3D, float* dL_dsh, cudaStream_t s);
 int launch_scan(const uint32_t* in, uint32_t* out, int n, void* temp, size_t temp_bytes, cudaStream_t s, bool debug);
 size_t scan_temp_bytes(int n);
 size_t sort_temp_bytes(int64_t n);
@@ -126,7 +126,7 @@ int launch_render_backward(const h3dgs_raster_args& a, const uint32_t* ranges, c
                            const uint32_t* point_list, const float* final_T, const uint32_t* n_contrib,
                            const uint32_t* tile_max_contrib, const float* dL_dcolor, const float* dL_dinvdepth,
                            float* accum /*[P][10] zeroed*/, cudaStream_t s);
-int launch_preprocess_backward(const h3dgs_raster_args& a, const int32_t* radii, const Record* records,
+int launch_preprocess_backward(const h3dgs_raster_args& a, const int32_t* radii, const uint8_t* rank_mask, const Record* records,
                                const float* accum, float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh,
                                float* dL_dcolors, float* dL_dopacities, float* dL_dscales, float* dL_drots,
                                float* dL_dcov3D, cudaStream_t s);
@@ -177,6 +177,37 @@ __device__ __forceinline__ int cyclic_row(const RowCycle& c, int local) {
     return ((((local >> c.shift) * c.world + c.rank)) << c.shift) + (local & ((1 << c.shift) - 1));
 }
 __device__ __forceinline__ bool cyclic_owned(const RowCycle& c, int row) { return ((row >> c.shift) % c.world) == c.rank; }
+#endif
+
+#ifdef __CUDACC__
+// Peer mode, backward phase 2 (K9): every rank's phase 1 has left its PARTIAL [P][10] sums in its own accumulator; the
+// owner of a row pulls the partial rows of the ranks whose tile rows the Gaussian touches (rank_mask, written by K1)
+// straight out of their memory -- plain 8-byte loads over NVLink, system-scope so that nothing stale is served -- and
+// adds them in rank order.  This IS the reduce-scatter of the per-Gaussian sums: no dense exchange, only rows that
+// exist travel (a Gaussian touches 1-2 tile rows on average), and the result does not depend on arrival order.
+__device__ __forceinline__ float2 ld_peer_f2(const float* p) {
+#ifdef H3_SIMT_EMU
+    return *reinterpret_cast<const float2*>(p);
+#else
+    float2 v;
+    asm volatile("ld.relaxed.sys.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+    return v;
+#endif
+}
+// pairs [2 * first, 2 * first + 2 * NPAIR) of accumulator row i, summed over the ranks of `mask`
+template <int NPAIR>
+__device__ __forceinline__ void pull_accum_pairs(const PeerPtrs& peers, uint32_t mask, int i, int first, float (&out)[2 * NPAIR]) {
+#pragma unroll
+    for (int k = 0; k < 2 * NPAIR; k++) out[k] = 0.f;
+#pragma unroll
+    for (int r = 0; r < H3DGS_MAX_PEERS; r++) {
+        if (r < peers.n && ((mask >> r) & 1u)) {
+            const float* row = static_cast<const float*>(peers.p[r]) + (size_t)i * 10 + 2 * first;
+#pragma unroll
+            for (int k = 0; k < NPAIR; k++) { const float2 v = ld_peer_f2(row + 2 * k); out[2 * k] += v.x; out[2 * k + 1] += v.y; }
+        }
+    }
+}
 #endif
 
 // Loop statistics of the blend kernels, HOST EMULATION BUILD ONLY (tests/emul; the emulator is single-threaded):

@@ -49,25 +49,26 @@ preprocess_kernel(int P, const float* __restrict__ means3D, const float* __restr
                   int W, int H, float tanx, float tany, float fx, float fy,
                   int shard_count, int shard_index, int prefiltered, ScanInfo* __restrict__ info,
                   int* __restrict__ radii, float* __restrict__ depths, uint32_t* __restrict__ tiles_touched,
-                  Record* __restrict__ records, uint32_t* __restrict__ tile_count)
+                  uint8_t* __restrict__ rank_mask /* peer mode, else NULL */, Record* __restrict__ records,
+                  uint32_t* __restrict__ tile_count)
 {
     __shared__ float s_view[16], s_proj[16];
     if (threadIdx.x < 16) { s_view[threadIdx.x] = view[threadIdx.x]; s_proj[threadIdx.x] = proj[threadIdx.x]; }
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int out_radius = 0; uint32_t out_tiles = 0;
-    int hx0 = 0, hx1 = 0, hy0 = 0, hy1 = 0;          // tile rect for the histogram (empty unless the row is rendered)
-    bool skip_row = i >= P;
+    if (i >= P) return;
+
+    int out_radius = 0; uint32_t out_tiles = 0, out_mask = 0;
     // in-kernel cut gather + parent lerp: x = t*x[c] + (1-t)*x[p], evaluated as two rounded
     // products and one rounded sum (bit-identical to the PyTorch expression of render_post)
     int c = i, p = i;
     float t = 1.0f, u = 0.0f;
-    if (ridx && !skip_row) {
+    if (ridx) {
         c = ridx[i];
-        if (c < 0) { skip_row = true; c = 0; }                       // tail after a device-side LOD cut (h3dgs_lod_cut)
-        else { p = pidx[i]; if (p < 0) p = c; t = ts[i]; u = 1.0f - t; }
+        if (c < 0) { radii[i] = 0; tiles_touched[i] = 0; if (rank_mask) rank_mask[i] = 0; return; }   // tail after a device-side LOD cut (h3dgs_lod_cut)
+        p = pidx[i]; if (p < 0) p = c;
+        t = ts[i]; u = 1.0f - t;
     }
-    if (skip_row) { c = 0; p = 0; t = 1.0f; u = 0.0f; }
     const bool lerp = ridx != nullptr && u != 0.0f;
 #define LERP(a, b) (lerp ? (t * (a) + u * (b)) : (a))
     const float px_ = LERP(means3D[3 * c], means3D[3 * p]);
@@ -77,7 +78,7 @@ preprocess_kernel(int P, const float* __restrict__ means3D, const float* __restr
     const float vx = m[0] * px_ + m[4] * py_ + m[8] * pz_ + m[12];
     const float vy = m[1] * px_ + m[5] * py_ + m[9] * pz_ + m[13];
     const float vz = m[2] * px_ + m[6] * py_ + m[10] * pz_ + m[14];
-    if (vz > kNearPlane && !skip_row) {
+    if (vz > kNearPlane) {
         const float* q = s_proj;
         const float hx = q[0] * px_ + q[4] * py_ + q[8] * pz_ + q[12];
         const float hy = q[1] * px_ + q[5] * py_ + q[9] * pz_ + q[13];
@@ -179,32 +180,24 @@ preprocess_kernel(int P, const float* __restrict__ means3D, const float* __restr
                 const int rows = (rmaxy + shard_count - 1 - shard_index) / shard_count
                                - (rminy + shard_count - 1 - shard_index) / shard_count;
                 out_tiles = (uint32_t)(rows * (rmaxx - rminx));
-                hx0 = rminx; hx1 = rmaxx; hy0 = rminy; hy1 = rmaxy;
+                // peer mode: which ranks' tile rows the rect covers, i.e. whose accumulators will hold sums for this row
+                if (rank_mask) {
+                    if (rmaxy - rminy >= shard_count) out_mask = (1u << shard_count) - 1u;
+                    else for (int y = rminy; y < rmaxy; y++) out_mask |= 1u << (y % shard_count);
+                }
+                // per-tile histogram for the per-tile sort (binning.cu): replaces the scan over P
+                for (int y = rminy; y < rmaxy; y++) {
+                    if (shard_count > 1 && (y % shard_count) != shard_index) continue;
+                    for (int x = rminx; x < rmaxx; x++) atomicAdd(tile_count + (y * gx + x), 1u);
+                }
             }
         }
     }
-    else if (prefiltered && !skip_row) info->prefilter_bad = 1u;    // the caller promised that nothing is behind the near plane
+    else if (prefiltered) info->prefilter_bad = 1u;    // the caller promised that nothing is behind the near plane
 #undef LERP
-    if (i < P) { radii[i] = out_radius; tiles_touched[i] = out_tiles; }
-    // Per-tile histogram for the per-tile sort (binning.cu).  Rows arrive in hierarchy (Morton) order, so the lanes of a
-    // warp mostly hit the same few tiles: per step every lane proposes one tile of its rect, equal proposals are grouped
-    // with match.any and the lowest lane of a group adds the group's size -- one reduction per distinct tile instead of
-    // one per (Gaussian, tile).  All 32 lanes stay in the loop (full-mask collectives).
-    {
-        const int gx = (W + kTile - 1) / kTile;
-        const int w = hx1 - hx0, area = w * (hy1 - hy0);
-        const int steps = (int)__reduce_max_sync(0xffffffffu, (unsigned)area);
-        const int lane = threadIdx.x & 31;
-        for (int k = 0; k < steps; k++) {
-            uint32_t tile = 0x80000000u | (uint32_t)lane;                  // no proposal: a value nobody else has
-            if (k < area) {
-                const int y = hy0 + k / w, x = hx0 + k % w;
-                if (shard_count <= 1 || (y % shard_count) == shard_index) tile = (uint32_t)(y * gx + x);
-            }
-            const uint32_t grp = __match_any_sync(0xffffffffu, tile);
-            if (!(tile & 0x80000000u) && (__ffs(grp) - 1) == lane) atomicAdd(tile_count + tile, (uint32_t)__popc(grp));
-        }
-    }
+    radii[i] = out_radius;
+    tiles_touched[i] = out_tiles;
+    if (rank_mask) rank_mask[i] = (uint8_t)out_mask;
 }
 
 // K1b: SH -> RGB for the visible Gaussians only (192 B/row, x2 on lerped rows): reads the same
@@ -295,7 +288,7 @@ preprocess_color_kernel(int P, int deg, int M, const float* __restrict__ means3D
 }
 
 int launch_preprocess(const h3dgs_raster_args& a, int32_t* radii, float* depths, uint32_t* tiles_touched,
-                      Record* records, uint32_t* tile_count, ScanInfo* info, cudaStream_t s)
+                      uint8_t* rank_mask, Record* records, uint32_t* tile_count, ScanInfo* info, cudaStream_t s)
 {
     if (a.P == 0) return H3DGS_OK;
     const float fx = a.image_width / (2.0f * a.tanfovx), fy = a.image_height / (2.0f * a.tanfovy);
@@ -306,7 +299,7 @@ int launch_preprocess(const h3dgs_raster_args& a, int32_t* radii, float* depths,
                                                  a.num_node_kids, a.render_indices, a.parent_indices, a.viewmatrix,
                                                  a.projmatrix, a.image_width, a.image_height, a.tanfovx, a.tanfovy, fx, fy,
                                                  a.shard_count > 0 ? a.shard_count : 1, a.shard_count > 0 ? a.shard_index : 0,
-                                                 a.prefiltered, info, radii, depths, tiles_touched, records, tile_count);
+                                                 a.prefiltered, info, radii, depths, tiles_touched, a.peer_count > 1 ? rank_mask : nullptr, records, tile_count);
     H3_LAUNCHED("preprocess", a.debug, s);
     return H3DGS_OK;
 }

@@ -33,7 +33,8 @@ preprocess_backward_kernel(int row0, int P, const RowCycle cyc, int deg, int M, 
                            const float* __restrict__ ts, const int* __restrict__ ridx, const int* __restrict__ pidx,
                            const float* __restrict__ view, const float* __restrict__ proj,
                            const float* __restrict__ campos, int W, int H, float tanx, float tany, float fx, float fy,
-                           int use_depth, const int* __restrict__ radii, const Record* __restrict__ records,
+                           int use_depth, const int* __restrict__ radii, const uint8_t* __restrict__ rank_mask, const PeerPtrs peers,
+                           const Record* __restrict__ records,
                            const float* __restrict__ accum, float* __restrict__ dL_dmeans3D,
                            float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dsh, float* __restrict__ dL_dcolors,
                            float* __restrict__ dL_dopacities, float* __restrict__ dL_dscales,
@@ -59,7 +60,13 @@ preprocess_backward_kernel(int row0, int P, const RowCycle cyc, int deg, int M, 
     }
 
     const float* v = s_view;
-    const float* ac = accum + (size_t)i * kAccum;
+    float ac[kAccum];
+    if (peers.n > 1) pull_accum_pairs<5>(peers, rank_mask[i], i, 0, ac);      // the partial sums of the ranks that touch row i
+    else {
+        const float2* row = reinterpret_cast<const float2*>(accum + (size_t)i * kAccum);
+#pragma unroll
+        for (int k = 0; k < 5; k++) { const float2 v = row[k]; ac[2 * k] = v.x; ac[2 * k + 1] = v.y; }
+    }
     // the per-tile replay leaves its constant factors to us: d(pixel)/d(ndc) = 0.5 W, 0.5 H and the
     // -1/2 of the quadratic form
     const float g_mx = ac[0] * (0.5f * W), g_my = ac[1] * (0.5f * H);
@@ -163,7 +170,8 @@ preprocess_backward_kernel(int row0, int P, const RowCycle cyc, int deg, int M, 
 __global__ void __launch_bounds__(128)
 sh_backward_kernel(int row0, int P, const RowCycle cyc, int deg, int M, const float* __restrict__ means3D, const float* __restrict__ shs,
                    const float* __restrict__ ts, const int* __restrict__ ridx, const int* __restrict__ pidx,
-                   const float* __restrict__ campos, const int* __restrict__ radii, const Record* __restrict__ records,
+                   const float* __restrict__ campos, const int* __restrict__ radii, const uint8_t* __restrict__ rank_mask,
+                   const PeerPtrs peers, const Record* __restrict__ records,
                    const float* __restrict__ accum, float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dsh)
 {
     const int local = blockIdx.x * blockDim.x + threadIdx.x;
@@ -189,10 +197,12 @@ sh_backward_kernel(int row0, int P, const RowCycle cyc, int deg, int M, const fl
     const float mx = LERP(means3D[3 * c], means3D[3 * p]);
     const float my = LERP(means3D[3 * c + 1], means3D[3 * p + 1]);
     const float mz = LERP(means3D[3 * c + 2], means3D[3 * p + 2]);
-    const float* ac = accum + (size_t)i * kAccum;
+    float col[4];                                          // accum columns 6..9: dL/dRGB (and dL/dinvdepth, unused here)
+    if (peers.n > 1) pull_accum_pairs<2>(peers, rank_mask[i], i, 3, col);
+    else { const float* ac = accum + (size_t)i * kAccum; col[0] = ac[6]; col[1] = ac[7]; col[2] = ac[8]; }
     const uint32_t kb = __float_as_uint(records[i].b.w);
-    const float dRGB[3] = {(kb >> kClampShift) & 1u ? 0.f : ac[6], (kb >> (kClampShift + 1)) & 1u ? 0.f : ac[7],
-                           (kb >> (kClampShift + 2)) & 1u ? 0.f : ac[8]};
+    const float dRGB[3] = {(kb >> kClampShift) & 1u ? 0.f : col[0], (kb >> (kClampShift + 1)) & 1u ? 0.f : col[1],
+                           (kb >> (kClampShift + 2)) & 1u ? 0.f : col[2]};
     const float d0x = mx - campos[0], d0y = my - campos[1], d0z = mz - campos[2];
     const float len = sqrtf(d0x * d0x + d0y * d0y + d0z * d0z);
     const float x = d0x / len, y = d0y / len, z = d0z / len;
@@ -301,7 +311,7 @@ sh_backward_kernel(int row0, int P, const RowCycle cyc, int deg, int M, const fl
 #undef LERP
 }
 
-int launch_preprocess_backward(const h3dgs_raster_args& a, const int32_t* radii, const Record* records,
+int launch_preprocess_backward(const h3dgs_raster_args& a, const int32_t* radii, const uint8_t* rank_mask, const Record* records,
                                const float* accum, float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh,
                                float* dL_dcolors, float* dL_dopacities, float* dL_dscales, float* dL_drots,
                                float* dL_dcov3D, cudaStream_t s)
@@ -317,14 +327,14 @@ int launch_preprocess_backward(const h3dgs_raster_args& a, const int32_t* radii,
     preprocess_backward_kernel<<<(rows + 127) / 128, 128, 0, s>>>(
         r0, r1, cyc, a.sh_degree, a.sh_coeffs, a.means3D, a.scales, a.scale_modifier, a.rotations, a.shs, a.cov3D_precomp,
         a.colors_precomp, a.interpolation_weights, a.render_indices, a.parent_indices, a.viewmatrix, a.projmatrix, a.campos, a.image_width, a.image_height, a.tanfovx, a.tanfovy,
-        fx, fy, a.do_depth, radii, records, accum, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacities,
+        fx, fy, a.do_depth, radii, rank_mask, peer_ptrs(a.peer_accum, a.peer_count), records, accum, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacities,
         dL_dscales, dL_drots, dL_dcov3D);
     H3_LAUNCHED("preprocess_backward", a.debug, s);
     return H3DGS_OK;
 }
 
-int launch_sh_backward(const h3dgs_raster_args& a, const int32_t* radii, const Record* records, const float* accum,
-                       float* dL_dmeans3D, float* dL_dsh, cudaStream_t s)
+int launch_sh_backward(const h3dgs_raster_args& a, const int32_t* radii, const uint8_t* rank_mask, const Record* records,
+                       const float* accum, float* dL_dmeans3D, float* dL_dsh, cudaStream_t s)
 {
     if (a.P == 0 || a.colors_precomp) return H3DGS_OK;
     const RowCycle cyc = row_cycle(a);
@@ -335,7 +345,8 @@ int launch_sh_backward(const h3dgs_raster_args& a, const int32_t* radii, const R
     ProfScope prof(H3DGS_STAGE_SH_BACKWARD, s);
     sh_backward_kernel<<<(rows + 127) / 128, 128, 0, s>>>(r0, r1, cyc, a.sh_degree, a.sh_coeffs, a.means3D, a.shs,
                                                          a.interpolation_weights, a.render_indices, a.parent_indices,
-                                                         a.campos, radii, records, accum, dL_dmeans3D, dL_dsh);
+                                                         a.campos, radii, rank_mask, peer_ptrs(a.peer_accum, a.peer_count), records, accum,
+                                                         dL_dmeans3D, dL_dsh);
     H3_LAUNCHED("sh_backward", a.debug, s);
     return H3DGS_OK;
 }

@@ -76,22 +76,23 @@ __device__ __forceinline__ void transpose_reduce10_g8(const float (&v)[10], int 
 
 constexpr int kBwdThreads = 128;      // two vertically adjacent pixels per thread (see render_forward.cu)
 
-// PEER: the 10 sums of a (tile, Gaussian) pair are added into the accumulator of the rank that owns the Gaussian's
-// row (system-scope red over NVLink) -- the reduce-scatter of the per-Gaussian gradients, fused into the replay.
-template <bool HIER, bool DEPTH, bool GROUPS, bool PEER>
+// Tile-sharded frames (NCCL or peer mode): the sums of a rank's own tiles go into ITS accumulator; the exchange follows
+// in phase 2 (peer mode: the owner of a row pulls the partial rows over NVLink, common.cuh::pull_accum_pairs).  A first
+// version added every (tile, Gaussian) row straight into the owner's memory with system-scope red.add: 4-byte
+// reductions over NVLink made the replay 3.5x slower (2 GPUs: 1.28 vs 0.36 ms, profiles/r02_m2_*).
+template <bool HIER, bool DEPTH, bool GROUPS>
 __global__ void __launch_bounds__(kBwdThreads)
 render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, const uint2* __restrict__ ranges,
                        const Record* __restrict__ sorted, const uint32_t* __restrict__ point_list,
                        const float* __restrict__ bg, const float* __restrict__ final_T,
                        const uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ tile_max_contrib,
                        const float* __restrict__ dL_dcolor, const float* __restrict__ dL_dinvdepth,
-                       float* __restrict__ accum, const PeerPtrs peers, const int peer_shift)
+                       float* __restrict__ accum)
 {
     __shared__ __align__(128) Record s_rec[kBwdStages][kBwdBatch];
     __shared__ uint32_t s_id[kBwdStages][kBwdBatch];
     __shared__ __align__(8) uint64_t s_full[kBwdStages];
     __shared__ uint8_t s_list[GROUPS ? kBwdThreads / 32 : 1][4][GROUPS ? kBwdBatch : 4];   // group walk: per warp, four lists of entry positions
-    __shared__ float* s_peer[PEER ? H3DGS_MAX_PEERS : 1];      // peer mode: the accumulators of the ranks, indexed by a row's owner
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int slot = reduce_slot(lane);
@@ -119,10 +120,6 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
     if (tid == 0) {
         for (int s = 0; s < kBwdStages; s++) mbar_init(&s_full[s], 1);
         fence_mbar_init();
-    }
-    if (PEER) {
-#pragma unroll
-        for (int r = 0; r < H3DGS_MAX_PEERS; r++) if (tid == r) s_peer[r] = static_cast<float*>(peers.p[r]);
     }
     __syncthreads();
     auto issue = [&](int it) {
@@ -215,13 +212,13 @@ render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, c
                 const bool taker = ((__ballot_sync(0xffffffffu, v0 || v1) >> (8 * grp)) & 0xFFu) != 0u;
                 float r0, r1;
                 transpose_reduce10_g8(v, lane, r0, r1);
-                float* row = (PEER ? s_peer[(gid >> peer_shift) & (uint32_t)(peers.n - 1)] : accum) + (size_t)gid * kAccum;
-                if (taker && gs0 >= 0 && (DEPTH || gs0 < 9)) { if (PEER) atomicAdd_system(row + gs0, r0); else atomicAdd(row + gs0, r0); }
-                if (taker && gs1 >= 0 && (DEPTH || gs1 < 9)) { if (PEER) atomicAdd_system(row + gs1, r1); else atomicAdd(row + gs1, r1); }
+                float* row = accum + (size_t)gid * kAccum;
+                if (taker && gs0 >= 0 && (DEPTH || gs0 < 9)) atomicAdd(row + gs0, r0);
+                if (taker && gs1 >= 0 && (DEPTH || gs1 < 9)) atomicAdd(row + gs1, r1);
             } else {
                 const float total = transpose_reduce10(v, lane);
-                float* row = (PEER ? s_peer[(gid >> peer_shift) & (uint32_t)(peers.n - 1)] : accum) + (size_t)gid * kAccum;
-                if (slot >= 0 && (DEPTH || slot < 9)) { if (PEER) atomicAdd_system(row + slot, total); else atomicAdd(row + slot, total); }
+                float* row = accum + (size_t)gid * kAccum;
+                if (slot >= 0 && (DEPTH || slot < 9)) atomicAdd(row + slot, total);
             }
         };
         if (GROUPS) {
@@ -288,14 +285,11 @@ int launch_render_backward(const h3dgs_raster_args& a, const uint32_t* ranges, c
     const dim3 grid(gx * rows), block(kBwdThreads);
     ProfScope prof(H3DGS_STAGE_RENDER_BWD, s);
     const bool groups = use_group_walk();
-    const PeerPtrs peers = peer_ptrs(a.peer_accum, a.peer_count);
-    const bool peer = peers.n > 1;
-#define LAUNCH(HI, DE, GR, PE)                                                                                          \
-    render_backward_kernel<HI, DE, GR, PE><<<grid, block, 0, s>>>(W, H, gx, sc, si, (const uint2*)ranges, sorted_records, \
-                                                                  point_list, a.bg, final_T, n_contrib, tile_max_contrib, \
-                                                                  dL_dcolor, dL_dinvdepth, accum, peers, a.grad_cyclic_log2)
-#define LAUNCH2(HI, DE) do { if (groups) { if (peer) LAUNCH(HI, DE, true, true); else LAUNCH(HI, DE, true, false); }          \
-                             else { if (peer) LAUNCH(HI, DE, false, true); else LAUNCH(HI, DE, false, false); } } while (0)
+#define LAUNCH(HI, DE, GR)                                                                                          \
+    render_backward_kernel<HI, DE, GR><<<grid, block, 0, s>>>(W, H, gx, sc, si, (const uint2*)ranges, sorted_records, \
+                                                              point_list, a.bg, final_T, n_contrib, tile_max_contrib, \
+                                                              dL_dcolor, dL_dinvdepth, accum)
+#define LAUNCH2(HI, DE) do { if (groups) LAUNCH(HI, DE, true); else LAUNCH(HI, DE, false); } while (0)
     if (hier) { if (depth) LAUNCH2(true, true); else LAUNCH2(true, false); }
     else      { if (depth) LAUNCH2(false, true); else LAUNCH2(false, false); }
 #undef LAUNCH2

@@ -16,11 +16,13 @@ the critical path.  Here nothing returns to the host inside the step:
 
 Sharded over G > 1 ranks the step has two forms.  peer=False: the image slabs travel in one NCCL all-gather, the
 [P,10] gradient sums in one NCCL reduce-scatter (h3dgs.dist).  peer=True (G in {2,4,8} on one NVLink box): the
-collectives are fused into the blend kernels through peer memory (h3dgs.peer, csrc/peer.cu) -- the forward stores every
-finished pixel into the image of every rank, the backward adds each (tile, Gaussian) row of sums into the accumulator of
-the rank that owns the Gaussian (block-cyclic row ownership), the L1 kernel evaluates only the rank's own tile rows and
-adds its partial loss into every rank's sum; what remains are three device-side barrier kernels per step (start: every
-rank's accumulator is zero and its image buffer free; middle of backward: all sums have landed; end: image complete).
+collectives are fused into the kernels through peer memory (h3dgs.peer, csrc/peer.cu) -- the forward stores every
+finished pixel into the image of every rank; the backward replay leaves each rank's partial (tile, Gaussian) sums in its
+own accumulator and the per-Gaussian chain rule (K9) of the rank that owns a row (block-cyclic row ownership) pulls the
+partial rows of the ranks that touch the Gaussian straight out of their memory; the L1 kernel evaluates only the rank's
+own tile rows and adds its partial loss into every rank's sum.  What remains are two device-side barrier kernels per
+step (start: every rank is done reading the others' accumulators and its image buffer is free; middle of backward:
+every rank's replay has finished, all pixels and partial sums are in place).
 
 With every size static the step is captured once: graph A = LOD cut + forward (+ the all-gather of
 the image slabs when sharded), graph B = L1 loss + its gradient + backward (+ the reduce-scatter of
@@ -158,7 +160,8 @@ class GraphedStep:
         """LOD cut -> forward (-> image all-gather)."""
         sc, L = self.scene, self.L
         if self.peer:
-            # every rank has zeroed its accumulator / loss sum and is done with its image buffer (end of its previous step)
+            # every rank has finished its previous step: it no longer reads our accumulator (phase 1 zeroes it) or its image
+            # buffer (our forward stores into it), and its loss sum is zero again
             self.arena.barrier()
         if self.N > self.N_nodes:
             sc.render_indices[self.N_nodes:].fill_(-1)  # the library marks [n, N_nodes); these are the skybox slots beyond
@@ -205,7 +208,8 @@ class GraphedStep:
         if self.world == 1:
             _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 3, self._stream()))
         elif self.peer:
-            # phase 1 adds into the owners' accumulators over NVLink; the barrier is the whole "reduce-scatter"
+            # phase 1 fills this rank's partial sums; after the barrier phase 2 pulls the rows it owns from every rank that
+            # touched them (loads over NVLink inside K9): that is the whole "reduce-scatter"
             _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 1, self._stream()))
             self.arena.barrier()
             _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 2, self._stream()))
@@ -221,8 +225,7 @@ class GraphedStep:
         self.status_dev[:5].copy_(torch.cat([loss.reshape(1), rows_needed, info]))
         self.status_dev[5:].copy_((rows_needed > self.P).double())
         if self.peer:
-            self.accum.zero_(); self.loss_sum.zero_()       # for the next step; ordered before anybody's next phase 1 by the barriers
-            self.arena.barrier()                              # every rank's pixels have landed: self.image is the whole frame
+            self.loss_sum.zero_()       # for the next step: ordered before anybody's next L1 kernel by the start barrier
 
     def scan_info(self):
         """int32 view [D, longest tile list, overflow] inside the image state."""

@@ -121,12 +121,14 @@ typedef struct h3dgs_raster_args {
      *  forward : every finished pixel of this rank's tile rows is stored into peer_image[r] ([3,H,W], one per rank,
      *            peer_image[shard_index] = the local one) for all r -- the all-gather of rendered tiles, tile by tile;
      *            out_color is not written.
-     *  backward: phase 1 adds each (tile, Gaussian) row of the [P][10] sums into peer_accum[owner(row)] (each a full
-     *            [P][10] array on its rank; owner(row) = (row >> grad_cyclic_log2) % peer_count, i.e. blocks of
-     *            2^grad_cyclic_log2 rendered rows dealt round-robin) -- the reduce-scatter is the red.global.add itself.
-     *            `scratch` must be peer_accum[shard_index]; it is NOT zeroed by the call (the owner zeroes it between
-     *            its phase 2 and the next barrier).  Phase 2 finishes exactly the rows this rank owns.
-     * The caller separates the phases with h3dgs_peer_barrier.  peer_count <= 1: off (grad_row_begin/end apply). */
+     *  backward: phase 1 leaves this rank's PARTIAL [P][10] sums (its own tiles) in `scratch`, which must be
+     *            peer_accum[shard_index] (zeroed by the call); phase 2 finishes exactly the rows this rank owns --
+     *            owner(row) = (row >> grad_cyclic_log2) % peer_count, i.e. blocks of 2^grad_cyclic_log2 rendered rows
+     *            dealt round-robin -- and pulls, for each of them, the partial rows of the ranks whose tile rows the
+     *            Gaussian touches out of peer_accum[r] (loads over NVLink inside the chain-rule kernels): the
+     *            reduce-scatter of the per-Gaussian sums without a dense exchange, summed in rank order.
+     * The caller separates the phases with h3dgs_peer_barrier, and the next step's phase 1 from this step's phase 2
+     * of the other ranks (a barrier at the start of every step does).  peer_count <= 1: off (grad_row_begin/end apply). */
     int32_t peer_count;
     int32_t grad_cyclic_log2;
     void* peer_image[H3DGS_MAX_PEERS];

@@ -328,9 +328,10 @@ def test_fused_l1_loss_and_gradient(emu, W, shard):
 def test_peer_mode_fused_collectives_schedule(emu, G):
     """Peer mode (h3dgs_raster_args.peer_count) on one CPU: G "ranks" run one after the other with numpy arrays standing in
     for peer memory.  Forward: every rank stores the pixels of ITS tile rows into the image of EVERY rank -> all G images
-    equal the unsharded one bit for bit.  Backward phase 1: each rank adds its (tile, Gaussian) sums straight into the
-    accumulator of the rank that owns the row (block-cyclic, 2^5 rows) -> the owners' accumulators hold the complete sums of
-    their rows and nothing else; phase 2 finishes exactly the owned rows.  Fused gather/scatter (render_indices) on top."""
+    equal the unsharded one bit for bit.  Backward phase 1: each rank leaves the (tile, Gaussian) sums of ITS tiles in its
+    own accumulator; phase 2 of the rank that owns a row (block-cyclic, 2^5 rows) pulls the partial rows of the ranks whose
+    tile rows the Gaussian touches (the rank mask K1 wrote) and finishes exactly the owned rows.  Fused gather/scatter
+    (render_indices) on top."""
     from oracle import oracle
     from emu_api import aligned, ptr
     cam = synth.make_camera(160, 112)
@@ -365,9 +366,10 @@ def test_peer_mode_fused_collectives_schedule(emu, G):
         emu.backward(a, fw, gcol, phases=1, scratch=accums[a.shard_index])
     rows = np.arange(P)
     owner = (rows >> SHIFT) % G
-    for r in range(G):
-        acc = accums[r].view(np.float32)[: P * 10].reshape(P, 10)
-        assert not acc[owner != r].any() and acc[owner == r].any()
+    parts = [accums[r].view(np.float32)[: P * 10].reshape(P, 10).copy() for r in range(G)]
+    assert all(p_.any() for p_ in parts)
+    touched = np.stack([np.abs(p_).sum(1) > 0 for p_ in parts])            # [G, P]: a small Gaussian reaches few ranks' tile rows
+    assert touched.sum(0).mean() < 0.75 * G
     total = {k: np.zeros(b[k].shape, np.float64) for k in ("means3D", "sh", "opacities", "scales", "rotations")}
     m2d = np.zeros((P, 3), np.float32)
     for a, keep, fw in ranks:

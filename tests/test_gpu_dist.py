@@ -14,6 +14,21 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
+def _spawn(fn, args, world, timeout_s=240):
+    """mp.spawn with a deadline: a multi-rank hang (a peer that never arrives, a stuck collective) must fail this test
+    instead of stalling the whole GPU tier; the children are killed by their exact pids."""
+    import time
+    import torch.multiprocessing as mp
+    ctx = mp.spawn(fn, args=args, nprocs=world, join=False)
+    deadline = time.time() + timeout_s
+    while not ctx.join(timeout=5):
+        if time.time() > deadline:
+            for p in ctx.processes:
+                if p.is_alive():
+                    p.kill()
+            pytest.fail(f"{fn.__name__}: {world} ranks did not finish within {timeout_s} s")
+
+
 def _worker(rank, world, port, out):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, os.path.join(root, "hierarchical-3d-gaussians_b200")); sys.path.insert(0, os.path.join(root, "tests"))
@@ -115,35 +130,32 @@ def _graph_worker(rank, world, port, out, peer=False):
 def test_graphed_peer_step_equals_single_gpu(tmp_path):
     """peer mode: no NCCL inside the step"""
     import torch
-    import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 4 if torch.cuda.device_count() >= 4 else 2
     out = str(tmp_path / "r.pt")
-    mp.spawn(_graph_worker, args=(world, _free_port(), out, True), nprocs=world, join=True)
+    _spawn(_graph_worker, (world, _free_port(), out, True), world)
     ok, errs = torch.load(out)
     assert ok, errs
 
 
 def test_graphed_sharded_step_equals_single_gpu(tmp_path):
     import torch
-    import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     world = min(torch.cuda.device_count(), 4)
     out = str(tmp_path / "r.pt")
-    mp.spawn(_graph_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    _spawn(_graph_worker, (world, _free_port(), out), world)
     ok, errs = torch.load(out)
     assert ok, errs
 
 
 def test_tile_sharded_step_equals_single_gpu(tmp_path):
     import torch
-    import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     world = min(torch.cuda.device_count(), 4)
     out = str(tmp_path / "r.pt")
-    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    _spawn(_worker, (world, _free_port(), out), world)
     ok, errs = torch.load(out)
     assert ok, errs
