@@ -25,9 +25,11 @@ def _needs_build(src, obj, deps):
     return any(os.path.getmtime(d) > t for d in [src] + deps)
 
 
-def build(verbose=False, force=False):
+def build(verbose=False, force=False, variant=None, defs=()):
+    """variant / defs: an A/B build with extra -D switches -> lib/libh3dgs_<variant>.so (objects under build_<variant>/);
+    h3dgs/_lib.py loads it when H3DGS_LIBRARY names it."""
     os.makedirs(OUT, exist_ok=True)
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build" + (f"_{variant}" if variant else ""))
     os.makedirs(objdir, exist_ok=True)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     deps.append(os.path.join(HERE, "..", "include", "h3dgs.h"))
@@ -39,7 +41,7 @@ def build(verbose=False, force=False):
         if not force and not _needs_build(src, obj, deps):
             return obj, ""
         cmd = [NVCC] + ARCH + COMMON + (["-fmad=false"] if name in NO_FMAD else []) + \
-            (["-DH3_PAIR_SCALAR"] if os.environ.get("H3DGS_PAIR_SCALAR") == "1" else []) + ["-c", src, "-o", obj]
+            (["-DH3_PAIR_SCALAR"] if os.environ.get("H3DGS_PAIR_SCALAR") == "1" else []) + [f"-D{d}" for d in defs] + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {name}:\n{r.stdout}\n{r.stderr}")
@@ -53,7 +55,7 @@ def build(verbose=False, force=False):
         f.write(log)
     if verbose and log:
         print(log)
-    so = os.path.join(OUT, "libh3dgs.so")
+    so = os.path.join(OUT, f"libh3dgs_{variant}.so" if variant else "libh3dgs.so")
     if force or not os.path.exists(so) or any(os.path.getmtime(o) > os.path.getmtime(so) for o in objs):
         cmd = [NVCC] + ARCH + ["-shared", "-o", so] + objs + ["-ccbin", "/usr/bin/g++"]
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -63,4 +65,7 @@ def build(verbose=False, force=False):
 
 
 if __name__ == "__main__":
-    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
+    # python build.py [-v] [-f] [--variant NAME -DSWITCH ...]
+    var = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv, variant=var,
+                defs=[a[2:] for a in sys.argv if a.startswith("-D")]))

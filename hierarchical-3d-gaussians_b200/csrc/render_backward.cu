@@ -11,7 +11,15 @@
 
 namespace h3dgs {
 
+// H3_BLEND_OCC8 (build switch, A/B on hardware): 224-entry batches (26.8 KB of shared memory per CTA) and a 64-register
+// cap, so that 8 instead of 7 CTAs share an SM
+#ifdef H3_BLEND_OCC8
+constexpr int kBwdBatch = 224;
+constexpr int kBwdMinBlocks = 8;
+#else
 constexpr int kBwdBatch = 256;
+constexpr int kBwdMinBlocks = 1;
+#endif
 constexpr int kBwdStages = 2;
 
 // Reduce NV per-lane values over the 32 lanes of a warp with a transpose-reduce: at every
@@ -81,7 +89,7 @@ constexpr int kBwdThreads = 128;      // two vertically adjacent pixels per thre
 // version added every (tile, Gaussian) row straight into the owner's memory with system-scope red.add: 4-byte
 // reductions over NVLink made the replay 3.5x slower (2 GPUs: 1.28 vs 0.36 ms, profiles/r02_m2_*).
 template <bool HIER, bool DEPTH, bool GROUPS>
-__global__ void __launch_bounds__(kBwdThreads)
+__global__ void __launch_bounds__(kBwdThreads, kBwdMinBlocks)
 render_backward_kernel(int W, int H, int gx, int shard_count, int shard_index, const uint2* __restrict__ ranges,
                        const Record* __restrict__ sorted, const uint32_t* __restrict__ point_list,
                        const float* __restrict__ bg, const float* __restrict__ final_T,

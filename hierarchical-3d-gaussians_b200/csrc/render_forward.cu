@@ -13,7 +13,13 @@
 
 namespace h3dgs {
 
+#ifdef H3_BLEND_OCC8      /* see render_backward.cu */
+constexpr int kFwdBatch = 224;
+constexpr int kFwdMinBlocks = 8;
+#else
 constexpr int kFwdBatch = 256;
+constexpr int kFwdMinBlocks = 1;
+#endif
 constexpr int kFwdStages = 2;
 
 // Two vertically adjacent pixels per thread: CTA = 128 threads = 4 warps, warp q owns one 8x8-pixel
@@ -24,7 +30,7 @@ constexpr int kFwdStages = 2;
 constexpr int kFwdThreads = 128;
 
 template <bool HIER, bool DEPTH, bool GROUPS>
-__global__ void __launch_bounds__(kFwdThreads)
+__global__ void __launch_bounds__(kFwdThreads, kFwdMinBlocks)
 render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, const uint2* __restrict__ ranges,
                       const Record* __restrict__ sorted, const float* __restrict__ bg, float* __restrict__ out_color,
                       float* __restrict__ out_invdepth, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,

@@ -7,7 +7,11 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+# H3DGS_LIBRARY: another build of the same sources (an A/B variant from build.py --variant), by file name under lib/ or by path
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libh3dgs.so")
+if os.environ.get("H3DGS_LIBRARY"):
+    _v = os.environ["H3DGS_LIBRARY"]
+    LIB_PATH = _v if os.path.isabs(_v) else os.path.join(os.path.dirname(_HERE), "lib", _v)
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_int, C.c_size_t)
 
