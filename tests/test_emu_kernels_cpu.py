@@ -384,19 +384,24 @@ def test_peer_mode_fused_collectives_schedule(emu, G):
     grad_close(m2d, b["means2D"], "means2D")
 
 
-@pytest.mark.parametrize("tau,misalign", [(0.0, False), (6.0, False), (60.0, False), (6.0, True)])
-def test_single_pass_cut_over_many_tiles(emu_lib, tau, misalign):
-    """lod_cut_fused_kernel with 80 tiles of 1024 nodes: the decoupled look-back walks more than one window of 32
-    predecessor tiles; indices, parents, nodes, weights (bit-exact) and kids against the oracle."""
+@pytest.mark.parametrize("tau,misalign,agg_only", [(0.0, False, False), (6.0, False, False), (60.0, False, False), (6.0, True, False),
+                                                   (6.0, False, True)])
+def test_single_pass_cut_over_many_tiles(emu_lib, tau, misalign, agg_only, monkeypatch):
+    """lod_cut_fused_kernel with 600+ tiles of 1024 nodes; indices, parents, nodes, weights (bit-exact) and kids against the
+    oracle.  agg_only: the emulator runs the CTAs one after the other, so every predecessor would already show its inclusive
+    prefix; the switch keeps all tiles but every 300th at "aggregate only", and the CTA-wide look-back has to add up to 299
+    aggregates over two rounds of 256 status words."""
+    if agg_only:
+        monkeypatch.setenv("H3DGS_EMU_CUT_AGG_ONLY", "1")
     from emu_api import aligned, f32, i32, ptr
     from oracle import oracle
     cam = synth.make_camera(320, 200)
-    leaves = synth.cloud_v1(41000, cam, zmin=2.0, zmax=40.0, seed=11, scale_k=1.0)
+    leaves = synth.cloud_v1(310000 if agg_only else 41000, cam, zmin=2.0, zmax=40.0, seed=11, scale_k=1.0)
     z = leaves["means3D"][:, 2:3]
     leaves["scales"] = (4e-3 * np.sqrt(2 * z) * np.ones((1, 3))).astype(np.float32)
     h = synth.build_hierarchy(leaves)
     N = h["nodes"].shape[0]
-    assert N > 80 * 1024
+    assert N > (600 if agg_only else 80) * 1024
     thr = synth.tau_threshold(tau, cam)
     n, ri, pi, ni = oracle.expand_to_size(h["nodes"], h["boxes"], thr, cam.camera_center)
     ts, kids = oracle.get_interpolation_weights(ni, thr, h["nodes"], h["boxes"], cam.camera_center)
