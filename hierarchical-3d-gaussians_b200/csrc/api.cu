@@ -144,7 +144,7 @@ static int check_args(const h3dgs_raster_args* a) {
             return H3DGS_EINVAL;
         }
         for (int r = 0; r < n; r++)
-            if (!a->peer_image[r] || !a->peer_accum[r]) { set_error("peer mode: peer_image / peer_accum [%d] is NULL", r); return H3DGS_EINVAL; }
+            if (!a->peer_image[r] || !a->peer_stage[r]) { set_error("peer mode: peer_image / peer_stage [%d] is NULL", r); return H3DGS_EINVAL; }
     }
     if (a->bin_capacity > 0 && a->debug) { set_error("capacity mode has no host synchronisation: debug must be off"); return H3DGS_EINVAL; }
     if (!a->means3D && a->P > 0) { set_error("means3D is NULL"); return H3DGS_EINVAL; }
@@ -321,17 +321,17 @@ extern "C" int h3dgs_rasterize_backward(const h3dgs_raster_args* a, const int32_
         H3_CUDA(cudaEventRecord(ss->join, ss->s));
         zero_joined = false;
     }
-    if (a->peer_count > 1 && scratch != a->peer_accum[a->shard_index]) {
-        set_error("peer mode: scratch must be peer_accum[shard_index]"); return H3DGS_EINVAL;
-    }
-    // peer mode: phase 1 fills THIS rank's partial sums; the owners pull them in phase 2, after the caller's barrier --
-    // and the barrier at the start of the caller's next step orders their reads before this memset (see h3dgs.h)
     if (phases & 1) H3_CUDA(cudaMemsetAsync(accum, 0, (size_t)a->P * kAccum * sizeof(float), s));
     if (D > 0 && (phases & 1)) {
         rc = launch_render_backward(b, (const uint32_t*)(img + il.ranges), (const Record*)(bin + bl.sorted_records),
                                     (const uint32_t*)(bin + bl.vals_sorted), (const float*)(img + il.final_T),
                                     (const uint32_t*)(img + il.n_contrib), (const uint32_t*)(img + il.tile_max_contrib),
                                     dL_dcolor, dL_dinvdepth, accum, s);
+        if (rc) return rc;
+    }
+    if ((phases & 1) && a->peer_count > 1) {
+        // peer mode: the partial rows of Gaussians other ranks own go into the owners' staging areas (posted stores over NVLink)
+        rc = launch_peer_push(b, geom + gl.rank_mask, accum, s);
         if (rc) return rc;
     }
     if (!(phases & 2)) return H3DGS_OK;

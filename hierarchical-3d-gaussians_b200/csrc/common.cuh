@@ -180,35 +180,38 @@ __device__ __forceinline__ bool cyclic_owned(const RowCycle& c, int row) { retur
 #endif
 
 #ifdef __CUDACC__
-// Peer mode, backward phase 2 (K9): every rank's phase 1 has left its PARTIAL [P][10] sums in its own accumulator; the
-// owner of a row pulls the partial rows of the ranks whose tile rows the Gaussian touches (rank_mask, written by K1)
-// straight out of their memory -- plain 8-byte loads over NVLink, system-scope so that nothing stale is served -- and
-// adds them in rank order.  This IS the reduce-scatter of the per-Gaussian sums: no dense exchange, only rows that
-// exist travel (a Gaussian touches 1-2 tile rows on average), and the result does not depend on arrival order.
-__device__ __forceinline__ float2 ld_peer_f2(const float* p) {
-#ifdef H3_SIMT_EMU
-    return *reinterpret_cast<const float2*>(p);
-#else
-    float2 v;
-    asm volatile("ld.relaxed.sys.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
-    return v;
-#endif
-}
+// Peer mode, backward phase 2 (K9): every rank's phase 1 has left its PARTIAL [P][10] sums in its own accumulator and
+// pushed the rows other ranks own into the owners' staging areas (preprocess_backward.cu::peer_push_kernel).  The owner
+// of row i adds its own partial row and the staged rows of the ranks whose tile rows the Gaussian touches (rank_mask,
+// written by K1), in rank order: the reduce-scatter of the per-Gaussian sums -- sparse (a Gaussian touches 1-2 tile
+// rows on average), independent of arrival order, all loads local.  (A first version PULLED the rows with loads over
+// NVLink inside K9: 8-byte remote reads made K9 2x slower on 2 GPUs, profiles/r02_m2b_*; remote stores are posted.)
+struct StagePtrs { const float* own; const float* stage; int n, rank; size_t slot_floats; };   // stage: [n][P][10] on this rank
 // pairs [2 * first, 2 * first + 2 * NPAIR) of accumulator row i, summed over the ranks of `mask`
 template <int NPAIR>
-__device__ __forceinline__ void pull_accum_pairs(const PeerPtrs& peers, uint32_t mask, int i, int first, float (&out)[2 * NPAIR]) {
+__device__ __forceinline__ void gather_accum_pairs(const StagePtrs& sp, uint32_t mask, int i, int first, float (&out)[2 * NPAIR]) {
 #pragma unroll
     for (int k = 0; k < 2 * NPAIR; k++) out[k] = 0.f;
 #pragma unroll
     for (int r = 0; r < H3DGS_MAX_PEERS; r++) {
-        if (r < peers.n && ((mask >> r) & 1u)) {
-            const float* row = static_cast<const float*>(peers.p[r]) + (size_t)i * 10 + 2 * first;
+        if (r < sp.n && ((mask >> r) & 1u)) {
+            const float* row = (r == sp.rank ? sp.own : sp.stage + (size_t)r * sp.slot_floats) + (size_t)i * 10 + 2 * first;
 #pragma unroll
-            for (int k = 0; k < NPAIR; k++) { const float2 v = ld_peer_f2(row + 2 * k); out[2 * k] += v.x; out[2 * k + 1] += v.y; }
+            for (int k = 0; k < NPAIR; k++) {
+                const float2 v = __ldcg(reinterpret_cast<const float2*>(row + 2 * k));      // L2: written by a peer through NVLink
+                out[2 * k] += v.x; out[2 * k + 1] += v.y;
+            }
         }
     }
 }
 #endif
+inline StagePtrs stage_ptrs(const h3dgs_raster_args& a, const float* accum) {
+    StagePtrs sp; sp.own = accum; sp.n = a.peer_count > 1 ? a.peer_count : 0; sp.rank = a.shard_index;
+    sp.stage = sp.n ? static_cast<const float*>(a.peer_stage[a.shard_index]) : nullptr;
+    sp.slot_floats = (size_t)a.P * 10;
+    return sp;
+}
+int launch_peer_push(const h3dgs_raster_args& a, const uint8_t* rank_mask, const float* accum, cudaStream_t s);
 
 // Loop statistics of the blend kernels, HOST EMULATION BUILD ONLY (tests/emul; the emulator is single-threaded):
 // 0 bwd warp iterations | 1 bwd iterations left at the no-taker vote | 2 bwd pixel-entries taken | 3 bwd group-iterations

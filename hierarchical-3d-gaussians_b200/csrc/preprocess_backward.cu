@@ -33,7 +33,7 @@ preprocess_backward_kernel(int row0, int P, const RowCycle cyc, int deg, int M, 
                            const float* __restrict__ ts, const int* __restrict__ ridx, const int* __restrict__ pidx,
                            const float* __restrict__ view, const float* __restrict__ proj,
                            const float* __restrict__ campos, int W, int H, float tanx, float tany, float fx, float fy,
-                           int use_depth, const int* __restrict__ radii, const uint8_t* __restrict__ rank_mask, const PeerPtrs peers,
+                           int use_depth, const int* __restrict__ radii, const uint8_t* __restrict__ rank_mask, const StagePtrs peers,
                            const Record* __restrict__ records,
                            const float* __restrict__ accum, float* __restrict__ dL_dmeans3D,
                            float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dsh, float* __restrict__ dL_dcolors,
@@ -61,7 +61,7 @@ preprocess_backward_kernel(int row0, int P, const RowCycle cyc, int deg, int M, 
 
     const float* v = s_view;
     float ac[kAccum];
-    if (peers.n > 1) pull_accum_pairs<5>(peers, rank_mask[i], i, 0, ac);      // the partial sums of the ranks that touch row i
+    if (peers.n > 1) gather_accum_pairs<5>(peers, rank_mask[i], i, 0, ac);    // the partial sums of the ranks that touch row i
     else {
         const float2* row = reinterpret_cast<const float2*>(accum + (size_t)i * kAccum);
 #pragma unroll
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(128)
 sh_backward_kernel(int row0, int P, const RowCycle cyc, int deg, int M, const float* __restrict__ means3D, const float* __restrict__ shs,
                    const float* __restrict__ ts, const int* __restrict__ ridx, const int* __restrict__ pidx,
                    const float* __restrict__ campos, const int* __restrict__ radii, const uint8_t* __restrict__ rank_mask,
-                   const PeerPtrs peers, const Record* __restrict__ records,
+                   const StagePtrs peers, const Record* __restrict__ records,
                    const float* __restrict__ accum, float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dsh)
 {
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
@@ -265,7 +265,7 @@ sh_backward_kernel(int row0, int P, const RowCycle cyc, int deg, int M, const fl
     float col[4] = {0.f, 0.f, 0.f, 0.f};                   // accum columns 6..9: dL/dRGB (and dL/dinvdepth, unused here)
     uint32_t kb = 0;
     if (visible) {
-        if (peers.n > 1) pull_accum_pairs<2>(peers, rank_mask[i], i, 3, col);
+        if (peers.n > 1) gather_accum_pairs<2>(peers, rank_mask[i], i, 3, col);
         else { const float* ac = accum + (size_t)i * kAccum; col[0] = ac[6]; col[1] = ac[7]; col[2] = ac[8]; }
         kb = __float_as_uint(records[i].b.w);
     }
@@ -363,6 +363,38 @@ sh_backward_kernel(int row0, int P, const RowCycle cyc, int deg, int M, const fl
 #undef LERP
 }
 
+// Peer mode, end of backward phase 1: this rank's partial [P][10] sums are complete.  Rows another rank owns travel
+// now: 40 bytes per row this rank touched (its bit in the rank mask), stored into slot [rank] of the owner's staging
+// area.  One thread per row, five 8-byte stores: a warp writes 32 consecutive rows = 1280 contiguous bytes, and
+// consecutive rows have the same owner (blocks of 2^shift rows), so the stores leave as full lines -- posted writes
+// over NVLink, nothing waits for them until the barrier kernel that follows.
+__global__ void __launch_bounds__(256)
+peer_push_kernel(int P, const RowCycle cyc, const uint8_t* __restrict__ rank_mask, const float* __restrict__ accum,
+                 const PeerPtrs stages)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    if (!((rank_mask[i] >> cyc.rank) & 1u)) return;                   // no tile of ours holds this Gaussian: nothing to report
+    const int owner = (i >> cyc.shift) % cyc.world;
+    if (owner == cyc.rank) return;                                    // our own rows stay in `accum`
+    float* dst = nullptr;
+#pragma unroll
+    for (int r = 0; r < H3DGS_MAX_PEERS; r++) if (r == owner) dst = static_cast<float*>(stages.p[r]);    // parameter-bank indexing
+    float2* d2 = reinterpret_cast<float2*>(dst + ((size_t)cyc.rank * P + i) * kAccum);
+    const float2* s2 = reinterpret_cast<const float2*>(accum + (size_t)i * kAccum);
+#pragma unroll
+    for (int k = 0; k < kAccum / 2; k++) d2[k] = s2[k];
+}
+
+int launch_peer_push(const h3dgs_raster_args& a, const uint8_t* rank_mask, const float* accum, cudaStream_t s)
+{
+    if (a.P == 0 || a.peer_count <= 1) return H3DGS_OK;
+    const RowCycle cyc = row_cycle(a);
+    peer_push_kernel<<<(a.P + 255) / 256, 256, 0, s>>>(a.P, cyc, rank_mask, accum, peer_ptrs(a.peer_stage, a.peer_count));
+    H3_LAUNCHED("peer_push", a.debug, s);
+    return H3DGS_OK;
+}
+
 int launch_preprocess_backward(const h3dgs_raster_args& a, const int32_t* radii, const uint8_t* rank_mask, const Record* records,
                                const float* accum, float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dsh,
                                float* dL_dcolors, float* dL_dopacities, float* dL_dscales, float* dL_drots,
@@ -379,7 +411,7 @@ int launch_preprocess_backward(const h3dgs_raster_args& a, const int32_t* radii,
     preprocess_backward_kernel<<<(rows + 127) / 128, 128, 0, s>>>(
         r0, r1, cyc, a.sh_degree, a.sh_coeffs, a.means3D, a.scales, a.scale_modifier, a.rotations, a.shs, a.cov3D_precomp,
         a.colors_precomp, a.interpolation_weights, a.render_indices, a.parent_indices, a.viewmatrix, a.projmatrix, a.campos, a.image_width, a.image_height, a.tanfovx, a.tanfovy,
-        fx, fy, a.do_depth, radii, rank_mask, peer_ptrs(a.peer_accum, a.peer_count), records, accum, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacities,
+        fx, fy, a.do_depth, radii, rank_mask, stage_ptrs(a, accum), records, accum, dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacities,
         dL_dscales, dL_drots, dL_dcov3D);
     H3_LAUNCHED("preprocess_backward", a.debug, s);
     return H3DGS_OK;
@@ -397,7 +429,7 @@ int launch_sh_backward(const h3dgs_raster_args& a, const int32_t* radii, const u
     ProfScope prof(H3DGS_STAGE_SH_BACKWARD, s);
     sh_backward_kernel<<<(int)(((size_t)rows * kShSplit + 127) / 128), 128, 0, s>>>(r0, r1, cyc, a.sh_degree, a.sh_coeffs, a.means3D, a.shs,
                                                          a.interpolation_weights, a.render_indices, a.parent_indices,
-                                                         a.campos, radii, rank_mask, peer_ptrs(a.peer_accum, a.peer_count), records, accum,
+                                                         a.campos, radii, rank_mask, stage_ptrs(a, accum), records, accum,
                                                          dL_dmeans3D, dL_dsh);
     H3_LAUNCHED("sh_backward", a.debug, s);
     return H3DGS_OK;

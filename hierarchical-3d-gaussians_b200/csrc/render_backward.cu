@@ -85,8 +85,8 @@ __device__ __forceinline__ void transpose_reduce10_g8(const float (&v)[10], int 
 constexpr int kBwdThreads = 128;      // two vertically adjacent pixels per thread (see render_forward.cu)
 
 // Tile-sharded frames (NCCL or peer mode): the sums of a rank's own tiles go into ITS accumulator; the exchange follows
-// in phase 2 (peer mode: the owner of a row pulls the partial rows over NVLink, common.cuh::pull_accum_pairs).  A first
-// version added every (tile, Gaussian) row straight into the owner's memory with system-scope red.add: 4-byte
+// (peer mode: preprocess_backward.cu::peer_push_kernel stores the finished partial rows into the owners' staging areas).
+// A first version added every (tile, Gaussian) row straight into the owner's memory with system-scope red.add: 4-byte
 // reductions over NVLink made the replay 3.5x slower (2 GPUs: 1.28 vs 0.36 ms, profiles/r02_m2_*).
 template <bool HIER, bool DEPTH, bool GROUPS>
 __global__ void __launch_bounds__(kBwdThreads, kBwdMinBlocks)

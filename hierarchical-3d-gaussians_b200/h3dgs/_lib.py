@@ -45,7 +45,7 @@ class RasterArgs(C.Structure):
         ("grad_row_begin", C.c_int32), ("grad_row_end", C.c_int32),
         ("bin_capacity", C.c_int64), ("sort_capacity", C.c_int32),
         ("peer_count", C.c_int32), ("grad_cyclic_log2", C.c_int32),
-        ("peer_image", C.c_void_p * 8), ("peer_accum", C.c_void_p * 8),
+        ("peer_image", C.c_void_p * 8), ("peer_stage", C.c_void_p * 8),
     ]
 
 

@@ -18,11 +18,12 @@ Sharded over G > 1 ranks the step has two forms.  peer=False: the image slabs tr
 [P,10] gradient sums in one NCCL reduce-scatter (h3dgs.dist).  peer=True (G in {2,4,8} on one NVLink box): the
 collectives are fused into the kernels through peer memory (h3dgs.peer, csrc/peer.cu) -- the forward stores every
 finished pixel into the image of every rank; the backward replay leaves each rank's partial (tile, Gaussian) sums in its
-own accumulator and the per-Gaussian chain rule (K9) of the rank that owns a row (block-cyclic row ownership) pulls the
-partial rows of the ranks that touch the Gaussian straight out of their memory; the L1 kernel evaluates only the rank's
+own accumulator, a push kernel stores the partial rows that other ranks own (block-cyclic row ownership) into the owners'
+staging areas (coalesced posted stores over NVLink), and the owner's per-Gaussian chain rule (K9) adds the staged rows of
+the ranks that touch the Gaussian; the L1 kernel evaluates only the rank's
 own tile rows and adds its partial loss into every rank's sum.  What remains are two device-side barrier kernels per
-step (start: every rank is done reading the others' accumulators and its image buffer is free; middle of backward:
-every rank's replay has finished, all pixels and partial sums are in place).
+step (start: every rank is done reading its staging area and its image buffer is free; middle of backward:
+every rank's replay and push have finished, all pixels and partial rows are in place).
 
 With every size static the step is captured once: graph A = LOD cut + forward (+ the all-gather of
 the image slabs when sharded), graph B = L1 loss + its gradient + backward (+ the reduce-scatter of
@@ -84,7 +85,7 @@ class GraphedStep:
         self.arena = None
         if self.peer:
             from .peer import PeerArena
-            self.arena = PeerArena({"loss": 8, "image": 3 * H * W * 4, "accum": max(self.P, 1) * 10 * 4}, world, rank, dev, group)
+            self.arena = PeerArena({"loss": 8, "image": 3 * H * W * 4, "stage": world * max(self.P, 1) * 10 * 4}, world, rank, dev, group)
             self.image = self.arena.tensor("image", torch.float32, (3, H, W))
             self.loss_sum = self.arena.tensor("loss", torch.float64, (1,))
             self._loss_ptrs = (C.c_void_p * world)(*self.arena.ptrs("loss"))
@@ -105,7 +106,7 @@ class GraphedStep:
         self.d_means2D = f(self.P, 3)
         chunk = (self.P + world - 1) // world
         if self.peer:
-            self.accum = self.arena.tensor("accum", torch.float32, (max(self.P, 1) * 10,))
+            self.accum = torch.zeros(max(self.P, 1) * 10, dtype=torch.float32, device=dev)      # local; partial rows travel through "stage"
         else:
             self.accum = torch.zeros(max(world * chunk, 1) * 10, dtype=torch.float32, device=dev)
         self.lod_scratch = torch.empty(int(self.L.h3dgs_expand_scratch_bytes(self.N_nodes)), dtype=torch.uint8, device=dev)
@@ -149,7 +150,7 @@ class GraphedStep:
         if self.peer:
             a.peer_count, a.grad_cyclic_log2 = self.world, self.cyclic_log2
             for r in range(self.world):
-                a.peer_image[r], a.peer_accum[r] = self.arena.ptr("image", r), self.arena.ptr("accum", r)
+                a.peer_image[r], a.peer_stage[r] = self.arena.ptr("image", r), self.arena.ptr("stage", r)
         return a
 
     def _stream(self):
@@ -160,8 +161,8 @@ class GraphedStep:
         """LOD cut -> forward (-> image all-gather)."""
         sc, L = self.scene, self.L
         if self.peer:
-            # every rank has finished its previous step: it no longer reads our accumulator (phase 1 zeroes it) or its image
-            # buffer (our forward stores into it), and its loss sum is zero again
+            # every rank has finished its previous step: it no longer reads its staging area (our phase 1 stores into it) or
+            # its image buffer (our forward stores into it), and its loss sum is zero again
             self.arena.barrier()
         if self.N > self.N_nodes:
             sc.render_indices[self.N_nodes:].fill_(-1)  # the library marks [n, N_nodes); these are the skybox slots beyond
@@ -208,8 +209,8 @@ class GraphedStep:
         if self.world == 1:
             _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 3, self._stream()))
         elif self.peer:
-            # phase 1 fills this rank's partial sums; after the barrier phase 2 pulls the rows it owns from every rank that
-            # touched them (loads over NVLink inside K9): that is the whole "reduce-scatter"
+            # phase 1 fills this rank's partial sums and pushes the rows other ranks own into their staging areas; after the
+            # barrier phase 2 adds, for the rows it owns, what the ranks that touched them have staged: the whole "reduce-scatter"
             _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 1, self._stream()))
             self.arena.barrier()
             _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 2, self._stream()))

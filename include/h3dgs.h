@@ -121,18 +121,21 @@ typedef struct h3dgs_raster_args {
      *  forward : every finished pixel of this rank's tile rows is stored into peer_image[r] ([3,H,W], one per rank,
      *            peer_image[shard_index] = the local one) for all r -- the all-gather of rendered tiles, tile by tile;
      *            out_color is not written.
-     *  backward: phase 1 leaves this rank's PARTIAL [P][10] sums (its own tiles) in `scratch`, which must be
-     *            peer_accum[shard_index] (zeroed by the call); phase 2 finishes exactly the rows this rank owns --
-     *            owner(row) = (row >> grad_cyclic_log2) % peer_count, i.e. blocks of 2^grad_cyclic_log2 rendered rows
-     *            dealt round-robin -- and pulls, for each of them, the partial rows of the ranks whose tile rows the
-     *            Gaussian touches out of peer_accum[r] (loads over NVLink inside the chain-rule kernels): the
-     *            reduce-scatter of the per-Gaussian sums without a dense exchange, summed in rank order.
+     *  backward: phase 1 leaves this rank's PARTIAL [P][10] sums (its own tiles) in `scratch` and then PUSHES, for every
+     *            row it touched that another rank owns, the 40-byte partial row into that owner's staging area:
+     *            peer_stage[owner] is [peer_count][P][10] floats on rank `owner`, slot [shard_index] is ours
+     *            (coalesced posted stores over NVLink: consecutive rows have the same owner).  owner(row) =
+     *            (row >> grad_cyclic_log2) % peer_count, i.e. blocks of 2^grad_cyclic_log2 rendered rows dealt
+     *            round-robin.  Phase 2 finishes exactly the rows this rank owns: per row it adds its own partial row
+     *            and the staged rows of the ranks whose tile rows the Gaussian touches (a mask K1 keeps), in rank
+     *            order -- the reduce-scatter of the per-Gaussian sums, sparse (only rows that exist travel) and
+     *            independent of arrival order.  Nothing in the staging areas needs zeroing.
      * The caller separates the phases with h3dgs_peer_barrier, and the next step's phase 1 from this step's phase 2
      * of the other ranks (a barrier at the start of every step does).  peer_count <= 1: off (grad_row_begin/end apply). */
     int32_t peer_count;
     int32_t grad_cyclic_log2;
     void* peer_image[H3DGS_MAX_PEERS];
-    void* peer_accum[H3DGS_MAX_PEERS];
+    void* peer_stage[H3DGS_MAX_PEERS];
 } h3dgs_raster_args;   /* NOTE: keep hierarchical-3d-gaussians_b200/h3dgs/_lib.py::RasterArgs in sync */
 
 /* Forward: K1 preprocess -> scan -> duplicateWithKeys -> radix sort -> tile ranges

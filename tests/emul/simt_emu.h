@@ -88,6 +88,7 @@ static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c);
 #define __expf(x) expf(x)
 #define __logf(x) logf(x)
 template <class T> static inline T __ldg(const T* p) { return *p; }
+template <class T> static inline T __ldcg(const T* p) { return *p; }
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
 static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }

@@ -329,8 +329,9 @@ def test_peer_mode_fused_collectives_schedule(emu, G):
     """Peer mode (h3dgs_raster_args.peer_count) on one CPU: G "ranks" run one after the other with numpy arrays standing in
     for peer memory.  Forward: every rank stores the pixels of ITS tile rows into the image of EVERY rank -> all G images
     equal the unsharded one bit for bit.  Backward phase 1: each rank leaves the (tile, Gaussian) sums of ITS tiles in its
-    own accumulator; phase 2 of the rank that owns a row (block-cyclic, 2^5 rows) pulls the partial rows of the ranks whose
-    tile rows the Gaussian touches (the rank mask K1 wrote) and finishes exactly the owned rows.  Fused gather/scatter
+    own accumulator and pushes the rows other ranks own (block-cyclic, 2^5 rows) into the owners' staging areas; phase 2 of
+    the owner adds the staged rows of the ranks whose tile rows the Gaussian touches (the rank mask K1 wrote) and finishes
+    exactly the owned rows.  Fused gather/scatter
     (render_indices) on top."""
     from oracle import oracle
     from emu_api import aligned, ptr
@@ -353,12 +354,15 @@ def test_peer_mode_fused_collectives_schedule(emu, G):
     P, SHIFT = n, 5
     images = [aligned(3 * cam.H * cam.W * 4, np.float32, (3, cam.H, cam.W)) for _ in range(G)]
     accums = [aligned(emu.L.h3dgs_backward_scratch_bytes(P)) for _ in range(G)]
+    stages = [aligned(G * P * 40) for _ in range(G)]            # [source rank][P][10] floats on every rank, never zeroed
+    for st_ in stages:
+        st_.view(np.float32)[:] = np.nan                        # a row that is read without having been pushed this step would show
     ranks = []
     for r in range(G):
         a, keep = emu.args(cam, bg, h, ts=ts, kids=kids, ridx=ri, pidx=pi, shard=(G, r))
         a.peer_count, a.grad_cyclic_log2 = G, SHIFT
         for k in range(G):
-            a.peer_image[k], a.peer_accum[k] = ptr(images[k]), ptr(accums[k])
+            a.peer_image[k], a.peer_stage[k] = ptr(images[k]), ptr(stages[k])
         ranks.append((a, keep, emu.forward(a, keep)))
     for img in images:
         assert np.array_equal(img, whole["color"])
