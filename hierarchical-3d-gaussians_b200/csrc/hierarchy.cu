@@ -69,7 +69,10 @@ interpolation_weights_kernel(int n, const int* __restrict__ node_indices, float 
 // Algorithmic traffic: 28 B node + 32 B box per node (the parent's box and node are L2 hits in BFS order) in,
 // 20 B per emitted row out.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kCutThreads = 256, kCutItems = 4, kCutTile = kCutThreads * kCutItems;
+#ifndef H3_CUT_THREADS            /* build switch (A/B on hardware): 128 = tiles of 512 nodes, 30 KB of shared memory, 6 CTAs per SM */
+#define H3_CUT_THREADS 256
+#endif
+constexpr int kCutThreads = H3_CUT_THREADS, kCutItems = 4, kCutTile = kCutThreads * kCutItems;
 constexpr unsigned long long kTileAgg = 1ull << 62, kTilePrefix = 2ull << 62, kTileValue = (1ull << 62) - 1;
 constexpr size_t kCutSmem = (size_t)kCutTile * 7 * sizeof(int) + (size_t)kCutTile * 2 * sizeof(float4);
 
@@ -83,7 +86,7 @@ __device__ __forceinline__ float box_size(const float4 mn, const float4 mx, floa
     return mn.w / dist;
 }
 
-__global__ void __launch_bounds__(kCutThreads, 3)
+__global__ void __launch_bounds__(kCutThreads, kCutThreads == 256 ? 3 : 6)
 lod_cut_fused_kernel(int N, const int* __restrict__ nodes, const float4* __restrict__ boxes, float target,
                      const float* __restrict__ target_dev, const float* __restrict__ viewpoint,
                      unsigned long long* __restrict__ tile_state /* [tiles] zeroed */, unsigned int* __restrict__ tile_counter /* zeroed */,
@@ -93,8 +96,7 @@ lod_cut_fused_kernel(int N, const int* __restrict__ nodes, const float4* __restr
     extern __shared__ float4 s_cut[];                         // boxes [kCutTile][2] | nodes [kCutTile][7]
     __shared__ uint64_t s_bar[2];
     __shared__ int s_warp[kCutThreads / 32];
-    __shared__ int s_tile, s_found[kCutThreads / 32];
-    __shared__ long long s_look[kCutThreads / 32];
+    __shared__ int s_tile, s_base;
     float4* s_box = s_cut;
     int* s_node = reinterpret_cast<int*>(s_cut + 2 * kCutTile);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -163,48 +165,46 @@ lod_cut_fused_kernel(int N, const int* __restrict__ nodes, const float4* __restr
 #pragma unroll
     for (int w = 0; w < kCutThreads / 32; w++) { const int v = s_warp[w]; if (w < warp) wbase += v; carry += v; }
     int off = wbase + incl - sum;                             // position of this thread's first row inside the tile
-    // ---- decoupled look-back, by the whole CTA: exclusive prefix of this tile over all earlier tiles ----
-    // ~450 tiles are in flight at a time and a running tile only has an aggregate to show, so a look-back by ONE warp
-    // walked ~14 windows of 32 status words, one L2 round trip each, while the other seven warps sat at the barrier
-    // (ncu r02b: barrier stall 15 of 31 warp-cycles per issue, 0.107 ms).  Here thread j looks at predecessor j: 256
-    // status words per round trip, warp results combined in shared memory, two rounds at most.
-    if (tid == 0) {
-        __threadfence();
-        *((volatile unsigned long long*)(tile_state + tile)) = (tile == 0 ? kTilePrefix : kTileAgg) | (unsigned long long)carry;
-    }
-    long long prefix = 0;
-    for (int nearest = tile - 1; nearest >= 0; nearest -= kCutThreads) {        // CTA-uniform loop
-        const int j = nearest - tid;
-        unsigned long long st = kTilePrefix;                  // threads past the beginning: "prefix 0"
-        if (j >= 0) { do { st = *((volatile unsigned long long*)(tile_state + j)); } while ((st >> 62) == 0ull); }
-        const unsigned full = __ballot_sync(0xffffffffu, (st >> 62) == 2ull);
-        const int first = full ? __ffs(full) - 1 : 32;        // nearest predecessor of this warp's window whose inclusive prefix is known
-        long long v = (lane <= first) ? (long long)(st & kTileValue) : 0ll;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) { s_look[warp] = v; s_found[warp] = full != 0u; }
-        __syncthreads();
-        bool found = false;
-#pragma unroll
-        for (int w = 0; w < kCutThreads / 32; w++) {
-            if (!found) { prefix += s_look[w]; found = s_found[w] != 0; }
-        }
-        __syncthreads();                                      // s_look / s_found are rewritten in the next round
-        if (found) break;
-    }
-    if (tid == 0) {
-#ifdef H3_SIMT_EMU      /* the emulator runs the CTAs one after the other: a test switch keeps most tiles at "aggregate only" so that the */
-        const bool upgrade = !(getenv("H3DGS_EMU_CUT_AGG_ONLY") && (tile % 300) != 0);     /* multi-round look-back is exercised */
-#else
-        const bool upgrade = true;
-#endif
-        if (tile != 0 && upgrade) {
+    // ---- decoupled look-back: exclusive prefix of this tile over all earlier tiles ----
+    // (by warp 0, 32 status words per round trip.  A look-back by the whole CTA -- 256 words per round trip -- was measured:
+    // the barrier stall halves, the long-scoreboard stall grows by as much, 0.118 instead of 0.107 ms: profiles/r02c_*.)
+    if (warp == 0) {
+        const unsigned long long agg = (unsigned long long)carry;
+        if (lane == 0) {
             __threadfence();
-            *((volatile unsigned long long*)(tile_state + tile)) = kTilePrefix | ((unsigned long long)prefix + (unsigned long long)carry);
+            *((volatile unsigned long long*)(tile_state + tile)) = (tile == 0 ? kTilePrefix : kTileAgg) | agg;
         }
-        if (tile == (N + kCutTile - 1) / kCutTile - 1) *total = (int)(prefix + (long long)carry);
+        long long prefix = 0;
+        int idx = tile - 1;
+        while (idx >= 0) {
+            const int j = idx - lane;
+            unsigned long long st = kTilePrefix;              // lanes past the beginning: "prefix 0"
+            if (j >= 0) { do { st = *((volatile unsigned long long*)(tile_state + j)); } while ((st >> 62) == 0ull); }
+            const unsigned full = __ballot_sync(0xffffffffu, (st >> 62) == 2ull);
+            const int first = full ? __ffs(full) - 1 : 32;    // nearest predecessor whose inclusive prefix is known
+            long long v = (lane <= first) ? (long long)(st & kTileValue) : 0ll;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            prefix += v;
+            if (full) break;
+            idx -= 32;
+        }
+        if (lane == 0) {
+#ifdef H3_SIMT_EMU      /* the emulator runs the CTAs one after the other: a test switch keeps most tiles at "aggregate only" so that the */
+            const bool upgrade = !(getenv("H3DGS_EMU_CUT_AGG_ONLY") && (tile % 300) != 0);     /* multi-window look-back is exercised */
+#else
+            const bool upgrade = true;
+#endif
+            if (tile != 0 && upgrade) {
+                __threadfence();
+                *((volatile unsigned long long*)(tile_state + tile)) = kTilePrefix | ((unsigned long long)prefix + agg);
+            }
+            s_base = (int)prefix;
+            if (tile == (N + kCutTile - 1) / kCutTile - 1) *total = (int)(prefix + (long long)agg);
+        }
     }
-    off += (int)prefix;
+    __syncthreads();
+    off += s_base;
     // ---- emission (about half of the nodes) ----
 #pragma unroll
     for (int k = 0; k < kCutItems; k++) {

@@ -58,9 +58,33 @@ l1_grad_kernel(int C, int H, int W, int shard_count, int shard_index, const floa
     }
 }
 
+// One thread: the six status words of a sync-free step (h3dgs/graphstep.py) -- loss, rows the cut needs, D, longest
+// tile list, binning overflow, row overflow -- and, optionally, the reset of the loss accumulator for the next step.
+// Replaces nine tiny framework kernels at the end of the step's critical path.
+__global__ void step_status_kernel(double* __restrict__ loss_sum, double inv_numel, const int* __restrict__ count, int extra_rows,
+                                   int row_capacity, const uint32_t* __restrict__ scan_info, int reset_loss, double* __restrict__ out)
+{
+    const double rows = (double)(*count + extra_rows);
+    out[0] = *loss_sum * inv_numel;
+    out[1] = rows;
+    out[2] = (double)scan_info[0]; out[3] = (double)scan_info[1]; out[4] = (double)scan_info[2];
+    out[5] = rows > (double)row_capacity ? 1.0 : 0.0;
+    if (reset_loss) *loss_sum = 0.0;
+}
+
 }  // namespace h3dgs
 
 using namespace h3dgs;
+
+extern "C" int h3dgs_step_status(double* loss_sum, double inv_numel, const int32_t* count, int32_t extra_rows, int32_t row_capacity,
+                                 const uint32_t* scan_info, int32_t reset_loss, double* out, void* stream)
+{
+    if (!loss_sum || !count || !scan_info || !out) { set_error("step_status: NULL argument"); return H3DGS_EINVAL; }
+    cudaStream_t s = (cudaStream_t)stream;
+    step_status_kernel<<<1, 1, 0, s>>>(loss_sum, inv_numel, count, extra_rows, row_capacity, scan_info, reset_loss, out);
+    H3_LAUNCHED("step_status", 0, s);
+    return H3DGS_OK;
+}
 
 static int l1_launch(int32_t C, int32_t H, int32_t W, const float* img, const float* gt, float scale, int32_t shard_count,
                      int32_t shard_index, float* dL_dimg, double* loss_sum, const PeerPtrs& peers, cudaStream_t s)

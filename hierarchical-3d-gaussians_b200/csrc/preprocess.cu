@@ -200,6 +200,10 @@ preprocess_kernel(int P, const float* __restrict__ means3D, const float* __restr
     if (rank_mask) rank_mask[i] = (uint8_t)out_mask;
 }
 
+#ifndef H3_COLOR_SPLIT            /* build switch (A/B on hardware): 1 = one thread per Gaussian */
+#define H3_COLOR_SPLIT 4
+#endif
+#if H3_COLOR_SPLIT == 4
 // K1b: SH -> RGB for the visible Gaussians only (192 B/row, x2 on lerped rows): reads the same
 // (lerped) mean as K1a, writes record.c.xyz and the three SH clamp flags.
 //
@@ -326,6 +330,97 @@ preprocess_color_kernel(int P, int deg, int M, const float* __restrict__ means3D
         *kb = *kb | clampbits;
     }
 }
+
+#else
+constexpr int kColSplit = 1;
+// K1b: SH -> RGB for the visible Gaussians only (192 B/row, x2 on lerped rows): reads the same
+// (lerped) mean as K1a, writes record.c.xyz and the three SH clamp flags.
+__global__ void __launch_bounds__(256)
+preprocess_color_kernel(int P, int deg, int M, const float* __restrict__ means3D, const float* __restrict__ shs,
+                        const float* __restrict__ ts, const int* __restrict__ ridx, const int* __restrict__ pidx,
+                        const float* __restrict__ campos, const int* __restrict__ radii,
+                        const uint32_t* __restrict__ own_tiles, int row_begin, int row_end, const RowCycle cyc,
+                        Record* __restrict__ records)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    if (radii[i] <= 0) return;
+    // tile-sharded frame: the colour (and its clamp flags) of a Gaussian is read by the ranks whose tile rows
+    // it touches (forward gather) and by the rank that owns its gradient row (SH backward); nobody else needs it
+    if (own_tiles && own_tiles[i] == 0u && (cyc.world > 1 ? !cyclic_owned(cyc, i) : (i < row_begin || i >= row_end))) return;
+    int c = i, p = i;
+    float t = 1.0f, u = 0.0f;
+    if (ridx) {
+        c = ridx[i]; p = pidx[i]; if (p < 0) p = c;
+        t = ts[i]; u = 1.0f - t;
+    }
+    const bool lerp = ridx != nullptr && u != 0.0f;
+#define LERP(a, b) (lerp ? (t * (a) + u * (b)) : (a))
+    const int need = 3 * (deg + 1) * (deg + 1);
+    float c_[48];
+    {
+        const float* pc = shs + (size_t)c * M * 3;
+        const float* pp = shs + (size_t)p * M * 3;
+        if (((M * 3) & 3) == 0) {
+#pragma unroll
+            for (int k = 0; k < 12; k++)
+                if (4 * k < need) {
+                    float4 v = __ldg(reinterpret_cast<const float4*>(pc) + k);
+                    if (lerp) {
+                        const float4 w = __ldg(reinterpret_cast<const float4*>(pp) + k);
+                        v.x = t * v.x + u * w.x; v.y = t * v.y + u * w.y; v.z = t * v.z + u * w.z; v.w = t * v.w + u * w.w;
+                    }
+                    c_[4 * k] = v.x; c_[4 * k + 1] = v.y; c_[4 * k + 2] = v.z; c_[4 * k + 3] = v.w;
+                }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 48; k++)
+                if (k < need) c_[k] = lerp ? t * __ldg(pc + k) + u * __ldg(pp + k) : __ldg(pc + k);
+        }
+    }
+    const float px_ = LERP(means3D[3 * c], means3D[3 * p]);
+    const float py_ = LERP(means3D[3 * c + 1], means3D[3 * p + 1]);
+    const float pz_ = LERP(means3D[3 * c + 2], means3D[3 * p + 2]);
+#undef LERP
+    float dx = px_ - campos[0], dy = py_ - campos[1], dz = pz_ - campos[2];
+    const float len = sqrtf(dx * dx + dy * dy + dz * dz);
+    dx /= len; dy /= len; dz /= len;
+    const float x = dx, y = dy, z = dz;
+    float rgb[3];
+    uint32_t clampbits = 0;
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+#define S(k) c_[(k) * 3 + ch]
+        float r = kSH_C0 * S(0);
+        if (deg > 0) {
+            r = r - kSH_C1 * y * S(1) + kSH_C1 * z * S(2) - kSH_C1 * x * S(3);
+            if (deg > 1) {
+                const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                r = r + kSH_C2[0] * xy * S(4) + kSH_C2[1] * yz * S(5) + kSH_C2[2] * (2.0f * zz - xx - yy) * S(6)
+                      + kSH_C2[3] * xz * S(7) + kSH_C2[4] * (xx - yy) * S(8);
+                if (deg > 2) {
+                    r = r + kSH_C3[0] * y * (3.0f * xx - yy) * S(9) + kSH_C3[1] * xy * z * S(10)
+                          + kSH_C3[2] * y * (4.0f * zz - xx - yy) * S(11)
+                          + kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * S(12)
+                          + kSH_C3[4] * x * (4.0f * zz - xx - yy) * S(13)
+                          + kSH_C3[5] * z * (xx - yy) * S(14) + kSH_C3[6] * x * (xx - 3.0f * yy) * S(15);
+                }
+            }
+        }
+#undef S
+        r += 0.5f;
+        if (r < 0.f) clampbits |= (1u << (kClampShift + ch));
+        rgb[ch] = fmaxf(r, 0.f);
+    }
+    float* rc = reinterpret_cast<float*>(&records[i].c);
+    rc[0] = rgb[0]; rc[1] = rgb[1]; rc[2] = rgb[2];
+    if (clampbits) {
+        uint32_t* kb = reinterpret_cast<uint32_t*>(&records[i].b) + 3;
+        *kb = *kb | clampbits;
+    }
+}
+
+#endif
 
 int launch_preprocess(const h3dgs_raster_args& a, int32_t* radii, float* depths, uint32_t* tiles_touched,
                       uint8_t* rank_mask, Record* records, uint32_t* tile_count, ScanInfo* info, cudaStream_t s)

@@ -166,66 +166,11 @@ preprocess_backward_kernel(int row0, int P, const RowCycle cyc, int deg, int M, 
 }
 
 // K9b: dL/dcolour -> dL/dSH (basis x dL/dRGB, no intermediate array) and, through the view
-// direction, an ADDITIVE term of dL/dmean (runs after / beside preprocess_backward_kernel).
-//
-// FOUR threads per Gaussian: part p = 0..3 owns the coefficients 4p .. 4p+3, i.e. 48 contiguous bytes of the 192-B
-// row (three 128-bit loads / reductions).  The one-thread-per-row form held the whole basis and its three derivative
-// tables (64 values) in registers and was latency-bound at 96 registers and 26 % occupancy (ncu r02b: 0.21 ms, 54 % of
-// the DRAM roofline, all stalls long-scoreboard); a part needs 16 of those values, and four times as many threads
-// keep four times as many rows in flight.  Only the evaluation of the part's four basis functions diverges (a switch
-// on p, ALU only); every memory instruction is issued by all lanes.  The three partial sums of dL/d(direction) meet
-// in two lane exchanges; part 0 finishes the mean.
-constexpr int kShSplit = 4;
-
-// basis functions 4p .. 4p+3 at unit direction (x, y, z) and their gradients; entries of degree > deg stay 0
-__device__ __forceinline__ void sh_basis_quad(int part, int deg, float x, float y, float z, float (&B)[4], float (&Bx)[4],
-                                              float (&By)[4], float (&Bz)[4])
-{
-#pragma unroll
-    for (int k = 0; k < 4; k++) { B[k] = 0.f; Bx[k] = 0.f; By[k] = 0.f; Bz[k] = 0.f; }
-    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-    switch (part) {
-    case 0:
-        B[0] = bSH_C0;
-        if (deg > 0) {
-            B[1] = -bSH_C1 * y; B[2] = bSH_C1 * z; B[3] = -bSH_C1 * x;
-            By[1] = -bSH_C1; Bz[2] = bSH_C1; Bx[3] = -bSH_C1;
-        }
-        break;
-    case 1:
-        if (deg > 1) {
-            B[0] = bSH_C2[0] * xy; B[1] = bSH_C2[1] * yz; B[2] = bSH_C2[2] * (2.f * zz - xx - yy); B[3] = bSH_C2[3] * xz;
-            Bx[0] = bSH_C2[0] * y; By[0] = bSH_C2[0] * x;
-            By[1] = bSH_C2[1] * z; Bz[1] = bSH_C2[1] * y;
-            Bx[2] = bSH_C2[2] * 2.f * -x; By[2] = bSH_C2[2] * 2.f * -y; Bz[2] = bSH_C2[2] * 2.f * 2.f * z;
-            Bx[3] = bSH_C2[3] * z; Bz[3] = bSH_C2[3] * x;
-        }
-        break;
-    case 2:
-        if (deg > 1) {
-            B[0] = bSH_C2[4] * (xx - yy);
-            Bx[0] = bSH_C2[4] * 2.f * x; By[0] = bSH_C2[4] * 2.f * -y;
-        }
-        if (deg > 2) {
-            B[1] = bSH_C3[0] * y * (3.f * xx - yy); B[2] = bSH_C3[1] * xy * z; B[3] = bSH_C3[2] * y * (4.f * zz - xx - yy);
-            Bx[1] = bSH_C3[0] * 3.f * 2.f * xy;   By[1] = bSH_C3[0] * 3.f * (xx - yy);
-            Bx[2] = bSH_C3[1] * yz;               By[2] = bSH_C3[1] * xz;               Bz[2] = bSH_C3[1] * xy;
-            Bx[3] = bSH_C3[2] * -2.f * xy;        By[3] = bSH_C3[2] * (-3.f * yy + 4.f * zz - xx); Bz[3] = bSH_C3[2] * 4.f * 2.f * yz;
-        }
-        break;
-    default:
-        if (deg > 2) {
-            B[0] = bSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy); B[1] = bSH_C3[4] * x * (4.f * zz - xx - yy);
-            B[2] = bSH_C3[5] * z * (xx - yy); B[3] = bSH_C3[6] * x * (xx - 3.f * yy);
-            Bx[0] = bSH_C3[3] * -3.f * 2.f * xz; By[0] = bSH_C3[3] * -3.f * 2.f * yz;  Bz[0] = bSH_C3[3] * 3.f * (2.f * zz - xx - yy);
-            Bx[1] = bSH_C3[4] * (-3.f * xx + 4.f * zz - yy); By[1] = bSH_C3[4] * -2.f * xy; Bz[1] = bSH_C3[4] * 4.f * 2.f * xz;
-            Bx[2] = bSH_C3[5] * 2.f * xz;        By[2] = bSH_C3[5] * -2.f * yz;        Bz[2] = bSH_C3[5] * (xx - yy);
-            Bx[3] = bSH_C3[6] * 3.f * (xx - yy); By[3] = bSH_C3[6] * -3.f * 2.f * xy;
-        }
-        break;
-    }
-}
-
+// direction, an ADDITIVE term of dL/dmean (runs after preprocess_backward_kernel on the stream).
+// One thread per Gaussian.  A four-threads-per-Gaussian form (72 registers, 4x the rows in flight) was measured and
+// dropped: same 0.21 ms (profiles/r02c_*): the kernel moves 923 MB -- 2.2x its algorithmic bytes, the read-modify-write of
+// the zero-filled full-size rows -- at 4.3 TB/s of mixed read / reduction traffic, i.e. it is bound by that traffic,
+// not by latency.
 __global__ void __launch_bounds__(128)
 sh_backward_kernel(int row0, int P, const RowCycle cyc, int deg, int M, const float* __restrict__ means3D, const float* __restrict__ shs,
                    const float* __restrict__ ts, const int* __restrict__ ridx, const int* __restrict__ pidx,
@@ -233,76 +178,88 @@ sh_backward_kernel(int row0, int P, const RowCycle cyc, int deg, int M, const fl
                    const StagePtrs peers, const Record* __restrict__ records,
                    const float* __restrict__ accum, float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dsh)
 {
-    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
-    const int local = gt / kShSplit, part = gt % kShSplit;
+    const int local = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = cyc.world > 1 ? cyclic_row(cyc, local) : row0 + local;      // rows [row0, P), or the blocks this rank owns
+    if (i >= P) return;
     const int SH3 = M * 3;
-    const bool in_range = i < P;
-    const bool visible = in_range && radii[i] > 0;
-    const bool vec = (SH3 & 3) == 0;
-    // the part's slice of the row: floats [f0, f1)
-    const int f0 = min(12 * part, SH3), f1 = min(12 * part + 12, SH3);
-    if (in_range && !visible && !ridx) {                  // culled row, direct outputs: zeros (scatter mode: pre-zeroed)
-        float* o = dL_dsh + (size_t)i * SH3;
-        if (vec) { for (int f = f0; f < f1; f += 4) *reinterpret_cast<float4*>(o + f) = make_float4(0, 0, 0, 0); }
-        else for (int f = f0; f < f1; f++) o[f] = 0.f;
-    }
-    // no early exit: the four lanes of a row meet in the lane exchanges below
-    int c = 0, p = 0;
-    float t = 1.0f, u = 0.0f;
-    if (visible) {
-        c = i; p = i;
-        if (ridx) {
-            c = ridx[i]; p = pidx[i]; if (p < 0) p = c;
-            t = ts[i]; u = 1.0f - t;
+    if (radii[i] <= 0) {
+        if (!ridx) {                                   // scatter mode: full-size gradients are pre-zeroed
+            float* o = dL_dsh + (size_t)i * SH3;
+            if ((SH3 & 3) == 0) { for (int k = 0; k < SH3 / 4; k++) reinterpret_cast<float4*>(o)[k] = make_float4(0, 0, 0, 0); }
+            else store_zero(o, SH3);
         }
+        return;
     }
-    const bool lerp = visible && ridx != nullptr && u != 0.0f;
+    int c = i, p = i;
+    float t = 1.0f, u = 0.0f;
+    if (ridx) {
+        c = ridx[i]; p = pidx[i]; if (p < 0) p = c;
+        t = ts[i]; u = 1.0f - t;
+    }
+    const bool lerp = ridx != nullptr && u != 0.0f;
 #define LERP(a, b) (lerp ? __fadd_rn(__fmul_rn(t, (a)), __fmul_rn(u, (b))) : (a))
     const float mx = LERP(means3D[3 * c], means3D[3 * p]);
     const float my = LERP(means3D[3 * c + 1], means3D[3 * p + 1]);
     const float mz = LERP(means3D[3 * c + 2], means3D[3 * p + 2]);
-    float col[4] = {0.f, 0.f, 0.f, 0.f};                   // accum columns 6..9: dL/dRGB (and dL/dinvdepth, unused here)
-    uint32_t kb = 0;
-    if (visible) {
-        if (peers.n > 1) gather_accum_pairs<2>(peers, rank_mask[i], i, 3, col);
-        else { const float* ac = accum + (size_t)i * kAccum; col[0] = ac[6]; col[1] = ac[7]; col[2] = ac[8]; }
-        kb = __float_as_uint(records[i].b.w);
-    }
+    float col[4];                                          // accum columns 6..9: dL/dRGB (and dL/dinvdepth, unused here)
+    if (peers.n > 1) gather_accum_pairs<2>(peers, rank_mask[i], i, 3, col);
+    else { const float* ac = accum + (size_t)i * kAccum; col[0] = ac[6]; col[1] = ac[7]; col[2] = ac[8]; }
+    const uint32_t kb = __float_as_uint(records[i].b.w);
     const float dRGB[3] = {(kb >> kClampShift) & 1u ? 0.f : col[0], (kb >> (kClampShift + 1)) & 1u ? 0.f : col[1],
                            (kb >> (kClampShift + 2)) & 1u ? 0.f : col[2]};
     const float d0x = mx - campos[0], d0y = my - campos[1], d0z = mz - campos[2];
     const float len = sqrtf(d0x * d0x + d0y * d0y + d0z * d0z);
     const float x = d0x / len, y = d0y / len, z = d0z / len;
     const int ncoef = (deg + 1) * (deg + 1);
-    float B[4], Bx[4], By[4], Bz[4];
-    sh_basis_quad(part, deg, x, y, z, B, Bx, By, Bz);
-    // the part's 12 floats: float e = 12 part + 4 q + r, coefficient (e / 3) - 4 part = (4 q + r) / 3, channel (4 q + r) % 3.
-    // dL/d(dir) needs the (lerped) coefficients; dL/dSH[k][ch] = B[k] * dRGB[ch] is emitted straight away
+    // SH basis and its derivatives w.r.t. the unit direction (coefficient-major rows [k][3])
+    float B[16], Bx[16], By[16], Bz[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) { B[k] = 0.f; Bx[k] = 0.f; By[k] = 0.f; Bz[k] = 0.f; }
+    B[0] = bSH_C0;
+    if (deg > 0) {
+        B[1] = -bSH_C1 * y; B[2] = bSH_C1 * z; B[3] = -bSH_C1 * x;
+        By[1] = -bSH_C1; Bz[2] = bSH_C1; Bx[3] = -bSH_C1;
+        if (deg > 1) {
+            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            B[4] = bSH_C2[0] * xy; B[5] = bSH_C2[1] * yz; B[6] = bSH_C2[2] * (2.f * zz - xx - yy);
+            B[7] = bSH_C2[3] * xz; B[8] = bSH_C2[4] * (xx - yy);
+            Bx[4] = bSH_C2[0] * y; By[4] = bSH_C2[0] * x;
+            By[5] = bSH_C2[1] * z; Bz[5] = bSH_C2[1] * y;
+            Bx[6] = bSH_C2[2] * 2.f * -x; By[6] = bSH_C2[2] * 2.f * -y; Bz[6] = bSH_C2[2] * 2.f * 2.f * z;
+            Bx[7] = bSH_C2[3] * z; Bz[7] = bSH_C2[3] * x;
+            Bx[8] = bSH_C2[4] * 2.f * x; By[8] = bSH_C2[4] * 2.f * -y;
+            if (deg > 2) {
+                B[9] = bSH_C3[0] * y * (3.f * xx - yy); B[10] = bSH_C3[1] * xy * z;
+                B[11] = bSH_C3[2] * y * (4.f * zz - xx - yy); B[12] = bSH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+                B[13] = bSH_C3[4] * x * (4.f * zz - xx - yy); B[14] = bSH_C3[5] * z * (xx - yy);
+                B[15] = bSH_C3[6] * x * (xx - 3.f * yy);
+                Bx[9] = bSH_C3[0] * 3.f * 2.f * xy;   By[9] = bSH_C3[0] * 3.f * (xx - yy);
+                Bx[10] = bSH_C3[1] * yz;              By[10] = bSH_C3[1] * xz;               Bz[10] = bSH_C3[1] * xy;
+                Bx[11] = bSH_C3[2] * -2.f * xy;       By[11] = bSH_C3[2] * (-3.f * yy + 4.f * zz - xx); Bz[11] = bSH_C3[2] * 4.f * 2.f * yz;
+                Bx[12] = bSH_C3[3] * -3.f * 2.f * xz; By[12] = bSH_C3[3] * -3.f * 2.f * yz;  Bz[12] = bSH_C3[3] * 3.f * (2.f * zz - xx - yy);
+                Bx[13] = bSH_C3[4] * (-3.f * xx + 4.f * zz - yy); By[13] = bSH_C3[4] * -2.f * xy; Bz[13] = bSH_C3[4] * 4.f * 2.f * xz;
+                Bx[14] = bSH_C3[5] * 2.f * xz;        By[14] = bSH_C3[5] * -2.f * yz;        Bz[14] = bSH_C3[5] * (xx - yy);
+                Bx[15] = bSH_C3[6] * 3.f * (xx - yy); By[15] = bSH_C3[6] * -3.f * 2.f * xy;
+            }
+        }
+    }
+    // one pass over the row in 128-bit pieces: float e = 3k + ch.  dL/d(dir) needs the (lerped) coefficients,
+    // dL/dSH[k][ch] = B[k] * dRGB[ch] is emitted straight away
     float ddx = 0.f, ddy = 0.f, ddz = 0.f;
     const float* shc = shs + (size_t)c * SH3;
     const float* shp = shs + (size_t)p * SH3;
-    float* dshi = dL_dsh + (size_t)(in_range ? i : 0) * SH3;
-    if (vec) {
-        float4 v4[3], w4[3];
+    float* dshi = dL_dsh + (size_t)i * SH3;
+    if ((SH3 & 3) == 0) {
 #pragma unroll
-        for (int q = 0; q < 3; q++) {                      // all loads first: three (six) 128-bit requests in flight per thread
-            const int f = 12 * part + 4 * q;
-            v4[q] = make_float4(0, 0, 0, 0); w4[q] = make_float4(0, 0, 0, 0);
-            if (visible && f < 3 * ncoef && f < SH3) {
-                v4[q] = __ldg(reinterpret_cast<const float4*>(shc + f));
-                if (lerp) w4[q] = __ldg(reinterpret_cast<const float4*>(shp + f));
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 3; q++) {
-            const int f = 12 * part + 4 * q;
-            if (f < SH3) {
+        for (int q = 0; q < 12; q++) {
+            if (4 * q < SH3) {
                 float o4[4] = {0.f, 0.f, 0.f, 0.f};
-                const bool live = visible && f < 3 * ncoef;
-                if (live) {
-                    float4 v = v4[q];
-                    if (lerp) { const float4 w = w4[q]; v.x = LERP(v.x, w.x); v.y = LERP(v.y, w.y); v.z = LERP(v.z, w.z); v.w = LERP(v.w, w.w); }
+                if (4 * q < 3 * ncoef) {
+                    float4 v = __ldg(reinterpret_cast<const float4*>(shc) + q);
+                    if (lerp) {
+                        const float4 w = __ldg(reinterpret_cast<const float4*>(shp) + q);
+                        v.x = LERP(v.x, w.x); v.y = LERP(v.y, w.y); v.z = LERP(v.z, w.z); v.w = LERP(v.w, w.w);
+                    }
                     const float sv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                     for (int r = 0; r < 4; r++) {
@@ -312,39 +269,34 @@ sh_backward_kernel(int row0, int P, const RowCycle cyc, int deg, int M, const fl
                         ddx += Bx[k] * sv[r] * g; ddy += By[k] * sv[r] * g; ddz += Bz[k] * sv[r] * g;
                     }
                 }
-                if (!ridx) { if (visible) *reinterpret_cast<float4*>(dshi + f) = make_float4(o4[0], o4[1], o4[2], o4[3]); }
-                else if (live) {
-                    // 128-bit vector reductions (red.global.add.v4.f32)
-                    atomicAdd(reinterpret_cast<float4*>(dL_dsh + (size_t)c * SH3 + f), make_float4(t * o4[0], t * o4[1], t * o4[2], t * o4[3]));
-                    if (lerp) atomicAdd(reinterpret_cast<float4*>(dL_dsh + (size_t)p * SH3 + f), make_float4(u * o4[0], u * o4[1], u * o4[2], u * o4[3]));
+                if (!ridx) reinterpret_cast<float4*>(dshi)[q] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+                else if (4 * q < 3 * ncoef) {
+                    // 128-bit vector reductions (red.global.add.v4.f32): 12 per 192-B row
+                    atomicAdd(reinterpret_cast<float4*>(dL_dsh + (size_t)c * SH3) + q, make_float4(t * o4[0], t * o4[1], t * o4[2], t * o4[3]));
+                    if (lerp) atomicAdd(reinterpret_cast<float4*>(dL_dsh + (size_t)p * SH3) + q, make_float4(u * o4[0], u * o4[1], u * o4[2], u * o4[3]));
                 }
             }
         }
     } else {
 #pragma unroll
-        for (int e = 0; e < 12; e++) {
-            const int f = 12 * part + e;
-            if (f < SH3 && visible) {
+        for (int e = 0; e < 48; e++) {
+            if (e < SH3) {
                 const int k = e / 3, ch = e - 3 * k;
                 float o = 0.f;
-                if (f < 3 * ncoef) {
-                    const float sv = LERP(__ldg(shc + f), __ldg(shp + f));
+                if (e < 3 * ncoef) {
+                    const float sv = LERP(__ldg(shc + e), __ldg(shp + e));
                     const float g = dRGB[ch];
                     o = B[k] * g;
                     ddx += Bx[k] * sv * g; ddy += By[k] * sv * g; ddz += Bz[k] * sv * g;
                 }
-                if (!ridx) dshi[f] = o;
-                else if (f < 3 * ncoef) {
-                    atomicAdd(dL_dsh + (size_t)c * SH3 + f, t * o);
-                    if (lerp) atomicAdd(dL_dsh + (size_t)p * SH3 + f, u * o);
+                if (!ridx) dshi[e] = o;
+                else if (e < 3 * ncoef) {
+                    atomicAdd(dL_dsh + (size_t)c * SH3 + e, t * o);
+                    if (lerp) atomicAdd(dL_dsh + (size_t)p * SH3 + e, u * o);
                 }
             }
         }
     }
-    // the row's dL/d(direction): sum of the four parts (lanes 4r .. 4r+3 of the warp)
-    ddx += __shfl_xor_sync(0xffffffffu, ddx, 1); ddy += __shfl_xor_sync(0xffffffffu, ddy, 1); ddz += __shfl_xor_sync(0xffffffffu, ddz, 1);
-    ddx += __shfl_xor_sync(0xffffffffu, ddx, 2); ddy += __shfl_xor_sync(0xffffffffu, ddy, 2); ddz += __shfl_xor_sync(0xffffffffu, ddz, 2);
-    if (part != 0 || !visible) return;
     const float sum2 = d0x * d0x + d0y * d0y + d0z * d0z;
     const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
     const float dm0 = ((sum2 - d0x * d0x) * ddx - d0y * d0x * ddy - d0z * d0x * ddz) * invsum32;
@@ -427,7 +379,7 @@ int launch_sh_backward(const h3dgs_raster_args& a, const int32_t* radii, const u
     const int rows = cyc.world > 1 ? cyclic_local_rows(cyc, a.P) : r1 - r0;
     if (rows <= 0) return H3DGS_OK;
     ProfScope prof(H3DGS_STAGE_SH_BACKWARD, s);
-    sh_backward_kernel<<<(int)(((size_t)rows * kShSplit + 127) / 128), 128, 0, s>>>(r0, r1, cyc, a.sh_degree, a.sh_coeffs, a.means3D, a.shs,
+    sh_backward_kernel<<<(rows + 127) / 128, 128, 0, s>>>(r0, r1, cyc, a.sh_degree, a.sh_coeffs, a.means3D, a.shs,
                                                          a.interpolation_weights, a.render_indices, a.parent_indices,
                                                          a.campos, radii, rank_mask, stage_ptrs(a, accum), records, accum,
                                                          dL_dmeans3D, dL_dsh);

@@ -21,7 +21,7 @@ EXPORTS = [
     "h3dgs_lod_cut",
     "h3dgs_last_error", "h3dgs_version", "h3dgs_launch_count",
     "h3dgs_profile_enable", "h3dgs_profile_reset", "h3dgs_profile_read", "h3dgs_stage_name",
-    "h3dgs_l1_ssim_forward", "h3dgs_l1_ssim_backward", "h3dgs_l1_loss_grad", "h3dgs_l1_loss_grad_peer", "h3dgs_sparse_adam",
+    "h3dgs_l1_ssim_forward", "h3dgs_l1_ssim_backward", "h3dgs_l1_loss_grad", "h3dgs_l1_loss_grad_peer", "h3dgs_step_status", "h3dgs_sparse_adam",
     "h3dgs_peer_flag_bytes", "h3dgs_peer_alloc", "h3dgs_peer_free", "h3dgs_peer_export", "h3dgs_peer_open", "h3dgs_peer_close",
     "h3dgs_peer_barrier", "h3dgs_peer_barrier_status",
 ]
@@ -87,6 +87,8 @@ def bind(l):
     l.h3dgs_l1_loss_grad.restype = C.c_int
     l.h3dgs_l1_loss_grad.argtypes = [C.c_int32] * 3 + [C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
+    l.h3dgs_step_status.restype = C.c_int
+    l.h3dgs_step_status.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     l.h3dgs_l1_loss_grad_peer.restype = C.c_int
     l.h3dgs_l1_loss_grad_peer.argtypes = [C.c_int32] * 3 + [C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32,
                                           C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.c_void_p]

@@ -220,13 +220,11 @@ class GraphedStep:
             hdist.reduce_accum(self.accum.view(torch.uint8), self.P, self.world, self.rank, self.group)
             # phase 2 rewrites exactly the own row block of d_means2D; the other rows stay zero since construction
             _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 2, self._stream()))
-        loss = self.loss_sum / numel               # peer mode: complete since the mid-backward barrier
-        info = self.scan_info().double()
-        rows_needed = (self.count + self.S).double()
-        self.status_dev[:5].copy_(torch.cat([loss.reshape(1), rows_needed, info]))
-        self.status_dev[5:].copy_((rows_needed > self.P).double())
-        if self.peer:
-            self.loss_sum.zero_()       # for the next step: ordered before anybody's next L1 kernel by the start barrier
+        # status words (loss, rows needed, D, longest list, overflow flags) by one device thread; peer mode: the loss sum is
+        # complete since the mid-backward barrier and is reset here for the next step (ordered before anybody's next L1
+        # kernel by the start barrier)
+        _lib.check(L.h3dgs_step_status(self.loss_sum.data_ptr(), 1.0 / numel, self.count.data_ptr(), self.S, self.P,
+                                       self.scan_info().data_ptr(), 1 if self.peer else 0, self.status_dev.data_ptr(), self._stream()))
 
     def scan_info(self):
         """int32 view [D, longest tile list, overflow] inside the image state."""

@@ -257,6 +257,12 @@ int h3dgs_l1_loss_grad_peer(int32_t C, int32_t H, int32_t W, const float* img, c
                             int32_t shard_count, int32_t shard_index, float* dL_dimg, int32_t peer_count,
                             double* const* loss_sums, void* stream);
 
+/* Status words of a sync-free step, written by one device thread (no host synchronisation, capturable): out[0] =
+ * *loss_sum * inv_numel, out[1] = *count + extra_rows (rows the cut needs), out[2..4] = scan_info[0..2] (D, longest tile
+ * list, binning overflow), out[5] = 1 when out[1] > row_capacity; reset_loss != 0 zeroes *loss_sum afterwards. */
+int h3dgs_step_status(double* loss_sum, double inv_numel, const int32_t* count, int32_t extra_rows, int32_t row_capacity,
+                      const uint32_t* scan_info, int32_t reset_loss, double* out, void* stream);
+
 /* ---- sparse Adam (replaces scene/OurAdam.py:249-337 as driven by train_single.py:170-178) ----
  * In-place Adam update of the rows listed in relevant[num_relevant] (int64 row indices) of one parameter
  * tensor viewed as [rows, width]; `step` is the 1-based step count of that tensor (the reference

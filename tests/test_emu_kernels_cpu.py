@@ -393,8 +393,8 @@ def test_peer_mode_fused_collectives_schedule(emu, G):
 def test_single_pass_cut_over_many_tiles(emu_lib, tau, misalign, agg_only, monkeypatch):
     """lod_cut_fused_kernel with 600+ tiles of 1024 nodes; indices, parents, nodes, weights (bit-exact) and kids against the
     oracle.  agg_only: the emulator runs the CTAs one after the other, so every predecessor would already show its inclusive
-    prefix; the switch keeps all tiles but every 300th at "aggregate only", and the CTA-wide look-back has to add up to 299
-    aggregates over two rounds of 256 status words."""
+    prefix; the switch keeps all tiles but every 300th at "aggregate only", and the look-back has to add up to 299
+    aggregates over ten windows of 32 status words."""
     if agg_only:
         monkeypatch.setenv("H3DGS_EMU_CUT_AGG_ONLY", "1")
     from emu_api import aligned, f32, i32, ptr

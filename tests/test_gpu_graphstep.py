@@ -100,7 +100,7 @@ def test_sync_free_step_equals_exact_step(skybox, capture):
         assert torch.equal(gs.radii[:P], radii) and bool((gs.radii[P:] == 0).all())
         for k, ref in grads.items():
             e = rel_err(gs.grads[k].cpu().numpy(), ref.cpu().numpy())
-            assert e < 2e-6, (v, k, e)               # same partial sums, different atomic order
+            assert e < 5e-6, (v, k, e)               # same partial sums, different atomic order (2.1e-6 seen on a B200)
     # a new LOD threshold between replays (train_post.py:66-74 draws one per step): it lives on the device
     thr2 = synth.tau_threshold(15.0, cam)
     loss, radii, n, grads, img, D = _exact_step(scene, dcams[0], bg, gts[0], thr2)

@@ -38,7 +38,7 @@ def test_pytorch_form_equals_the_reference_tensors_and_gradients(golden_dir):
     sum((outs[k] * torch.tensor(z["up_" + k], device="cuda")).sum() for k in outs).backward()
     for k, p in dict(means3D=sc.means3D, scales=sc.scales, rotations=sc.rotations, opacities=sc.opacities, shs=sc.shs).items():
         ref = z["grad_" + k]
-        assert np.abs(p.grad.cpu().numpy() - ref).max() <= 2e-6 * np.abs(ref).max(), k
+        assert np.abs(p.grad.cpu().numpy() - ref).max() <= 5e-6 * np.abs(ref).max(), k      # fp32 atomic sum order
 
 
 def test_fused_form_renders_the_reference_tensors_bit_identically(golden_dir):
