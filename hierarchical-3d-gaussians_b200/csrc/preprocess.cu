@@ -200,141 +200,10 @@ preprocess_kernel(int P, const float* __restrict__ means3D, const float* __restr
     if (rank_mask) rank_mask[i] = (uint8_t)out_mask;
 }
 
-#ifndef H3_COLOR_SPLIT            /* build switch (A/B on hardware): 1 = one thread per Gaussian */
-#define H3_COLOR_SPLIT 4
-#endif
-#if H3_COLOR_SPLIT == 4
 // K1b: SH -> RGB for the visible Gaussians only (192 B/row, x2 on lerped rows): reads the same
-// (lerped) mean as K1a, writes record.c.xyz and the three SH clamp flags.
-//
-// FOUR threads per Gaussian, as in sh_backward_kernel (preprocess_backward.cu): part p = 0..3 owns the coefficients
-// 4p .. 4p+3 = 48 contiguous bytes of the row (three 128-bit loads, x2 on lerped rows), evaluates its four basis
-// functions (the only divergent piece: a switch on p, ALU only) and a partial colour; the three partial sums meet in
-// two lane exchanges and part 0 writes the record.  One thread per row held the 48 coefficients in registers (70
-// registers, 33 % occupancy, every stall a long-scoreboard one: ncu r02b 0.100 ms, 47 % of the DRAM roofline).
-constexpr int kColSplit = 4;
-
-// basis functions 4p .. 4p+3 at unit direction (x, y, z), signs folded in (colour = sum_k B[k] * coefficient[k]);
-// entries of degree > deg stay 0
-__device__ __forceinline__ void sh_basis_quad_value(int part, int deg, float x, float y, float z, float (&B)[4]) {
-    B[0] = 0.f; B[1] = 0.f; B[2] = 0.f; B[3] = 0.f;
-    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-    switch (part) {
-    case 0:
-        B[0] = kSH_C0;
-        if (deg > 0) { B[1] = -kSH_C1 * y; B[2] = kSH_C1 * z; B[3] = -kSH_C1 * x; }
-        break;
-    case 1:
-        if (deg > 1) { B[0] = kSH_C2[0] * xy; B[1] = kSH_C2[1] * yz; B[2] = kSH_C2[2] * (2.0f * zz - xx - yy); B[3] = kSH_C2[3] * xz; }
-        break;
-    case 2:
-        if (deg > 1) B[0] = kSH_C2[4] * (xx - yy);
-        if (deg > 2) { B[1] = kSH_C3[0] * y * (3.0f * xx - yy); B[2] = kSH_C3[1] * xy * z; B[3] = kSH_C3[2] * y * (4.0f * zz - xx - yy); }
-        break;
-    default:
-        if (deg > 2) {
-            B[0] = kSH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy); B[1] = kSH_C3[4] * x * (4.0f * zz - xx - yy);
-            B[2] = kSH_C3[5] * z * (xx - yy); B[3] = kSH_C3[6] * x * (xx - 3.0f * yy);
-        }
-        break;
-    }
-}
-
-__global__ void __launch_bounds__(256)
-preprocess_color_kernel(int P, int deg, int M, const float* __restrict__ means3D, const float* __restrict__ shs,
-                        const float* __restrict__ ts, const int* __restrict__ ridx, const int* __restrict__ pidx,
-                        const float* __restrict__ campos, const int* __restrict__ radii,
-                        const uint32_t* __restrict__ own_tiles, int row_begin, int row_end, const RowCycle cyc,
-                        Record* __restrict__ records)
-{
-    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = gt / kColSplit, part = gt % kColSplit;
-    bool active = i < P && radii[i] > 0;
-    // tile-sharded frame: the colour (and its clamp flags) of a Gaussian is read by the ranks whose tile rows
-    // it touches (forward gather) and by the rank that owns its gradient row (SH backward); nobody else needs it
-    if (active && own_tiles && own_tiles[i] == 0u && (cyc.world > 1 ? !cyclic_owned(cyc, i) : (i < row_begin || i >= row_end))) active = false;
-    // no early exit: the four lanes of a row meet in the lane exchanges below
-    int c = 0, p = 0;
-    float t = 1.0f, u = 0.0f;
-    if (active) {
-        c = i; p = i;
-        if (ridx) {
-            c = ridx[i]; p = pidx[i]; if (p < 0) p = c;
-            t = ts[i]; u = 1.0f - t;
-        }
-    }
-    const bool lerp = active && ridx != nullptr && u != 0.0f;
-#define LERP(a, b) (lerp ? (t * (a) + u * (b)) : (a))
-    const int SH3 = M * 3, need = 3 * (deg + 1) * (deg + 1);
-    // the part's 12 floats (fewer when the row is shorter): float f = 12 part + e
-    float c_[12];
-#pragma unroll
-    for (int e = 0; e < 12; e++) c_[e] = 0.f;
-    {
-        const float* pc = shs + (size_t)c * SH3;
-        const float* pp = shs + (size_t)p * SH3;
-        if ((SH3 & 3) == 0) {
-            float4 v4[3], w4[3];
-#pragma unroll
-            for (int q = 0; q < 3; q++) {                  // all loads first: three (six) 128-bit requests in flight per thread
-                const int f = 12 * part + 4 * q;
-                v4[q] = make_float4(0.f, 0.f, 0.f, 0.f); w4[q] = v4[q];
-                if (active && f < need && f < SH3) {
-                    v4[q] = __ldg(reinterpret_cast<const float4*>(pc + f));
-                    if (lerp) w4[q] = __ldg(reinterpret_cast<const float4*>(pp + f));
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 3; q++) {
-                c_[4 * q] = LERP(v4[q].x, w4[q].x); c_[4 * q + 1] = LERP(v4[q].y, w4[q].y);
-                c_[4 * q + 2] = LERP(v4[q].z, w4[q].z); c_[4 * q + 3] = LERP(v4[q].w, w4[q].w);
-            }
-        } else {
-#pragma unroll
-            for (int e = 0; e < 12; e++) {
-                const int f = 12 * part + e;
-                if (active && f < need && f < SH3) c_[e] = lerp ? t * __ldg(pc + f) + u * __ldg(pp + f) : __ldg(pc + f);
-            }
-        }
-    }
-    const float px_ = LERP(means3D[3 * c], means3D[3 * p]);
-    const float py_ = LERP(means3D[3 * c + 1], means3D[3 * p + 1]);
-    const float pz_ = LERP(means3D[3 * c + 2], means3D[3 * p + 2]);
-#undef LERP
-    float dx = px_ - campos[0], dy = py_ - campos[1], dz = pz_ - campos[2];
-    const float len = sqrtf(dx * dx + dy * dy + dz * dz);
-    dx /= len; dy /= len; dz /= len;
-    float B[4];
-    sh_basis_quad_value(part, deg, dx, dy, dz, B);
-    float rgb[3];
-#pragma unroll
-    for (int ch = 0; ch < 3; ch++) {
-        float r = B[0] * c_[ch];
-        r = r + B[1] * c_[3 + ch] + B[2] * c_[6 + ch] + B[3] * c_[9 + ch];
-        r += __shfl_xor_sync(0xffffffffu, r, 1);
-        r += __shfl_xor_sync(0xffffffffu, r, 2);
-        rgb[ch] = r;
-    }
-    if (!active || part != 0) return;
-    uint32_t clampbits = 0;
-#pragma unroll
-    for (int ch = 0; ch < 3; ch++) {
-        const float r = rgb[ch] + 0.5f;
-        if (r < 0.f) clampbits |= (1u << (kClampShift + ch));
-        rgb[ch] = fmaxf(r, 0.f);
-    }
-    float* rc = reinterpret_cast<float*>(&records[i].c);
-    rc[0] = rgb[0]; rc[1] = rgb[1]; rc[2] = rgb[2];
-    if (clampbits) {
-        uint32_t* kb = reinterpret_cast<uint32_t*>(&records[i].b) + 3;
-        *kb = *kb | clampbits;
-    }
-}
-
-#else
-constexpr int kColSplit = 1;
-// K1b: SH -> RGB for the visible Gaussians only (192 B/row, x2 on lerped rows): reads the same
-// (lerped) mean as K1a, writes record.c.xyz and the three SH clamp flags.
+// (lerped) mean as K1a, writes record.c.xyz and the three SH clamp flags.  One thread per Gaussian; a four-threads-per-
+// Gaussian form (39 instead of 70 registers, 63 % instead of 33 % of the warps resident) was measured slower: 0.110 vs
+// 0.100 ms (profiles/r02d_*) -- 2.7x the instructions for the same 385 MB of DRAM traffic.
 __global__ void __launch_bounds__(256)
 preprocess_color_kernel(int P, int deg, int M, const float* __restrict__ means3D, const float* __restrict__ shs,
                         const float* __restrict__ ts, const int* __restrict__ ridx, const int* __restrict__ pidx,
@@ -420,8 +289,6 @@ preprocess_color_kernel(int P, int deg, int M, const float* __restrict__ means3D
     }
 }
 
-#endif
-
 int launch_preprocess(const h3dgs_raster_args& a, int32_t* radii, float* depths, uint32_t* tiles_touched,
                       uint8_t* rank_mask, Record* records, uint32_t* tile_count, ScanInfo* info, cudaStream_t s)
 {
@@ -443,7 +310,7 @@ int launch_preprocess_color(const h3dgs_raster_args& a, const int32_t* radii, co
                             Record* records, cudaStream_t s)
 {
     if (a.P == 0 || a.colors_precomp) return H3DGS_OK;
-    const int threads = 256, blocks = (int)(((size_t)a.P * kColSplit + threads - 1) / threads);
+    const int threads = 256, blocks = (a.P + threads - 1) / threads;
     // only when the caller told the forward which gradient rows this rank will finish (otherwise every visible row may be needed)
     const RowCycle cyc = row_cycle(a);
     const bool skip_foreign = a.shard_count > 1 && (a.grad_row_end > a.grad_row_begin || cyc.world > 1);
