@@ -12,6 +12,11 @@ $T python -m pytest tests -m gpu -q -p no:cacheprovider -rs -x > gpurun_out/${ta
 tail -6 gpurun_out/${tag}_tests.log
 lean="--no-extras --no-cpu-baseline"; [ $full = 1 ] && lean=""
 $T python bench.py --steps 20 --warmup 3 $lean > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
+if [ $full = 1 ]; then    # the record lines of a round: config #2 with the classic-formulation stand-in, the CPU reference arm, the reference-CUDA probe
+  $T python bench.py --workload flat1m --classic --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_flat1m.json 2> gpurun_out/${tag}_bench_flat1m.err
+  $T python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err
+  $T python bench.py --impl reference-cuda > gpurun_out/${tag}_bench_refcuda.json 2> gpurun_out/${tag}_bench_refcuda.err
+fi
 for v in "$@"; do
   env $v $T python bench.py --steps 20 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/${tag}_bench_${v%%=*}.json 2> gpurun_out/${tag}_bench_${v%%=*}.err
 done
@@ -20,6 +25,8 @@ import json, glob
 for f in sorted(glob.glob("gpurun_out/${tag}_bench*.json")):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
+        if "ms_per_step" not in d or "e2e" not in d or "value" not in d:
+            print(f, json.dumps(d)[:300]); continue
         print(f, round(d["value"], 1), "img/s", round(d["ms_per_step"], 4), "ms  e2e", round(d["e2e"]["value"], 1), d.get("stage_ms"), "gap", d.get("host_gap_ms"),
               {k: round(d[k]["value"], 1) for k in ("value_api", "value_dropin") if k in d})
         print("   hbm_frac", d.get("stage_hbm_frac"))
