@@ -464,9 +464,9 @@ def main():
             mode = "api"
             config["mode"] = "call by call through the drop-in packages, cut gather/lerp fused into K1/K9"
     if mode == "graph":
-        config["collectives"] = ("fused into the kernels over NVLink peer memory (forward: stores into every rank's image; backward: the "
-                                 "owner's chain-rule kernels pull the partial [P,10] rows of the ranks that touch a Gaussian) + 2 device-side "
-                                 "barrier kernels per step" if use_peer else
+        config["collectives"] = ("fused into the kernels over NVLink peer memory (image: the L1 kernel forwards a rank's rendered tile rows to "
+                                 "every rank with coalesced stores; gradients: a push of the partial [P,10] rows into the owners' staging areas, "
+                                 "summed by the owner's chain-rule kernels) + 2 device-side barrier kernels per step" if use_peer else
                                  ("NCCL all-gather (image slabs) + reduce-scatter ([P,10] sums)" if world > 1 else "none"))
         mk = lambda **kw: GraphedStep(scene, W, H, c0.tanfovx, c0.tanfovy, bg, thr[0], world=world, rank=rank, peer=use_peer, **kw)
         # capacities: one eager sync-free pass over the views with generous sizes, then +15 % head room

@@ -144,7 +144,7 @@ static int check_args(const h3dgs_raster_args* a) {
             return H3DGS_EINVAL;
         }
         for (int r = 0; r < n; r++)
-            if (!a->peer_image[r] || !a->peer_stage[r]) { set_error("peer mode: peer_image / peer_stage [%d] is NULL", r); return H3DGS_EINVAL; }
+            if ((r == a->shard_index && !a->peer_image[r]) || !a->peer_stage[r]) { set_error("peer mode: peer_image[shard_index] / peer_stage[%d] is NULL", r); return H3DGS_EINVAL; }
     }
     if (a->bin_capacity > 0 && a->debug) { set_error("capacity mode has no host synchronisation: debug must be off"); return H3DGS_EINVAL; }
     if (!a->means3D && a->P > 0) { set_error("means3D is NULL"); return H3DGS_EINVAL; }

@@ -20,7 +20,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
 l1_grad_kernel(int C, int H, int W, int shard_count, int shard_index, const float* __restrict__ img,
                const float* __restrict__ gt, float scale, float* __restrict__ dL_dimg, double* __restrict__ loss_sum,
-               const PeerPtrs peers)
+               const PeerPtrs peers, const PeerPtrs images)
 {
     __shared__ float s_red[8];
     const int W4 = W / VEC;                                  // VEC = 4 needs W % 4 == 0 (launcher)
@@ -36,6 +36,14 @@ l1_grad_kernel(int C, int H, int W, int shard_count, int shard_index, const floa
             continue;
         }
         const float4 a = reinterpret_cast<const float4*>(img)[i], b = reinterpret_cast<const float4*>(gt)[i];
+        if (images.n > 1) {
+            // peer mode: this rank's pixels travel to the other ranks' images from HERE -- one coalesced 128-bit store per
+            // lane and rank (512 contiguous bytes per warp), posted over NVLink -- instead of pixel by pixel out of the
+            // blend kernel (8 GPUs: render_forward 0.132 ms with the stores, profiles/r02_m8_*)
+#pragma unroll
+            for (int r = 0; r < H3DGS_MAX_PEERS; r++)
+                if (r < images.n && r != shard_index && images.p[r]) reinterpret_cast<float4*>(images.p[r])[i] = a;
+        }
         const float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z, d3 = a.w - b.w;
         acc += (fabsf(d0) + fabsf(d1)) + (fabsf(d2) + fabsf(d3));
         float4 g;
@@ -87,14 +95,14 @@ extern "C" int h3dgs_step_status(double* loss_sum, double inv_numel, const int32
 }
 
 static int l1_launch(int32_t C, int32_t H, int32_t W, const float* img, const float* gt, float scale, int32_t shard_count,
-                     int32_t shard_index, float* dL_dimg, double* loss_sum, const PeerPtrs& peers, cudaStream_t s)
+                     int32_t shard_index, float* dL_dimg, double* loss_sum, const PeerPtrs& peers, const PeerPtrs& images, cudaStream_t s)
 {
     const bool vec = (W & 3) == 0;
     const size_t total = (size_t)C * H * (vec ? (W >> 2) : W);
     const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
     const int sc = shard_count > 1 ? shard_count : 1, si = shard_count > 1 ? shard_index : 0;
-    if (vec) l1_grad_kernel<4><<<blocks, 256, 0, s>>>(C, H, W, sc, si, img, gt, scale, dL_dimg, loss_sum, peers);
-    else l1_grad_kernel<1><<<blocks, 256, 0, s>>>(C, H, W, sc, si, img, gt, scale, dL_dimg, loss_sum, peers);
+    if (vec) l1_grad_kernel<4><<<blocks, 256, 0, s>>>(C, H, W, sc, si, img, gt, scale, dL_dimg, loss_sum, peers, images);
+    else l1_grad_kernel<1><<<blocks, 256, 0, s>>>(C, H, W, sc, si, img, gt, scale, dL_dimg, loss_sum, peers, images);
     H3_LAUNCHED("l1_loss_grad", 0, s);
     return H3DGS_OK;
 }
@@ -108,17 +116,23 @@ extern "C" int h3dgs_l1_loss_grad(int32_t C, int32_t H, int32_t W, const float* 
     H3_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(double), s));
     PeerPtrs none; none.n = 0;
     for (int k = 0; k < H3DGS_MAX_PEERS; k++) none.p[k] = nullptr;
-    return l1_launch(C, H, W, img, gt, scale, shard_count, shard_index, dL_dimg, loss_sum, none, s);
+    return l1_launch(C, H, W, img, gt, scale, shard_count, shard_index, dL_dimg, loss_sum, none, none, s);
 }
 
 extern "C" int h3dgs_l1_loss_grad_peer(int32_t C, int32_t H, int32_t W, const float* img, const float* gt, float scale,
                                        int32_t shard_count, int32_t shard_index, float* dL_dimg, int32_t peer_count,
-                                       double* const* loss_sums, void* stream)
+                                       double* const* loss_sums, float* const* peer_images, void* stream)
 {
     if (C <= 0 || H <= 0 || W <= 0 || !img || !gt || !dL_dimg || !loss_sums || peer_count < 2 || peer_count > H3DGS_MAX_PEERS) {
         set_error("l1_loss_grad_peer: bad arguments"); return H3DGS_EINVAL;
     }
     if (shard_count > 1 && (shard_index < 0 || shard_index >= shard_count)) { set_error("l1_loss_grad_peer: bad shard"); return H3DGS_EINVAL; }
+    PeerPtrs images; images.n = 0;
+    for (int k = 0; k < H3DGS_MAX_PEERS; k++) images.p[k] = nullptr;
+    if (peer_images) {
+        if (shard_count != peer_count || (W & 3)) { set_error("l1_loss_grad_peer: the image exchange needs shard_count == peer_count and W %% 4 == 0"); return H3DGS_EINVAL; }
+        images = peer_ptrs(reinterpret_cast<void* const*>(peer_images), peer_count);
+    }
     return l1_launch(C, H, W, img, gt, scale, shard_count, shard_index, dL_dimg, nullptr,
-                     peer_ptrs(reinterpret_cast<void* const*>(loss_sums), peer_count), (cudaStream_t)stream);
+                     peer_ptrs(reinterpret_cast<void* const*>(loss_sums), peer_count), images, (cudaStream_t)stream);
 }

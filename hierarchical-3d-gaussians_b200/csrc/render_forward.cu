@@ -193,7 +193,7 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
             const float v0 = c0 + T * bg0, v1 = c1 + T * bg1, v2 = c2 + T * bg2;
 #pragma unroll
             for (int r = 0; r < H3DGS_MAX_PEERS; r++)        // compile-time indices: the pointers stay in the parameter bank
-                if (r < peers.n) {
+                if (r < peers.n && peers.p[r]) {
                     float* o = static_cast<float*>(peers.p[r]);
                     o[pix] = v0; o[plane + pix] = v1; o[2 * plane + pix] = v2;
                 }

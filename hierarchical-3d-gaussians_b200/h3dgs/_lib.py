@@ -91,7 +91,7 @@ def bind(l):
     l.h3dgs_step_status.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     l.h3dgs_l1_loss_grad_peer.restype = C.c_int
     l.h3dgs_l1_loss_grad_peer.argtypes = [C.c_int32] * 3 + [C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32,
-                                          C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.c_void_p]
+                                          C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]
     if hasattr(l, "h3dgs_peer_alloc"):           # peer memory (CUDA IPC, device-side barrier): absent from the emulation build
         l.h3dgs_peer_flag_bytes.restype = C.c_size_t
         l.h3dgs_peer_alloc.restype = C.c_int

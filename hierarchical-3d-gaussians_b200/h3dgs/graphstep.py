@@ -16,8 +16,8 @@ the critical path.  Here nothing returns to the host inside the step:
 
 Sharded over G > 1 ranks the step has two forms.  peer=False: the image slabs travel in one NCCL all-gather, the
 [P,10] gradient sums in one NCCL reduce-scatter (h3dgs.dist).  peer=True (G in {2,4,8} on one NVLink box): the
-collectives are fused into the kernels through peer memory (h3dgs.peer, csrc/peer.cu) -- the forward stores every
-finished pixel into the image of every rank; the backward replay leaves each rank's partial (tile, Gaussian) sums in its
+collectives are fused into the kernels through peer memory (h3dgs.peer, csrc/peer.cu) -- the L1 kernel, which reads a rank's freshly rendered
+tile rows anyway, forwards them into the image of every other rank with coalesced 128-bit stores; the backward replay leaves each rank's partial (tile, Gaussian) sums in its
 own accumulator, a push kernel stores the partial rows that other ranks own (block-cyclic row ownership) into the owners'
 staging areas (coalesced posted stores over NVLink), and the owner's per-Gaussian chain rule (K9) adds the staged rows of
 the ranks that touch the Gaussian; the L1 kernel evaluates only the rank's
@@ -89,6 +89,7 @@ class GraphedStep:
             self.image = self.arena.tensor("image", torch.float32, (3, H, W))
             self.loss_sum = self.arena.tensor("loss", torch.float64, (1,))
             self._loss_ptrs = (C.c_void_p * world)(*self.arena.ptrs("loss"))
+            self._image_ptrs = (C.c_void_p * world)(*self.arena.ptrs("image"))
         elif world > 1:
             rows = hdist.owned_rows(H, world, rank)
             self.rpr = hdist.rows_per_rank(H, world)
@@ -150,7 +151,9 @@ class GraphedStep:
         if self.peer:
             a.peer_count, a.grad_cyclic_log2 = self.world, self.cyclic_log2
             for r in range(self.world):
-                a.peer_image[r], a.peer_stage[r] = self.arena.ptr("image", r), self.arena.ptr("stage", r)
+                # the forward stores only into this rank's own image: the L1 kernel forwards the rows to the peers (coalesced)
+                a.peer_image[r] = self.arena.ptr("image", r) if r == self.rank else None
+                a.peer_stage[r] = self.arena.ptr("stage", r)
         return a
 
     def _stream(self):
@@ -197,7 +200,7 @@ class GraphedStep:
             # own tile rows only (they were written locally); the partial sum goes into every rank's loss accumulator
             _lib.check(L.h3dgs_l1_loss_grad_peer(3, self.H, self.W, self.image.data_ptr(), self.gt.data_ptr(), 1.0 / numel,
                                                  self.world, self.rank, self.dcolor.data_ptr(), self.world, self._loss_ptrs,
-                                                 self._stream()))
+                                                 self._image_ptrs, self._stream()))
         else:
             _lib.check(L.h3dgs_l1_loss_grad(3, self.H, self.W, self.image.data_ptr(), self.gt.data_ptr(), 1.0 / numel, 1, 0,
                                             self.dcolor.data_ptr(), self.loss_sum.data_ptr(), self._stream()))

@@ -119,8 +119,10 @@ typedef struct h3dgs_raster_args {
     /* Peer mode of a tile-sharded frame (peer_count == shard_count > 1; one process per GPU on one NVLink / NVSwitch
      * box; memory from h3dgs_peer_alloc / h3dgs_peer_open): the collectives are fused into the blend kernels.
      *  forward : every finished pixel of this rank's tile rows is stored into peer_image[r] ([3,H,W], one per rank,
-     *            peer_image[shard_index] = the local one) for all r -- the all-gather of rendered tiles, tile by tile;
-     *            out_color is not written.
+     *            peer_image[shard_index] = the local one, required) for every r whose pointer is not NULL -- the
+     *            all-gather of rendered tiles, tile by tile; out_color is not written.  (Pixel-wise remote stores are
+     *            small NVLink packets: a caller that runs h3dgs_l1_loss_grad_peer next passes only its own pointer here
+     *            and lets that kernel forward the rows with coalesced stores.)
      *  backward: phase 1 leaves this rank's PARTIAL [P][10] sums (its own tiles) in `scratch` and then PUSHES, for every
      *            row it touched that another rank owns, the 40-byte partial row into that owner's staging area:
      *            peer_stage[owner] is [peer_count][P][10] floats on rank `owner`, slot [shard_index] is ours
@@ -252,10 +254,13 @@ int h3dgs_l1_ssim_backward(int32_t C, int32_t H, int32_t W, const float* img, co
 int h3dgs_l1_loss_grad(int32_t C, int32_t H, int32_t W, const float* img, const float* gt, float scale,
                        int32_t shard_count, int32_t shard_index, float* dL_dimg, double* loss_sum, void* stream);
 /* the same, adding this rank's partial sum into loss_sums[0..peer_count) [host array of device pointers, one double
- * per rank in peer memory; NOT zeroed here] so that every rank ends up with the loss of the whole frame */
+ * per rank in peer memory; NOT zeroed here] so that every rank ends up with the loss of the whole frame.
+ * peer_images (optional; needs shard_count == peer_count, W % 4 == 0): host array of the ranks' [C,H,W] images in peer
+ * memory -- the pixels of this rank's tile rows are copied from img into peer_images[r], r != shard_index, with
+ * coalesced 128-bit stores: the all-gather of the rendered tile rows, fused into the pass that reads them anyway. */
 int h3dgs_l1_loss_grad_peer(int32_t C, int32_t H, int32_t W, const float* img, const float* gt, float scale,
                             int32_t shard_count, int32_t shard_index, float* dL_dimg, int32_t peer_count,
-                            double* const* loss_sums, void* stream);
+                            double* const* loss_sums, float* const* peer_images, void* stream);
 
 /* Status words of a sync-free step, written by one device thread (no host synchronisation, capturable): out[0] =
  * *loss_sum * inv_numel, out[1] = *count + extra_rows (rows the cut needs), out[2..4] = scan_info[0..2] (D, longest tile

@@ -325,6 +325,37 @@ def test_fused_l1_loss_and_gradient(emu, W, shard):
 
 
 @pytest.mark.parametrize("G", [2, 4])
+def test_peer_l1_kernel_forwards_the_rendered_rows(emu_lib, G):
+    """h3dgs_l1_loss_grad_peer with peer_images: every "rank" holds only ITS tile rows of the frame; its L1 pass copies
+    them into the images of the other ranks (the fused all-gather of the peer-mode step) while it evaluates the loss of
+    those rows -- afterwards every image is the whole frame, every loss sum the loss of the whole frame."""
+    import ctypes as C
+    H, W = 70, 64
+    g = np.random.default_rng(3)
+    frame = g.uniform(0, 1, (3, H, W)).astype(np.float32); gt = g.uniform(0, 1, (3, H, W)).astype(np.float32)
+    rows = np.arange(H)
+    images = []
+    for r in range(G):
+        own = ((rows // 16) % G) == r
+        img = np.full((3, H, W), np.nan, np.float32)            # what a rank has not rendered is not there
+        img[:, own] = frame[:, own]
+        images.append(img)
+    sums = [np.zeros(1, np.float64) for _ in range(G)]
+    outs = [np.zeros((3, H, W), np.float32) for _ in range(G)]
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for r in range(G):
+        ls = (C.c_void_p * G)(*[s_.ctypes.data for s_ in sums])
+        ims = (C.c_void_p * G)(*[im.ctypes.data for im in images])
+        rc = emu_lib.L.h3dgs_l1_loss_grad_peer(3, H, W, p(images[r]), p(gt), C.c_float(0.5), G, r, p(outs[r]), G, ls, ims, None)
+        assert rc == 0, emu_lib.L.h3dgs_last_error()
+    for r in range(G):
+        assert np.array_equal(images[r], frame)
+        assert abs(sums[r][0] - np.abs((frame - gt).astype(np.float64)).sum()) < 1e-2
+        own = ((rows // 16) % G) == r
+        assert np.array_equal(outs[r][:, own], np.sign((frame - gt)[:, own]) * np.float32(0.5))
+
+
+@pytest.mark.parametrize("G", [2, 4])
 def test_peer_mode_fused_collectives_schedule(emu, G):
     """Peer mode (h3dgs_raster_args.peer_count) on one CPU: G "ranks" run one after the other with numpy arrays standing in
     for peer memory.  Forward: every rank stores the pixels of ITS tile rows into the image of EVERY rank -> all G images
