@@ -288,7 +288,7 @@ extern "C" int h3dgs_rasterize_backward(const h3dgs_raster_args* a, const int32_
     if (!geom_state || !binning_state || !image_state || ((phases & 1) && !dL_dcolor) || !scratch || !radii) {
         set_error("backward: missing saved state / scratch"); return H3DGS_EINVAL;
     }
-    if ((phases & 2) && (!dL_dmeans3D || !dL_dmeans2D || !dL_dopacities || (a->shs && !dL_dsh) ||
+    if ((phases & (2 | 4)) && (!dL_dmeans3D || !dL_dmeans2D || !dL_dopacities || (a->shs && !dL_dsh) ||
         (a->scales && (!dL_dscales || !dL_drotations)) || (a->cov3D_precomp && !dL_dcov3D))) {
         set_error("backward: missing gradient output"); return H3DGS_EINVAL;
     }
@@ -305,8 +305,11 @@ extern "C" int h3dgs_rasterize_backward(const h3dgs_raster_args* a, const int32_
     bool zero_joined = true;
     SideStream* ss = nullptr;
     SideJoin side_guard;
-    if ((phases & 2) && a->render_indices) {
-        // scatter mode: gradients have num_source rows and must start from zero
+    // scatter mode: gradients have num_source rows and must start from zero.  The fill (0.7 GB on config #3) runs on the side
+    // stream beside the issue-bound replay; a caller that splits the phases asks for it with the replay (phases = 1 | 4) and
+    // tells the chain-rule call that it has happened (phases = 2 | 8) -- otherwise it would sit between the two, exposed
+    const bool fill_now = a->render_indices && (((phases & 2) && !(phases & 8)) || (phases & 4));
+    if (fill_now) {
         rc = side_stream(&ss);
         if (rc) return rc;
         const size_t N = (size_t)a->num_source;

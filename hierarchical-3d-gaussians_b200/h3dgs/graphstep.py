@@ -214,15 +214,16 @@ class GraphedStep:
         elif self.peer:
             # phase 1 fills this rank's partial sums and pushes the rows other ranks own into their staging areas; after the
             # barrier phase 2 adds, for the rows it owns, what the ranks that touched them have staged: the whole "reduce-scatter"
-            _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 1, self._stream()))
+            # (1 | 4: the zero-fill of the full-size gradients runs beside the replay; 2 | 8: ... and is not repeated)
+            _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 1 | 4, self._stream()))
             self.arena.barrier()
-            _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 2, self._stream()))
+            _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 2 | 8, self._stream()))
         else:
             # rows [P, world*chunk) of accum are zero since construction and never written: the blocks reduce cleanly
-            _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 1, self._stream()))
+            _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 1 | 4, self._stream()))
             hdist.reduce_accum(self.accum.view(torch.uint8), self.P, self.world, self.rank, self.group)
             # phase 2 rewrites exactly the own row block of d_means2D; the other rows stay zero since construction
-            _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 2, self._stream()))
+            _lib.check(L.h3dgs_rasterize_backward(C.byref(self.args), *state, *outs, self.accum.data_ptr(), 2 | 8, self._stream()))
         # status words (loss, rows needed, D, longest list, overflow flags) by one device thread; peer mode: the loss sum is
         # complete since the mid-backward barrier and is reset here for the next step (ordered before anybody's next L1
         # kernel by the start barrier)

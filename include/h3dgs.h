@@ -164,7 +164,10 @@ int h3dgs_rasterize_backward(const h3dgs_raster_args* args, const int32_t* radii
                              void* scratch /* >= h3dgs_backward_scratch_bytes(P) device bytes */,
                              int phases /* 3 = whole backward; 1 = per-tile replay only (fills `scratch` with the
                                            [P][10] 2D-space sums); 2 = per-Gaussian chain rule only (consumes it).
-                                           The multi-GPU mode all-reduces `scratch` between 1 and 2. */,
+                                           The multi-GPU mode exchanges `scratch` between 1 and 2.  Scatter mode
+                                           (render_indices): | 4 with phase 1 = zero-fill the full-size gradient outputs
+                                           now, beside the replay (they must be passed); | 8 with phase 2 = they are
+                                           already zero (an earlier call filled them). */,
                              void* stream);
 size_t h3dgs_backward_scratch_bytes(int32_t P);
 

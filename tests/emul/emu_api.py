@@ -102,9 +102,9 @@ class Emu:
             out["keys_sorted"] = view(b[1], v.keys_sorted, np.uint64, D)
         return out
 
-    def backward(self, a, fwd, dL_dcolor, dL_dinvdepth=None, phases=3, scratch=None):
+    def backward(self, a, fwd, dL_dcolor, dL_dinvdepth=None, phases=3, scratch=None, outs=None):
         """phases / scratch as in h3dgs_rasterize_backward: 1 fills `scratch` with the [P][10] sums (returned as
-        g["scratch"]), 2 consumes it"""
+        g["scratch"]), 2 consumes it; outs: the gradient arrays of an earlier call (split phases with flags 4 / 8)"""
         P = a.P
         N = a.num_source if a.render_indices else P
         M = a.sh_coeffs
@@ -115,6 +115,8 @@ class Emu:
                  scales=aligned(N * 12, np.float32, (N, 3)) if a.scales else None,
                  rotations=aligned(N * 16, np.float32, (N, 4)) if a.rotations else None,
                  cov3Ds_precomp=aligned(N * 24, np.float32, (N, 6)) if a.cov3D_precomp else None)
+        if outs is not None:
+            g = {k: outs[k] for k in g}
         if scratch is None:
             scratch = aligned(self.L.h3dgs_backward_scratch_bytes(P))
         gcol = f32(dL_dcolor)

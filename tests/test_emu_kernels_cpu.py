@@ -324,6 +324,37 @@ def test_fused_l1_loss_and_gradient(emu, W, shard):
     assert np.all(out[:, ~own] == 7.0)
 
 
+def test_split_phases_fill_the_scatter_outputs_beside_the_replay(emu_lib):
+    """scatter mode, backward in two calls: phases 1|4 (replay + zero-fill of the full-size gradients) then 2|8 (chain rule,
+    outputs already zero) gives what the single call (3) gives; the outputs are poisoned first, so a missing fill shows."""
+    from oracle import oracle
+    cam = synth.make_camera(128, 96)
+    leaves = synth.cloud_v1(900, cam, zmin=2.0, zmax=30.0, seed=4, scale_k=1.0)
+    z = leaves["means3D"][:, 2:3]
+    leaves["scales"] = (8e-3 * np.sqrt(2 * z) * np.ones((1, 3))).astype(np.float32)
+    h = synth.build_hierarchy(leaves)
+    thr = synth.tau_threshold(6.0, cam)
+    n, ri, pi, ni = oracle.expand_to_size(h["nodes"], h["boxes"], thr, cam.camera_center)
+    ts, kids = oracle.get_interpolation_weights(ni, thr, h["nodes"], h["boxes"], cam.camera_center)
+    bg = np.array([0.3, 0.2, 0.1], np.float32)
+    a, keep = emu_lib.args(cam, bg, h, ts=ts, kids=kids, ridx=ri, pidx=pi)
+    fw = emu_lib.forward(a, keep)
+    gcol = synth.l1_grad(fw["color"])
+    whole = emu_lib.backward(a, fw, gcol)
+    first = emu_lib.backward(a, fw, gcol, phases=1 | 4)
+    assert all(not np.asarray(first[k]).any() for k in ("means3D", "sh", "opacities", "scales", "rotations"))
+    for k in ("means3D", "sh", "opacities", "scales", "rotations"):
+        first[k][...] += 0.0                                     # the arrays the second call continues with
+    second = emu_lib.backward(a, fw, gcol, phases=2 | 8, scratch=first["scratch"], outs=first)
+    for k in ("means3D", "sh", "opacities", "scales", "rotations", "means2D"):
+        assert np.allclose(second[k], whole[k], rtol=1e-5, atol=1e-9), k
+    # without the fill flag of the first call and with "already zero" claimed, stale contents would survive: the fill matters
+    stale = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in first.items()}
+    stale["means3D"][...] = 3.0
+    third = emu_lib.backward(a, fw, gcol, phases=2 | 8, scratch=first["scratch"], outs=stale)
+    assert not np.allclose(third["means3D"], whole["means3D"])
+
+
 @pytest.mark.parametrize("G", [2, 4])
 def test_peer_l1_kernel_forwards_the_rendered_rows(emu_lib, G):
     """h3dgs_l1_loss_grad_peer with peer_images: every "rank" holds only ITS tile rows of the frame; its L1 pass copies
