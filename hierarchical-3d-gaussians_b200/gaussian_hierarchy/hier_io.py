@@ -9,8 +9,10 @@ upstream.  What IS pinned by the call sites: the argument order of both function
 and that values pass through unchanged (`_scaling` is written and read back as log-scales, opacity as
 the `abs`-activated value).  A round trip through this module is exact.
 
-    int32   P                      number of Gaussians (P < 0 marks upstream's half-precision variant:
-                                   not supported here)
+    int32   P                      number of Gaussians; P < 0 marks upstream's COMPRESSED variant with |P| Gaussians:
+                                   positions stay float32, rotations / log-scales / opacities / SH are IEEE half
+                                   (same order, same shapes) -- recalled like the rest; the exact-size check below
+                                   makes a wrong recollection fail loudly instead of loading garbage
     float32 positions  [P][3]
     float32 rotations  [P][4]      w, x, y, z
     float32 log-scales [P][3]
@@ -39,19 +41,21 @@ def _np(t, dtype, shape, name):
         raise ValueError(f"write_hierarchy: {name} has shape {tuple(a.shape)}, expected {shape}") from None
 
 
-def write_hierarchy(path, xyz, shs, opacities, log_scales, rotations, nodes, boxes):
-    """Argument order of scene/gaussian_model.py:420-427.  Tensors may live on any device."""
+def write_hierarchy(path, xyz, shs, opacities, log_scales, rotations, nodes, boxes, compressed=False):
+    """Argument order of scene/gaussian_model.py:420-427.  Tensors may live on any device.  compressed (not used by the
+    reference's call site): the half-precision variant, count written as -P."""
     P = int(xyz.shape[0])
     N = int(nodes.shape[0])
+    ft = np.float16 if compressed else np.float32
     parts = [
-        _np(xyz, np.float32, (P, 3), "xyz"), _np(rotations, np.float32, (P, 4), "rotations"),
-        _np(log_scales, np.float32, (P, 3), "scales"), _np(opacities, np.float32, (P,), "opacities"),
-        _np(shs, np.float32, (P, 16, 3), "shs"),
+        _np(xyz, np.float32, (P, 3), "xyz"), _np(rotations, np.float32, (P, 4), "rotations").astype(ft),
+        _np(log_scales, np.float32, (P, 3), "scales").astype(ft), _np(opacities, np.float32, (P,), "opacities").astype(ft),
+        _np(shs, np.float32, (P, 16, 3), "shs").astype(ft),
     ]
     nd, bx = _np(nodes, np.int32, (N, 7), "nodes"), _np(boxes, np.float32, (N, 2, 4), "boxes")
     tmp = f"{path}.{os.getpid()}.tmp"
     with open(tmp, "wb") as f:
-        np.array([P], np.int32).tofile(f)
+        np.array([-P if compressed else P], np.int32).tofile(f)
         for a in parts:
             a.tofile(f)
         np.array([N], np.int32).tofile(f)
@@ -69,17 +73,19 @@ def load_hierarchy(path):
         if head.size != 1:
             raise ValueError(f"{path}: empty file")
         P = int(head[0])
-        if P < 0:
-            raise NotImplementedError(f"{path}: negative count {P} (upstream's half-precision .hier variant) is not supported")
-        need = 4 + 4 * P * sum(w for _, w in _FIELDS) + 4
+        compressed = P < 0
+        P = abs(P)
+        width = lambda name: 4 if (name == "positions" or not compressed) else 2
+        need = 4 + P * sum(w * width(name) for name, w in _FIELDS) + 4
         if size < need:
-            raise ValueError(f"{path}: {size} bytes, but {P} Gaussians need at least {need}")
+            raise ValueError(f"{path}: {size} bytes, but {P} Gaussians ({'half' if compressed else 'single'} precision) need at least {need}")
         out = {}
         for name, w in _FIELDS:
-            out[name] = np.fromfile(f, np.float32, P * w)
+            out[name] = np.fromfile(f, np.float32 if width(name) == 4 else np.float16, P * w).astype(np.float32)
         N = int(np.fromfile(f, np.int32, 1)[0])
         if N < 0 or size != need + N * (7 * 4 + 8 * 4):
-            raise ValueError(f"{path}: {size} bytes do not match P = {P}, N = {N} (expected {need + max(N, 0) * 60})")
+            raise ValueError(f"{path}: {size} bytes do not match P = {P}{' (compressed)' if compressed else ''}, N = {N} "
+                             f"(expected {need + max(N, 0) * 60}): not the layout this module assumes")
         nodes = np.fromfile(f, np.int32, N * 7).reshape(N, 7)
         boxes = np.fromfile(f, np.float32, N * 8).reshape(N, 2, 4)
     t = torch.from_numpy

@@ -56,6 +56,26 @@ def test_documented_byte_layout(tmp_path):
     assert np.array_equal(np.frombuffer(raw, np.float32, 8 * N, o).reshape(N, 2, 4), h["boxes"])
 
 
+def test_compressed_variant_round_trip(tmp_path):
+    """count written as -P: positions stay float32, rotations / log-scales / opacities / SH travel as IEEE half (layout
+    recalled, like the rest); the loader hands back float32 tensors of the call-site shapes"""
+    from gaussian_hierarchy._C import load_hierarchy, write_hierarchy
+    h = _hier(L=33)
+    P, N = h["means3D"].shape[0], h["nodes"].shape[0]
+    path = str(tmp_path / "c.hier")
+    args = [torch.tensor(h[k]) for k in ("means3D", "shs", "opacities", "scales", "rotations", "nodes", "boxes")]
+    write_hierarchy(path, *args, compressed=True)
+    raw = open(path, "rb").read()
+    assert struct.unpack_from("<i", raw, 0)[0] == -P
+    assert len(raw) == 4 + P * (12 + 2 * (4 + 3 + 1 + 48)) + 4 + N * 60
+    xyz, shs_all, alpha, scales, rots, nodes, boxes = load_hierarchy(path)
+    assert torch.equal(xyz, args[0]) and torch.equal(nodes, args[5]) and torch.equal(boxes, args[6])
+    half = lambda t: t.to(torch.float16).to(torch.float32)
+    assert torch.equal(shs_all, half(args[1])) and torch.equal(alpha, half(args[2]))
+    assert torch.equal(scales, half(args[3])) and torch.equal(rots, half(args[4]))
+    assert all(t.dtype == torch.float32 for t in (xyz, shs_all, alpha, scales, rots))
+
+
 def test_malformed_files_are_rejected(tmp_path):
     from gaussian_hierarchy._C import load_hierarchy, write_hierarchy
     h = _hier(L=9)
@@ -66,9 +86,9 @@ def test_malformed_files_are_rejected(tmp_path):
     open(trunc, "wb").write(raw[:len(raw) - 10])
     with pytest.raises(ValueError):
         load_hierarchy(trunc)
-    half = str(tmp_path / "half.hier")
-    open(half, "wb").write(struct.pack("<i", -17) + raw[4:])
-    with pytest.raises(NotImplementedError):
+    half = str(tmp_path / "half.hier")                          # a single-precision body under a "compressed" count: sizes disagree
+    open(half, "wb").write(struct.pack("<i", -h["means3D"].shape[0]) + raw[4:])
+    with pytest.raises(ValueError, match="do not match"):
         load_hierarchy(half)
     with pytest.raises(ValueError, match="shape"):
         write_hierarchy(path, torch.zeros(4, 3), torch.zeros(4, 15, 3), torch.zeros(4, 1), torch.zeros(4, 3), torch.zeros(4, 4),
