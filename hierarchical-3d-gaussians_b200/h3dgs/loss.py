@@ -63,8 +63,12 @@ def fused_l1_ssim(image, gt, lambda_dssim=0.2):
 
 
 def l1_loss(network_output, gt):
-    """utils/loss_utils.py:17-18"""
-    return _FusedL1SSIM.apply(network_output, gt, 0.0)[1]
+    """utils/loss_utils.py:17-18.  Images ([C,H,W] / [1,C,H,W]) go through the fused kernel; the reference's one-liner
+    accepts any shape, so anything else is evaluated as it writes it.  (A loop that needs both terms should call
+    fused_l1_ssim once: l1_loss + ssim each run the fused pass.)"""
+    if network_output.dim() == 3 or (network_output.dim() == 4 and network_output.shape[0] == 1):
+        return _FusedL1SSIM.apply(network_output, gt, 0.0)[1]
+    return torch.abs(network_output - gt).mean()
 
 
 def ssim(img1, img2, window_size=11, size_average=True):
