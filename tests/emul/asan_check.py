@@ -67,6 +67,19 @@ def run_cases(so, negative):
                   T.test_fused_cut_gather_and_scatter, T.test_device_lod_cut_and_skipped_rows):
             t(emu)
             n += 1
+        for G in (2, 4):                                   # peer mode: rank mask, push into the staging areas, gather in K9
+            T.test_peer_mode_fused_collectives_schedule(emu, G)
+            n += 1
+    # round 2: the in-register tile sort over all size classes, the TMA-staged single-pass cut (bulk and plain-load paths),
+    # the L1 kernel's image forwarding, the split-phase zero-fill
+    T.test_register_sort_size_classes_with_equal_depths(emu)
+    for tau, mis in ((6.0, False), (6.0, True)):
+        T.test_single_pass_cut_over_many_tiles.__wrapped__(emu, tau, mis, False, None) if hasattr(T.test_single_pass_cut_over_many_tiles, "__wrapped__") \
+            else T.test_single_pass_cut_over_many_tiles(emu, tau, mis, False, None)
+    for G in (2, 4):
+        T.test_peer_l1_kernel_forwards_the_rendered_rows(emu, G)
+    T.test_split_phases_fill_the_scatter_outputs_beside_the_replay(emu)
+    n += 6
     print(f"asan check complete: {n} cases, no report")
 
 
