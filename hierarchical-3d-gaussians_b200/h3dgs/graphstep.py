@@ -77,7 +77,11 @@ class GraphedStep:
         # static inputs
         self.view, self.proj, self.campos = f(16), f(16), f(3)
         self.bg = bg.to(dev).float().contiguous()
-        self.gt = f(3, H, W)
+        # two target buffers: the upload of the next step's target (25 MB over PCIe, ~1 ms) then overlaps the WHOLE current
+        # step instead of only its graph A; graph B is captured once per buffer.  self.gt is buffer 0 (gs.gt.copy_ / step(gt=))
+        self.gt_bufs = [f(3, H, W), f(3, H, W)]
+        self.gt = self.gt_bufs[0]
+        self._upload_slot, self._pending = 0, None          # buffer the next upload_target() writes; (slot, event) of an upload not yet consumed
         self.threshold_dev = torch.full((1,), self.threshold, dtype=torch.float32, device=dev)   # read by the cut kernels
         # static outputs
         self.count = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -118,8 +122,11 @@ class GraphedStep:
         self._scan_info = None
         self.graph_a = self.graph_b = None
         self.launches_per_step = 0
-        self._done = torch.cuda.Event()                 # recorded after part B: self.gt may be overwritten
+        self._done = torch.cuda.Event()                 # recorded after part B of every step
         self._done.record(torch.cuda.current_stream(dev))
+        self._slot_done = [torch.cuda.Event(), torch.cuda.Event()]      # recorded after the part B that read buffer k: it may be overwritten
+        for e in self._slot_done:
+            e.record(torch.cuda.current_stream(dev))
         if capture:
             self.capture()
 
@@ -190,19 +197,20 @@ class GraphedStep:
             dist.all_gather_into_tensor(self.slabs, self.slab, group=self.group)
             self.image = hdist.unpack(self.slabs.view(self.world, self.rpr, 3, 16, self.W), self.H, self.W, self.world)
 
-    def _part_b(self):
-        """L1 loss, its gradient, backward (-> reduce-scatter of the [P,10] sums between the phases)."""
+    def _part_b(self, slot=0):
+        """L1 loss against target buffer `slot`, its gradient, backward (-> exchange of the [P,10] sums between the phases)."""
         L = self.L
+        gt = self.gt_bufs[slot]
         # loss = mean |image - gt| and dL/dimage in one pass (csrc/l1_loss.cu); every rank evaluates the full image,
         # so the loss value needs no further exchange
         numel = self.image.numel()
         if self.peer:
             # own tile rows only (they were written locally); the partial sum goes into every rank's loss accumulator
-            _lib.check(L.h3dgs_l1_loss_grad_peer(3, self.H, self.W, self.image.data_ptr(), self.gt.data_ptr(), 1.0 / numel,
+            _lib.check(L.h3dgs_l1_loss_grad_peer(3, self.H, self.W, self.image.data_ptr(), gt.data_ptr(), 1.0 / numel,
                                                  self.world, self.rank, self.dcolor.data_ptr(), self.world, self._loss_ptrs,
                                                  self._image_ptrs, self._stream()))
         else:
-            _lib.check(L.h3dgs_l1_loss_grad(3, self.H, self.W, self.image.data_ptr(), self.gt.data_ptr(), 1.0 / numel, 1, 0,
+            _lib.check(L.h3dgs_l1_loss_grad(3, self.H, self.W, self.image.data_ptr(), gt.data_ptr(), 1.0 / numel, 1, 0,
                                             self.dcolor.data_ptr(), self.loss_sum.data_ptr(), self._stream()))
         g = self.grads
         outs = (g["means3D"].data_ptr(), self.d_means2D.data_ptr(), g["shs"].data_ptr(), None, g["opacities"].data_ptr(),
@@ -264,50 +272,66 @@ class GraphedStep:
         self.threshold_dev.fill_(self.threshold)
 
     def upload_target(self, src, stream):
-        """Copy this step's target (device tensor or pinned host tensor) into the static buffer on
-        `stream`, after the previous step has finished reading it; returns the event to hand to step()
-        as gt_ready.  The copy then overlaps the LOD cut and the forward pass (graph A)."""
+        """Copy the NEXT step's target (device tensor or pinned host tensor) into one of the two static target buffers on
+        `stream`, after the last step that read that buffer has finished; returns the event to hand to step() as gt_ready.
+        With two buffers the copy overlaps the whole step that is still running (and this step's graph A)."""
+        slot = self._upload_slot
+        self._upload_slot ^= 1
         with torch.cuda.stream(stream):
-            stream.wait_event(self._done)
-            self.gt.copy_(src, non_blocking=True)
+            stream.wait_event(self._slot_done[slot])
+            self.gt_bufs[slot].copy_(src, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(stream)
+        self._pending = (slot, ready)
         return ready
 
     def capture(self):
-        """One eager step (sizes the state buffers, creates the library's side stream), then capture."""
+        """One eager step (sizes the state buffers, creates the library's side stream), then capture: graph A, and graph B
+        once per target buffer."""
         s = torch.cuda.Stream(self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(s):
-            self._part_a(); self._part_b()
+            self._part_a(); self._part_b(0)
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
         l0 = _lib.launch_count()
-        self.graph_a, self.graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        self.graph_a = torch.cuda.CUDAGraph()
+        self.graph_b = [torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()]
         with torch.cuda.graph(self.graph_a):
             self._part_a()
-        with torch.cuda.graph(self.graph_b, pool=self.graph_a.pool()):
-            self._part_b()
+        with torch.cuda.graph(self.graph_b[0], pool=self.graph_a.pool()):
+            self._part_b(0)
         self.launches_per_step = _lib.launch_count() - l0      # library kernels inside one replay of A + B
+        with torch.cuda.graph(self.graph_b[1], pool=self.graph_a.pool()):
+            self._part_b(1)
 
     def step(self, cam=None, gt=None, gt_ready=None):
-        """cam/gt: optional new inputs (copied into the static buffers).  gt_ready: event after which
-        self.gt holds this step's target when the caller uploads it on another stream."""
+        """cam/gt: optional new inputs (copied into the static buffers; gt goes into buffer 0).  gt_ready: the event
+        upload_target() returned, when the caller uploads the target on another stream: this step then reads the buffer
+        that upload wrote."""
         if cam is not None:
             self.set_camera(cam)
+        slot = 0
         if gt is not None:
-            self.gt.copy_(gt, non_blocking=True)
+            self.gt_bufs[0].copy_(gt, non_blocking=True)
+            self._pending = None
+        elif self._pending is not None:
+            slot, ev = self._pending
+            self._pending = None
+            gt_ready = ev if gt_ready is None else gt_ready
+        cur = torch.cuda.current_stream(self.dev)
         if self.graph_a is None:
             self._part_a()
             if gt_ready is not None:
-                torch.cuda.current_stream(self.dev).wait_event(gt_ready)
-            self._part_b()
+                cur.wait_event(gt_ready)
+            self._part_b(slot)
         else:
             self.graph_a.replay()
             if gt_ready is not None:
-                torch.cuda.current_stream(self.dev).wait_event(gt_ready)
-            self.graph_b.replay()
-        self._done.record(torch.cuda.current_stream(self.dev))
+                cur.wait_event(gt_ready)
+            self.graph_b[slot].replay()
+        self._done.record(cur)
+        self._slot_done[slot].record(cur)
         return self.status_dev
 
     def status(self):

@@ -77,6 +77,19 @@ def test_public_api_step_and_sync_free_step(emu_so, skybox):
             assert torch.equal(gs.radii[:n_ref + skybox], radii) and bool((gs.radii[n_ref + skybox:] == 0).all())
             for k, ref in exact.items():
                 assert rel_err(gs.grads[k].numpy(), ref.numpy()) < 2e-6, k
+        # targets uploaded on another stream alternate between the two target buffers; a step reads the buffer its upload wrote
+        gt_b = torch.tensor(np.random.default_rng(9).uniform(0, 1, (3, cam.H, cam.W)).astype(np.float32))
+        loss_b = pipeline.l1_step(scene, dcam, bg, gt_b, thr, fused=True)[0].item()
+        side = torch.cuda.Stream() if hasattr(torch.cuda, "Stream") else None
+        for target, want in ((gtd, loss.item()), (gt_b, loss_b), (gt_b, loss_b), (gtd, loss.item())):
+            slot_before = gs._upload_slot
+            ready = gs.upload_target(target, side)
+            assert gs._upload_slot == 1 - slot_before and gs._pending[0] == slot_before
+            gs.set_camera(dcam)
+            gs.step(gt_ready=ready)
+            assert gs._pending is None and abs(gs.status()["loss"] - want) < 1e-7
+        gs.step(dcam, gt_b)                                  # step(gt=) goes through buffer 0 whatever was uploaded before
+        assert abs(gs.status()["loss"] - loss_b) < 1e-7 and torch.equal(gs.gt, gt_b)
         # a new threshold and a new camera between steps
         thr2 = synth.tau_threshold(15.0, cam)
         cam2 = pipeline.DeviceCamera(_cams(cam.W, cam.H)[1], device="cpu")
