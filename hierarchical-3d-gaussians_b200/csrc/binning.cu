@@ -113,7 +113,7 @@ gather_records_kernel(int64_t D, const uint32_t* __restrict__ point_list, const 
 // Per-tile path (default): K1 has left a per-tile histogram.  (1) one CTA scans it into
 // ranges[T] and reports D and the longest list; (2) every Gaussian drops (depth bits, idx) into
 // its tiles' segments (slot claimed with an atomic -- order inside a segment is arbitrary);
-// (3) one CTA per tile sorts its segment in shared memory by the 64-bit key (depth bits, idx)
+// (3) one CTA per tile sorts its segment -- in registers up to 1024 entries, in shared memory beyond -- by the 64-bit key (depth bits, idx)
 // -- exactly the order of a stable sort on depth over emission-in-index-order -- and, while the
 // index is in registers, gathers the 48-B record and its quadrant-reach mask.  HBM traffic:
 // 8 D (emit) + 8 D (read) + 12 D (keys/list out) + 96 D (records) instead of ~7 x 24 D for the

@@ -187,7 +187,7 @@ render_forward_kernel(int W, int H, int gx, int shard_count, int shard_index, co
         final_T[pix] = T;
         n_contrib[pix] = last;
         if (peers.n > 1) {
-            // peer mode: the finished pixel goes straight into the [3,H,W] image of EVERY rank (plain stores; remote ones
+            // peer mode: the finished pixel goes into the [3,H,W] image of every rank whose pointer is given (plain stores; remote ones
             // travel over NVLink while other tiles are still blending) -- the all-gather of rendered tiles, fused
             const size_t plane = (size_t)H * W;
             const float v0 = c0 + T * bg0, v1 = c1 + T * bg1, v2 = c2 + T * bg2;
